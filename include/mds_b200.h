@@ -1,0 +1,231 @@
+/*
+ * mds_b200.h -- C ABI of the B200-native batched multi-drone hot path.
+ *
+ * Drop-in boundary for the per-step loop of JasonTStanley/MultiDroneSim
+ *   traj(t) -> ctrl.compute(obs) -> qpTracker.compute_control(...) ->
+ *   ctrl.compute_low_level(...) -> env.step(action)
+ * (reference simulations/EnvGeometric.py:434-479, simulations/CBFTest.py:302-358).
+ *
+ * Conventions
+ *   - Every entry point returns int: 0 = ok, < 0 = error (see MDS_ERR_*); nothing
+ *     throws across the boundary; mds_last_error() gives a thread-local message.
+ *   - Every pointer named *_dev / inside MdsState / MdsPidState is a DEVICE pointer
+ *     (e.g. torch.Tensor.data_ptr()); structs of parameters are HOST pointers,
+ *     copied by value into the launch.  No global / __constant__ state is kept.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Suffix _f32 / _f64 selects the arithmetic type `Real` (float / double).
+ *   - D = E * N drones, index d = e * N + n (env-major).  N <= MDS_MAX_DRONES_PER_ENV.
+ *
+ * State layout in HBM (structure of arrays, 128-bit planes, 17 Real per drone):
+ *   pos_wx [D] Real4 = (px, py, pz, wx)      world position, body rate x
+ *   quat   [D] Real4 = (qx, qy, qz, qw)      PyBullet xyzw order
+ *   vel_wy [D] Real4 = (vx, vy, vz, wy)      world velocity, body rate y
+ *   rpm    [D] Real4 = last clipped motor RPM
+ *   wz     [D] Real  = body rate z
+ * Observation layout (reference layout, array of 20 Real per drone; consumed at
+ * reference utils/model_conversions.py:34-45,109-113):
+ *   [0:3] pos, [3:7] quat xyzw, [7:10] rpy, [10:13] vel world, [13:16] ang vel WORLD,
+ *   [16:20] last clipped RPM.
+ */
+#ifndef MDS_B200_H
+#define MDS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDS_ABI_VERSION 1
+#define MDS_MAX_DRONES_PER_ENV 32
+#define MDS_MAX_OBSTACLES 8
+#define MDS_OBS_DIM 20
+#define MDS_REF_DIM 11 /* pos3 vel3 acc3 yaw yaw_rate */
+
+#define MDS_OK 0
+#define MDS_ERR_ARG (-1)    /* bad argument (null pointer, size, enum) */
+#define MDS_ERR_LAUNCH (-2) /* CUDA launch / runtime error */
+#define MDS_ERR_UNSUPPORTED (-3)
+
+/* gym-pybullet-drones DroneModel / Physics (reference simulations/EnvGeometric.py:9,21-22) */
+enum { MDS_DRONE_CF2X = 0, MDS_DRONE_CF2P = 1 };
+enum { MDS_PHYSICS_DYN = 0, MDS_PHYSICS_DYN_GND_DRAG_DW = 1 };
+
+/* per-env QP status written by mds_cbf_qp / mds_rollout */
+enum { MDS_QP_OPTIMAL = 0, MDS_QP_INFEASIBLE = 1, MDS_QP_ITER_CAP = 2 };
+
+/* controller stack selected in mds_rollout */
+enum {
+  MDS_CTRL_GEOMETRIC = 0,   /* control/geometric.py -> input_to_action              */
+  MDS_CTRL_LQR_TORQUE = 1,  /* control/lqr/lqr_controller.py (12-dim) -> mixer     */
+  MDS_CTRL_LQR_OMEGA = 2,   /* lqr_omega_controller.py (9-dim) + ThrustOmega PID   */
+  MDS_CTRL_LQR_YANK = 3     /* lqr_YO_controller.py (10-dim) + YankOmega PID       */
+};
+
+/* trajectory generator kinds (reference trajectories/ package) */
+enum {
+  MDS_TRAJ_WAIT = 0,       /* LineTrajectory.py:4-14   p = {x,y,z,yaw}                              */
+  MDS_TRAJ_CIRCLE = 1,     /* Circle.py:5-45           p = {r,v,cx,cy,cz,yaw_rate}                  */
+  MDS_TRAJ_LEMNISCATE = 2, /* Lemniscate.py:3-63       p = {a,omega,cx,cy,cz,yaw_rate,phase_shift}  */
+  MDS_TRAJ_TABLE = 3       /* CompoundTrajectory.py:5-40 over a segment table (Line/Wait/Circle/...) */
+};
+enum { MDS_SEG_WAIT = 0, MDS_SEG_CIRCLE = 1, MDS_SEG_LEMNISCATE = 2, MDS_SEG_LINE = 3 };
+
+/* Drone + integrator constants: upstream BaseAviary attributes the reference reads
+ * (env.M, env.J, env.G, env.KF, env.KM, env.L, env.MAX_RPM, env.MAX_THRUST, ...). */
+typedef struct MdsDroneParams {
+  double m, g, kf, km, arm_l;
+  double ixx, iyy, izz;
+  double max_rpm, max_thrust;
+  double gnd_eff_coeff, prop_radius, gnd_eff_h_clip;
+  double drag_xy, drag_z;
+  double dw1, dw2, dw3;
+  double prop_x[4], prop_y[4]; /* prop link offsets, body frame */
+  double z_floor;              /* ground-plane contact clamp height */
+  double dt_phys;              /* PYB_TIMESTEP  */
+  double dt_ctrl;              /* CTRL_TIMESTEP */
+  int substeps;                /* PYB_STEPS_PER_CTRL */
+  int drone_model;             /* MDS_DRONE_*   */
+  int physics;                 /* MDS_PHYSICS_* */
+  int cf2x_torque_sign;        /* sign applied to the CF2X roll torque (SURVEY A.2 switch) */
+  int renormalize_quat;        /* 0 = upstream (no renormalisation) */
+  int ground_clamp;            /* 1 = clamp z at z_floor (composite mode default) */
+} MdsDroneParams;
+
+typedef struct MdsState {
+  void* pos_wx; void* quat; void* vel_wy; void* rpm; void* wz;
+} MdsState;
+
+/* ThrustOmegaController state: control/low_level/thrust_omega_ctrl.py:65-75 */
+typedef struct MdsPidState {
+  void* a; /* Real4[D] = (last_wx, last_wy, last_wz, integral_x) */
+  void* b; /* Real2[D] = (integral_y, integral_z) */
+} MdsPidState;
+
+/* control/geometric.py:14-23 */
+typedef struct MdsGeoGains {
+  double kp, kv, kr, kw, g_ctrl, max_tilt;
+} MdsGeoGains;
+
+/* LQR gain K (4 x dim row-major, dim in {12, 9, 10}); control/lqr/ package */
+typedef struct MdsLqrGains {
+  double K[48];
+  int dim;
+} MdsLqrGains;
+
+/* cbf/cbf.py:545-580 (DroneCBF) */
+typedef struct MdsCbfParams {
+  int order;             /* 2 (xdim 9) or 3 (xdim 10) */
+  double zscale;         /* c */
+  double safety_radius;
+  double kcbf[3];        /* place_poles gain, order entries */
+  double umax[4];
+  double fmin, fmax;     /* order-3 force-bound rows (cbf.py:446-464) */
+  int max_iter;          /* active-set iteration cap (0 = default 64) */
+} MdsCbfParams;
+
+/* per-drone trajectory descriptor, 48 B (f32) / 80 B (f64) */
+typedef struct MdsTrajSpecF32 { int kind, seg_begin, seg_count, pad; float p[8]; } MdsTrajSpecF32;
+typedef struct MdsTrajSpecF64 { int kind, seg_begin, seg_count, pad; double p[8]; } MdsTrajSpecF64;
+/* shared segment table entry for MDS_TRAJ_TABLE.  t_end = cumulative end time.
+ * LINE p[]: start3, v0 3, sgn_init3, cruise3, sgn_end3, end3, vf3, time_init, time_middle, total_time */
+typedef struct MdsTrajSegF32 { int kind; int has_rot; float t_end; float dur; float p[24]; float rot[12]; } MdsTrajSegF32;
+typedef struct MdsTrajSegF64 { int kind; int has_rot; double t_end; double dur; double p[24]; double rot[12]; } MdsTrajSegF64;
+
+/* rollout statistics (one block of doubles, accumulated with atomics) */
+enum {
+  MDS_STAT_DRONE_STEPS = 0, MDS_STAT_SUM_POS_ERR = 1, MDS_STAT_MAX_POS_ERR = 2,
+  MDS_STAT_MIN_BARRIER = 3, MDS_STAT_QP_SOLVES = 4, MDS_STAT_QP_ITERS = 5,
+  MDS_STAT_QP_INFEASIBLE = 6, MDS_STAT_QP_ITER_CAP = 7, MDS_STAT_COUNT = 8
+};
+
+typedef struct MdsRolloutCfg {
+  int ctrl;            /* MDS_CTRL_*                                       */
+  int use_cbf;         /* 0/1; requires ctrl LQR_OMEGA (order 2) or LQR_YANK (order 3) */
+  int num_obstacles;   /* spheres shared by all envs (<= N, reference quirk B14)        */
+  int write_obs_every; /* 0 = only after the last step; k>0 = log obs every k steps     */
+  double obstacles[MDS_MAX_OBSTACLES * 4]; /* cx, cy, cz, r */
+} MdsRolloutCfg;
+
+/* ---- library ------------------------------------------------------------------ */
+int mds_abi_version(void);
+const char* mds_last_error(void);
+int mds_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes);
+
+/* ---- env step: replaces CtrlAviary.step (call sites EnvGeometric.py:431,469) ----- */
+/* clip RPM to [0, max_rpm]; `substeps` explicit DYN / DYN_GND_DRAG_DW updates; write obs.
+ * ext_force_dev: optional [D*3] world-frame force per drone (wind, EnvGeometric.py:463-467). */
+int mds_physics_step_f32(const MdsDroneParams* prm, MdsState st, const float* action_dev,
+                         const float* ext_force_dev, float* obs_dev, int E, int N, void* stream);
+int mds_physics_step_f64(const MdsDroneParams* prm, MdsState st, const double* action_dev,
+                         const double* ext_force_dev, double* obs_dev, int E, int N, void* stream);
+/* (re)build obs from state without stepping (reset(); ang vel = R w) */
+int mds_obs_from_state_f32(const MdsDroneParams* prm, MdsState st, float* obs_dev, int D, void* stream);
+int mds_obs_from_state_f64(const MdsDroneParams* prm, MdsState st, double* obs_dev, int D, void* stream);
+
+/* ---- trajectories: replaces trajs[j](t) (EnvGeometric.py:437) -------------------- */
+int mds_traj_eval_f32(const MdsTrajSpecF32* specs_dev, const MdsTrajSegF32* segs_dev, double t,
+                      float* ref_dev, int D, void* stream);
+int mds_traj_eval_f64(const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double t,
+                      double* ref_dev, int D, void* stream);
+
+/* ---- controllers: replace ctrl[j].compute(obs[j]) -------------------------------- */
+/* GeometricControl.compute (control/geometric.py:59-115) + input_to_action.  u_out optional. */
+int mds_geometric_ctrl_f32(const MdsDroneParams* prm, const MdsGeoGains* gains, const float* obs_dev,
+                           const float* ref_dev, float* action_dev, float* u_dev, int D, void* stream);
+int mds_geometric_ctrl_f64(const MdsDroneParams* prm, const MdsGeoGains* gains, const double* obs_dev,
+                           const double* ref_dev, double* action_dev, double* u_dev, int D, void* stream);
+/* LQR*.compute(obs, skip_low_level): u = -K e (+ hover), capped as each variant does.
+ * variant = MDS_CTRL_LQR_*; action_dev may be NULL (skip_low_level=True).  For LQR_TORQUE the
+ * action is the mixer output; for LQR_OMEGA / LQR_YANK it runs the inner PID (pid required). */
+int mds_lqr_ctrl_f32(const MdsDroneParams* prm, const MdsLqrGains* gains, int variant, const float* obs_dev,
+                     const float* ref_dev, float* u_dev, float* action_dev, MdsPidState pid, int D, void* stream);
+int mds_lqr_ctrl_f64(const MdsDroneParams* prm, const MdsLqrGains* gains, int variant, const double* obs_dev,
+                     const double* ref_dev, double* u_dev, double* action_dev, MdsPidState pid, int D, void* stream);
+/* ctrl.compute_low_level(u, obs, idx): ThrustOmega / YankOmega inner loop -> RPM */
+int mds_lowlevel_f32(const MdsDroneParams* prm, int variant, const float* u_dev, const float* obs_dev,
+                     MdsPidState pid, float* action_dev, int D, void* stream);
+int mds_lowlevel_f64(const MdsDroneParams* prm, int variant, const double* u_dev, const double* obs_dev,
+                     MdsPidState pid, double* action_dev, int D, void* stream);
+
+/* ---- CBF-QP: replaces DroneQPTracker.compute_control (cbf/qptracker.py:22-34) ------ */
+/* xdes_dev [E*N*xdim]; u_nom_dev / u_safe_dev [E*N*4]; obstacles_dev [n_obs*4] = cx,cy,cz,r
+ * (shared by all envs) ; status_dev [E] int32 ; iters_dev [E] int32 (may be NULL). */
+int mds_cbf_qp_f32(const MdsDroneParams* prm, const MdsCbfParams* cbf, const float* obs_dev,
+                   const float* xdes_dev, const float* u_nom_dev, const float* obstacles_dev, int n_obs,
+                   float* u_safe_dev, int* status_dev, int* iters_dev, int E, int N, void* stream);
+int mds_cbf_qp_f64(const MdsDroneParams* prm, const MdsCbfParams* cbf, const double* obs_dev,
+                   const double* xdes_dev, const double* u_nom_dev, const double* obstacles_dev, int n_obs,
+                   double* u_safe_dev, int* status_dev, int* iters_dev, int E, int N, void* stream);
+/* dense G [E*m*4N], h [E*m] exactly as CBF._build_ineq_const (cbf/cbf.py:308-367); parity aid */
+int mds_cbf_rows_f32(const MdsDroneParams* prm, const MdsCbfParams* cbf, const float* obs_dev,
+                     const float* xdes_dev, const float* obstacles_dev, int n_obs, float* G_dev, float* h_dev,
+                     int E, int N, void* stream);
+int mds_cbf_rows_f64(const MdsDroneParams* prm, const MdsCbfParams* cbf, const double* obs_dev,
+                     const double* xdes_dev, const double* obstacles_dev, int n_obs, double* G_dev, double* h_dev,
+                     int E, int N, void* stream);
+int mds_cbf_num_rows(int order, int N, int n_obs);
+
+/* ---- model comparison: replaces the loop of simulations/CompareModels.py:48-55 ------ */
+/* kind 12: LinearizedModel.calc_xdot_from_obs; 9 / 10: builder-defined (quirk B23) */
+int mds_xdot_linear_f32(const MdsDroneParams* prm, int kind, const float* obs_dev, float* xdot_dev, int D, void* stream);
+int mds_xdot_linear_f64(const MdsDroneParams* prm, int kind, const double* obs_dev, double* xdot_dev, int D, void* stream);
+/* QuadrotorDynamics.dynamics via action_to_input / obs_to_geo_model / geo_x_dot_to_linear; J = diag(jx,jy,jz) */
+int mds_xdot_nonlinear_f32(const MdsDroneParams* prm, double jx, double jy, double jz, const float* obs_dev, float* xdot_dev, int D, void* stream);
+int mds_xdot_nonlinear_f64(const MdsDroneParams* prm, double jx, double jy, double jz, const double* obs_dev, double* xdot_dev, int D, void* stream);
+
+/* ---- fused K-step rollout: traj -> ctrl -> (CBF-QP) -> inner loop -> physics, state in registers */
+int mds_rollout_f32(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
+                    const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
+                    const MdsTrajSpecF32* specs_dev, const MdsTrajSegF32* segs_dev, float* obs_dev,
+                    float* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
+int mds_rollout_f64(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
+                    const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
+                    const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double* obs_dev,
+                    double* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
+
+/* ---- measurement aid: dependent-FMA-chain peak of the FP32 / FP64 pipes (TFLOP/s) ---- */
+int mds_fma_peak(int use_f64, int iters, double* tflops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDS_B200_H */

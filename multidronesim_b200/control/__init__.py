@@ -1,0 +1,7 @@
+from .base_controller import BaseController
+from .geometric import GeometricControl
+from .low_level import ThrustOmegaController, YankOmegaController
+from .lqr import LQRController, LQROmegaController, LQRYankOmegaController
+
+__all__ = ["BaseController", "GeometricControl", "ThrustOmegaController", "YankOmegaController",
+           "LQRController", "LQROmegaController", "LQRYankOmegaController"]

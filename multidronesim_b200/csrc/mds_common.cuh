@@ -1,0 +1,231 @@
+// mds_common.cuh -- Real-templated small math, parameter blocks and the SoA state
+// accessors shared by every kernel of the hot path (sm_100a, no tensor cores: nothing
+// here is a dense contraction; the rules that matter are coalesced 128-bit planes,
+// shared-memory staging of env neighbours and grids sized from the SM count).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "../../include/mds_b200.h"
+
+#define MDS_DEV __device__ __forceinline__
+
+namespace mds {
+
+// ---------------------------------------------------------------- vector types
+template <typename Real> struct Vec4T;
+template <> struct Vec4T<float> { using type = float4; };
+template <> struct Vec4T<double> { using type = double4; };
+template <typename Real> struct Vec2T;
+template <> struct Vec2T<float> { using type = float2; };
+template <> struct Vec2T<double> { using type = double2; };
+
+template <typename Real> struct V3 { Real x, y, z; };
+template <typename Real> struct M3 { Real m[9]; };  // row-major
+
+template <typename Real> MDS_DEV V3<Real> v3(Real x, Real y, Real z) { return V3<Real>{x, y, z}; }
+template <typename Real> MDS_DEV V3<Real> operator+(V3<Real> a, V3<Real> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename Real> MDS_DEV V3<Real> operator-(V3<Real> a, V3<Real> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename Real> MDS_DEV V3<Real> operator*(Real s, V3<Real> a) { return {s * a.x, s * a.y, s * a.z}; }
+template <typename Real> MDS_DEV Real dot(V3<Real> a, V3<Real> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename Real> MDS_DEV V3<Real> cross(V3<Real> a, V3<Real> b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+template <typename Real> MDS_DEV V3<Real> mul(const M3<Real>& A, V3<Real> v) {
+  return {A.m[0] * v.x + A.m[1] * v.y + A.m[2] * v.z, A.m[3] * v.x + A.m[4] * v.y + A.m[5] * v.z,
+          A.m[6] * v.x + A.m[7] * v.y + A.m[8] * v.z};
+}
+template <typename Real> MDS_DEV V3<Real> mulT(const M3<Real>& A, V3<Real> v) {  // A^T v
+  return {A.m[0] * v.x + A.m[3] * v.y + A.m[6] * v.z, A.m[1] * v.x + A.m[4] * v.y + A.m[7] * v.z,
+          A.m[2] * v.x + A.m[5] * v.y + A.m[8] * v.z};
+}
+template <typename Real> MDS_DEV M3<Real> matmul(const M3<Real>& A, const M3<Real>& B) {
+  M3<Real> C;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C.m[3 * i + j] = A.m[3 * i] * B.m[j] + A.m[3 * i + 1] * B.m[3 + j] + A.m[3 * i + 2] * B.m[6 + j];
+  return C;
+}
+template <typename Real> MDS_DEV M3<Real> matmulTN(const M3<Real>& A, const M3<Real>& B) {  // A^T B
+  M3<Real> C;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C.m[3 * i + j] = A.m[i] * B.m[j] + A.m[3 + i] * B.m[3 + j] + A.m[6 + i] * B.m[6 + j];
+  return C;
+}
+template <typename Real> MDS_DEV M3<Real> from_cols(V3<Real> a, V3<Real> b, V3<Real> c) {
+  M3<Real> R;
+  R.m[0] = a.x; R.m[1] = b.x; R.m[2] = c.x;
+  R.m[3] = a.y; R.m[4] = b.y; R.m[5] = c.y;
+  R.m[6] = a.z; R.m[7] = b.z; R.m[8] = c.z;
+  return R;
+}
+
+// ---------------------------------------------------------------- scalar math
+MDS_DEV float rsqrt_(float x) { return rsqrtf(x); }
+MDS_DEV double rsqrt_(double x) { return 1.0 / sqrt(x); }
+MDS_DEV float sqrt_(float x) { return sqrtf(x); }
+MDS_DEV double sqrt_(double x) { return sqrt(x); }
+MDS_DEV void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+MDS_DEV void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
+MDS_DEV float atan2_(float y, float x) { return atan2f(y, x); }
+MDS_DEV double atan2_(double y, double x) { return atan2(y, x); }
+MDS_DEV float asin_(float x) { return asinf(x); }
+MDS_DEV double asin_(double x) { return asin(x); }
+MDS_DEV float acos_(float x) { return acosf(x); }
+MDS_DEV double acos_(double x) { return acos(x); }
+MDS_DEV float exp_(float x) { return expf(x); }
+MDS_DEV double exp_(double x) { return exp(x); }
+MDS_DEV float tan_(float x) { return tanf(x); }
+MDS_DEV double tan_(double x) { return tan(x); }
+MDS_DEV float abs_(float x) { return fabsf(x); }
+MDS_DEV double abs_(double x) { return fabs(x); }
+MDS_DEV float min_(float a, float b) { return fminf(a, b); }
+MDS_DEV double min_(double a, double b) { return fmin(a, b); }
+MDS_DEV float max_(float a, float b) { return fmaxf(a, b); }
+MDS_DEV double max_(double a, double b) { return fmax(a, b); }
+template <typename Real> MDS_DEV Real clamp_(Real x, Real lo, Real hi) { return min_(max_(x, lo), hi); }
+template <typename Real> MDS_DEV Real norm(V3<Real> a) { return sqrt_(dot(a, a)); }
+template <typename Real> MDS_DEV Real sign_(Real x) { return (x > Real(0)) ? Real(1) : ((x < Real(0)) ? Real(-1) : Real(0)); }
+
+// ---------------------------------------------------------------- device parameter blocks
+template <typename Real> struct DroneP {
+  Real m, g, kf, km, arm_l, ixx, iyy, izz, max_rpm, max_thrust;
+  Real gnd_eff_coeff, prop_radius, gnd_eff_h_clip, drag_xy, drag_z, dw1, dw2, dw3;
+  Real prop_x[4], prop_y[4];
+  Real z_floor, dt_phys, dt_ctrl;
+  int substeps, drone_model, physics, cf2x_torque_sign, renormalize_quat, ground_clamp;
+};
+template <typename Real> inline DroneP<Real> to_dev(const MdsDroneParams& p) {
+  DroneP<Real> d;
+  d.m = Real(p.m); d.g = Real(p.g); d.kf = Real(p.kf); d.km = Real(p.km); d.arm_l = Real(p.arm_l);
+  d.ixx = Real(p.ixx); d.iyy = Real(p.iyy); d.izz = Real(p.izz);
+  d.max_rpm = Real(p.max_rpm); d.max_thrust = Real(p.max_thrust);
+  d.gnd_eff_coeff = Real(p.gnd_eff_coeff); d.prop_radius = Real(p.prop_radius);
+  d.gnd_eff_h_clip = Real(p.gnd_eff_h_clip); d.drag_xy = Real(p.drag_xy); d.drag_z = Real(p.drag_z);
+  d.dw1 = Real(p.dw1); d.dw2 = Real(p.dw2); d.dw3 = Real(p.dw3);
+  for (int i = 0; i < 4; ++i) { d.prop_x[i] = Real(p.prop_x[i]); d.prop_y[i] = Real(p.prop_y[i]); }
+  d.z_floor = Real(p.z_floor); d.dt_phys = Real(p.dt_phys); d.dt_ctrl = Real(p.dt_ctrl);
+  d.substeps = p.substeps; d.drone_model = p.drone_model; d.physics = p.physics;
+  d.cf2x_torque_sign = p.cf2x_torque_sign; d.renormalize_quat = p.renormalize_quat; d.ground_clamp = p.ground_clamp;
+  return d;
+}
+template <typename Real> struct GeoP { Real kp, kv, kr, kw, g_ctrl, max_tilt, tan_max_tilt; };
+template <typename Real> inline GeoP<Real> to_dev(const MdsGeoGains& g) {
+  return GeoP<Real>{Real(g.kp), Real(g.kv), Real(g.kr), Real(g.kw), Real(g.g_ctrl), Real(g.max_tilt), Real(tan(g.max_tilt))};
+}
+template <typename Real> struct LqrP { Real K[48]; int dim; };
+template <typename Real> inline LqrP<Real> to_dev(const MdsLqrGains& g) {
+  LqrP<Real> d;
+  for (int i = 0; i < 48; ++i) d.K[i] = Real(g.K[i]);
+  d.dim = g.dim;
+  return d;
+}
+template <typename Real> struct CbfP {
+  int order, max_iter;
+  Real c4inv, inv_c, rs, k0, k1, k2, umax[4], fmin, fmax;
+};
+template <typename Real> inline CbfP<Real> to_dev(const MdsCbfParams& c) {
+  CbfP<Real> d;
+  d.order = c.order; d.max_iter = c.max_iter > 0 ? c.max_iter : 64;
+  double c4 = c.zscale * c.zscale * c.zscale * c.zscale;
+  d.c4inv = Real(1.0 / c4); d.inv_c = Real(1.0 / c.zscale); d.rs = Real(c.safety_radius);
+  d.k0 = Real(c.kcbf[0]); d.k1 = Real(c.kcbf[1]); d.k2 = Real(c.order == 3 ? c.kcbf[2] : 0.0);
+  for (int i = 0; i < 4; ++i) d.umax[i] = Real(c.umax[i]);
+  d.fmin = Real(c.fmin); d.fmax = Real(c.fmax);
+  return d;
+}
+
+// ---------------------------------------------------------------- per-drone state in registers
+template <typename Real> struct Drone {
+  V3<Real> p;       // world position
+  Real qx, qy, qz, qw;
+  V3<Real> v;       // world velocity
+  V3<Real> w;       // BODY rates (upstream rpy_rates)
+  Real rpm[4];      // last clipped action
+};
+template <typename Real> struct StateP {
+  typename Vec4T<Real>::type *pos_wx, *quat, *vel_wy, *rpm;
+  Real* wz;
+};
+template <typename Real> inline StateP<Real> to_dev(const MdsState& s) {
+  using R4 = typename Vec4T<Real>::type;
+  return StateP<Real>{(R4*)s.pos_wx, (R4*)s.quat, (R4*)s.vel_wy, (R4*)s.rpm, (Real*)s.wz};
+}
+template <typename Real> MDS_DEV Drone<Real> load_drone(const StateP<Real>& s, int d) {
+  auto a = s.pos_wx[d]; auto q = s.quat[d]; auto c = s.vel_wy[d]; auto r = s.rpm[d];
+  Drone<Real> o;
+  o.p = {a.x, a.y, a.z}; o.qx = q.x; o.qy = q.y; o.qz = q.z; o.qw = q.w;
+  o.v = {c.x, c.y, c.z}; o.w = {a.w, c.w, s.wz[d]};
+  o.rpm[0] = r.x; o.rpm[1] = r.y; o.rpm[2] = r.z; o.rpm[3] = r.w;
+  return o;
+}
+template <typename Real> MDS_DEV void store_drone(const StateP<Real>& s, int d, const Drone<Real>& o) {
+  typename Vec4T<Real>::type a, q, c, r;
+  a.x = o.p.x; a.y = o.p.y; a.z = o.p.z; a.w = o.w.x;
+  q.x = o.qx; q.y = o.qy; q.z = o.qz; q.w = o.qw;
+  c.x = o.v.x; c.y = o.v.y; c.z = o.v.z; c.w = o.w.y;
+  r.x = o.rpm[0]; r.y = o.rpm[1]; r.z = o.rpm[2]; r.w = o.rpm[3];
+  s.pos_wx[d] = a; s.quat[d] = q; s.vel_wy[d] = c; s.rpm[d] = r; s.wz[d] = o.w.z;
+}
+
+// Bullet getMatrixFromQuaternion (xyzw; self-normalising s = 2/|q|^2) -- SURVEY A.2
+template <typename Real> MDS_DEV M3<Real> quat_to_mat(Real x, Real y, Real z, Real w) {
+  Real d = x * x + y * y + z * z + w * w;
+  Real s = Real(2) / d;
+  Real xs = x * s, ys = y * s, zs = z * s;
+  Real wx = w * xs, wy = w * ys, wz = w * zs, xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+  M3<Real> R;
+  R.m[0] = Real(1) - (yy + zz); R.m[1] = xy - wz; R.m[2] = xz + wy;
+  R.m[3] = xy + wz; R.m[4] = Real(1) - (xx + zz); R.m[5] = yz - wx;
+  R.m[6] = xz - wy; R.m[7] = yz + wx; R.m[8] = Real(1) - (xx + yy);
+  return R;
+}
+// Bullet getEulerFromQuaternion (no normalisation; +-0.99999 gimbal branches)
+template <typename Real> MDS_DEV V3<Real> quat_to_rpy(Real x, Real y, Real z, Real w) {
+  Real sqx = x * x, sqy = y * y, sqz = z * z, squ = w * w;
+  Real sarg = Real(-2) * (x * z - w * y);
+  const Real half_pi = Real(1.5707963267948966);
+  if (sarg <= Real(-0.99999)) return {Real(0), -half_pi, Real(2) * atan2_(x, -y)};
+  if (sarg >= Real(0.99999)) return {Real(0), half_pi, Real(2) * atan2_(-x, y)};
+  return {atan2_(Real(2) * (y * z + w * x), squ - sqx - sqy + sqz), asin_(sarg),
+          atan2_(Real(2) * (x * y + w * z), squ + sqx - sqy - sqz)};
+}
+
+// The 20-float observation of one drone, in registers
+template <typename Real> struct Obs {
+  V3<Real> p; Real qx, qy, qz, qw; V3<Real> rpy, v, av; Real rpm[4];
+};
+template <typename Real> MDS_DEV Obs<Real> load_obs(const Real* __restrict__ obs, int d) {
+  using R4 = typename Vec4T<Real>::type;
+  const R4* o4 = reinterpret_cast<const R4*>(obs + (size_t)d * MDS_OBS_DIM);
+  R4 a = o4[0], b = o4[1], c = o4[2], e = o4[3], f = o4[4];
+  Obs<Real> o;
+  o.p = {a.x, a.y, a.z}; o.qx = a.w; o.qy = b.x; o.qz = b.y; o.qw = b.z;
+  o.rpy = {b.w, c.x, c.y}; o.v = {c.z, c.w, e.x}; o.av = {e.y, e.z, e.w};
+  o.rpm[0] = f.x; o.rpm[1] = f.y; o.rpm[2] = f.z; o.rpm[3] = f.w;
+  return o;
+}
+template <typename Real> MDS_DEV void store_obs(Real* __restrict__ obs, int d, const Obs<Real>& o) {
+  using R4 = typename Vec4T<Real>::type;
+  R4* o4 = reinterpret_cast<R4*>(obs + (size_t)d * MDS_OBS_DIM);
+  R4 a, b, c, e, f;
+  a.x = o.p.x; a.y = o.p.y; a.z = o.p.z; a.w = o.qx;
+  b.x = o.qy; b.y = o.qz; b.z = o.qw; b.w = o.rpy.x;
+  c.x = o.rpy.y; c.y = o.rpy.z; c.z = o.v.x; c.w = o.v.y;
+  e.x = o.v.z; e.y = o.av.x; e.z = o.av.y; e.w = o.av.z;
+  f.x = o.rpm[0]; f.y = o.rpm[1]; f.z = o.rpm[2]; f.w = o.rpm[3];
+  o4[0] = a; o4[1] = b; o4[2] = c; o4[3] = e; o4[4] = f;
+}
+template <typename Real> MDS_DEV Obs<Real> make_obs(const Drone<Real>& s, V3<Real> ang_v_world) {
+  Obs<Real> o;
+  o.p = s.p; o.qx = s.qx; o.qy = s.qy; o.qz = s.qz; o.qw = s.qw;
+  o.rpy = quat_to_rpy(s.qx, s.qy, s.qz, s.qw);
+  o.v = s.v; o.av = ang_v_world;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o.rpm[i] = s.rpm[i];
+  return o;
+}
+
+}  // namespace mds

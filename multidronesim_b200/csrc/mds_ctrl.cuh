@@ -1,0 +1,245 @@
+// mds_ctrl.cuh -- tracking controllers, mixer and inner-loop PID as device functions.
+// Replaces control/geometric.py:59-115, control/lqr/*.py compute()/cap_u()/compute_low_level(),
+// control/low_level/thrust_omega_ctrl.py:81-132, yank_omega_ctrl.py:39-55 and
+// utils/model_conversions.py:69-103,137-143 of the reference.  Appendix-B quirks of
+// SURVEY.md are reproduced on purpose (parity is against the reference, not the textbook).
+#pragma once
+#include "mds_common.cuh"
+#include "mds_traj.cuh"
+
+namespace mds {
+
+#define MDS_MIN_RPM 9440.3
+#define MDS_PWM2RPM_SCALE 0.2685
+#define MDS_PWM2RPM_CONST 4070.3
+#define MDS_MIN_PWM 20000.0
+#define MDS_MAX_PWM 65535.0
+
+// scipy Rotation.from_quat(q).as_matrix(): normalises first (model_conversions.py:110)
+template <typename Real> MDS_DEV M3<Real> quat_to_rot_scipy(Real x, Real y, Real z, Real w) {
+  Real inv = rsqrt_(x * x + y * y + z * z + w * w);
+  x *= inv; y *= inv; z *= inv; w *= inv;
+  M3<Real> R;
+  R.m[0] = Real(1) - Real(2) * (y * y + z * z); R.m[1] = Real(2) * (x * y - z * w); R.m[2] = Real(2) * (x * z + y * w);
+  R.m[3] = Real(2) * (x * y + z * w); R.m[4] = Real(1) - Real(2) * (x * x + z * z); R.m[5] = Real(2) * (y * z - x * w);
+  R.m[6] = Real(2) * (x * z - y * w); R.m[7] = Real(2) * (y * z + x * w); R.m[8] = Real(1) - Real(2) * (x * x + y * y);
+  return R;
+}
+
+// calc_z_thrust: model_conversions.py:137-143
+template <typename Real> MDS_DEV Real z_thrust(const DroneP<Real>& P, const Real rpm[4]) {
+  return P.kf * rpm[0] * rpm[0] + P.kf * rpm[1] * rpm[1] + P.kf * rpm[2] * rpm[2] + P.kf * rpm[3] * rpm[3];
+}
+
+// action_to_input: RPM -> [f, tx, ty, tz], PLUS-frame mixer (model_conversions.py:69-83)
+template <typename Real> MDS_DEV void action_to_input(const DroneP<Real>& P, const Real rpm_in[4], Real u[4]) {
+  Real T[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    Real r = clamp_(rpm_in[i], Real(0), P.max_rpm);
+    T[i] = P.kf * r * r;
+  }
+  Real kr = P.km / P.kf;
+  u[0] = T[0] + T[1] + T[2] + T[3];
+  u[1] = P.arm_l * (T[1] - T[3]);
+  u[2] = P.arm_l * (T[2] - T[0]);
+  u[3] = kr * (-T[0] + T[1] - T[2] + T[3]);
+}
+
+// input_to_action: [f, tx, ty, tz] -> RPM (model_conversions.py:85-103); clamps u[0] >= 0 in
+// place; closed-form inverse of the mixer; per-motor clip to [MIN_RPM^2 kf, MAX_THRUST] (B6).
+template <typename Real> MDS_DEV void input_to_action(const DroneP<Real>& P, Real u[4], Real rpm[4]) {
+  u[0] = max_(u[0], Real(0));
+  Real kr = P.km / P.kf;
+  Real q = Real(0.25) * u[0], a = u[1] / (Real(2) * P.arm_l), b = u[2] / (Real(2) * P.arm_l), c = u[3] / (Real(4) * kr);
+  Real T[4] = {q - b - c, q + a + c, q + b - c, q - a + c};
+  const Real tmin = Real(MDS_MIN_RPM * MDS_MIN_RPM) * P.kf;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rpm[i] = sqrt_(clamp_(T[i], tmin, P.max_thrust) / P.kf);
+}
+
+// GeometricControl.compute (control/geometric.py:59-114) -> u = [f, tau]
+template <typename Real>
+MDS_DEV void geometric_input(const DroneP<Real>& P, const GeoP<Real>& G, const Obs<Real>& o, const Ref<Real>& r, Real u[4]) {
+  const Real m = P.m;
+  M3<Real> R = quat_to_rot_scipy(o.qx, o.qy, o.qz, o.qw);
+  V3<Real> w = o.av;  // world rates used as body rates (B3)
+  V3<Real> RTvd = mulT(R, r.v);
+  V3<Real> ev = mulT(R, o.v) - RTvd;
+  V3<Real> ep = o.p - r.p;
+  V3<Real> RTa = mulT(R, r.a);
+  V3<Real> grav = mulT(R, v3(Real(0), Real(0), m * G.g_ctrl));
+  V3<Real> kp_ep = mulT(R, G.kp * ep);
+  V3<Real> f_b = grav - m * kp_ep - (m * G.kv) * ev + m * (RTa - cross(w, RTvd));
+  V3<Real> f_w = mul(R, f_b);
+  Real fn = norm(f_w);
+  Real tilt = acos_(f_w.z / fn);
+  if (tilt > G.max_tilt) {  // :79-84 (B5)
+    Real xy = sqrt_(f_w.x * f_w.x + f_w.y * f_w.y);
+    Real sc = f_w.z * G.tan_max_tilt / xy;
+    f_w.x *= sc;
+    f_w.y *= sc;
+    fn = norm(f_w);
+  }
+  f_b = mulT(R, f_w);
+  Real sy, cy;
+  sincos_(r.yaw, &sy, &cy);
+  V3<Real> b1c = {cy, sy, Real(0)};
+  V3<Real> b3 = (Real(1) / fn) * f_w;
+  V3<Real> c1 = cross(b3, b1c);
+  V3<Real> b2 = (Real(1) / norm(c1)) * c1;
+  V3<Real> c2 = cross(b2, b3);
+  V3<Real> b1 = (Real(1) / norm(c2)) * c2;
+  M3<Real> Rd = from_cols(b1, b2, b3);
+  V3<Real> b1c_dot = {-sy * r.yaw_rate, cy * r.yaw_rate, Real(0)};
+  V3<Real> f_dot = (m / fn) * mul(R, G.kp * ev);  // :96 (B4: Kp)
+  V3<Real> b3_dot = cross(cross(b3, f_dot), b3);
+  V3<Real> num = cross(b1c_dot, b3) + cross(b1c, b3_dot);
+  V3<Real> b2_dot = cross(cross(b2, (Real(1) / norm(cross(b1c, b3))) * num), b2);
+  V3<Real> b1_dot = cross(b3_dot, b2) + cross(b3, b2_dot);
+  M3<Real> Rd_dot = from_cols(b1_dot, b2_dot, b3_dot);
+  M3<Real> W = matmul(Rd, Rd_dot);  // :102 (B1: transpose(0,1) is a numpy no-op)
+  V3<Real> w_d = {W.m[7], W.m[2], W.m[3]};
+  M3<Real> A = matmulTN(Rd, R);  // Rd^T R ; R^T Rd is its transpose
+  // vee(A - A^T) with the reference's vee = (-M12, M02, -M01)
+  V3<Real> eR = {Real(0.5) * G.kr * -(A.m[5] - A.m[7]), Real(0.5) * G.kr * (A.m[2] - A.m[6]), Real(0.5) * G.kr * -(A.m[1] - A.m[3])};
+  V3<Real> ew = w - mulT(R, mul(Rd, w_d));
+  V3<Real> t0 = {-eR.x - G.kw * ew.x, -eR.y - G.kw * ew.y, -eR.z - G.kw * ew.z};
+  V3<Real> Jw = {P.ixx * w.x, P.iyy * w.y, P.izz * w.z};
+  V3<Real> gy = cross(w, Jw);
+  u[0] = max_(Real(0), f_b.z);
+  u[1] = P.ixx * t0.x - gy.x;
+  u[2] = P.iyy * t0.y - gy.y;
+  u[3] = P.izz * t0.z - gy.z;
+}
+
+// scipy from_euler('xyz') extrinsic = Rz(yaw) Ry(pitch) Rx(roll)
+template <typename Real> MDS_DEV M3<Real> euler_xyz_to_rot(V3<Real> e) {
+  Real sa, ca, sb, cb, sc, cc;
+  sincos_(e.x, &sa, &ca);
+  sincos_(e.y, &sb, &cb);
+  sincos_(e.z, &sc, &cc);
+  M3<Real> R;
+  R.m[0] = cb * cc; R.m[1] = sa * sb * cc - ca * sc; R.m[2] = ca * sb * cc + sa * sc;
+  R.m[3] = cb * sc; R.m[4] = sa * sb * sc + ca * cc; R.m[5] = ca * sb * sc - sa * cc;
+  R.m[6] = -sb; R.m[7] = sa * cb; R.m[8] = ca * cb;
+  return R;
+}
+
+// LQR error state + u = -K e (+ hover) for the three parametrisations (B8-B10).
+// variant: MDS_CTRL_LQR_TORQUE (dim 12), _OMEGA (9), _YANK (10).  Returns the UN-capped u.
+template <typename Real>
+MDS_DEV void lqr_input(const DroneP<Real>& P, const LqrP<Real>& L, int variant, const Obs<Real>& o, const Ref<Real>& r, Real u[4]) {
+  Real sy, cy;
+  sincos_(r.yaw, &sy, &cy);
+  // R_err = Rz(yaw_d)^T R(rpy); its xyz-extrinsic Euler angles
+  M3<Real> R = euler_xyz_to_rot(o.rpy);
+  M3<Real> Re;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    Re.m[j] = cy * R.m[j] + sy * R.m[3 + j];
+    Re.m[3 + j] = -sy * R.m[j] + cy * R.m[3 + j];
+    Re.m[6 + j] = R.m[6 + j];
+  }
+  Real e[12];
+  e[0] = atan2_(Re.m[7], Re.m[8]);
+  e[1] = asin_(clamp_(-Re.m[6], Real(-1), Real(1)));
+  e[2] = atan2_(Re.m[3], Re.m[0]);
+  V3<Real> dp = o.p - r.p, dv = o.v - r.v;
+  V3<Real> ep = {cy * dp.x + sy * dp.y, -sy * dp.x + cy * dp.y, dp.z};
+  V3<Real> ev = {cy * dv.x + sy * dv.y, -sy * dv.x + cy * dv.y, dv.z};
+  int dim;
+  if (variant == MDS_CTRL_LQR_TORQUE) {
+    dim = 12;
+    V3<Real> dw = {o.av.x, o.av.y, o.av.z - r.yaw_rate};
+    e[3] = cy * dw.x + sy * dw.y; e[4] = -sy * dw.x + cy * dw.y; e[5] = dw.z;
+    e[6] = ev.x; e[7] = ev.y; e[8] = ev.z; e[9] = ep.x; e[10] = ep.y; e[11] = ep.z;
+  } else if (variant == MDS_CTRL_LQR_OMEGA) {
+    dim = 9;
+    e[3] = ev.x; e[4] = ev.y; e[5] = ev.z; e[6] = ep.x; e[7] = ep.y; e[8] = ep.z;
+  } else {
+    dim = 10;
+    e[3] = z_thrust(P, o.rpm) - P.m * P.g;
+    e[4] = ev.x; e[5] = ev.y; e[6] = ev.z; e[7] = ep.x; e[8] = ep.y; e[9] = ep.z;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    Real acc = Real(0);
+    for (int k = 0; k < dim; ++k) acc += L.K[i * dim + k] * e[k];
+    u[i] = -acc;
+  }
+  if (variant != MDS_CTRL_LQR_YANK) u[0] += P.m * P.g;
+}
+
+// LQROmegaController.cap_u (lqr_omega_controller.py:116-119)
+template <typename Real> MDS_DEV Real cap_thrust(const DroneP<Real>& P, Real f) {
+  return clamp_(f, Real(4.0 * MDS_MIN_RPM * MDS_MIN_RPM) * P.kf, P.max_thrust);
+}
+
+template <typename Real> struct Pid {
+  V3<Real> last_w, integ;
+};
+template <typename Real> struct PidP {
+  typename Vec4T<Real>::type* a;
+  typename Vec2T<Real>::type* b;
+};
+template <typename Real> inline PidP<Real> to_dev(const MdsPidState& s) {
+  return PidP<Real>{(typename Vec4T<Real>::type*)s.a, (typename Vec2T<Real>::type*)s.b};
+}
+template <typename Real> MDS_DEV Pid<Real> load_pid(const PidP<Real>& s, int d) {
+  auto a = s.a[d]; auto b = s.b[d];
+  return Pid<Real>{{a.x, a.y, a.z}, {a.w, b.x, b.y}};
+}
+template <typename Real> MDS_DEV void store_pid(const PidP<Real>& s, int d, const Pid<Real>& p) {
+  typename Vec4T<Real>::type a; typename Vec2T<Real>::type b;
+  a.x = p.last_w.x; a.y = p.last_w.y; a.z = p.last_w.z; a.w = p.integ.x; b.x = p.integ.y; b.y = p.integ.z;
+  s.a[d] = a; s.b[d] = b;
+}
+
+// ThrustOmegaController.computeControlFromInput + omega_PID (thrust_omega_ctrl.py:81-132, B11).
+// `thrust` already resolved (yank variant integrates before calling).  w_b = body rates.
+template <typename Real>
+MDS_DEV void thrust_omega_pid(const DroneP<Real>& P, Pid<Real>& s, Real thrust, V3<Real> w_target, V3<Real> w_b, Real rpm[4]) {
+  const Real dt = P.dt_ctrl;
+  thrust = max_(thrust, Real(0));
+  Real pwm_t = clamp_((sqrt_(thrust / (P.kf * Real(4))) - Real(MDS_PWM2RPM_CONST)) / Real(MDS_PWM2RPM_SCALE),
+                      Real(MDS_MIN_PWM), Real(MDS_MAX_PWM));
+  V3<Real> rate_e = (Real(-1) / dt) * (w_b - s.last_w);
+  V3<Real> e = w_target - w_b;
+  s.last_w = w_b;
+  s.integ = s.integ - dt * e;
+  s.integ.x = clamp_(clamp_(s.integ.x, Real(-1500), Real(1500)), Real(-1), Real(1));
+  s.integ.y = clamp_(clamp_(s.integ.y, Real(-1500), Real(1500)), Real(-1), Real(1));
+  s.integ.z = clamp_(s.integ.z, Real(-1500), Real(1500));
+  const Real kp = Real(17500), ki = Real(10), kd = Real(0);
+  V3<Real> tq = {clamp_(kp * e.x + ki * s.integ.x + kd * rate_e.x, Real(-3200), Real(3200)),
+                 clamp_(kp * e.y + ki * s.integ.y + kd * rate_e.y, Real(-3200), Real(3200)),
+                 clamp_(kp * e.z + ki * s.integ.z + kd * rate_e.z, Real(-3200), Real(3200))};
+  Real pw[4];
+  if (P.drone_model == MDS_DRONE_CF2X) {
+    pw[0] = pwm_t + (Real(-0.5) * tq.x - Real(0.5) * tq.y - tq.z);
+    pw[1] = pwm_t + (Real(-0.5) * tq.x + Real(0.5) * tq.y + tq.z);
+    pw[2] = pwm_t + (Real(0.5) * tq.x + Real(0.5) * tq.y - tq.z);
+    pw[3] = pwm_t + (Real(0.5) * tq.x - Real(0.5) * tq.y + tq.z);
+  } else {
+    pw[0] = pwm_t + (-tq.y - tq.z);
+    pw[1] = pwm_t + (tq.x + tq.z);
+    pw[2] = pwm_t + (tq.y - tq.z);
+    pw[3] = pwm_t + (-tq.x + tq.z);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rpm[i] = Real(MDS_PWM2RPM_SCALE) * clamp_(pw[i], Real(MDS_MIN_PWM), Real(MDS_MAX_PWM)) + Real(MDS_PWM2RPM_CONST);
+}
+
+// compute_low_level (lqr_omega_controller.py:78-88, lqr_YO_controller.py:87-98): world ->
+// body rates with scipy's normalised R, then the inner loop.
+template <typename Real>
+MDS_DEV void low_level(const DroneP<Real>& P, int variant, Pid<Real>& s, const Real u[4], const Obs<Real>& o, Real rpm[4]) {
+  M3<Real> R = quat_to_rot_scipy(o.qx, o.qy, o.qz, o.qw);
+  V3<Real> w_b = mulT(R, o.av);
+  Real thrust = u[0];
+  if (variant == MDS_CTRL_LQR_YANK) thrust = z_thrust(P, o.rpm) + u[0] * P.dt_ctrl;
+  thrust_omega_pid(P, s, thrust, v3(u[1], u[2], u[3]), w_b, rpm);
+}
+
+}  // namespace mds

@@ -1,0 +1,839 @@
+// mds_kernels.cu -- __global__ kernels of the batched drone hot path and their C ABI
+// (include/mds_b200.h).  Built for sm_100a only.  One thread per drone; the drones of
+// an environment always share a thread block (blockDim = envs_per_block * N) so that
+// downwash neighbours and CBF rows are staged through shared memory.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mds_cbf.cuh"
+#include "mds_common.cuh"
+#include "mds_ctrl.cuh"
+#include "mds_physics.cuh"
+#include "mds_traj.cuh"
+
+using namespace mds;
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return MDS_ERR_LAUNCH;
+  }
+  return MDS_OK;
+}
+#define MDS_REQUIRE(cond, msg) \
+  if (!(cond)) return fail(MDS_ERR_ARG, "%s", msg)
+
+static inline int envs_per_block(int N) { int e = 256 / N; return e < 1 ? 1 : e; }
+
+// ------------------------------------------------------------------ block-cooperative pieces
+// Downwash sum for this thread's drone over its env mates, positions staged in smem.
+// All threads of the block must call (two barriers).
+template <typename Real>
+MDS_DEV Real downwash_block(const DroneP<Real>& P, typename Vec4T<Real>::type* sm_pos, V3<Real> p, int n, int N, bool valid) {
+  typename Vec4T<Real>::type me;
+  me.x = p.x; me.y = p.y; me.z = p.z; me.w = Real(0);
+  sm_pos[threadIdx.x] = me;
+  __syncthreads();
+  Real dw = Real(0);
+  if (valid) {
+    int base = threadIdx.x - n;
+    for (int j = 0; j < N; ++j) {
+      if (j == n) continue;
+      auto q = sm_pos[base + j];
+      dw += downwash_term(P, p, v3(q.x, q.y, q.z));
+    }
+  }
+  __syncthreads();
+  return dw;
+}
+
+// shared-memory carve-up for the CBF stage (per block)
+template <typename Real> struct CbfSmem {
+  int* qcount;   // [1]
+  int* flag;     // [epb]  bit0: needs QP, bit1: wz interval empty (infeasible)
+  int* status;   // [epb]
+  int* iters;    // [epb]
+  int* queue;    // [epb]
+  Real* env0;    // per-env block of `stride` Reals: agents[N*9] | rows[n_rows*4] | x[4N] | z[4N]
+  int stride, off_rows, off_x, off_z;
+};
+static inline size_t cbf_smem_ints(int epb) { return (size_t)(1 + 4 * epb + 3) & ~(size_t)3; }
+static inline int cbf_env_stride(int N, int n_obs) {
+  int s = 9 * N + 4 * (N * (N - 1) / 2 + N * n_obs) + 8 * N;
+  return s | 1;  // odd stride: the per-env solver threads hit distinct banks
+}
+template <typename Real> static size_t cbf_smem_bytes(int epb, int N, int n_obs) {
+  return cbf_smem_ints(epb) * sizeof(int) + (size_t)epb * cbf_env_stride(N, n_obs) * sizeof(Real) + 16;
+}
+template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw, int epb, int N, int n_obs) {
+  CbfSmem<Real> s;
+  int* ip = reinterpret_cast<int*>(raw);
+  s.qcount = ip; s.flag = ip + 1; s.status = s.flag + epb; s.iters = s.status + epb; s.queue = s.iters + epb;
+  size_t ints = (size_t)(1 + 4 * epb + 3) & ~(size_t)3;
+  s.env0 = reinterpret_cast<Real*>(raw + ((ints * sizeof(int) + 15) & ~(size_t)15));
+  int n_rows = N * (N - 1) / 2 + N * n_obs;
+  s.off_rows = 9 * N; s.off_x = s.off_rows + 4 * n_rows; s.off_z = s.off_x + 4 * N;
+  s.stride = (s.off_z + 4 * N) | 1;
+  return s;
+}
+
+// CBF safety filter for the whole block: every thread calls it (barriers inside).
+// u_nom -> u_safe for this thread's drone; per-env status/iters in smem (read via S).
+template <typename Real>
+MDS_DEV void cbf_filter_block(const DroneP<Real>& P, const CbfP<Real>& C, const CbfSmem<Real>& S, const Real* obstacles,
+                              int n_obs, int el, int n, int N, int epb, bool valid, const CbfAgent<Real>& ag, Real F,
+                              const Real unom[4], Real usafe[4], Real* min_h) {
+  const int n_pairs = N * (N - 1) / 2, n_rows = n_pairs + N * n_obs;
+  Real* env = S.env0 + (size_t)el * S.stride;
+  if (threadIdx.x == 0) *S.qcount = 0;
+  if (valid) {
+    Real* a = env + 9 * n;
+    a[0] = ag.p.x; a[1] = ag.p.y; a[2] = ag.p.z; a[3] = ag.dv.x; a[4] = ag.dv.y; a[5] = ag.dv.z;
+    a[6] = ag.da.x; a[7] = ag.da.y; a[8] = ag.da.z;
+    Real* x = env + S.off_x + 4 * n;
+    x[0] = unom[0]; x[1] = unom[1]; x[2] = unom[2]; x[3] = unom[3];
+    if (n == 0) { S.flag[el] = 0; S.status[el] = MDS_QP_OPTIMAL; S.iters[el] = 0; }
+  }
+  __syncthreads();
+  Real lo = Real(0), hi = Real(0);
+  if (valid) {
+    const Real tol = sizeof(Real) == 4 ? Real(2e-6) : Real(1e-11);
+    int fl = 0;
+    const Real* x = env + S.off_x;
+    for (int r = n; r < n_rows; r += N) {
+      int i, j;
+      CbfAgent<Real> ai, aj;
+      Real Ds;
+      if (r < n_pairs) {
+        pair_from_index(r, N, &i, &j);
+        const Real* b = env + 9 * j;
+        aj.p = {b[0], b[1], b[2]}; aj.dv = {b[3], b[4], b[5]}; aj.da = {b[6], b[7], b[8]};
+        Ds = Real(2) * C.rs;
+      } else {
+        i = (r - n_pairs) / n_obs;
+        int o = (r - n_pairs) - i * n_obs;
+        j = -1;
+        aj.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
+        aj.dv = {Real(0), Real(0), Real(0)}; aj.da = aj.dv;
+        Ds = C.rs + obstacles[4 * o + 3];
+      }
+      const Real* a = env + 9 * i;
+      ai.p = {a[0], a[1], a[2]}; ai.dv = {a[3], a[4], a[5]}; ai.da = {a[6], a[7], a[8]};
+      Real a3[3], rhs, h0;
+      cbf_row(P, C, ai, aj, Ds, a3, &rhs, &h0);
+      *min_h = min_(*min_h, h0);
+      Real* row = env + S.off_rows + 4 * r;
+      row[0] = a3[0]; row[1] = a3[1]; row[2] = a3[2]; row[3] = rhs;
+      // does u_nom violate this row?   G u = -a.u_i (+ a.u_j)
+      const Real* xi = x + 4 * i;
+      Real t0 = a3[0] * xi[0], t1 = a3[1] * xi[1], t2 = a3[2] * xi[2];
+      Real gx = -(t0 + t1 + t2), mag = abs_(t0) + abs_(t1) + abs_(t2);
+      if (j >= 0) {
+        const Real* xj = x + 4 * j;
+        Real u0 = a3[0] * xj[0], u1 = a3[1] * xj[1], u2 = a3[2] * xj[2];
+        gx += u0 + u1 + u2;
+        mag += abs_(u0) + abs_(u1) + abs_(u2);
+      }
+      if (rhs - gx < -tol * (abs_(rhs) + mag + Real(1e-12))) fl |= 1;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (abs_(unom[c]) > C.umax[c] * (Real(1) + tol)) fl |= 1;
+    if (!cbf_wz_bounds(C, F, &lo, &hi)) fl |= 2;
+    if (fl) atomicOr(&S.flag[el], fl);
+  }
+  __syncthreads();
+  if (valid && n == 0) {
+    int fl = S.flag[el];
+    if (fl & 2) S.status[el] = MDS_QP_INFEASIBLE;
+    else if (fl & 1) S.queue[atomicAdd(S.qcount, 1)] = el;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < *S.qcount) {  // compacted: one solver thread per env that needs it
+    int e2 = S.queue[threadIdx.x];
+    Real* env2 = S.env0 + (size_t)e2 * S.stride;
+    int it = 0;
+    int st = qp_solve(C, env2 + S.off_rows, env2 + S.off_x, env2 + S.off_z, N, n_pairs, n_rows, n_obs, &it);
+    S.status[e2] = st;
+    S.iters[e2] = it;
+  }
+  __syncthreads();
+  if (valid) {
+    if (S.status[el] == MDS_QP_OPTIMAL) {
+      const Real* x = env + S.off_x + 4 * n;
+      usafe[0] = x[0]; usafe[1] = x[1]; usafe[2] = x[2];
+      usafe[3] = clamp_(unom[3], lo, hi);
+    } else {  // reference falls back to the nominal input (cbf/qptracker.py:30-34)
+      usafe[0] = unom[0]; usafe[1] = unom[1]; usafe[2] = unom[2]; usafe[3] = unom[3];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ kernels: env step
+template <typename Real>
+__global__ void __launch_bounds__(256) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
+                                                            const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N, int epb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto* sm_pos = reinterpret_cast<typename Vec4T<Real>::type*>(smem_raw);
+  const int el = threadIdx.x / N, n = threadIdx.x - el * N;
+  const int e = blockIdx.x * epb + el;
+  const bool valid = (el < epb) && (e < E);
+  const int d = e * N + n;
+  Drone<Real> s;
+  Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
+  V3<Real> fx = {Real(0), Real(0), Real(0)}, av = {Real(0), Real(0), Real(0)};
+  if (valid) {
+    s = load_drone(st, d);
+    auto a = reinterpret_cast<const typename Vec4T<Real>::type*>(action)[d];
+    rpm[0] = clamp_(a.x, Real(0), P.max_rpm); rpm[1] = clamp_(a.y, Real(0), P.max_rpm);
+    rpm[2] = clamp_(a.z, Real(0), P.max_rpm); rpm[3] = clamp_(a.w, Real(0), P.max_rpm);
+    if (fext) fx = {fext[3 * d], fext[3 * d + 1], fext[3 * d + 2]};
+  } else {
+    s.p = {Real(0), Real(0), Real(0)};
+  }
+  const bool dwash = (P.physics == MDS_PHYSICS_DYN_GND_DRAG_DW) && (N > 1);
+  for (int k = 0; k < P.substeps; ++k) {
+    Real dw = Real(0);
+    if (dwash) dw = downwash_block(P, sm_pos, s.p, n, N, valid);
+    if (valid) {
+      av = physics_substep(P, s, rpm, dw, fx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s.rpm[i] = rpm[i];
+    }
+  }
+  if (valid) {
+    store_drone(st, d, s);
+    if (obs) store_obs(obs, d, make_obs(s, av));
+  }
+}
+
+template <typename Real>
+__global__ void obs_from_state_kernel(DroneP<Real> P, StateP<Real> st, Real* __restrict__ obs, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Drone<Real> s = load_drone(st, d);
+  M3<Real> R = quat_to_mat(s.qx, s.qy, s.qz, s.qw);
+  store_obs(obs, d, make_obs(s, mul(R, s.w)));
+}
+
+// ------------------------------------------------------------------ kernels: trajectories / controllers
+template <typename Real> MDS_DEV Ref<Real> load_ref(const Real* __restrict__ ref, int d) {
+  const Real* r = ref + (size_t)d * MDS_REF_DIM;
+  Ref<Real> o;
+  o.p = {r[0], r[1], r[2]}; o.v = {r[3], r[4], r[5]}; o.a = {r[6], r[7], r[8]}; o.yaw = r[9]; o.yaw_rate = r[10];
+  return o;
+}
+template <typename Real>
+__global__ void traj_eval_kernel(const typename TrajSpecT<Real>::spec* __restrict__ specs,
+                                 const typename TrajSpecT<Real>::seg* __restrict__ segs, double t, Real* __restrict__ ref, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Ref<Real> o = eval_traj<Real>(specs[d], segs, t);
+  Real* r = ref + (size_t)d * MDS_REF_DIM;
+  r[0] = o.p.x; r[1] = o.p.y; r[2] = o.p.z; r[3] = o.v.x; r[4] = o.v.y; r[5] = o.v.z;
+  r[6] = o.a.x; r[7] = o.a.y; r[8] = o.a.z; r[9] = o.yaw; r[10] = o.yaw_rate;
+}
+template <typename Real> MDS_DEV void store4(Real* p, int d, const Real v[4]) {
+  typename Vec4T<Real>::type o;
+  o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3];
+  reinterpret_cast<typename Vec4T<Real>::type*>(p)[d] = o;
+}
+template <typename Real> MDS_DEV void load4(const Real* p, int d, Real v[4]) {
+  auto o = reinterpret_cast<const typename Vec4T<Real>::type*>(p)[d];
+  v[0] = o.x; v[1] = o.y; v[2] = o.z; v[3] = o.w;
+}
+template <typename Real>
+__global__ void geometric_ctrl_kernel(DroneP<Real> P, GeoP<Real> G, const Real* __restrict__ obs, const Real* __restrict__ ref,
+                                      Real* __restrict__ action, Real* __restrict__ u_out, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Real u[4], rpm[4];
+  geometric_input(P, G, load_obs(obs, d), load_ref(ref, d), u);
+  input_to_action(P, u, rpm);
+  store4(action, d, rpm);
+  if (u_out) store4(u_out, d, u);
+}
+template <typename Real>
+__global__ void lqr_ctrl_kernel(DroneP<Real> P, LqrP<Real> L, int variant, const Real* __restrict__ obs, const Real* __restrict__ ref,
+                                Real* __restrict__ u_out, Real* __restrict__ action, PidP<Real> pid, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Obs<Real> o = load_obs(obs, d);
+  Real u[4], rpm[4];
+  lqr_input(P, L, variant, o, load_ref(ref, d), u);
+  if (variant == MDS_CTRL_LQR_TORQUE) {
+    input_to_action(P, u, rpm);  // clamps u[0] >= 0 in place, like the reference
+    if (action) store4(action, d, rpm);
+  } else {
+    if (action) {  // inner loop sees the un-capped u (quirk B9)
+      Pid<Real> ps = load_pid(pid, d);
+      low_level(P, variant, ps, u, o, rpm);
+      store_pid(pid, d, ps);
+      store4(action, d, rpm);
+      if (variant == MDS_CTRL_LQR_OMEGA) u[0] = max_(u[0], Real(0));
+    }
+    if (variant == MDS_CTRL_LQR_OMEGA) u[0] = cap_thrust(P, u[0]);
+  }
+  store4(u_out, d, u);
+}
+template <typename Real>
+__global__ void lowlevel_kernel(DroneP<Real> P, int variant, const Real* __restrict__ u_in, const Real* __restrict__ obs,
+                                PidP<Real> pid, Real* __restrict__ action, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Real u[4], rpm[4];
+  load4(u_in, d, u);
+  Pid<Real> ps = load_pid(pid, d);
+  low_level(P, variant, ps, u, load_obs(obs, d), rpm);
+  store_pid(pid, d, ps);
+  store4(action, d, rpm);
+}
+
+// ------------------------------------------------------------------ kernels: CBF
+template <typename Real>
+__global__ void __launch_bounds__(256) cbf_qp_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __restrict__ obs, const Real* __restrict__ xdes,
+                                                      const Real* __restrict__ unom_g, const Real* __restrict__ obstacles, int n_obs,
+                                                      Real* __restrict__ usafe_g, int* __restrict__ status, int* __restrict__ iters,
+                                                      int E, int N, int epb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, epb, N, n_obs);
+  const int el = threadIdx.x / N, n = threadIdx.x - el * N;
+  const int e = blockIdx.x * epb + el;
+  const bool valid = (el < epb) && (e < E);
+  const int d = e * N + n;
+  const int xdim = C.order == 2 ? 9 : 10;
+  CbfAgent<Real> ag;
+  ag.p = {Real(0), Real(0), Real(0)}; ag.dv = ag.p; ag.da = ag.p;
+  Real F = Real(0), unom[4] = {Real(0), Real(0), Real(0), Real(0)}, usafe[4];
+  if (valid) {
+    Obs<Real> o = load_obs(obs, d);
+    Real xd[10];
+    for (int k = 0; k < xdim; ++k) xd[k] = xdes[(size_t)d * xdim + k];
+    ag = cbf_agent(P, C, o, xd, &F);
+    load4(unom_g, d, unom);
+  }
+  Real min_h = Real(1e30);
+  cbf_filter_block(P, C, S, obstacles, n_obs, el, n, N, epb, valid, ag, F, unom, usafe, &min_h);
+  if (valid) {
+    store4(usafe_g, d, usafe);
+    if (n == 0) {
+      status[e] = S.status[el];
+      if (iters) iters[e] = S.iters[el];
+    }
+  }
+}
+
+// dense G, h in the reference's row order (parity aid; one thread per env)
+template <typename Real>
+__global__ void cbf_rows_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __restrict__ obs, const Real* __restrict__ xdes,
+                                const Real* __restrict__ obstacles, int n_obs, Real* __restrict__ Gm, Real* __restrict__ hv, int E, int N) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int xdim = C.order == 2 ? 9 : 10;
+  const int n_pairs = N * (N - 1) / 2, W = 4 * N;
+  const int m = n_pairs + 8 * N + (C.order == 3 ? 2 * N : 0) + N * n_obs;
+  Real* G = Gm + (size_t)e * m * W;
+  Real* h = hv + (size_t)e * m;
+  for (size_t k = 0; k < (size_t)m * W; ++k) G[k] = Real(0);
+  auto agent = [&](int i, Real* F) {
+    Obs<Real> o = load_obs(obs, e * N + i);
+    Real xd[10];
+    for (int k = 0; k < xdim; ++k) xd[k] = xdes[(size_t)(e * N + i) * xdim + k];
+    return cbf_agent(P, C, o, xd, F);
+  };
+  int row = 0;
+  Real F, a3[3], rhs, h0;
+  for (int i = 0; i < N - 1; ++i)
+    for (int j = i + 1; j < N; ++j) {
+      CbfAgent<Real> ai = agent(i, &F), aj = agent(j, &F);
+      cbf_row(P, C, ai, aj, Real(2) * C.rs, a3, &rhs, &h0);
+      for (int c = 0; c < 3; ++c) { G[(size_t)row * W + 4 * i + c] = -a3[c]; G[(size_t)row * W + 4 * j + c] = a3[c]; }
+      h[row++] = rhs;
+    }
+  for (int k = 0; k < W; ++k) { G[(size_t)row * W + k] = Real(1); h[row++] = C.umax[k & 3]; }
+  for (int k = 0; k < W; ++k) { G[(size_t)row * W + k] = Real(-1); h[row++] = C.umax[k & 3]; }
+  if (C.order == 3)
+    for (int i = 0; i < N; ++i) {
+      agent(i, &F);
+      G[(size_t)row * W + 4 * i + 3] = Real(1); h[row++] = C.k2 * (C.fmax - F);
+      G[(size_t)row * W + 4 * i + 3] = Real(-1); h[row++] = C.k2 * (F - C.fmin);
+    }
+  for (int i = 0; i < N; ++i)
+    for (int o = 0; o < n_obs; ++o) {
+      CbfAgent<Real> ai = agent(i, &F), aj;
+      aj.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
+      aj.dv = {Real(0), Real(0), Real(0)}; aj.da = aj.dv;
+      cbf_row(P, C, ai, aj, C.rs + obstacles[4 * o + 3], a3, &rhs, &h0);
+      for (int c = 0; c < 3; ++c) G[(size_t)row * W + 4 * i + c] = -a3[c];
+      h[row++] = rhs;
+    }
+}
+
+// ------------------------------------------------------------------ kernels: model comparison
+template <typename Real>
+__global__ void xdot_linear_kernel(DroneP<Real> P, int kind, const Real* __restrict__ obs, Real* __restrict__ xdot, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Obs<Real> o = load_obs(obs, d);
+  Real* out = xdot + (size_t)d * kind;
+  if (kind == 12) {  // model/linearized.py:83-104: x = [rpy, w(obs 13:16), v, p], u from action_to_input
+    Real u[4];
+    action_to_input(P, o.rpm, u);
+    out[0] = o.av.x; out[1] = o.av.y; out[2] = o.av.z;
+    out[3] = u[1] / P.ixx; out[4] = u[2] / P.iyy; out[5] = u[3] / P.izz;
+    out[6] = P.g * o.rpy.y; out[7] = -P.g * o.rpy.x; out[8] = (u[0] - P.m * P.g) / P.m;
+    out[9] = o.v.x; out[10] = o.v.y; out[11] = o.v.z;
+    return;
+  }
+  // builder-defined 9 / 10-dim (quirk B23): u = [f | yank = 0, body rates]
+  M3<Real> R = quat_to_rot_scipy(o.qx, o.qy, o.qz, o.qw);
+  V3<Real> wb = mulT(R, o.av);
+  Real F = z_thrust(P, o.rpm);
+  out[0] = wb.x; out[1] = wb.y; out[2] = wb.z;
+  if (kind == 9) {
+    out[3] = P.g * o.rpy.y; out[4] = -P.g * o.rpy.x; out[5] = (F - P.m * P.g) / P.m;
+    out[6] = o.v.x; out[7] = o.v.y; out[8] = o.v.z;
+  } else {
+    out[3] = Real(0);
+    out[4] = P.g * o.rpy.y; out[5] = -P.g * o.rpy.x; out[6] = (F - P.m * P.g) / P.m;
+    out[7] = o.v.x; out[8] = o.v.y; out[9] = o.v.z;
+  }
+}
+template <typename Real>
+__global__ void xdot_nonlinear_kernel(DroneP<Real> P, Real jx, Real jy, Real jz, const Real* __restrict__ obs, Real* __restrict__ xdot, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Obs<Real> o = load_obs(obs, d);
+  Real u[4];
+  action_to_input(P, o.rpm, u);
+  M3<Real> R = quat_to_rot_scipy(o.qx, o.qy, o.qz, o.qw);
+  V3<Real> w = o.av;
+  V3<Real> Jw = {jx * w.x, jy * w.y, jz * w.z};
+  V3<Real> g = cross(w, Jw);
+  Real* out = xdot + (size_t)d * 12;  // geo_x_dot_to_linear order: (w, wdot, vdot, v)
+  out[0] = w.x; out[1] = w.y; out[2] = w.z;
+  out[3] = (u[1] - g.x) / jx; out[4] = (u[2] - g.y) / jy; out[5] = (u[3] - g.z) / jz;
+  Real a = u[0] / P.m;
+  out[6] = R.m[2] * a; out[7] = R.m[5] * a; out[8] = R.m[8] * a - P.g;
+  out[9] = o.v.x; out[10] = o.v.y; out[11] = o.v.z;
+}
+
+// ------------------------------------------------------------------ kernel: fused K-step rollout
+template <typename Real> struct RolloutP {
+  int ctrl, use_cbf, n_obs, write_obs_every;
+  Real u0_pre, u0_post;
+  Real obstacles[MDS_MAX_OBSTACLES * 4];
+};
+
+MDS_DEV void atomic_min_double(double* addr, double v) {
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double(assumed) <= v) break;
+    old = atomicCAS(a, assumed, __double_as_longlong(v));
+  } while (assumed != old);
+}
+MDS_DEV void atomic_max_double(double* addr, double v) {
+  unsigned long long* a = (unsigned long long*)addr;
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double(assumed) >= v) break;
+    old = atomicCAS(a, assumed, __double_as_longlong(v));
+  } while (assumed != old);
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) rollout_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+                                                       StateP<Real> st, PidP<Real> pid,
+                                                       const typename TrajSpecT<Real>::spec* __restrict__ specs,
+                                                       const typename TrajSpecT<Real>::seg* __restrict__ segs, Real* __restrict__ obs,
+                                                       Real* __restrict__ obs_log, double* __restrict__ stats, double t0, int K, int E, int N, int epb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto* sm_pos = reinterpret_cast<typename Vec4T<Real>::type*>(smem_raw);
+  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw + 256 * sizeof(typename Vec4T<Real>::type), epb, N, Rc.n_obs);
+  const int el = threadIdx.x / N, n = threadIdx.x - el * N;
+  const int e = blockIdx.x * epb + el;
+  const bool valid = (el < epb) && (e < E);
+  const int d = e * N + n;
+  const size_t Dtot = (size_t)E * N;
+
+  Drone<Real> s;
+  s.p = {Real(0), Real(0), Real(0)};
+  Pid<Real> ps;
+  typename TrajSpecT<Real>::spec sp;
+  V3<Real> av = {Real(0), Real(0), Real(0)};
+  const bool has_pid = (Rc.ctrl == MDS_CTRL_LQR_OMEGA || Rc.ctrl == MDS_CTRL_LQR_YANK);
+  if (valid) {
+    s = load_drone(st, d);
+    sp = specs[d];
+    if (has_pid) ps = load_pid(pid, d);
+    const Real* o = obs + (size_t)d * MDS_OBS_DIM;
+    av = {o[13], o[14], o[15]};
+  }
+  const bool dwash = (P.physics == MDS_PHYSICS_DYN_GND_DRAG_DW) && (N > 1);
+  double sum_err = 0.0, max_err = 0.0, min_h = 1e30;
+  int qp_solves = 0, qp_iters = 0, qp_infeas = 0, qp_cap = 0;
+
+  for (int k = 0; k < K; ++k) {
+    const double t = t0 + (double)k * (double)P.dt_ctrl;
+    Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
+    Ref<Real> ref;
+    Obs<Real> o;
+    Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
+    if (valid) {
+      ref = eval_traj<Real>(sp, segs, t);
+      o = make_obs(s, av);
+      double ex = (double)(s.p.x - ref.p.x), ey = (double)(s.p.y - ref.p.y), ez = (double)(s.p.z - ref.p.z);
+      double er = sqrt(ex * ex + ey * ey + ez * ez);
+      sum_err += er;
+      max_err = er > max_err ? er : max_err;
+      if (Rc.ctrl == MDS_CTRL_GEOMETRIC) {
+        geometric_input(P, G, o, ref, u);
+        input_to_action(P, u, rpm);
+      } else {
+        lqr_input(P, L, Rc.ctrl, o, ref, u);
+        if (Rc.ctrl == MDS_CTRL_LQR_TORQUE) input_to_action(P, u, rpm);
+      }
+    }
+    if (has_pid) {
+      if (Rc.use_cbf) {  // block-uniform branch: barriers inside
+        CbfAgent<Real> ag;
+        ag.p = {Real(0), Real(0), Real(0)}; ag.dv = ag.p; ag.da = ag.p;
+        Real F = Real(0), unom[4] = {Real(0), Real(0), Real(0), Real(0)}, usafe[4] = {Real(0), Real(0), Real(0), Real(0)};
+        if (valid) {
+          if (Rc.ctrl == MDS_CTRL_LQR_OMEGA) u[0] = cap_thrust(P, u[0]);  // skip_low_level=True returns cap_u(u)
+          Real xd[10];
+          xd[0] = Real(0); xd[1] = Real(0); xd[2] = ref.yaw;
+          if (C.order == 2) { xd[3] = ref.v.x; xd[4] = ref.v.y; xd[5] = ref.v.z; }
+          else { xd[3] = P.g * P.m; xd[4] = ref.v.x; xd[5] = ref.v.y; xd[6] = ref.v.z; }
+          ag = cbf_agent(P, C, o, xd, &F);
+          unom[0] = u[0] - Rc.u0_pre; unom[1] = u[1]; unom[2] = u[2]; unom[3] = u[3];
+        }
+        Real mh = Real(1e30);
+        cbf_filter_block(P, C, S, Rc.obstacles, Rc.n_obs, el, n, N, epb, valid, ag, F, unom, usafe, &mh);
+        if (valid) {
+          min_h = fmin(min_h, (double)mh);
+          if (n == 0) {
+            int stt = S.status[el], it = S.iters[el];
+            qp_solves += (it > 0 || stt != MDS_QP_OPTIMAL);
+            qp_iters += it;
+            qp_infeas += (stt == MDS_QP_INFEASIBLE);
+            qp_cap += (stt == MDS_QP_ITER_CAP);
+          }
+          u[0] = usafe[0] + Rc.u0_post; u[1] = usafe[1]; u[2] = usafe[2]; u[3] = usafe[3];
+        }
+        __syncthreads();  // S.status/iters are re-initialised by the next step
+      }
+      if (valid) low_level(P, Rc.ctrl, ps, u, o, rpm);
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rpm[i] = clamp_(rpm[i], Real(0), P.max_rpm);
+    }
+    for (int ss = 0; ss < P.substeps; ++ss) {
+      Real dw = Real(0);
+      if (dwash) dw = downwash_block(P, sm_pos, s.p, n, N, valid);
+      if (valid) {
+        av = physics_substep(P, s, rpm, dw, v3(Real(0), Real(0), Real(0)));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s.rpm[i] = rpm[i];
+      }
+    }
+    if (valid && obs_log && Rc.write_obs_every > 0 && ((k + 1) % Rc.write_obs_every) == 0) {
+      size_t slot = (size_t)((k + 1) / Rc.write_obs_every - 1);
+      store_obs(obs_log + slot * Dtot * MDS_OBS_DIM, d, make_obs(s, av));
+    }
+  }
+  if (valid) {
+    store_drone(st, d, s);
+    if (has_pid) store_pid(pid, d, ps);
+    store_obs(obs, d, make_obs(s, av));
+  }
+  if (stats) {
+    // warp reduce, then one atomic per warp
+    double cnt = valid ? (double)K : 0.0, qs = qp_solves, qi = qp_iters, qf = qp_infeas, qc = qp_cap;
+    for (int off = 16; off > 0; off >>= 1) {
+      cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+      sum_err += __shfl_down_sync(0xffffffffu, sum_err, off);
+      max_err = fmax(max_err, __shfl_down_sync(0xffffffffu, max_err, off));
+      min_h = fmin(min_h, __shfl_down_sync(0xffffffffu, min_h, off));
+      qs += __shfl_down_sync(0xffffffffu, qs, off);
+      qi += __shfl_down_sync(0xffffffffu, qi, off);
+      qf += __shfl_down_sync(0xffffffffu, qf, off);
+      qc += __shfl_down_sync(0xffffffffu, qc, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&stats[MDS_STAT_DRONE_STEPS], cnt);
+      atomicAdd(&stats[MDS_STAT_SUM_POS_ERR], sum_err);
+      atomic_max_double(&stats[MDS_STAT_MAX_POS_ERR], max_err);
+      atomic_min_double(&stats[MDS_STAT_MIN_BARRIER], min_h);
+      if (qs > 0) atomicAdd(&stats[MDS_STAT_QP_SOLVES], qs);
+      if (qi > 0) atomicAdd(&stats[MDS_STAT_QP_ITERS], qi);
+      if (qf > 0) atomicAdd(&stats[MDS_STAT_QP_INFEASIBLE], qf);
+      if (qc > 0) atomicAdd(&stats[MDS_STAT_QP_ITER_CAP], qc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ FMA-chain peak microbenchmark
+template <typename Real> __global__ void fma_peak_kernel(Real* out, int iters) {
+  Real a0 = Real(threadIdx.x) * Real(1e-3), a1 = a0 + Real(1), a2 = a0 + Real(2), a3 = a0 + Real(3);
+  Real a4 = a0 + Real(4), a5 = a0 + Real(5), a6 = a0 + Real(6), a7 = a0 + Real(7);
+  const Real b = Real(0.999), c = Real(1e-3);
+  for (int i = 0; i < iters; ++i) {
+    a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+    a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ================================================================== C ABI
+template <typename Real>
+static int physics_step_impl(const MdsDroneParams* prm, MdsState st, const Real* action, const Real* fext, Real* obs, int E, int N, void* stream) {
+  MDS_REQUIRE(prm && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && action, "physics_step: null pointer");
+  MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV, "physics_step: bad E or N");
+  MDS_REQUIRE(prm->substeps >= 1, "physics_step: substeps must be >= 1");
+  MDS_REQUIRE(prm->physics == MDS_PHYSICS_DYN || prm->physics == MDS_PHYSICS_DYN_GND_DRAG_DW, "physics_step: unknown physics mode");
+  int epb = envs_per_block(N), threads = epb * N, blocks = (E + epb - 1) / epb;
+  size_t smem = 256 * sizeof(typename Vec4T<Real>::type);
+  physics_step_kernel<Real><<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(st), action, fext, obs, E, N, epb);
+  return check_launch("physics_step");
+}
+template <typename Real> static int obs_from_state_impl(const MdsDroneParams* prm, MdsState st, Real* obs, int D, void* stream) {
+  MDS_REQUIRE(prm && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && obs && D > 0, "obs_from_state: bad argument");
+  obs_from_state_kernel<Real><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(st), obs, D);
+  return check_launch("obs_from_state");
+}
+template <typename Real>
+static int traj_eval_impl(const typename TrajSpecT<Real>::spec* specs, const typename TrajSpecT<Real>::seg* segs, double t, Real* ref, int D, void* stream) {
+  MDS_REQUIRE(specs && ref && D > 0, "traj_eval: bad argument");
+  traj_eval_kernel<Real><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(specs, segs, t, ref, D);
+  return check_launch("traj_eval");
+}
+template <typename Real>
+static int geometric_impl(const MdsDroneParams* prm, const MdsGeoGains* g, const Real* obs, const Real* ref, Real* action, Real* u, int D, void* stream) {
+  MDS_REQUIRE(prm && g && obs && ref && action && D > 0, "geometric_ctrl: bad argument");
+  geometric_ctrl_kernel<Real><<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*g), obs, ref, action, u, D);
+  return check_launch("geometric_ctrl");
+}
+static bool lqr_dim_ok(int variant, int dim) {
+  return (variant == MDS_CTRL_LQR_TORQUE && dim == 12) || (variant == MDS_CTRL_LQR_OMEGA && dim == 9) || (variant == MDS_CTRL_LQR_YANK && dim == 10);
+}
+template <typename Real>
+static int lqr_impl(const MdsDroneParams* prm, const MdsLqrGains* g, int variant, const Real* obs, const Real* ref, Real* u, Real* action,
+                    MdsPidState pid, int D, void* stream) {
+  MDS_REQUIRE(prm && g && obs && ref && u && D > 0, "lqr_ctrl: bad argument");
+  MDS_REQUIRE(lqr_dim_ok(variant, g->dim), "lqr_ctrl: variant / gain dimension mismatch");
+  MDS_REQUIRE(!(action && variant != MDS_CTRL_LQR_TORQUE) || (pid.a && pid.b), "lqr_ctrl: inner loop needs PID state");
+  lqr_ctrl_kernel<Real><<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*g), variant, obs, ref, u, action,
+                                                                             to_dev<Real>(pid), D);
+  return check_launch("lqr_ctrl");
+}
+template <typename Real>
+static int lowlevel_impl(const MdsDroneParams* prm, int variant, const Real* u, const Real* obs, MdsPidState pid, Real* action, int D, void* stream) {
+  MDS_REQUIRE(prm && u && obs && pid.a && pid.b && action && D > 0, "lowlevel: bad argument");
+  MDS_REQUIRE(variant == MDS_CTRL_LQR_OMEGA || variant == MDS_CTRL_LQR_YANK, "lowlevel: variant must be LQR_OMEGA or LQR_YANK");
+  lowlevel_kernel<Real><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), variant, u, obs, to_dev<Real>(pid), action, D);
+  return check_launch("lowlevel");
+}
+static int cbf_args_ok(const MdsCbfParams* c, int N, int n_obs) {
+  if (!c) return fail(MDS_ERR_ARG, "%s", "cbf: null params");
+  if (c->order != 2 && c->order != 3) return fail(MDS_ERR_ARG, "%s", "cbf: order must be 2 or 3");
+  if (N < 1 || N > MDS_MAX_DRONES_PER_ENV) return fail(MDS_ERR_ARG, "%s", "cbf: bad N");
+  if (n_obs < 0 || n_obs > MDS_MAX_OBSTACLES || n_obs > N) return fail(MDS_ERR_ARG, "%s", "cbf: n_obs must be <= min(N, MDS_MAX_OBSTACLES) (reference quirk B14)");
+  return MDS_OK;
+}
+template <typename Real>
+static int cbf_qp_impl(const MdsDroneParams* prm, const MdsCbfParams* c, const Real* obs, const Real* xdes, const Real* unom, const Real* obstacles,
+                       int n_obs, Real* usafe, int* status, int* iters, int E, int N, void* stream) {
+  int rc = cbf_args_ok(c, N, n_obs);
+  if (rc) return rc;
+  MDS_REQUIRE(prm && obs && xdes && unom && usafe && status && E > 0, "cbf_qp: bad argument");
+  MDS_REQUIRE(n_obs == 0 || obstacles, "cbf_qp: obstacles pointer is null");
+  int epb = envs_per_block(N), threads = epb * N, blocks = (E + epb - 1) / epb;
+  size_t smem = cbf_smem_bytes<Real>(epb, N, n_obs);
+  cudaError_t e = cudaFuncSetAttribute(cbf_qp_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "cbf_qp: shared memory opt-in failed: %s", cudaGetErrorString(e));
+  cbf_qp_kernel<Real><<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*c), obs, xdes, unom, obstacles, n_obs, usafe,
+                                                                        status, iters, E, N, epb);
+  return check_launch("cbf_qp");
+}
+template <typename Real>
+static int cbf_rows_impl(const MdsDroneParams* prm, const MdsCbfParams* c, const Real* obs, const Real* xdes, const Real* obstacles, int n_obs,
+                         Real* Gm, Real* h, int E, int N, void* stream) {
+  int rc = cbf_args_ok(c, N, n_obs);
+  if (rc) return rc;
+  MDS_REQUIRE(prm && obs && xdes && Gm && h && E > 0, "cbf_rows: bad argument");
+  cbf_rows_kernel<Real><<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*c), obs, xdes, obstacles, n_obs, Gm, h, E, N);
+  return check_launch("cbf_rows");
+}
+template <typename Real> static int xdot_linear_impl(const MdsDroneParams* prm, int kind, const Real* obs, Real* xdot, int D, void* stream) {
+  MDS_REQUIRE(prm && obs && xdot && D > 0, "xdot_linear: bad argument");
+  MDS_REQUIRE(kind == 12 || kind == 9 || kind == 10, "xdot_linear: kind must be 12, 9 or 10");
+  xdot_linear_kernel<Real><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), kind, obs, xdot, D);
+  return check_launch("xdot_linear");
+}
+template <typename Real>
+static int xdot_nonlinear_impl(const MdsDroneParams* prm, double jx, double jy, double jz, const Real* obs, Real* xdot, int D, void* stream) {
+  MDS_REQUIRE(prm && obs && xdot && D > 0 && jx > 0 && jy > 0 && jz > 0, "xdot_nonlinear: bad argument");
+  xdot_nonlinear_kernel<Real><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), Real(jx), Real(jy), Real(jz), obs, xdot, D);
+  return check_launch("xdot_nonlinear");
+}
+template <typename Real>
+static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr, const MdsCbfParams* cbf,
+                        MdsState st, MdsPidState pid, const typename TrajSpecT<Real>::spec* specs, const typename TrajSpecT<Real>::seg* segs,
+                        Real* obs, Real* obs_log, double* stats, double t0, int K, int E, int N, void* stream) {
+  MDS_REQUIRE(prm && cfg && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && specs && obs, "rollout: null pointer");
+  MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV && K > 0, "rollout: bad E, N or K");
+  MDS_REQUIRE(cfg->ctrl >= MDS_CTRL_GEOMETRIC && cfg->ctrl <= MDS_CTRL_LQR_YANK, "rollout: unknown controller");
+  RolloutP<Real> R;
+  memset(&R, 0, sizeof(R));
+  R.ctrl = cfg->ctrl; R.use_cbf = cfg->use_cbf; R.n_obs = cfg->num_obstacles; R.write_obs_every = cfg->write_obs_every;
+  GeoP<Real> G;
+  memset(&G, 0, sizeof(G));
+  LqrP<Real> L;
+  memset(&L, 0, sizeof(L));
+  CbfP<Real> C;
+  memset(&C, 0, sizeof(C));
+  C.order = 2;
+  if (cfg->ctrl == MDS_CTRL_GEOMETRIC) {
+    MDS_REQUIRE(geo, "rollout: geometric gains missing");
+    G = to_dev<Real>(*geo);
+  } else {
+    MDS_REQUIRE(lqr && lqr_dim_ok(cfg->ctrl, lqr->dim), "rollout: LQR gains missing or of the wrong dimension");
+    L = to_dev<Real>(*lqr);
+    if (cfg->ctrl != MDS_CTRL_LQR_TORQUE) MDS_REQUIRE(pid.a && pid.b, "rollout: PID state missing");
+  }
+  if (cfg->use_cbf) {
+    int rc = cbf_args_ok(cbf, N, cfg->num_obstacles);
+    if (rc) return rc;
+    MDS_REQUIRE((cfg->ctrl == MDS_CTRL_LQR_OMEGA && cbf->order == 2) || (cfg->ctrl == MDS_CTRL_LQR_YANK && cbf->order == 3),
+                "rollout: CBF order 2 needs LQR_OMEGA, order 3 needs LQR_YANK");
+    C = to_dev<Real>(*cbf);
+    for (int i = 0; i < cfg->num_obstacles * 4; ++i) R.obstacles[i] = Real(cfg->obstacles[i]);
+    // reference caller: nominal_us[:,0] -= M*G before the QP (CBFTest.py:339, CBFTestOrd3.py:344);
+    // added back only for order 2 (CBFTest.py:346 vs CBFTestOrd3.py:350)
+    R.u0_pre = Real(prm->m * prm->g);
+    R.u0_post = cbf->order == 2 ? Real(prm->m * prm->g) : Real(0);
+  } else {
+    R.n_obs = 0;
+  }
+  MDS_REQUIRE(!(cfg->write_obs_every > 0) || obs_log, "rollout: obs_log buffer missing");
+  int epb = envs_per_block(N), threads = epb * N, blocks = (E + epb - 1) / epb;
+  size_t smem = 256 * sizeof(typename Vec4T<Real>::type) + cbf_smem_bytes<Real>(epb, N, R.n_obs);
+  cudaError_t e = cudaFuncSetAttribute(rollout_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: shared memory opt-in failed: %s", cudaGetErrorString(e));
+  rollout_kernel<Real><<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), R, G, L, C, to_dev<Real>(st), to_dev<Real>(pid), specs, segs,
+                                                                         obs, obs_log, stats, t0, K, E, N, epb);
+  return check_launch("rollout");
+}
+
+extern "C" {
+
+int mds_abi_version(void) { return MDS_ABI_VERSION; }
+const char* mds_last_error(void) { return g_err; }
+int mds_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "device_info: %s", cudaGetErrorString(e));
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "device_info: %s", cudaGetErrorString(e));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (l2_bytes) *l2_bytes = p.l2CacheSize;
+  return MDS_OK;
+}
+int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 * N + (order == 3 ? 2 * N : 0) + N * n_obs; }
+
+#define MDS_DEFINE(SUF, REAL, SPEC, SEG)                                                                                                          \
+  int mds_physics_step_##SUF(const MdsDroneParams* prm, MdsState st, const REAL* action, const REAL* fext, REAL* obs, int E, int N, void* stream) { \
+    return physics_step_impl<REAL>(prm, st, action, fext, obs, E, N, stream);                                                                      \
+  }                                                                                                                                                \
+  int mds_obs_from_state_##SUF(const MdsDroneParams* prm, MdsState st, REAL* obs, int D, void* stream) {                                           \
+    return obs_from_state_impl<REAL>(prm, st, obs, D, stream);                                                                                     \
+  }                                                                                                                                                \
+  int mds_traj_eval_##SUF(const SPEC* specs, const SEG* segs, double t, REAL* ref, int D, void* stream) {                                          \
+    return traj_eval_impl<REAL>(specs, segs, t, ref, D, stream);                                                                                   \
+  }                                                                                                                                                \
+  int mds_geometric_ctrl_##SUF(const MdsDroneParams* prm, const MdsGeoGains* g, const REAL* obs, const REAL* ref, REAL* action, REAL* u, int D,    \
+                               void* stream) {                                                                                                     \
+    return geometric_impl<REAL>(prm, g, obs, ref, action, u, D, stream);                                                                           \
+  }                                                                                                                                                \
+  int mds_lqr_ctrl_##SUF(const MdsDroneParams* prm, const MdsLqrGains* g, int variant, const REAL* obs, const REAL* ref, REAL* u, REAL* action,    \
+                         MdsPidState pid, int D, void* stream) {                                                                                   \
+    return lqr_impl<REAL>(prm, g, variant, obs, ref, u, action, pid, D, stream);                                                                   \
+  }                                                                                                                                                \
+  int mds_lowlevel_##SUF(const MdsDroneParams* prm, int variant, const REAL* u, const REAL* obs, MdsPidState pid, REAL* action, int D,             \
+                         void* stream) {                                                                                                           \
+    return lowlevel_impl<REAL>(prm, variant, u, obs, pid, action, D, stream);                                                                      \
+  }                                                                                                                                                \
+  int mds_cbf_qp_##SUF(const MdsDroneParams* prm, const MdsCbfParams* c, const REAL* obs, const REAL* xdes, const REAL* unom,                      \
+                       const REAL* obstacles, int n_obs, REAL* usafe, int* status, int* iters, int E, int N, void* stream) {                       \
+    return cbf_qp_impl<REAL>(prm, c, obs, xdes, unom, obstacles, n_obs, usafe, status, iters, E, N, stream);                                       \
+  }                                                                                                                                                \
+  int mds_cbf_rows_##SUF(const MdsDroneParams* prm, const MdsCbfParams* c, const REAL* obs, const REAL* xdes, const REAL* obstacles, int n_obs,    \
+                         REAL* Gm, REAL* h, int E, int N, void* stream) {                                                                          \
+    return cbf_rows_impl<REAL>(prm, c, obs, xdes, obstacles, n_obs, Gm, h, E, N, stream);                                                          \
+  }                                                                                                                                                \
+  int mds_xdot_linear_##SUF(const MdsDroneParams* prm, int kind, const REAL* obs, REAL* xdot, int D, void* stream) {                               \
+    return xdot_linear_impl<REAL>(prm, kind, obs, xdot, D, stream);                                                                                \
+  }                                                                                                                                                \
+  int mds_xdot_nonlinear_##SUF(const MdsDroneParams* prm, double jx, double jy, double jz, const REAL* obs, REAL* xdot, int D, void* stream) {     \
+    return xdot_nonlinear_impl<REAL>(prm, jx, jy, jz, obs, xdot, D, stream);                                                                       \
+  }                                                                                                                                                \
+  int mds_rollout_##SUF(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr,                       \
+                        const MdsCbfParams* cbf, MdsState st, MdsPidState pid, const SPEC* specs, const SEG* segs, REAL* obs, REAL* obs_log,       \
+                        double* stats, double t0, int K, int E, int N, void* stream) {                                                             \
+    return rollout_impl<REAL>(prm, cfg, geo, lqr, cbf, st, pid, specs, segs, obs, obs_log, stats, t0, K, E, N, stream);                            \
+  }
+
+MDS_DEFINE(f32, float, MdsTrajSpecF32, MdsTrajSegF32)
+MDS_DEFINE(f64, double, MdsTrajSpecF64, MdsTrajSegF64)
+
+int mds_fma_peak(int use_f64, int iters, double* tflops_out, void* stream) {
+  MDS_REQUIRE(tflops_out && iters > 0, "fma_peak: bad argument");
+  int sms = 0;
+  int rc = mds_device_info(&sms, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  const int threads = 1024, blocks = sms * 2;
+  void* buf = nullptr;
+  cudaError_t e = cudaMalloc(&buf, (size_t)threads * blocks * sizeof(double));
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "fma_peak: %s", cudaGetErrorString(e));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaStream_t s = (cudaStream_t)stream;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(a, s);
+    if (use_f64) fma_peak_kernel<double><<<blocks, threads, 0, s>>>((double*)buf, iters);
+    else fma_peak_kernel<float><<<blocks, threads, 0, s>>>((float*)buf, iters);
+    cudaEventRecord(b, s);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(buf);
+  rc = check_launch("fma_peak");
+  if (rc) return rc;
+  double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+  *tflops_out = flops / ((double)best * 1e-3) / 1e12;
+  return MDS_OK;
+}
+
+}  // extern "C"

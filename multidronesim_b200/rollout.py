@@ -1,0 +1,79 @@
+"""Fused K-step rollout: trajectory -> controller -> (CBF-QP) -> inner loop -> physics, with
+each drone's state held in registers across the K control steps (``mds_rollout``).
+
+It is the device equivalent of the reference's per-step Python loops
+(simulations/EnvGeometric.py:434-479, simulations/CBFTest.py:302-358,
+simulations/CBFTestOrd3.py:305-360) including what those callers do around the library calls
+(``nominal_us[:,0] -= M*G`` before the QP, ``+= M*G`` after it for order 2 only)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .control.geometric import GeometricControl
+from .control.lqr import LQRController, LQROmegaController, LQRYankOmegaController
+
+
+class FusedRollout:
+    def __init__(self, env, trajs, controller, qp_tracker=None, obstacles=None):
+        """env: BatchedCtrlAviary; trajs: TrajectorySet (one per drone); controller: GeometricControl |
+        LQRController | LQROmegaController | LQRYankOmegaController; qp_tracker: DroneQPTracker or None;
+        obstacles: tensor/list [N_obs, 4] = cx, cy, cz, r (shared by all envs)."""
+        self.env, self.trajs, self.controller, self.qp = env, trajs, controller, qp_tracker
+        if trajs.num != env.NUM_TOTAL:
+            raise ValueError("need one trajectory per drone")
+        cfg = _lib.RolloutCfg()
+        if isinstance(controller, GeometricControl):
+            cfg.ctrl = _lib.CTRL_GEOMETRIC
+        elif isinstance(controller, LQROmegaController):
+            cfg.ctrl = _lib.CTRL_LQR_OMEGA
+        elif isinstance(controller, LQRYankOmegaController):
+            cfg.ctrl = _lib.CTRL_LQR_YANK
+        elif isinstance(controller, LQRController):
+            cfg.ctrl = _lib.CTRL_LQR_TORQUE
+        else:
+            raise TypeError("unsupported controller type")
+        cfg.use_cbf = int(qp_tracker is not None)
+        rows = [] if obstacles is None else (obstacles.tolist() if isinstance(obstacles, torch.Tensor) else list(obstacles))
+        if len(rows) > _lib.MAX_OBSTACLES:
+            raise ValueError("too many obstacles")
+        cfg.num_obstacles = len(rows) if qp_tracker is not None else 0
+        for i, r in enumerate(rows):
+            for k in range(4):
+                cfg.obstacles[4 * i + k] = float(r[k])
+        cfg.write_obs_every = 0
+        self.cfg = cfg
+        self.stats = torch.zeros(_lib.STAT_COUNT, device=env.device, dtype=torch.float64)
+        self.reset_stats()
+        self.t = 0.0
+
+    def reset_stats(self):
+        self.stats.zero_()
+        self.stats[3] = 1e30  # MDS_STAT_MIN_BARRIER
+
+    def run(self, K, t0=None, obs_log=None, log_every=0):
+        """Advance every environment K control steps.  ``obs_log`` [K//log_every, E, N, 20] receives the
+        observation after every ``log_every``-th step (the reference's ``observations.append(obs)``).
+        Returns the env's obs buffer (observation after the last step)."""
+        env = self.env
+        if t0 is None:
+            t0 = self.t
+        self.cfg.write_obs_every = int(log_every) if obs_log is not None else 0
+        if obs_log is not None:
+            _lib.require_cuda(obs_log, "obs_log", env.dtype)
+            if obs_log.numel() < (K // max(1, log_every)) * env.NUM_TOTAL * _lib.OBS_DIM:
+                raise ValueError("obs_log too small")
+        geo = self.controller.c_gains() if self.cfg.ctrl == _lib.CTRL_GEOMETRIC else None
+        lqr = self.controller.c_gains() if self.cfg.ctrl != _lib.CTRL_GEOMETRIC else None
+        pid = self.controller._pid() if self.cfg.ctrl != _lib.CTRL_GEOMETRIC else _lib.PidState(None, None)
+        cbf = self.qp.cbf.c_params() if self.qp is not None else None
+        _lib.call("mds_rollout", env.dtype, env._prm, self.cfg, geo, lqr, cbf, env._state_struct(), pid,
+                  _lib.ptr(self.trajs.specs), _lib.ptr(self.trajs.segs), _lib.ptr(env._obs), _lib.ptr(obs_log),
+                  _lib.ptr(self.stats), float(t0), int(K), env.NUM_ENVS, env.NUM_DRONES, _lib.stream_ptr(env.device))
+        env.step_counter += K * env.PYB_STEPS_PER_CTRL
+        self.t = t0 + K * env.CTRL_TIMESTEP
+        return env._obs
+
+    def stats_dict(self):
+        v = self.stats.tolist()
+        return dict(zip(_lib.STAT_NAMES, v))

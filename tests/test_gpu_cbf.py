@@ -1,0 +1,117 @@
+"""GPU parity of the CBF stage: device rows vs the REFERENCE's dense G, h (fixtures), device QP vs the
+oracle solver on the same rows (CBF-filtered actions within 1e-4, BASELINE.json north_star), per-env
+status flags and the nominal fallback."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import scaled_err
+from oracle.qp import kkt_residuals, solve_qp
+
+pytestmark = pytest.mark.gpu
+CASES = [("o2_n2_obs1", 2, 2), ("o2_n8_obs1", 2, 8), ("o3_n7_obs0", 3, 7), ("o3_n8_obs1", 3, 8), ("o3_n4_obs3", 3, 4)]
+
+
+def setup(golden, name, order, N, dtype):
+    import multidronesim_b200 as mds
+    g = golden["cbf_rows"]
+    obs, xdes, obst, unom = g[f"{name}_obs"], g[f"{name}_xdes"], g[f"{name}_obstacles"], g[f"{name}_unom"]
+    E = obs.shape[0]
+    env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=N, num_envs=E, dtype=dtype)
+    Mdl = mds.model.LinearizedOmegaModel if order == 2 else mds.model.LinearizedYankOmegaModel
+    poles = np.array([-2.2, -2.4]) if order == 2 else np.array([-3.0, -3.6, -5.6])
+    rs, zs = (0.1, 1.0) if order == 2 else (0.125, 2.0)
+    cbf = mds.cbf.DroneCBF(env, [Mdl(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=order, cbf_poles=poles)
+    trk = mds.cbf.DroneQPTracker(cbf, order=order, num_robots=N, xdim=cbf.xdim, env=env)
+    dev = lambda a: torch.as_tensor(a, device="cuda", dtype=dtype).contiguous()
+    return g, env, cbf, trk, dev(obs), dev(xdes), (dev(obst) if len(obst) else None), dev(unom)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name,order,N", CASES)
+def test_rows_match_reference(golden, name, order, N, dtype, lib_built):
+    g, env, cbf, trk, obs, xdes, obst, unom = setup(golden, name, order, N, dtype)
+    assert np.allclose(cbf.Kcbf, g[f"{name}_Kcbf"], rtol=1e-12) and np.allclose(cbf.umax, g[f"{name}_umax"], rtol=1e-12)
+    G, h = cbf.build_ineq_const(obs, xdes, obst)
+    Gr, hr = g[f"{name}_G"], g[f"{name}_h"]
+    assert tuple(G.shape) == Gr.shape and tuple(h.shape) == hr.shape
+    tol = 1e-9 if dtype == torch.float64 else 2e-5
+    G, h = G.double().cpu().numpy(), h.double().cpu().numpy()
+    # row-wise: each row against its own magnitude (rows span 1e-3 .. 1e3)
+    gs = 1.0 + np.max(np.abs(Gr), axis=2, keepdims=True)
+    assert np.max(np.abs(G - Gr) / gs) < tol
+    # rhs sums terms of mixed sign: compare against the size of its summands (|h| + K0 * Ds^4 scale)
+    assert np.max(np.abs(h - hr) / (1.0 + np.abs(hr))) < (tol if dtype == torch.float64 else 5e-4)
+
+
+@pytest.mark.parametrize("name,order,N", CASES)
+def test_qp_matches_oracle_fp64(golden, name, order, N, lib_built):
+    g, env, cbf, trk, obs, xdes, obst, unom = setup(golden, name, order, N, torch.float64)
+    u = trk.compute_control(obs, xdes, unom, x_obs=obst).cpu().numpy()
+    st = trk.status.cpu().numpy()
+    n_solved = 0
+    for e in range(obs.shape[0]):
+        Gr, hr, un = g[f"{name}_G"][e], g[f"{name}_h"][e], g[f"{name}_unom"][e]
+        uo, lam, so, _ = solve_qp(np.eye(4 * N), -un.reshape(-1), Gr, hr)
+        if so == 0 and st[e] == 0:
+            assert np.max(np.abs(u[e].reshape(-1) - uo)) < 1e-7 * (1 + np.max(np.abs(uo))), e
+            n_solved += 1
+        elif so == 1:
+            assert st[e] != 0, e                      # infeasible must never be reported optimal
+        if st[e] != 0:
+            assert np.array_equal(u[e], un), e        # nominal fallback (cbf/qptracker.py:30-34)
+        else:
+            # independent certificate: the device answer is primal feasible and no worse than the oracle's optimum
+            x = u[e].reshape(-1)
+            assert np.max(Gr @ x - hr) < 1e-7 * (1 + np.max(np.abs(hr)))
+            if so == 0:
+                assert 0.5 * np.sum((x - un.reshape(-1)) ** 2) <= 0.5 * np.sum((uo - un.reshape(-1)) ** 2) + 1e-7
+    assert n_solved >= 3
+
+
+@pytest.mark.parametrize("name,order,N", CASES)
+def test_qp_fp32_within_1e4(golden, name, order, N, lib_built):
+    g, env, cbf, trk, obs, xdes, obst, unom = setup(golden, name, order, N, torch.float32)
+    u = trk.compute_control(obs, xdes, unom, x_obs=obst).double().cpu().numpy()
+    st = trk.status.cpu().numpy()
+    checked = 0
+    for e in range(obs.shape[0]):
+        Gr, hr, un = g[f"{name}_G"][e], g[f"{name}_h"][e], g[f"{name}_unom"][e]
+        uo, lam, so, _ = solve_qp(np.eye(4 * N), -un.reshape(-1), Gr, hr)
+        if so == 0 and st[e] == 0:
+            # per input column, relative to that column's bound (yank O(1), rates O(10))
+            err = np.abs(u[e] - uo.reshape(N, 4)) / np.maximum(1.0, np.abs(np.asarray(cbf.umax))[None, :])
+            assert np.max(err) < 1e-4, (e, np.max(err))
+            checked += 1
+        if st[e] != 0:
+            assert np.allclose(u[e], un.astype(np.float32))
+    assert checked >= 2
+
+
+def test_anchor_and_status_codes(lib_built):
+    """SURVEY App. C anchor (u_safe[0,0] = -0.113260464) + an infeasible env + an untouched env."""
+    import multidronesim_b200 as mds
+    for dtype, tol in ((torch.float64, 1e-8), (torch.float32, 1e-5)):
+        env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=2, num_envs=3, pyb_freq=100, ctrl_freq=100, dtype=dtype)
+        cbf = mds.cbf.DroneCBF(env, [mds.model.LinearizedOmegaModel(env) for _ in range(2)], safety_radius=.1, zscale=1)
+        trk = mds.cbf.DroneQPTracker(cbf, num_robots=2)
+        obs = torch.zeros(3, 2, 20, device="cuda", dtype=dtype)
+        obs[..., 6] = 1.0
+        obs[..., 16:20] = env.HOVER_RPM
+        obs[0, 0, 0:3] = torch.tensor([0, 0, .75]); obs[0, 0, 12] = -.8
+        obs[0, 1, 0:3] = torch.tensor([1, 1, 1.5])
+        obs[1, 0, 0:3] = torch.tensor([0, 0, .62]); obs[1, 0, 12] = -3.0      # diving into the obstacle: thrust box too small
+        obs[1, 1, 0:3] = torch.tensor([1, 1, 1.5])
+        obs[2, 0, 0:3] = torch.tensor([2, 0, 1.0]); obs[2, 1, 0:3] = torch.tensor([-2, 0, 1.5])
+        xdes = torch.zeros(3, 2, 9, device="cuda", dtype=dtype)
+        xdes[..., 6:9] = obs[..., 0:3]
+        unom = torch.zeros(3, 2, 4, device="cuda", dtype=dtype)
+        unom[0, 0, 0] = -0.2
+        unom[2, 1, 1] = 3.0
+        x_obs = np.array([np.array([[0, 0, .5], np.zeros(3)])])
+        u = trk.compute_control(obs, xdes, unom, x_obs=x_obs, obs_r_list=[.1])
+        assert abs(float(u[0, 0, 0]) - (-0.113260464)) < tol and float(u[0].abs().sum()) == pytest.approx(0.113260464, abs=tol)
+        assert trk.status.tolist() == [0, 1, 0] and int(trk.iters[0]) >= 1 and int(trk.iters[2]) == 0
+        assert torch.equal(u[1], unom[1]) and torch.equal(u[2], unom[2])
+        with pytest.raises(mds._lib.MdsError):  # N_obs > N is rejected like the reference's IndexError (quirk B14)
+            trk.compute_control(obs, xdes, unom, x_obs=torch.zeros(3, 4, device="cuda", dtype=dtype))

@@ -1,0 +1,157 @@
+"""GPU: the fused K-step rollout equals the per-call API loop, and both track the oracle's reference-style
+closed loops (<= 1 mm over 1 s of hover / circle tracking in fp32; CBF closed loop)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as opl
+from oracle import trajectories as otj
+from oracle.aviary import OracleCtrlAviary
+from oracle.constants import DroneModel as ODM, Physics as OPH
+
+pytestmark = pytest.mark.gpu
+
+
+def build(E, N, dtype, physics, trajs_dev, ctrl, cbf_order=None, obstacles=None, init=None):
+    import multidronesim_b200 as mds
+    env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=N, physics=mds.Physics(physics), num_envs=E, dtype=dtype,
+                                initial_xyzs=init)
+    M = mds.model
+    if ctrl == "geometric":
+        c = mds.control.GeometricControl(env)
+    elif ctrl == "torque12":
+        c = mds.control.LQRController(env, M.LinearizedModel(env))
+    elif ctrl == "omega9":
+        c = mds.control.LQROmegaController(env, M.LinearizedOmegaModel(env), mds.control.ThrustOmegaController(env))
+    else:
+        c = mds.control.LQRYankOmegaController(env, M.LinearizedYankOmegaModel(env), mds.control.YankOmegaController(env))
+    trk = None
+    if cbf_order is not None:
+        Mdl = M.LinearizedOmegaModel if cbf_order == 2 else M.LinearizedYankOmegaModel
+        poles = np.array([-2.2, -2.4]) if cbf_order == 2 else np.array([-3.0, -3.6, -5.6])
+        rs, zs = (0.1, 1.0) if cbf_order == 2 else (0.125, 2.0)
+        cbf = mds.cbf.DroneCBF(env, [Mdl(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=cbf_order, cbf_poles=poles)
+        trk = mds.cbf.DroneQPTracker(cbf, order=cbf_order, num_robots=N, xdim=cbf.xdim, env=env)
+    ts = mds.trajectories.TrajectorySet(trajs_dev, dtype=dtype)
+    return mds, env, c, trk, ts, mds.FusedRollout(env, ts, c, trk, obstacles)
+
+
+def percall_loop(mds, env, c, trk, ts, steps, obstacles):
+    """the reference's loop structure through the per-call device API"""
+    obs = env.obs
+    t = 0.0
+    obst = None if obstacles is None else torch.as_tensor(obstacles, device="cuda", dtype=env.dtype)
+    mg = env.M * env.G
+    for _ in range(steps):
+        ref = ts.eval(t)
+        c.set_reference(ref)
+        if trk is None:
+            out = c.compute(obs)
+            action = out if isinstance(out, torch.Tensor) else out[0]
+        else:
+            _, u = c.compute(obs, skip_low_level=True)
+            unom = u.clone()
+            unom[..., 0] -= mg
+            r3 = ref.view(env.NUM_ENVS, env.NUM_DRONES, 11)
+            z = torch.zeros_like(r3[..., 0:1])
+            if trk.order == 2:
+                xdes = torch.cat([z, z, r3[..., 9:10], r3[..., 3:6], r3[..., 0:3]], dim=-1).contiguous()
+            else:
+                xdes = torch.cat([z, z, r3[..., 9:10], z + mg, r3[..., 3:6], r3[..., 0:3]], dim=-1).contiguous()
+            us = trk.compute_control(obs, xdes, unom, x_obs=obst).clone()
+            if trk.order == 2:
+                us[..., 0] += mg
+            action = c.compute_low_level(us, obs)
+        obs = env.step(action)[0]
+        t += env.CTRL_TIMESTEP
+    return obs
+
+
+def lem_params(N, E, rng, a=1.0, omega=0.5, z=0.5):
+    ph = (2 * np.pi / (N + 0.25)) * np.arange(N)
+    return [dict(a=a, center=np.array([0, 0, z]), omega=omega, yaw_rate=0.0, phase_shift=float(p)) for p in ph]
+
+
+@pytest.mark.parametrize("ctrl,cbf_order,physics,N", [("geometric", None, "dyn_gnd_drag_dw", 1), ("torque12", None, "dyn", 2),
+                                                      ("omega9", None, "dyn_gnd_drag_dw", 3), ("yank10", None, "dyn", 2),
+                                                      ("omega9", 2, "dyn_gnd_drag_dw", 2), ("yank10", 3, "dyn_gnd_drag_dw", 8)])
+def test_fused_equals_percall(ctrl, cbf_order, physics, N, lib_built):
+    import multidronesim_b200.trajectories as T
+    E, steps, dtype = 5, 40, torch.float64
+    rng = np.random.default_rng(2)
+    specs = lem_params(N, E, rng)
+    obstacles = [[0.0, 0.0, 0.5, 0.1]] if cbf_order is not None else None
+    init = np.zeros((E, N, 3))
+    for e in range(E):
+        for j, sp in enumerate(specs):
+            init[e, j] = otj.Lemniscate(**sp)(0.0)[0] + rng.normal(0, 0.02, 3) + np.array([0, 0, 0.03 * j])
+    runs = []
+    for fused in (True, False):
+        mds, env, c, trk, ts, ro = build(E, N, dtype, physics, [T.Lemniscate(**sp) for sp in specs] * E, ctrl, cbf_order, obstacles, init)
+        obs = ro.run(steps) if fused else percall_loop(mds, env, c, trk, ts, steps, obstacles)
+        runs.append(obs.cpu().numpy().copy())
+        if fused:
+            st = ro.stats_dict()
+            assert st["drone_steps"] == E * N * steps
+    assert np.max(np.abs(runs[0] - runs[1])) < 1e-9 * (1 + np.max(np.abs(runs[1])))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-7), (torch.float32, 1e-3)])
+def test_c2_tracking_vs_oracle_1s(dtype, tol, lib_built):
+    """config C2 in miniature: geometric controller tracking Circle / Lemniscate for 1 s (240 steps),
+    DYN_GND_DRAG_DW; fp32 position within 1 mm of the fp64 oracle loop."""
+    import multidronesim_b200.trajectories as T
+    E, N, steps = 6, 1, 240
+    rng = np.random.default_rng(1)
+    dev_trajs, ora_trajs, init = [], [], np.zeros((E, N, 3))
+    for e in range(E):
+        if e % 2 == 0:
+            kw = dict(r=1.0, v=0.5, center=np.array([0, 0, 1.0]), yaw_rate=0.0)
+            dev_trajs.append(T.CircleTrajectory(**kw)); ora_trajs.append(otj.Circle(**kw))
+        else:
+            kw = dict(a=1.0, omega=1.5, center=np.array([0, 0, 0.5]), yaw_rate=0.0, phase_shift=float(rng.uniform(0, 2 * np.pi)))
+            dev_trajs.append(T.Lemniscate(**kw)); ora_trajs.append(otj.Lemniscate(**kw))
+        p0 = ora_trajs[-1](0.0)[0] + rng.normal(0, 0.05, 3)
+        p0[2] = max(p0[2], 0.1)
+        init[e, 0] = np.float32(p0)
+    mds, env, c, trk, ts, ro = build(E, N, dtype, "dyn_gnd_drag_dw", dev_trajs, "geometric", init=init)
+    log = torch.zeros(steps, E, N, 20, device="cuda", dtype=dtype)
+    ro.run(steps, obs_log=log, log_every=1)
+    got = log.double().cpu().numpy()
+    worst = 0.0
+    for e in range(E):
+        o = OracleCtrlAviary(ODM.CF2P, N, initial_xyzs=init[e], physics=OPH.DYN_GND_DRAG_DW)
+        want, _ = opl.run_tracking(o, [ora_trajs[e]], "geometric", steps)
+        worst = max(worst, float(np.max(np.abs(got[:, e, :, 0:3] - want[:, :, 0:3]))))
+    assert worst < tol, worst
+    assert ro.stats_dict()["max_pos_err"] < 0.5
+
+
+@pytest.mark.parametrize("order,N,dtype,tol", [(2, 2, torch.float64, 1e-6), (3, 4, torch.float64, 1e-6), (3, 8, torch.float32, 2e-3)])
+def test_cbf_closed_loop_vs_oracle(order, N, dtype, tol, lib_built):
+    """config C3 in miniature: LQR nominal -> CBF-QP -> inner loop -> DYN_GND_DRAG_DW, drones on one
+    lemniscate through a sphere obstacle at its centre (simulations/CBFTest.py:418-424)."""
+    import multidronesim_b200.trajectories as T
+    E, steps = 3, 120
+    rng = np.random.default_rng(3)
+    specs = lem_params(N, E, rng, omega=0.5)
+    obstacles = [[0.0, 0.0, 0.5, 0.1]]
+    init = np.zeros((E, N, 3))
+    for e in range(E):
+        for j, sp in enumerate(specs):
+            init[e, j] = np.float32(otj.Lemniscate(**sp)(0.0)[0] + rng.normal(0, 0.02, 3) + np.array([0, 0, 0.04 * j]))
+    ctrl = "omega9" if order == 2 else "yank10"
+    mds, env, c, trk, ts, ro = build(E, N, dtype, "dyn_gnd_drag_dw", [T.Lemniscate(**sp) for sp in specs] * E, ctrl, order, obstacles, init)
+    log = torch.zeros(steps, E, N, 20, device="cuda", dtype=dtype)
+    ro.run(steps, obs_log=log, log_every=1)
+    got = log.double().cpu().numpy()
+    worst, n_active = 0.0, 0
+    for e in range(E):
+        o = OracleCtrlAviary(ODM.CF2P, N, initial_xyzs=init[e], physics=OPH.DYN_GND_DRAG_DW)
+        want, _, info = opl.run_cbf(o, [otj.Lemniscate(**sp) for sp in specs], order, steps, obstacles=obstacles)
+        n_active += info["solves"]
+        if info["status"][1] + info["status"][2] == 0:      # compare trajectories only where the oracle's QP always solved
+            worst = max(worst, float(np.max(np.abs(got[:, e, :, 0:3] - want[:, :, 0:3]))))
+    st = ro.stats_dict()
+    assert worst < tol, worst
+    assert st["qp_solves"] > 0 and n_active > 0

@@ -1,0 +1,146 @@
+"""GPU parity vs the REFERENCE-generated fixtures: trajectories, geometric / LQR controllers, inner
+PID, linear / nonlinear xdot.  fp64 1e-9, fp32 1e-5 (relative, per call)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float64: 1e-9, torch.float32: 1e-5}
+DTYPES = [torch.float64, torch.float32]
+
+
+def traj_gens(T):
+    Rz = np.array([[np.cos(.7), -np.sin(.7), 0], [np.sin(.7), np.cos(.7), 0], [0, 0, 1]])
+    return {
+        "circle": T.CircleTrajectory(r=1, v=.5, center=np.array([0, 0, 1]), yaw_rate=.1),
+        "circle2": T.CircleTrajectory(r=0.7, v=1.3, center=np.array([0.2, -0.4, 0.8]), yaw_rate=-0.35),
+        "lemniscate": T.Lemniscate(center=np.array([0, 0, .5]), omega=1.5, yaw_rate=.1, phase_shift=-np.pi / 4),
+        "lemniscate2": T.Lemniscate(a=1.4, center=np.array([0.3, 0.1, 1.5]), omega=0.5, yaw_rate=0, phase_shift=2.1),
+        "wait": T.WaitTrajectory(np.array([0.5, -0.2, 1.0]), 3.0, yaw=0.4),
+        "line": T.LineTrajectory(np.array([0, 0, 0.5]), np.array([2.0, 1.0, 1.5]), speed=0.8),
+        "line_short": T.LineTrajectory(np.array([0, 0, 0.5]), np.array([0.2, 0.1, 0.6]), speed=1.5),
+        "line_s0": T.LineTrajectory(np.array([1.0, 0, 0.5]), np.array([-2.0, 1.0, 0.5]), speed=1.0, s0=0.3, sf=0.2),
+        "rotate": T.RotateTrajectory(T.Lemniscate(center=np.array([0, 0, .5]), omega=0.8), Rz, np.array([0.1, 0.2, 0.5])),
+    }
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_trajectories(golden, dtype, lib_built):
+    import multidronesim_b200.trajectories as T
+    g = golden["trajectories"]
+    gens = traj_gens(T)
+    names = list(gens)
+    ts = T.TrajectorySet([gens[n] for n in names], dtype=dtype)
+    for k, t in enumerate(g["t"]):
+        got = ts.eval(float(t)).cpu().numpy()
+        for i, n in enumerate(names):
+            assert scaled_err(got[i, :9], g[n][k, :9]) < TOL[dtype], (n, t)
+            assert scaled_err(got[i, 9:], g[n][k, 9:]) < TOL[dtype], (n, t)
+    comp = T.CompoundTrajectory([T.WaitTrajectory(np.array([0, 0, 0.5]), 1.0),
+                                 T.LineTrajectory(np.array([0, 0, 0.5]), np.array([1.5, 0.5, 1.0]), speed=0.7),
+                                 T.CircleTrajectory(r=0.5, v=0.4, center=np.array([1.0, 0.5, 1.0]), duration=4.0),
+                                 T.WaitTrajectory(np.array([1.5, 0.5, 1.0]), 2.0, yaw=0.0)])
+    tc = T.TrajectorySet([comp, gens["circle"]], dtype=dtype)
+    for k, t in enumerate(g["compound_t"]):
+        got = tc.eval(float(t)).cpu().numpy()[0]
+        assert scaled_err(got, g["compound"][k]) < TOL[dtype], t
+    pos, vel, acc, yaw, om = ts(0.75)  # reference call contract
+    assert pos.shape == (len(names), 3) and yaw.shape == (len(names),)
+    assert abs(float(yaw[0]) - 6.358185307179586) < 1e-5  # quirk B18
+
+
+def make_env(model, n, dtype):
+    import multidronesim_b200 as mds
+    return mds.BatchedCtrlAviary(drone_model=mds.DroneModel(model), num_drones=1, num_envs=n, dtype=dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("model", ["cf2p", "cf2x"])
+def test_controllers(golden, dtype, model, lib_built):
+    import multidronesim_b200 as mds
+    g = golden["controllers"]
+    obs_np, ref_np = g[f"{model}_obs"], g[f"{model}_ref"]
+    n = obs_np.shape[0]
+    env = make_env(model, n, dtype)
+    obs = torch.as_tensor(obs_np, device="cuda", dtype=dtype).reshape(n, 1, 20).contiguous()
+    ref = torch.as_tensor(ref_np, device="cuda", dtype=dtype).contiguous()
+    geo = mds.control.GeometricControl(env)
+    geo.set_reference(ref)
+    act = geo.compute(obs).cpu().numpy().reshape(n, 4)
+    assert rel_err(act, g[f"{model}_geometric_action"]) < TOL[dtype]
+    # set_desired_trajectory path gives the same answer as the zero-copy reference buffer
+    geo.set_desired_trajectory(None, ref_np[:, 0:3], ref_np[:, 3:6], ref_np[:, 6:9], ref_np[:, 9], ref_np[:, 10])
+    assert np.array_equal(geo.compute(obs).cpu().numpy().reshape(n, 4), act)
+    M = mds.model
+    variants = {
+        "torque12": lambda: mds.control.LQRController(env, M.LinearizedModel(env)),
+        "omega9": lambda: mds.control.LQROmegaController(env, M.LinearizedOmegaModel(env), mds.control.ThrustOmegaController(env)),
+        "yank10": lambda: mds.control.LQRYankOmegaController(env, M.LinearizedYankOmegaModel(env), mds.control.YankOmegaController(env)),
+    }
+    for name, mk in variants.items():
+        c = mk()
+        Kg = g[f"{model}_{name}_K"]
+        assert np.allclose(c.K, Kg, rtol=1e-8, atol=1e-9 * np.abs(Kg).max())
+        c.set_reference(ref)
+        if name != "torque12":
+            _, u_skip = c.compute(obs, skip_low_level=True)
+            assert scaled_err(u_skip.cpu().numpy().reshape(n, 4), g[f"{model}_{name}_u_skip"]) < 10 * TOL[dtype], name
+        a, u = c.compute(obs)
+        # u mixes thrust O(0.3) with rates O(10): compare column-wise against the column scale
+        ug, ud = g[f"{model}_{name}_u"], u.cpu().numpy().reshape(n, 4)
+        for col in range(4):
+            assert scaled_err(ud[:, col], ug[:, col]) < 10 * TOL[dtype], (name, col)
+        assert rel_err(a.cpu().numpy().reshape(n, 4), g[f"{model}_{name}_action"]) < 10 * TOL[dtype], name
+    # inner loop state update over two consecutive calls (quirk B11)
+    pid = mds.control.ThrustOmegaController(env)
+    u_seq = torch.as_tensor(g[f"{model}_pid_u"], device="cuda", dtype=dtype).reshape(n, 1, 4).contiguous()
+    fake = torch.zeros(n, 1, 20, device="cuda", dtype=dtype)
+    fake[..., 6] = 1.0  # identity attitude: body rates == world rates
+    outs = []
+    for k in range(2):
+        fake[..., 13:16] = torch.as_tensor(g[f"{model}_pid_w"][k], device="cuda", dtype=dtype).reshape(n, 1, 3)
+        outs.append(pid.compute_from_obs(u_seq, fake).cpu().numpy().reshape(n, 4).copy())
+    want = g[f"{model}_pid_out"]
+    assert rel_err(outs[0], want[:, 0:4]) < TOL[dtype] and rel_err(outs[1], want[:, 4:8]) < TOL[dtype]
+    assert scaled_err(pid.last_omega.cpu().numpy(), want[:, 8:11]) < TOL[dtype]
+    assert scaled_err(pid.integral_omega_e.cpu().numpy(), want[:, 11:14]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_models(golden, dtype, lib_built):
+    import multidronesim_b200 as mds
+    g = golden["models"]
+    n = g["obs"].shape[0]
+    env = make_env("cf2p", n, dtype)
+    obs = torch.as_tensor(g["obs"], device="cuda", dtype=dtype).contiguous()
+    lin = mds.model.LinearizedModel(env)
+    got = lin.calc_xdot_from_obs(obs).cpu().numpy()
+    want = g["xdot_linear12"]
+    for a, b in ((0, 3), (3, 6), (6, 9), (9, 12)):
+        assert scaled_err(got[:, a:b], want[:, a:b]) < 20 * TOL[dtype]
+    qd = mds.model.QuadrotorDynamics(env.PYB_FREQ)
+    qd.load_env_params(env)
+    assert np.allclose(np.diag(qd.J), g["J_dynamics"])
+    got = qd.dynamics_from_obs(obs).cpu().numpy()
+    want = g["xdot_nonlinear"]
+    for a, b in ((0, 3), (3, 6), (6, 9), (9, 12)):
+        assert scaled_err(got[:, a:b], want[:, a:b]) < 20 * TOL[dtype]
+    for name, cls in (("torque12", mds.model.LinearizedModel), ("omega9", mds.model.LinearizedOmegaModel), ("yank10", mds.model.LinearizedYankOmegaModel)):
+        m = cls(env)
+        for key in ("A", "B", "Ahat", "Bhat"):
+            assert np.array_equal(getattr(m, key), g[f"{name}_{key}"]), (name, key)
+    # right-sized 9/10-dim xdot (builder-defined, quirk B23) against the oracle's definition
+    from oracle.constants import drone_params
+    from oracle.models import xdot_linear_generic
+    oenv = drone_params("cf2p", 240, 240)
+    for kind, cls in (("omega9", mds.model.LinearizedOmegaModel), ("yank10", mds.model.LinearizedYankOmegaModel)):
+        got = cls(env).calc_xdot_from_obs(obs).cpu().numpy()
+        want = np.array([xdot_linear_generic(oenv, o, kind) for o in g["obs"]])
+        assert scaled_err(got, want) < 20 * TOL[dtype]
+    # conversions
+    U = mds.utils
+    assert scaled_err(U.obs_to_lin_model(obs, 10, env).cpu().numpy(), g["lin10"]) < TOL[dtype]
+    assert scaled_err(U.obs_to_geo_model(obs).cpu().numpy(), g["geo18"]) < TOL[dtype]
+    assert rel_err(U.input_to_action(env, torch.as_tensor(g["input_to_action_in"], device="cuda", dtype=dtype)).cpu().numpy(), g["input_to_action"]) < 10 * TOL[dtype]

@@ -1,0 +1,87 @@
+"""CPU: self-tests of the restated env step (oracle/aviary.py) against closed-form cases.  The upstream
+simulator is absent (parity unpinned), so these pin the restatement to physics instead."""
+import math
+
+import numpy as np
+
+from oracle.aviary import OracleCtrlAviary, integrate_q, quat_to_matrix, quat_to_rpy, rpy_to_quat
+from oracle.constants import DroneModel, Physics, drone_params
+
+
+def test_constants():
+    p = drone_params("cf2p")
+    assert abs(p.HOVER_RPM - 14468.429) < 1e-3 and abs(p.MAX_RPM - 21702.64) < 1e-2 and abs(p.MAX_THRUST - 0.59535) < 1e-5
+    assert np.allclose(np.diag(p.J), [2.3951e-5, 2.3951e-5, 3.2347e-5])      # utils/graph_fedce.py:45-47
+    assert p.G == 9.8 and p.M == 0.027 and p.KF == 3.16e-10 and p.KM == 7.94e-12
+
+
+def test_free_fall_semi_implicit_euler():
+    env = OracleCtrlAviary(DroneModel.CF2P, 1, initial_xyzs=[[0, 0, 10.0]], physics=Physics.DYN)
+    n, dt = 100, 1 / 240
+    for _ in range(n):
+        obs = env.step(np.zeros((1, 4)))[0]
+    # v_k = -g k dt ; z_k = z0 - g dt^2 k(k+1)/2
+    assert abs(obs[0, 12] + 9.8 * n * dt) < 1e-12 and abs(obs[0, 2] - (10.0 - 9.8 * dt * dt * n * (n + 1) / 2)) < 1e-12
+
+
+def test_hover_is_stationary_and_obs_layout():
+    env = OracleCtrlAviary(DroneModel.CF2X, 2, initial_xyzs=[[0, 0, 1.0], [1, 0, 1.0]], physics=Physics.DYN)
+    for _ in range(240):
+        obs, r, term, trunc, info = env.step(np.full((2, 4), env.HOVER_RPM))
+    assert np.allclose(obs[:, 0:3], [[0, 0, 1.0], [1, 0, 1.0]], atol=1e-9) and np.allclose(obs[:, 3:7], [0, 0, 0, 1])
+    assert np.allclose(obs[:, 16:20], env.HOVER_RPM) and obs.shape == (2, 20)
+    assert (r, term, trunc, info) == (-1, False, False, {"answer": 42})
+
+
+def test_pure_yaw_spin_and_world_rates():
+    env = OracleCtrlAviary(DroneModel.CF2P, 1, initial_xyzs=[[0, 0, 1.0]], physics=Physics.DYN)
+    env.set_state([[0, 0, 1.0]], [rpy_to_quat([0.3, 0.0, 0.0])], [[0, 0, 0]], [[0, 0, 2.0]])
+    q0 = env.quat[0].copy()
+    obs = env.step(np.full((1, 4), env.HOVER_RPM))[0]
+    assert np.allclose(env.quat[0], integrate_q(q0, env.rpy_rates[0], 1 / 240))
+    assert abs(np.linalg.norm(env.quat[0]) - 1) < 1e-14
+    assert np.allclose(obs[0, 13:16], quat_to_matrix(q0) @ env.rpy_rates[0])   # world rates = R(old) w(new)
+
+
+def test_euler_roundtrip_and_clip():
+    for rpy in ([0.1, -0.2, 0.3], [1.0, 0.5, -2.5], [0, 0, 0]):
+        assert np.allclose(quat_to_rpy(rpy_to_quat(rpy)), rpy, atol=1e-12)
+    env = OracleCtrlAviary(DroneModel.CF2P, 1, physics=Physics.DYN)
+    obs = env.step(np.array([[-5.0, 1e9, 100.0, env.MAX_RPM]]))[0]
+    assert np.allclose(obs[0, 16:20], [0, env.MAX_RPM, 100.0, env.MAX_RPM])
+
+
+def test_composite_effects_have_the_right_sign():
+    prm = dict(physics=Physics.DYN_GND_DRAG_DW)
+    low = OracleCtrlAviary(DroneModel.CF2P, 1, initial_xyzs=[[0, 0, 0.05]], **prm)
+    high = OracleCtrlAviary(DroneModel.CF2P, 1, initial_xyzs=[[0, 0, 5.0]], **prm)
+    a = np.full((1, 4), low.HOVER_RPM)
+    assert low.step(a)[0][0, 12] > high.step(a)[0][0, 12] >= -1e-9            # ground effect adds lift near the floor
+    pair = OracleCtrlAviary(DroneModel.CF2P, 2, initial_xyzs=[[0, 0, 1.0], [0, 0, 1.4]], **prm)
+    o = pair.step(np.full((2, 4), pair.HOVER_RPM))[0]
+    assert o[0, 12] < -1e-3 and abs(o[1, 12]) < 1e-4                           # downwash acts on the lower drone only
+    drag = OracleCtrlAviary(DroneModel.CF2P, 1, initial_xyzs=[[0, 0, 5.0]], **prm)
+    drag.set_state([[0, 0, 5.0]], [[0, 0, 0, 1]], [[1.0, 0, 0]], [[0, 0, 0]], [[drag.HOVER_RPM] * 4])
+    assert drag.step(np.full((1, 4), drag.HOVER_RPM))[0][0, 10] < 1.0         # drag opposes velocity
+    floor = OracleCtrlAviary(DroneModel.CF2P, 1, initial_xyzs=[[0, 0, 0.02]], **prm)
+    for _ in range(60):
+        o = floor.step(np.zeros((1, 4)))[0]
+    assert o[0, 2] == floor.Z_FLOOR and o[0, 12] == 0.0                         # contact clamp
+    dyn = OracleCtrlAviary(DroneModel.CF2P, 1, initial_xyzs=[[0, 0, 0.02]], physics=Physics.DYN)
+    for _ in range(60):
+        o = dyn.step(np.zeros((1, 4)))[0]
+    assert o[0, 2] < 0                                                          # upstream DYN has no ground
+
+
+def test_dslpid_hover_config1():
+    """config C1: 2 CF2X drones under the (halved-gain) DSL PID climb 1 m and hold, 240 Hz, DYN."""
+    from oracle.controllers import DslPid
+    init = np.array([[1.0, 0, 0], [-1.0, 0, 0]])
+    env = OracleCtrlAviary(DroneModel.CF2X, 2, initial_xyzs=init, physics=Physics.DYN)
+    ctrls = [DslPid(env, gain_scale=0.5) for _ in range(2)]
+    obs = env.step(np.zeros((2, 4)))[0]
+    target = init + np.array([0, 0, 1.0])
+    for _ in range(240 * 6):
+        act = np.array([ctrls[j].compute_from_state(env.CTRL_TIMESTEP, obs[j], target[j])[0] for j in range(2)])
+        obs = env.step(act)[0]
+    assert np.max(np.abs(obs[:, 0:3] - target)) < 0.05
