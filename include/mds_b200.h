@@ -122,7 +122,8 @@ typedef struct MdsCbfParams {
   int max_iter;          /* active-set iteration cap (0 = default 64) */
 } MdsCbfParams;
 
-/* per-drone trajectory descriptor, 48 B (f32) / 80 B (f64) */
+/* per-drone trajectory descriptor, 48 B (f32) / 80 B (f64).  MDS_TRAJ_TABLE: segments
+ * [seg_begin, seg_begin + seg_count); pad != 0 marks a stand-alone single segment (no compound end clamp) */
 typedef struct MdsTrajSpecF32 { int kind, seg_begin, seg_count, pad; float p[8]; } MdsTrajSpecF32;
 typedef struct MdsTrajSpecF64 { int kind, seg_begin, seg_count, pad; double p[8]; } MdsTrajSpecF64;
 /* shared segment table entry for MDS_TRAJ_TABLE.  t_end = cumulative end time.

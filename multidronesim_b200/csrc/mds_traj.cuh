@@ -145,6 +145,7 @@ MDS_DEV Ref<Real> eval_traj(const typename TrajSpecT<Real>::spec& sp, const type
     default: break;
   }
   int b = sp.seg_begin, n = sp.seg_count;
+  if (sp.pad) return eval_segment<Real>(segs[b], t);  // stand-alone generator: no compound end clamp
   double total = (double)segs[b + n - 1].t_end;
   if (t >= total) return eval_segment<Real>(segs[b + n - 1], (double)segs[b + n - 1].dur);
   int k = 0;

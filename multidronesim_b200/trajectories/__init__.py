@@ -196,6 +196,9 @@ class TrajectorySet:
                 sg = tr.segments()
                 specs[d]["kind"] = _lib.TRAJ_TABLE
                 specs[d]["seg_begin"], specs[d]["seg_count"] = len(segs), len(sg)
+                # a generator used on its own keeps its own behaviour past total_time (e.g. Line returns
+                # (end, vf, 0); Rotate(Lemniscate) stays periodic); only CompoundTrajectory clamps at the end
+                specs[d]["pad"] = 0 if isinstance(tr, CompoundTrajectory) else 1
                 t_end = 0.0
                 for kind, dur, p, rot in sg:
                     t_end += dur

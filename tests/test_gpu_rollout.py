@@ -67,8 +67,8 @@ def percall_loop(mds, env, c, trk, ts, steps, obstacles):
     return obs
 
 
-def lem_params(N, E, rng, a=1.0, omega=0.5, z=0.5):
-    ph = (2 * np.pi / (N + 0.25)) * np.arange(N)
+def lem_params(N, E, rng, a=1.0, omega=0.5, z=0.5, ph0=0.0):
+    ph = ph0 + (2 * np.pi / (N + 0.25)) * np.arange(N)
     return [dict(a=a, center=np.array([0, 0, z]), omega=omega, yaw_rate=0.0, phase_shift=float(p)) for p in ph]
 
 
@@ -134,7 +134,8 @@ def test_cbf_closed_loop_vs_oracle(order, N, dtype, tol, lib_built):
     import multidronesim_b200.trajectories as T
     E, steps = 3, 120
     rng = np.random.default_rng(3)
-    specs = lem_params(N, E, rng, omega=0.5)
+    # drone 0 starts 0.3 rad before the lemniscate's centre crossing, i.e. heading into the obstacle
+    specs = lem_params(N, E, rng, omega=0.5, ph0=np.pi / 2 - 0.3)
     obstacles = [[0.0, 0.0, 0.5, 0.1]]
     init = np.zeros((E, N, 3))
     for e in range(E):
@@ -150,7 +151,9 @@ def test_cbf_closed_loop_vs_oracle(order, N, dtype, tol, lib_built):
         o = OracleCtrlAviary(ODM.CF2P, N, initial_xyzs=init[e], physics=OPH.DYN_GND_DRAG_DW)
         want, _, info = opl.run_cbf(o, [otj.Lemniscate(**sp) for sp in specs], order, steps, obstacles=obstacles)
         n_active += info["solves"]
-        if info["status"][1] + info["status"][2] == 0:      # compare trajectories only where the oracle's QP always solved
+        # fp64 follows the oracle through infeasible steps too (same nominal fallback); fp32 is compared only
+        # where the oracle's QP always solved (a borderline feasibility flip would fork the trajectories)
+        if dtype == torch.float64 or info["status"][1] + info["status"][2] == 0:
             worst = max(worst, float(np.max(np.abs(got[:, e, :, 0:3] - want[:, :, 0:3]))))
     st = ro.stats_dict()
     assert worst < tol, worst
