@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Headline benchmark: drone-steps/s of the full hot path on synthetic swarms (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's algorithms on the host cores
+
+Workload (config.workload): SURVEY.md 8(d) C5 -- per GPU 125 000 independent environments x 8 drones
+(1M drones), 240 Hz; every drone-step = Lemniscate reference -> LQR-yank-omega nominal -> order-3
+CBF-QP (28 pair rows + 8 obstacle rows + box/force bounds per env) -> YankOmega inner loop ->
+DYN_GND_DRAG_DW physics (ground effect, drag, pairwise downwash) -> 20-float observation.
+
+One bench "step" = one launch of the fused rollout kernel = ``--fuse`` control steps of every drone.
+``value``  : drone-steps/s, state resident in HBM, CUDA events on the launching stream, max over ranks.
+``e2e``    : the same metric through the per-call API with HOST buffers: every control step copies the
+             step's references (host -> device, pinned) in and the observations (device -> host) out.
+``roofline``: FP32 pipe (no tensor cores on this path; nothing is a dense contraction) for the fused
+             kernel, peak measured live with an FMA-chain microbenchmark; plus ``roofline_hbm`` for the
+             per-call physics-step kernel against MEASURED_PEAKS.json's HBM copy bandwidth.
+``cpu_baseline``: oracle/ (numpy restatement of the reference's algorithms) on all host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+# one BLAS thread per worker process: the CPU arm parallelises over processes (one env per core)
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_DRONES = 8
+CBF_ORDER = 3
+# Algorithmic work per drone-step of the C5 path (DESIGN.md "Roofline"): FP32 operations of the closed-form
+# math (add/mul = 1, fma = 2, transcendental/div/sqrt = 1), hand-counted per stage and cross-checked against
+# ncu's smsp__sass_thread_inst_executed_op_f{add,mul,fma} for the QP-inactive path.
+ALGO_FLOP_PER_DRONE_STEP = {"traj": 70, "lqr_yank": 330, "cbf_rows": 520, "cbf_check": 60, "lowlevel": 110,
+                            "physics_gnd_drag_dw_n8": 640, "obs": 60}
+ALGO_BYTES_PER_DRONE_STEP_PERCALL_F32 = 232  # read state 17 + action 4, write state 17 + obs 20 floats
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=125000, help="environments per GPU (weak scaling)")
+    ap.add_argument("--fuse", type=int, default=24, help="control steps per fused launch (one bench step)")
+    ap.add_argument("--e2e-steps", type=int, default=48, help="control steps timed on the host-buffer path")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the cpu_baseline sample")
+    ap.add_argument("--ref-steps-per-step", type=int, default=48, help="control steps per reference-arm step and worker")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle's reference-style loop (numpy, per-drone Python loops) on the host cores
+# ----------------------------------------------------------------------------------------------
+def _oracle_env(env_index, seed=3):
+    import numpy as np
+    from oracle import trajectories as otj
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel as ODM, Physics as OPH
+    N = N_DRONES
+    phase = (2 * np.pi / (N + 0.25)) * np.arange(N)
+    specs = [dict(a=1.0, center=np.array([0, 0, 0.5]), omega=0.5, yaw_rate=0.0, phase_shift=float(p)) for p in phase]
+    rng = np.random.default_rng(np.random.SeedSequence([seed, 10_000_000 + env_index]))
+    init = np.array([otj.Lemniscate(**sp)(0.0)[0] for sp in specs]) + rng.normal(0, 0.02, (N, 3))
+    init[:, 2] += 0.04 * np.arange(N)
+    env = OracleCtrlAviary(ODM.CF2P, N, initial_xyzs=init, physics=OPH.DYN_GND_DRAG_DW)
+    return env, [otj.Lemniscate(**sp) for sp in specs]
+
+
+_WORKER = {}
+
+
+def _cpu_worker_step(args):
+    """advance this worker's private environment by `steps` control steps; returns drone-steps done"""
+    from oracle import pipeline as opl
+    env_index, steps = args
+    key = env_index
+    if key not in _WORKER:
+        env, trajs = _oracle_env(env_index)
+        _WORKER[key] = dict(env=env, trajs=trajs, ctrls=opl.make_controllers(env, "yank10"), t=0.0)
+    w = _WORKER[key]
+    opl.run_cbf(w["env"], w["trajs"], CBF_ORDER, steps, obstacles=[[0.0, 0.0, 0.5, 0.1]], ctrls=w["ctrls"], t0=w["t"], log=False)
+    w["t"] += steps * w["env"].CTRL_TIMESTEP
+    return N_DRONES * steps
+
+
+def cpu_baseline(seconds, steps_per_task=24):
+    """bounded sample: every host core advances its own C5 environment in 24-step tasks for ~`seconds`"""
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker_step, [(i, 2) for i in range(cores)], chunksize=1)  # warm-up: imports, gains
+        done, t0 = 0, time.perf_counter()
+        rounds = 0
+        while time.perf_counter() - t0 < seconds:
+            done += sum(pool.map(_cpu_worker_step, [(i, steps_per_task) for i in range(cores)], chunksize=1))
+            rounds += 1
+        dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "drone-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} C5 environments x {N_DRONES} drones (one per core), {rounds * steps_per_task} control steps each "
+                      f"from t=0, oracle/pipeline.run_cbf (reference algorithms in numpy; cvxopt -> oracle active-set QP, "
+                      f"PyBullet env -> restated DYN_GND_DRAG_DW step), {dt:.1f} s wall"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    S = args.ref_steps_per_step
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(1, args.warmup)):
+            pool.map(_cpu_worker_step, [(i, 4) for i in range(cores)], chunksize=1)
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(args.steps):
+            done += sum(pool.map(_cpu_worker_step, [(i, S) for i in range(cores)], chunksize=1))
+        dt = time.perf_counter() - t0
+    value = done / dt
+    sample = (f"each step: {cores} C5 environments x {N_DRONES} drones (one per host core) advance {S} control steps; "
+              f"oracle/pipeline.run_cbf = the reference's algorithms restated in numpy (reference is pure Python and cannot "
+              f"travel to the GPU box; cvxopt and gym-pybullet-drones are not installable offline)")
+    line = {"impl": "reference", "metric": "drone-steps/sec (DYN_GND_DRAG_DW + LQR + order-3 CBF-QP, 8 drones/env)", "value": value,
+            "unit": "drone-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, cores * 1, per_gpu=False),
+            "cpu_baseline": {"value": value, "unit": "drone-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "drone-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, envs, per_gpu=True):
+    return {"workload": "C5 swarm sweep: envs x 8 drones, Physics.DYN_GND_DRAG_DW 240 Hz, Lemniscate refs, LQR-yank-omega nominal, "
+                        "order-3 CBF-QP (r_safe 0.125, zscale 2, poles -3/-3.6/-5.6) + sphere obstacle r=0.1, YankOmega inner loop",
+            "envs_per_gpu" if per_gpu else "envs": envs, "drones_per_env": N_DRONES, "drone_model": "cf2p", "cbf_order": CBF_ORDER,
+            "control_steps_per_step": args.fuse if per_gpu else args.ref_steps_per_step, "parallelism": f"env-sharded x{args.gpus}",
+            "l2": "working set (state+obs+traj specs+PID > 200 MB per GPU) exceeds the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        return None
+
+
+def run_gpu_arm(args):
+    cpu = None
+    rank_env = int(os.environ.get("RANK", "0"))
+    if rank_env == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.cpu_seconds)  # before CUDA is initialised in this process (fork-safe)
+
+    import torch
+    import torch.distributed as dist
+
+    import multidronesim_b200 as mds
+    from multidronesim_b200 import scenarios
+
+    rank, local_rank, world = mds.dist.init_from_env()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    E, N, F, K, W = args.envs, N_DRONES, args.fuse, args.steps, max(3, args.warmup)
+    D = E * N
+
+    sc = scenarios.cbf_swarm(E, N, order=CBF_ORDER, dtype=dtype, device=dev, env_offset=rank * E)
+    env, ro = sc["env"], sc["rollout"]
+    fma_peak = mds._lib.fma_peak_tflops(use_f64=(dtype == torch.float64))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident headline -------------------------------------------------------------
+    for _ in range(W):
+        ro.run(F)
+    torch.cuda.synchronize()
+    ro.reset_stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        for _ in range(K):
+            ro.run(F)
+        ev1.record()
+        torch.cuda.synchronize()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * D * F * K / (ms_max * 1e-3)
+    stats_all = mds.dist.gather_stats(ro.stats)  # the path's only collective (NCCL all-gather of 8 doubles per rank)
+    stats = dict(zip(mds._lib.STAT_NAMES, mds.dist.reduce_stats(stats_all).tolist()))
+    clocks = clk.summary()
+
+    # ---- roofline of the dominant kernel (this rank) -------------------------------------------
+    flop_unit = sum(ALGO_FLOP_PER_DRONE_STEP.values())
+    launch_ms = ms / K
+    achieved_tf = flop_unit * D * F / (launch_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32", "kernel": "rollout_kernel<float>" if dtype == torch.float32 else "rollout_kernel<double>",
+                "achieved": achieved_tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tf / fma_peak,
+                "peak_source": "measured live: mds_fma_peak dependent-FMA chains, 2 x 1024 threads per SM (no FP32 figure in MEASURED_PEAKS.json)",
+                "algorithmic_flop_per_drone_step": flop_unit, "launch_ms": launch_ms, "traffic": None,
+                "note": "QP-inactive path flops; active-set iterations (stats.qp_iters) are extra work not counted"}
+
+    # per-call physics-step kernel: HBM roofline (232 B per drone-step)
+    act = torch.full((E, N, 4), float(env.HOVER_RPM), device=dev, dtype=dtype)
+    for _ in range(3):
+        env.step(act)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        env.step(act)
+    e1.record()
+    torch.cuda.synchronize()
+    step_ms = e0.elapsed_time(e1) / reps
+    peaks = measured_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    bytes_unit = ALGO_BYTES_PER_DRONE_STEP_PERCALL_F32 * (1 if dtype == torch.float32 else 2)
+    hbm_gbs = bytes_unit * D / (step_ms * 1e-3) / 1e9
+    roofline_hbm = {"bound": "hbm", "kernel": "physics_step_kernel", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_gbs / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
+                    "algorithmic_bytes_per_drone_step": bytes_unit, "launch_ms": step_ms, "traffic": None,
+                    "drone_steps_per_s": D / (step_ms * 1e-3)}
+
+    # ---- end to end through the per-call API with host buffers --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, mds, sc, dev, dtype, world, barrier)
+
+    if rank == 0:
+        line = {"metric": "drone-steps/sec (DYN_GND_DRAG_DW + LQR + order-3 CBF-QP, 8 drones/env)", "value": value, "unit": "drone-steps/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, E),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "roofline_hbm": roofline_hbm,
+                "cpu_baseline": cpu, "rollout_stats": stats, "sm_count": mds._lib.device_info()["sm_count"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, mds, sc, dev, dtype, world, barrier):
+    """Reference-facing per-call sequence with HOST buffers, every control step:
+       H2D refs (what the reference passes to set_desired_trajectory) -> LQR (skip_low_level) -> caller glue
+       (nominal -= mg, xdes) -> CBF-QP -> inner loop -> env.step -> D2H observations."""
+    import torch
+    import torch.distributed as dist
+    env, ctrl, trk, trajs = sc["env"], sc["ctrl"], sc["tracker"], sc["trajs"]
+    E, N = env.NUM_ENVS, env.NUM_DRONES
+    D = E * N
+    S = args.e2e_steps
+    env.reset()
+    ctrl.low_level.reset()
+    # the host owns the references (pre-evaluated for the S steps, as a host-side planner would) and receives obs
+    ref_host = torch.empty(S, D, 11, dtype=dtype).pin_memory()
+    for k in range(S):
+        ref_host[k].copy_(trajs.eval(k * env.CTRL_TIMESTEP))
+    torch.cuda.synchronize()
+    obs_host = torch.empty(E, N, 20, dtype=dtype).pin_memory()
+    ref_dev = torch.empty(D, 11, device=dev, dtype=dtype)
+    pipe = mds.rollout.PerCallPipeline(env, ctrl, trk, sc["obstacles"])
+    for k in range(3):
+        ref_dev.copy_(ref_host[k], non_blocking=True)
+        pipe.step(ref_dev)
+        obs_host.copy_(env.obs, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for k in range(S):
+        ref_dev.copy_(ref_host[k], non_blocking=True)
+        pipe.step(ref_dev)
+        obs_host.copy_(env.obs, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    esz = 4 if dtype == torch.float32 else 8
+    return {"value": world * D * S / (ms * 1e-3), "unit": "drone-steps/s", "h2d_bytes_per_step": D * 11 * esz, "d2h_bytes_per_step": D * 20 * esz,
+            "control_steps": S, "ms_per_control_step": ms / S, "kernels_per_control_step": pipe.launches_per_step,
+            "path": "H2D refs -> mds_lqr_ctrl -> mds_cbf_prepare -> mds_cbf_qp -> mds_lowlevel -> mds_physics_step -> D2H obs (one stream)"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

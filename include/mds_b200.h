@@ -78,6 +78,7 @@ typedef struct MdsDroneParams {
   double gnd_eff_coeff, prop_radius, gnd_eff_h_clip;
   double drag_xy, drag_z;
   double dw1, dw2, dw3;
+  double dw_dz_clip;           /* lower clip of the vertical separation in the downwash magnitude (0 = upstream-exact, singular at dz -> 0+) */
   double prop_x[4], prop_y[4]; /* prop link offsets, body frame */
   double z_floor;              /* ground-plane contact clamp height */
   double dt_phys;              /* PYB_TIMESTEP  */
@@ -204,6 +205,12 @@ int mds_cbf_rows_f64(const MdsDroneParams* prm, const MdsCbfParams* cbf, const d
                      const double* xdes_dev, const double* obstacles_dev, int n_obs, double* G_dev, double* h_dev,
                      int E, int N, void* stream);
 int mds_cbf_num_rows(int order, int N, int n_obs);
+/* the glue the reference's callers do around the QP (simulations/CBFTest.py:339-343, CBFTestOrd3.py:344-347):
+ * u[:,0] -= u0_offset (in place) and xdes = [0, 0, yaw, (m g,) vel, pos] from the reference samples */
+int mds_cbf_prepare_f32(const MdsDroneParams* prm, int order, double u0_offset, const float* ref_dev, float* u_inout_dev,
+                        float* xdes_dev, int D, void* stream);
+int mds_cbf_prepare_f64(const MdsDroneParams* prm, int order, double u0_offset, const double* ref_dev, double* u_inout_dev,
+                        double* xdes_dev, int D, void* stream);
 
 /* ---- model comparison: replaces the loop of simulations/CompareModels.py:48-55 ------ */
 /* kind 12: LinearizedModel.calc_xdot_from_obs; 9 / 10: builder-defined (quirk B23) */

@@ -35,7 +35,7 @@ class MdsError(RuntimeError):
 class DroneParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "m", "g", "kf", "km", "arm_l", "ixx", "iyy", "izz", "max_rpm", "max_thrust",
-        "gnd_eff_coeff", "prop_radius", "gnd_eff_h_clip", "drag_xy", "drag_z", "dw1", "dw2", "dw3")] + [
+        "gnd_eff_coeff", "prop_radius", "gnd_eff_h_clip", "drag_xy", "drag_z", "dw1", "dw2", "dw3", "dw_dz_clip")] + [
         ("prop_x", C.c_double * 4), ("prop_y", C.c_double * 4),
         ("z_floor", C.c_double), ("dt_phys", C.c_double), ("dt_ctrl", C.c_double),
         ("substeps", C.c_int), ("drone_model", C.c_int), ("physics", C.c_int),
@@ -96,6 +96,7 @@ _SIGS = {
     "mds_lowlevel": [_PRM, _I, _P, _P, PidState, _P, _I, _P],
     "mds_cbf_qp": [_PRM, C.POINTER(CbfParams), _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P],
     "mds_cbf_rows": [_PRM, C.POINTER(CbfParams), _P, _P, _P, _I, _P, _P, _I, _I, _P],
+    "mds_cbf_prepare": [_PRM, _I, _D, _P, _P, _P, _I, _P],
     "mds_xdot_linear": [_PRM, _I, _P, _P, _I, _P],
     "mds_xdot_nonlinear": [_PRM, _D, _D, _D, _P, _P, _I, _P],
     "mds_rollout": [_PRM, C.POINTER(RolloutCfg), C.POINTER(GeoGains), C.POINTER(LqrGains), C.POINTER(CbfParams),

@@ -32,7 +32,7 @@ class DroneConstants:
     """Attributes named as the reference reads them from ``env``."""
 
     def __init__(self, drone_model=DroneModel.CF2P, physics=Physics.DYN, pyb_freq=240, ctrl_freq=240,
-                 cf2x_torque_sign=-1, renormalize_quat=False, ground_clamp=None):
+                 cf2x_torque_sign=-1, renormalize_quat=False, ground_clamp=None, dw_dz_clip=None):
         self.DRONE_MODEL = DroneModel(drone_model)
         self.PHYSICS = Physics(physics)
         u = URDF[self.DRONE_MODEL]
@@ -69,6 +69,10 @@ class DroneConstants:
         self.cf2x_torque_sign = int(cf2x_torque_sign)
         self.renormalize_quat = bool(renormalize_quat)
         self.ground_clamp = (self.PHYSICS == Physics.DYN_GND_DRAG_DW) if ground_clamp is None else bool(ground_clamp)
+        # Downwash magnitude alpha = DW1 (PROP_RADIUS / (4 dz))^2 is singular as dz -> 0+ (upstream only ever flies one
+        # drone well above another).  The composite mode clips dz from below where alpha would exceed the drone's
+        # weight -- the same device upstream uses for ground effect (GND_EFF_H_CLIP).  0 restores the upstream formula.
+        self.DW_DZ_CLIP = 0.25 * self.PROP_RADIUS * math.sqrt(self.DW_COEFF_1 / self.GRAVITY) if dw_dz_clip is None else float(dw_dz_clip)
 
     def c_params(self) -> _lib.DroneParams:
         p = _lib.DroneParams()
@@ -78,6 +82,7 @@ class DroneConstants:
         p.gnd_eff_coeff, p.prop_radius, p.gnd_eff_h_clip = self.GND_EFF_COEFF, self.PROP_RADIUS, self.GND_EFF_H_CLIP
         p.drag_xy, p.drag_z = self.DRAG_COEFF[0], self.DRAG_COEFF[2]
         p.dw1, p.dw2, p.dw3 = self.DW_COEFF_1, self.DW_COEFF_2, self.DW_COEFF_3
+        p.dw_dz_clip = self.DW_DZ_CLIP
         for i in range(4):
             p.prop_x[i], p.prop_y[i] = self.PROP_XY[i]
         p.z_floor, p.dt_phys, p.dt_ctrl = self.Z_FLOOR, self.PYB_TIMESTEP, self.CTRL_TIMESTEP

@@ -92,7 +92,7 @@ template <typename Real> MDS_DEV Real sign_(Real x) { return (x > Real(0)) ? Rea
 // ---------------------------------------------------------------- device parameter blocks
 template <typename Real> struct DroneP {
   Real m, g, kf, km, arm_l, ixx, iyy, izz, max_rpm, max_thrust;
-  Real gnd_eff_coeff, prop_radius, gnd_eff_h_clip, drag_xy, drag_z, dw1, dw2, dw3;
+  Real gnd_eff_coeff, prop_radius, gnd_eff_h_clip, drag_xy, drag_z, dw1, dw2, dw3, dw_dz_clip;
   Real prop_x[4], prop_y[4];
   Real z_floor, dt_phys, dt_ctrl;
   int substeps, drone_model, physics, cf2x_torque_sign, renormalize_quat, ground_clamp;
@@ -104,7 +104,7 @@ template <typename Real> inline DroneP<Real> to_dev(const MdsDroneParams& p) {
   d.max_rpm = Real(p.max_rpm); d.max_thrust = Real(p.max_thrust);
   d.gnd_eff_coeff = Real(p.gnd_eff_coeff); d.prop_radius = Real(p.prop_radius);
   d.gnd_eff_h_clip = Real(p.gnd_eff_h_clip); d.drag_xy = Real(p.drag_xy); d.drag_z = Real(p.drag_z);
-  d.dw1 = Real(p.dw1); d.dw2 = Real(p.dw2); d.dw3 = Real(p.dw3);
+  d.dw1 = Real(p.dw1); d.dw2 = Real(p.dw2); d.dw3 = Real(p.dw3); d.dw_dz_clip = Real(p.dw_dz_clip);
   for (int i = 0; i < 4; ++i) { d.prop_x[i] = Real(p.prop_x[i]); d.prop_y[i] = Real(p.prop_y[i]); }
   d.z_floor = Real(p.z_floor); d.dt_phys = Real(p.dt_phys); d.dt_ctrl = Real(p.dt_ctrl);
   d.substeps = p.substeps; d.drone_model = p.drone_model; d.physics = p.physics;

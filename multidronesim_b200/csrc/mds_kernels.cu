@@ -331,6 +331,21 @@ __global__ void __launch_bounds__(256) cbf_qp_kernel(DroneP<Real> P, CbfP<Real> 
   }
 }
 
+template <typename Real>
+__global__ void cbf_prepare_kernel(DroneP<Real> P, int order, Real u0_offset, const Real* __restrict__ ref, Real* __restrict__ u,
+                                   Real* __restrict__ xdes, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Ref<Real> r = load_ref(ref, d);
+  u[(size_t)d * 4] -= u0_offset;
+  const int xdim = order == 2 ? 9 : 10;
+  Real* x = xdes + (size_t)d * xdim;
+  x[0] = Real(0); x[1] = Real(0); x[2] = r.yaw;
+  int o = 3;
+  if (order == 3) x[o++] = P.g * P.m;
+  x[o] = r.v.x; x[o + 1] = r.v.y; x[o + 2] = r.v.z; x[o + 3] = r.p.x; x[o + 4] = r.p.y; x[o + 5] = r.p.z;
+}
+
 // dense G, h in the reference's row order (parity aid; one thread per env)
 template <typename Real>
 __global__ void cbf_rows_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __restrict__ obs, const Real* __restrict__ xdes,
@@ -677,6 +692,13 @@ static int cbf_rows_impl(const MdsDroneParams* prm, const MdsCbfParams* c, const
   cbf_rows_kernel<Real><<<(E + 63) / 64, 64, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*c), obs, xdes, obstacles, n_obs, Gm, h, E, N);
   return check_launch("cbf_rows");
 }
+template <typename Real>
+static int cbf_prepare_impl(const MdsDroneParams* prm, int order, double u0, const Real* ref, Real* u, Real* xdes, int D, void* stream) {
+  MDS_REQUIRE(prm && ref && u && xdes && D > 0, "cbf_prepare: bad argument");
+  MDS_REQUIRE(order == 2 || order == 3, "cbf_prepare: order must be 2 or 3");
+  cbf_prepare_kernel<Real><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), order, Real(u0), ref, u, xdes, D);
+  return check_launch("cbf_prepare");
+}
 template <typename Real> static int xdot_linear_impl(const MdsDroneParams* prm, int kind, const Real* obs, Real* xdot, int D, void* stream) {
   MDS_REQUIRE(prm && obs && xdot && D > 0, "xdot_linear: bad argument");
   MDS_REQUIRE(kind == 12 || kind == 9 || kind == 10, "xdot_linear: kind must be 12, 9 or 10");
@@ -786,6 +808,9 @@ int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 *
   int mds_cbf_rows_##SUF(const MdsDroneParams* prm, const MdsCbfParams* c, const REAL* obs, const REAL* xdes, const REAL* obstacles, int n_obs,    \
                          REAL* Gm, REAL* h, int E, int N, void* stream) {                                                                          \
     return cbf_rows_impl<REAL>(prm, c, obs, xdes, obstacles, n_obs, Gm, h, E, N, stream);                                                          \
+  }                                                                                                                                                \
+  int mds_cbf_prepare_##SUF(const MdsDroneParams* prm, int order, double u0, const REAL* ref, REAL* u, REAL* xdes, int D, void* stream) {        \
+    return cbf_prepare_impl<REAL>(prm, order, u0, ref, u, xdes, D, stream);                                                                        \
   }                                                                                                                                                \
   int mds_xdot_linear_##SUF(const MdsDroneParams* prm, int kind, const REAL* obs, REAL* xdot, int D, void* stream) {                               \
     return xdot_linear_impl<REAL>(prm, kind, obs, xdot, D, stream);                                                                                \

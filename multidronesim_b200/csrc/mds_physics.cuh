@@ -15,7 +15,7 @@ MDS_DEV Real downwash_term(const DroneP<Real>& P, V3<Real> pi, V3<Real> pj) {
   Real dx = pj.x - pi.x, dy = pj.y - pi.y;
   Real dxy2 = dx * dx + dy * dy;
   if (dz > Real(0) && dxy2 < Real(100)) {
-    Real q = P.prop_radius / (Real(4) * dz);
+    Real q = P.prop_radius / (Real(4) * max_(dz, P.dw_dz_clip));  // clip: App. A.4 regularisation (0 = upstream)
     Real alpha = P.dw1 * q * q;
     Real beta = P.dw2 * dz + P.dw3;
     return alpha * exp_(Real(-0.5) * dxy2 / (beta * beta));

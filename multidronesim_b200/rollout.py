@@ -77,3 +77,36 @@ class FusedRollout:
     def stats_dict(self):
         v = self.stats.tolist()
         return dict(zip(_lib.STAT_NAMES, v))
+
+
+class PerCallPipeline:
+    """One control step through the per-call device API in the reference's call order
+    (simulations/CBFTest.py:302-350): references in -> ctrl.compute(skip_low_level) -> caller glue
+    (mds_cbf_prepare) -> qp_tracker.compute_control -> ctrl.compute_low_level -> env.step."""
+
+    def __init__(self, env, controller, qp_tracker=None, obstacles=None):
+        self.env, self.ctrl, self.qp = env, controller, qp_tracker
+        self.obst = None
+        if qp_tracker is not None and obstacles is not None and len(obstacles):
+            self.obst = torch.as_tensor(obstacles, device=env.device, dtype=env.dtype).reshape(-1, 4).contiguous()
+        if qp_tracker is not None:
+            self.xdes = torch.zeros(env.NUM_ENVS, env.NUM_DRONES, qp_tracker.xdim, device=env.device, dtype=env.dtype)
+        self.mg = env.M * env.G
+        self.launches_per_step = 5 if qp_tracker is not None else 2
+
+    def step(self, ref):
+        env, c = self.env, self.ctrl
+        c.set_reference(ref)
+        obs = env.obs
+        if self.qp is None:
+            out = c.compute(obs)
+            action = out if isinstance(out, torch.Tensor) else out[0]
+        else:
+            _, u = c.compute(obs, skip_low_level=True)
+            _lib.call("mds_cbf_prepare", env.dtype, env._prm, self.qp.order, self.mg, _lib.ptr(ref), _lib.ptr(u), _lib.ptr(self.xdes),
+                      env.NUM_TOTAL, _lib.stream_ptr(env.device))
+            us = self.qp.compute_control(obs, self.xdes, u, x_obs=self.obst)
+            if self.qp.order == 2:
+                us[..., 0] += self.mg
+            action = c.compute_low_level(us, obs)
+        return env.step(action)[0]

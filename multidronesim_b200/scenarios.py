@@ -1,0 +1,88 @@
+"""Synthetic swarm set-ups of SURVEY.md 8(d): the configurations bench.py / smoke() time and the
+parity tests replay in miniature.  Everything here is init-time host work (numpy) that ends in
+device tensors; the per-step path never touches it."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cbf import DroneCBF, DroneQPTracker
+from .control import (GeometricControl, LQROmegaController, LQRYankOmegaController, ThrustOmegaController,
+                      YankOmegaController)
+from .enums import DroneModel, Physics
+from .envs import BatchedCtrlAviary
+from .model import LinearizedOmegaModel, LinearizedYankOmegaModel
+from .rollout import FusedRollout
+from .trajectories import TrajectorySet
+
+
+def lemniscate_pos(a, theta, center):
+    """Lemniscate.py:51-53 at phase theta (vectorised)."""
+    s, c = np.sin(theta), np.cos(theta)
+    den = 1 + s * s
+    return np.stack([center[0] + a * s * c / den, center[1] + a * c / den, np.full_like(theta, center[2])], axis=-1)
+
+
+def cbf_swarm(num_envs, num_drones=8, order=3, dtype=torch.float32, device="cuda", seed=3, env_offset=0,
+              omega=0.5, obstacle=True, physics=Physics.DYN_GND_DRAG_DW, pyb_freq=240, ctrl_freq=240):
+    """C3 / C5: N drones per env on one lemniscate (a=1, centre (0,0,0.5)) with phase shifts
+    2 pi k / (N + 0.25) (reference simulations/CBFTestOrd3.py:450), one sphere obstacle r=0.1 at the
+    lemniscate's centre (simulations/CBFTest.py:421-424), per-env position jitter N(0, 0.02^2) with a
+    distinct z offset per drone (order-2 rows vanish at ez = 0).  LQR nominal -> CBF-QP -> inner loop.
+    ``env_offset`` makes per-env random streams independent of how envs are sharded over GPUs."""
+    E, N = int(num_envs), int(num_drones)
+    center = np.array([0.0, 0.0, 0.5])
+    phase = (2 * np.pi / (N + 0.25)) * np.arange(N)
+    init = np.empty((E, N, 3))
+    base = lemniscate_pos(1.0, phase, center)
+    # counter-based per-env streams: env e always draws the same jitter, whatever the sharding
+    for lo in range(0, E, 65536):
+        hi = min(E, lo + 65536)
+        ss = np.random.SeedSequence([seed, env_offset + lo])
+        rng = np.random.default_rng(ss)
+        init[lo:hi] = base[None] + rng.normal(0, 0.02, (hi - lo, N, 3))
+    init[..., 2] += 0.04 * np.arange(N)[None, :]
+    env = BatchedCtrlAviary(drone_model=DroneModel.CF2P, num_drones=N, initial_xyzs=init, physics=physics,
+                            pyb_freq=pyb_freq, ctrl_freq=ctrl_freq, num_envs=E, device=device, dtype=dtype)
+    if order == 3:
+        mdl = LinearizedYankOmegaModel(env)
+        ctrl = LQRYankOmegaController(env, mdl, YankOmegaController(env))
+        cbf = DroneCBF(env, [mdl] * N, safety_radius=0.125, zscale=2, order=3, cbf_poles=np.array([-3.0, -3.6, -5.6]))
+        trk = DroneQPTracker(cbf, order=3, num_robots=N, xdim=10, env=env)
+    else:
+        mdl = LinearizedOmegaModel(env)
+        ctrl = LQROmegaController(env, mdl, ThrustOmegaController(env))
+        cbf = DroneCBF(env, [mdl] * N, safety_radius=0.1, zscale=1, order=2, cbf_poles=np.array([-2.2, -2.4]))
+        trk = DroneQPTracker(cbf, order=2, num_robots=N, xdim=9, env=env)
+    params = np.zeros((N, 7))
+    params[:, 0], params[:, 1], params[:, 2:5], params[:, 5], params[:, 6] = 1.0, omega, center, 0.0, phase
+    trajs = TrajectorySet.from_arrays(_lib.TRAJ_LEMNISCATE, np.tile(params, (E, 1)), device=device, dtype=dtype)
+    obstacles = [[0.0, 0.0, 0.5, 0.1]] if obstacle else None
+    rollout = FusedRollout(env, trajs, ctrl, trk, obstacles)
+    return dict(env=env, ctrl=ctrl, cbf=cbf, tracker=trk, trajs=trajs, obstacles=obstacles, rollout=rollout, init=init)
+
+
+def tracking_swarm(num_envs, dtype=torch.float32, device="cuda", seed=1, env_offset=0, physics=Physics.DYN_GND_DRAG_DW):
+    """C2: one drone per env, geometric SE(3) controller; even envs track CircleTrajectory(r=1, v=0.5,
+    centre (0,0,1)), odd envs Lemniscate(a=1, omega=1.5, centre (0,0,0.5)) with a random phase shift;
+    initial position = traj(0) + N(0, 0.05^2), z >= 0.1."""
+    E = int(num_envs)
+    rng = np.random.default_rng(np.random.SeedSequence([seed, env_offset]))
+    kind = np.where(np.arange(E) % 2 == 0, _lib.TRAJ_CIRCLE, _lib.TRAJ_LEMNISCATE)
+    phase = rng.uniform(0, 2 * np.pi, E)
+    params = np.zeros((E, 7))
+    circ = kind == _lib.TRAJ_CIRCLE
+    params[circ, 0:6] = [1.0, 0.5, 0.0, 0.0, 1.0, 0.0]
+    params[~circ, 0:5] = [1.0, 1.5, 0.0, 0.0, 0.5]
+    params[~circ, 6] = phase[~circ]
+    p0 = np.where(circ[:, None], np.array([1.0, 0.0, 1.0])[None], lemniscate_pos(1.0, phase, np.array([0.0, 0.0, 0.5])))
+    init = p0 + rng.normal(0, 0.05, (E, 3))
+    init[:, 2] = np.maximum(init[:, 2], 0.1)
+    env = BatchedCtrlAviary(drone_model=DroneModel.CF2P, num_drones=1, initial_xyzs=init.reshape(E, 1, 3), physics=physics,
+                            num_envs=E, device=device, dtype=dtype)
+    ctrl = GeometricControl(env)
+    trajs = TrajectorySet.from_arrays(kind, params, device=device, dtype=dtype)
+    return dict(env=env, ctrl=ctrl, trajs=trajs, rollout=FusedRollout(env, trajs, ctrl), init=init, kind=kind, params=params)

@@ -86,7 +86,7 @@ class OracleCtrlAviary:
     def __init__(self, drone_model=DroneModel.CF2P, num_drones=1, initial_xyzs=None,
                  initial_rpys=None, physics=Physics.DYN, pyb_freq=240, ctrl_freq=240,
                  gui=False, record=False, user_debug_gui=False, output_folder="results",
-                 cf2x_torque_sign=-1.0, renormalize_quat=False, ground_clamp=None):
+                 cf2x_torque_sign=-1.0, renormalize_quat=False, ground_clamp=None, dw_dz_clip=None):
         prm = drone_params(drone_model, pyb_freq, ctrl_freq)
         self.__dict__.update(prm.__dict__)
         self.NUM_DRONES = int(num_drones)
@@ -95,6 +95,8 @@ class OracleCtrlAviary:
             raise ValueError("oracle supports Physics.DYN and Physics.DYN_GND_DRAG_DW only")
         self.cf2x_torque_sign = float(cf2x_torque_sign)
         self.renormalize_quat = bool(renormalize_quat)
+        if dw_dz_clip is not None:
+            self.DW_DZ_CLIP = float(dw_dz_clip)
         # ground-plane clamp belongs to the composite mode only (DYN stays upstream-exact)
         self.ground_clamp = (self.PHYSICS == Physics.DYN_GND_DRAG_DW) if ground_clamp is None else bool(ground_clamp)
         N = self.NUM_DRONES
@@ -160,7 +162,7 @@ class OracleCtrlAviary:
                 dz = snap_pos[j, 2] - pos[2]
                 dxy = math.hypot(snap_pos[j, 0] - pos[0], snap_pos[j, 1] - pos[1])
                 if dz > 0 and dxy < 10:
-                    alpha = self.DW_COEFF_1 * (self.PROP_RADIUS / (4 * dz)) ** 2
+                    alpha = self.DW_COEFF_1 * (self.PROP_RADIUS / (4 * max(dz, self.DW_DZ_CLIP))) ** 2
                     beta = self.DW_COEFF_2 * dz + self.DW_COEFF_3
                     dw += alpha * math.exp(-0.5 * (dxy / beta) ** 2)
         thrust_body = np.array([0.0, 0.0, np.sum(forces) - dw])

@@ -89,6 +89,8 @@ def drone_params(drone_model="cf2p", pyb_freq=240, ctrl_freq=240):
     p.CTRL_TIMESTEP = 1.0 / p.CTRL_FREQ
     p.PYB_TIMESTEP = 1.0 / p.PYB_FREQ
     p.Z_FLOOR = p.COLLISION_H / 2 - p.COLLISION_Z_OFFSET
+    # App. A.4 regularisation of the downwash singularity at dz -> 0+: clip dz where alpha would exceed the weight
+    p.DW_DZ_CLIP = 0.25 * p.PROP_RADIUS * math.sqrt(p.DW_COEFF_1 / p.GRAVITY)
     return p
 
 
