@@ -220,14 +220,18 @@ int mds_xdot_linear_f64(const MdsDroneParams* prm, int kind, const double* obs_d
 int mds_xdot_nonlinear_f32(const MdsDroneParams* prm, double jx, double jy, double jz, const float* obs_dev, float* xdot_dev, int D, void* stream);
 int mds_xdot_nonlinear_f64(const MdsDroneParams* prm, double jx, double jy, double jz, const double* obs_dev, double* xdot_dev, int D, void* stream);
 
-/* ---- fused K-step rollout: traj -> ctrl -> (CBF-QP) -> inner loop -> physics, state in registers */
+/* ---- K-step rollout: per control step ONE fused controller kernel (reference -> tracking controller ->
+ * CBF-QP -> inner loop, all in registers / shared memory) and ONE physics kernel (all sub-steps in registers),
+ * enqueued back to back on `stream` with no host synchronisation (capturable in a CUDA graph).
+ * obs_dev [D*20] in/out (observation before the first / after the last step); action_dev [D*4] scratch;
+ * obs_log_dev optional [K/write_obs_every][D*20]; stats_dev optional [MDS_STAT_COUNT] doubles (accumulated). */
 int mds_rollout_f32(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
                     const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
-                    const MdsTrajSpecF32* specs_dev, const MdsTrajSegF32* segs_dev, float* obs_dev,
+                    const MdsTrajSpecF32* specs_dev, const MdsTrajSegF32* segs_dev, float* obs_dev, float* action_dev,
                     float* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
 int mds_rollout_f64(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
                     const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
-                    const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double* obs_dev,
+                    const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double* obs_dev, double* action_dev,
                     double* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
 
 /* ---- measurement aid: dependent-FMA-chain peak of the FP32 / FP64 pipes (TFLOP/s) ---- */

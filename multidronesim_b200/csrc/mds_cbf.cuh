@@ -18,7 +18,7 @@
 
 namespace mds {
 
-#define MDS_QP_QMAX 24  // max simultaneously active constraints handled (else status ITER_CAP)
+#define MDS_QP_QMAX 12  // max simultaneously active constraints handled (else status ITER_CAP)
 
 // what a barrier row needs from one agent: position, velocity error, linearised acceleration error
 template <typename Real> struct CbfAgent {
@@ -86,32 +86,45 @@ MDS_DEV void pair_from_index(int r, int N, int* i, int* j) {
 }
 
 // ----------------------------------------------------------------------------------------
-// Per-env QP over the coupled inputs x[4n + c], c in {0,1,2}, n < N (c == 3 is decoupled).
+// Per-env QP over the coupled inputs x[4n + c], c in {0,1,2}, n < N (c == 3 is decoupled), solved
+// COOPERATIVELY by the env's lane group (NP = next power of two >= N consecutive lanes of one warp;
+// lane n owns drone n).  Only group-level synchronisation is used (__syncwarp / shuffles with the
+// group's lane mask), so groups of one warp iterate independently and no block barrier exists.
+//
 // Constraint index space:  [0, n_rows): barrier rows (pairs, then obstacles i*n_obs + o)
 //                          [n_rows, n_rows + 6N): box  s * x[i,c] <= umax[c], k = i*6 + (s<0)*3 + c
-// rows[r*4 + 0..2] = a3, rows[r*4 + 3] = rhs.  All arrays may live in shared memory.
+// Shared-memory row record (MDS_ROW_W words): a0, a1, a2, rhs, |g|^2, (i | j<<8 | active<<16) as int bits.
+#define MDS_ROW_W 6
+#define MDS_QP_WS_WORDS (4 * MDS_QP_QMAX + MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2 + 4)  // act, lam, d, r, chol, header
+
 template <typename Real> struct QpCon {
   int i, j;      // drone blocks (j < 0: single block)
   Real gi[3];    // coefficients on block i; block j carries -gi (pair rows)
-  Real rhs;
+  Real rhs, g2;
 };
+MDS_DEV int real_as_int(float v) { return __float_as_int(v); }
+MDS_DEV int real_as_int(double v) { return (int)__double2loint(v); }
+MDS_DEV float int_as_real(int v, float) { return __int_as_float(v); }
+MDS_DEV double int_as_real(int v, double) { return __hiloint2double(0, v); }
 
 template <typename Real>
-MDS_DEV QpCon<Real> qp_get(const Real* rows, const CbfP<Real>& C, int idx, int N, int n_pairs, int n_rows, int n_obs) {
+MDS_DEV QpCon<Real> qp_get(const Real* rows, const CbfP<Real>& C, int idx, int n_rows) {
   QpCon<Real> c;
   if (idx < n_rows) {
-    const Real* r = rows + 4 * idx;
-    c.gi[0] = -r[0]; c.gi[1] = -r[1]; c.gi[2] = -r[2]; c.rhs = r[3];
-    if (idx < n_pairs) pair_from_index(idx, N, &c.i, &c.j);
-    else { c.i = (idx - n_pairs) / n_obs; c.j = -1; }
+    const Real* r = rows + MDS_ROW_W * idx;
+    c.gi[0] = -r[0]; c.gi[1] = -r[1]; c.gi[2] = -r[2]; c.rhs = r[3]; c.g2 = r[4];
+    int ij = real_as_int(r[5]);
+    c.i = ij & 0xff;
+    c.j = (ij >> 8) & 0xff;
+    if (c.j == 0xff) c.j = -1;
   } else {
     int k = idx - n_rows;
     c.i = k / 6; c.j = -1;
     int rem = k - 6 * c.i;
-    int comp = rem % 3;
+    int comp = rem >= 3 ? rem - 3 : rem;
     Real s = rem < 3 ? Real(1) : Real(-1);
     c.gi[0] = comp == 0 ? s : Real(0); c.gi[1] = comp == 1 ? s : Real(0); c.gi[2] = comp == 2 ? s : Real(0);
-    c.rhs = C.umax[comp];
+    c.rhs = C.umax[comp]; c.g2 = Real(1);
   }
   return c;
 }
@@ -137,108 +150,211 @@ template <typename Real> MDS_DEV Real qp_dot_g(const QpCon<Real>& a, const QpCon
   if (b.j >= 0 && b.j == a.i) s -= ab;
   return s;
 }
+// coefficient of constraint c on drone block n, component k
+template <typename Real> MDS_DEV Real qp_coef(const QpCon<Real>& c, int n, int k) {
+  return (c.i == n) ? c.gi[k] : ((c.j == n) ? -c.gi[k] : Real(0));
+}
 
-// Goldfarb-Idnani dual active set, P = I.  x holds u_nom on entry, the minimiser on exit.
-// z: work vector of 4N Reals.  Returns MDS_QP_*; *iters_out = inner iterations.
+// Goldfarb-Idnani dual active set, P = I, executed by the env's lane group.
+//   rows : smem barrier-row records;  x : smem iterate [4N] (u_nom on entry, minimiser on exit);
+//   ws   : smem workspace of MDS_QP_WS_WORDS Reals;  n : this lane's drone (valid = n < N).
+// Work split: the O(#constraints) scan for the most violated row and the O(N) primal update are spread
+// over the lanes (lane n owns drone n's inputs and box bounds); the O(q^2) scalar part (triangular solves
+// with the Cholesky factor of the active Gram matrix, step lengths, multiplier and factor updates) is done
+// by the group's lane 0 and published through shared memory between __syncwarp(gmask) points.
+enum { MDS_QP_ACT_FULL = 0, MDS_QP_ACT_DROP = 1, MDS_QP_ACT_STOP = 2 };
+
 template <typename Real>
-MDS_DEV int qp_solve(const CbfP<Real>& C, const Real* rows, Real* x, Real* z, int N, int n_pairs, int n_rows, int n_obs, int* iters_out) {
+MDS_DEV int qp_solve_group(const CbfP<Real>& C, Real* rows, Real* x, Real* ws, int N, int NP, int n_rows, int n, bool valid,
+                           unsigned gmask, int* iters_out) {
   const Real tol = sizeof(Real) == 4 ? Real(2e-6) : Real(1e-11);
+  const Real zn_eps = sizeof(Real) == 4 ? Real(1e-5) : Real(1e-10);
   const Real INF = Real(1e30);
-  int act[MDS_QP_QMAX];
-  Real lam[MDS_QP_QMAX], r[MDS_QP_QMAX];
-  Real Lc[MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2];
-  int q = 0, iters = 0;
-  const int n_con = n_rows + 6 * N;
+  // workspace: one int per Real slot for act / header ints
+  Real* lam = ws + MDS_QP_QMAX;
+  Real* dv = ws + 2 * MDS_QP_QMAX;
+  Real* rv = ws + 3 * MDS_QP_QMAX;
+  Real* Lc = ws + 4 * MDS_QP_QMAX;  // packed lower-triangular Cholesky factor of the active Gram matrix
+  Real* hdr = Lc + MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2;  // [0] t, [1] action, [2] dropped index, [3] status
+  auto iref = [](Real* slot) -> int& { return *reinterpret_cast<int*>(slot); };
+  int q = 0, iters = 0, status = MDS_QP_OPTIMAL;
+  unsigned boxmask = 0;  // this lane's own active box constraints (6 bits)
+  Real xn[3] = {Real(0), Real(0), Real(0)};
+  if (valid) { xn[0] = x[4 * n]; xn[1] = x[4 * n + 1]; xn[2] = x[4 * n + 2]; }
+  // ONE flat loop (scan-if-needed -> scalar part -> primal step -> add or drop) instead of nested
+  // outer/inner loops: the lane groups of a warp then stay converged on the same instructions even when
+  // one group takes a full step and another a partial step (nested loops serialised the groups, ~4x).
+  bool need_scan = true;
+  int p = 0;
+  QpCon<Real> cp;
+  cp.i = 0; cp.j = -1; cp.gi[0] = cp.gi[1] = cp.gi[2] = Real(0); cp.rhs = Real(0); cp.g2 = Real(1);
+  Real lam_p = Real(0);  // meaningful on lane 0 only
   for (;;) {
-    // ---- most violated inactive constraint (normalised by |g|)
-    int p = -1;
-    Real worst = Real(0);
-    for (int idx = 0; idx < n_con; ++idx) {
-      bool is_act = false;
-      for (int k = 0; k < q; ++k) is_act |= (act[k] == idx);
-      if (is_act) continue;
-      QpCon<Real> c = qp_get(rows, C, idx, N, n_pairs, n_rows, n_obs);
-      Real mag, gx = qp_dot_x(c, x, &mag);
-      Real s = c.rhs - gx;
-      if (s < -tol * (abs_(c.rhs) + mag + Real(1e-12))) {
-        Real g2 = qp_dot_g(c, c);
-        if (g2 <= Real(0)) { *iters_out = iters; return MDS_QP_INFEASIBLE; }  // 0 <= rhs < 0
-        Real v = s * rsqrt_(g2);
-        if (v < worst) { worst = v; p = idx; }
+    if (need_scan) {
+      // ---- most violated inactive constraint: barrier rows strided over the group, own box bounds
+      Real best = Real(0);
+      int bidx = 0x7fffffff;
+      for (int r = n; r < n_rows; r += NP) {
+        if (real_as_int(rows[MDS_ROW_W * r + 5]) & 0x10000) continue;
+        QpCon<Real> c = qp_get(rows, C, r, n_rows);
+        Real mag, gx = qp_dot_x(c, x, &mag);
+        Real sl = c.rhs - gx;
+        if (sl < -tol * (abs_(c.rhs) + mag + Real(1e-12))) {
+          Real v = (c.g2 > Real(0)) ? sl * rsqrt_(c.g2) : -INF;  // zero row with rhs < 0: infeasible
+          if (v < best || (v == best && r < bidx)) { best = v; bidx = r; }
+        }
       }
-    }
-    if (p < 0) { *iters_out = iters; return MDS_QP_OPTIMAL; }
-    QpCon<Real> cp = qp_get(rows, C, p, N, n_pairs, n_rows, n_obs);
-    Real g2p = qp_dot_g(cp, cp);
-    Real lam_p = Real(0);
-    for (;;) {
-      if (++iters > C.max_iter) { *iters_out = iters; return MDS_QP_ITER_CAP; }
-      // ---- r = (Na Na')^-1 Na g_p by Cholesky of the active Gram matrix
-      for (int a = 0; a < q; ++a) {
-        QpCon<Real> ca = qp_get(rows, C, act[a], N, n_pairs, n_rows, n_obs);
-        for (int b = 0; b <= a; ++b) {
-          QpCon<Real> cb = qp_get(rows, C, act[b], N, n_pairs, n_rows, n_obs);
-          Real s = qp_dot_g(ca, cb);
-          for (int k = 0; k < b; ++k) s -= Lc[a * (a + 1) / 2 + k] * Lc[b * (b + 1) / 2 + k];
-          if (a == b) {
-            if (s <= Real(0)) { *iters_out = iters; return MDS_QP_ITER_CAP; }
-            Lc[a * (a + 1) / 2 + a] = sqrt_(s);
-          } else {
-            Lc[a * (a + 1) / 2 + b] = s / Lc[b * (b + 1) / 2 + b];
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          if (boxmask & (1u << k)) continue;
+          int comp = k >= 3 ? k - 3 : k;
+          Real sg = k < 3 ? Real(1) : Real(-1);
+          Real sl = C.umax[comp] - sg * xn[comp];
+          if (sl < -tol * (C.umax[comp] + abs_(xn[comp]) + Real(1e-12))) {
+            int idx = n_rows + 6 * n + k;
+            if (sl < best || (sl == best && idx < bidx)) { best = sl; bidx = idx; }
           }
         }
-        r[a] = qp_dot_g(ca, cp);
       }
-      for (int a = 0; a < q; ++a) {  // forward
-        Real s = r[a];
-        for (int k = 0; k < a; ++k) s -= Lc[a * (a + 1) / 2 + k] * r[k];
-        r[a] = s / Lc[a * (a + 1) / 2 + a];
+      for (int off = NP >> 1; off > 0; off >>= 1) {
+        Real ov = __shfl_xor_sync(gmask, best, off);
+        int oi = __shfl_xor_sync(gmask, bidx, off);
+        if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
       }
-      for (int a = q - 1; a >= 0; --a) {  // backward
-        Real s = r[a];
-        for (int k = a + 1; k < q; ++k) s -= Lc[k * (k + 1) / 2 + a] * r[k];
-        r[a] = s / Lc[a * (a + 1) / 2 + a];
+      if (bidx == 0x7fffffff) break;  // optimal
+      if (best <= -INF) { status = MDS_QP_INFEASIBLE; break; }
+      p = bidx;
+      cp = qp_get(rows, C, p, n_rows);
+      lam_p = Real(0);
+    }
+    ++iters;
+    // ---- scalar part (lane 0): d = L^-1 Na g_p, zn = |g_p|^2 - |d|^2, r = L^-T d, step lengths, multipliers
+    if (n == 0) {
+      int action = MDS_QP_ACT_FULL, st = MDS_QP_OPTIMAL, kdrop = -1;
+      Real t = Real(0), zn = cp.g2;
+      if (iters > C.max_iter) {
+        action = MDS_QP_ACT_STOP; st = MDS_QP_ITER_CAP;
+      } else {
+        Real dd = Real(0);
+        for (int a = 0; a < q; ++a) {
+          QpCon<Real> ca = qp_get(rows, C, iref(ws + a), n_rows);
+          Real sacc = qp_dot_g(ca, cp);
+          for (int k = 0; k < a; ++k) sacc -= Lc[a * (a + 1) / 2 + k] * dv[k];
+          sacc /= Lc[a * (a + 1) / 2 + a];
+          dv[a] = sacc;
+          dd += sacc * sacc;
+        }
+        zn = cp.g2 - dd;
+        for (int a = q - 1; a >= 0; --a) {
+          Real sacc = dv[a];
+          for (int k = a + 1; k < q; ++k) sacc -= Lc[k * (k + 1) / 2 + a] * rv[k];
+          rv[a] = sacc / Lc[a * (a + 1) / 2 + a];
+        }
+        Real t1 = INF;
+        for (int a = 0; a < q; ++a) {
+          Real ra = rv[a];
+          if (ra > tol) {
+            Real cnd = lam[a] / ra;
+            if (cnd < t1) { t1 = cnd; kdrop = a; }
+          }
+        }
+        Real mag, gx = qp_dot_x(cp, x, &mag);
+        Real s_p = cp.rhs - gx;
+        Real t2 = (zn > zn_eps * cp.g2) ? -s_p / zn : INF;
+        t = min_(t1, t2);
+        if (t >= INF) {
+          action = MDS_QP_ACT_STOP; st = MDS_QP_INFEASIBLE;
+        } else {
+          for (int a = 0; a < q; ++a) lam[a] -= t * rv[a];
+          lam_p += t;
+          if (t2 <= t1) {
+            action = (q == MDS_QP_QMAX) ? MDS_QP_ACT_STOP : MDS_QP_ACT_FULL;
+            if (q == MDS_QP_QMAX) st = MDS_QP_ITER_CAP;
+          } else {
+            action = MDS_QP_ACT_DROP;
+          }
+          if (t2 >= INF) t = -t;  // sign bit tells the lanes "dual step only, no primal move"
+        }
       }
-      // ---- z = g_p - Na' r  (dense over the 3 coupled inputs of every drone)
-      for (int k = 0; k < 4 * N; ++k) z[k] = Real(0);
-      for (int c = 0; c < 3; ++c) {
-        z[4 * cp.i + c] += cp.gi[c];
-        if (cp.j >= 0) z[4 * cp.j + c] -= cp.gi[c];
-      }
+      hdr[0] = t;
+      iref(hdr + 1) = action;
+      iref(hdr + 2) = kdrop;
+      iref(hdr + 3) = st;
+    }
+    __syncwarp(gmask);
+    const int action = iref(hdr + 1), kdrop = iref(hdr + 2);
+    if (action == MDS_QP_ACT_STOP) { status = iref(hdr + 3); break; }
+    const Real t = hdr[0];
+    // ---- own block of z = g_p - Na' r and the primal step (skipped for a pure dual step)
+    if (!(t < Real(0)) && valid) {
+      Real zk[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) zk[k] = qp_coef(cp, n, k);
       for (int a = 0; a < q; ++a) {
-        QpCon<Real> ca = qp_get(rows, C, act[a], N, n_pairs, n_rows, n_obs);
-        for (int c = 0; c < 3; ++c) {
-          z[4 * ca.i + c] -= r[a] * ca.gi[c];
-          if (ca.j >= 0) z[4 * ca.j + c] += r[a] * ca.gi[c];
-        }
+        QpCon<Real> ca = qp_get(rows, C, iref(ws + a), n_rows);
+        Real ra = rv[a];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) zk[k] -= ra * qp_coef(ca, n, k);
       }
-      Real mag, zn = qp_dot_x(cp, z, &mag);
-      // ---- step lengths
-      Real t1 = INF;
-      int kdrop = -1;
-      for (int a = 0; a < q; ++a)
-        if (r[a] > tol) {
-          Real cnd = lam[a] / r[a];
-          if (cnd < t1) { t1 = cnd; kdrop = a; }
-        }
-      Real gx = qp_dot_x(cp, x, &mag);
-      Real s_p = cp.rhs - gx;
-      Real t2 = (zn > Real(sizeof(Real) == 4 ? 1e-5 : 1e-10) * g2p) ? -s_p / zn : INF;
-      Real t = min_(t1, t2);
-      if (t >= INF) { *iters_out = iters; return MDS_QP_INFEASIBLE; }
-      if (t2 < INF)
-        for (int k = 0; k < 4 * N; ++k) x[k] -= t * z[k];
-      for (int a = 0; a < q; ++a) lam[a] -= t * r[a];
-      lam_p += t;
-      if (t2 <= t1) {
-        if (q == MDS_QP_QMAX) { *iters_out = iters; return MDS_QP_ITER_CAP; }
-        act[q] = p; lam[q] = lam_p; ++q;
-        break;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) xn[k] -= t * zk[k];
+      x[4 * n] = xn[0]; x[4 * n + 1] = xn[1]; x[4 * n + 2] = xn[2];
+    }
+    const int pd = (action == MDS_QP_ACT_DROP) ? iref(ws + kdrop) : -1;
+    __syncwarp(gmask);  // x updated; every lane has consumed act / r of this iteration
+    if (action == MDS_QP_ACT_FULL) {  // constraint p becomes active: append its row to the Cholesky factor
+      if (n == 0) {
+        Real dd = Real(0);
+        for (int k = 0; k < q; ++k) { Real v = dv[k]; Lc[q * (q + 1) / 2 + k] = v; dd += v * v; }
+        Lc[q * (q + 1) / 2 + q] = sqrt_(cp.g2 - dd);
+        iref(ws + q) = p;
+        lam[q] = lam_p;
+        if (p < n_rows) rows[MDS_ROW_W * p + 5] = int_as_real(real_as_int(rows[MDS_ROW_W * p + 5]) | 0x10000, Real(0));
       }
-      for (int a = kdrop; a < q - 1; ++a) { act[a] = act[a + 1]; lam[a] = lam[a + 1]; }
+      if (p >= n_rows && valid && (p - n_rows) / 6 == n) boxmask |= 1u << ((p - n_rows) - 6 * n);
+      ++q;
+      need_scan = true;
+    } else {  // partial step: drop constraint kdrop, rebuild the (small) factor, keep working on p
+      if (pd >= n_rows && valid && (pd - n_rows) / 6 == n) boxmask &= ~(1u << ((pd - n_rows) - 6 * n));
       --q;
+      need_scan = false;
+      if (n == 0) {
+        if (pd < n_rows) rows[MDS_ROW_W * pd + 5] = int_as_real(real_as_int(rows[MDS_ROW_W * pd + 5]) & ~0x10000, Real(0));
+        for (int a = kdrop; a < q; ++a) { iref(ws + a) = iref(ws + a + 1); lam[a] = lam[a + 1]; }
+        int st = MDS_QP_OPTIMAL;
+        for (int a = 0; a < q; ++a) {
+          QpCon<Real> ca = qp_get(rows, C, iref(ws + a), n_rows);
+          for (int b2 = 0; b2 <= a; ++b2) {
+            QpCon<Real> cb = qp_get(rows, C, iref(ws + b2), n_rows);
+            Real sacc = qp_dot_g(ca, cb);
+            for (int k = 0; k < b2; ++k) sacc -= Lc[a * (a + 1) / 2 + k] * Lc[b2 * (b2 + 1) / 2 + k];
+            if (a == b2) {
+              if (sacc <= Real(0)) { st = MDS_QP_ITER_CAP; sacc = Real(1); }
+              Lc[a * (a + 1) / 2 + a] = sqrt_(sacc);
+            } else {
+              Lc[a * (a + 1) / 2 + b2] = sacc / Lc[b2 * (b2 + 1) / 2 + b2];
+            }
+          }
+        }
+        iref(hdr + 3) = st;
+      }
+    }
+    __syncwarp(gmask);
+    if (action == MDS_QP_ACT_DROP && iref(hdr + 3) != MDS_QP_OPTIMAL) { status = iref(hdr + 3); break; }
+  }
+  __syncwarp(gmask);
+  if (status == MDS_QP_OPTIMAL && q > 0) {
+    // certify: rows held active must still be satisfied (guards breakdown on nearly dependent active sets)
+    const Real ctol = sizeof(Real) == 4 ? Real(1e-3) : Real(1e-7);
+    for (int a = 0; a < q; ++a) {
+      QpCon<Real> ca = qp_get(rows, C, iref(ws + a), n_rows);
+      Real mag, gx = qp_dot_x(ca, x, &mag);
+      if (ca.rhs - gx < -ctol * (abs_(ca.rhs) + mag + Real(1e-12))) status = MDS_QP_ITER_CAP;
     }
   }
+  *iters_out = iters;
+  return status;
 }
 
 // decoupled 4th input (wz): box +-umax[3] merged with the order-3 force-bound rows, which the

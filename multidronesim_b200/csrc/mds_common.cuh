@@ -67,7 +67,22 @@ MDS_DEV float rsqrt_(float x) { return rsqrtf(x); }
 MDS_DEV double rsqrt_(double x) { return 1.0 / sqrt(x); }
 MDS_DEV float sqrt_(float x) { return sqrtf(x); }
 MDS_DEV double sqrt_(double x) { return sqrt(x); }
-MDS_DEV void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+// fp32 sincos for the bounded arguments of this path (|x| < ~1e4): Cody-Waite reduction by pi/2 and
+// minimax polynomials on [-pi/4, pi/4] (max error ~1 ulp).  libdevice's sincosf drags a Payne-Hanek slow
+// path (local array, ~200 instructions) into every call site, which the fused kernels pay in I-cache.
+MDS_DEV void sincos_(float x, float* s, float* c) {
+  float j = rintf(x * 0.636619772367581343f);
+  int q = (int)j;
+  float r = fmaf(j, -1.5703125f, x);
+  r = fmaf(j, -4.837512969970703125e-4f, r);
+  r = fmaf(j, -7.54978995489188216e-8f, r);
+  float r2 = r * r;
+  float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+  float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2, fmaf(-0.5f, r2, 1.0f));
+  float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
+}
 MDS_DEV void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
 MDS_DEV float atan2_(float y, float x) { return atan2f(y, x); }
 MDS_DEV double atan2_(double y, double x) { return atan2(y, x); }

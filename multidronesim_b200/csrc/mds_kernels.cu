@@ -31,187 +31,191 @@ static int check_launch(const char* what) {
 #define MDS_REQUIRE(cond, msg) \
   if (!(cond)) return fail(MDS_ERR_ARG, "%s", msg)
 
-static inline int envs_per_block(int N) { int e = 256 / N; return e < 1 ? 1 : e; }
+// ------------------------------------------------------------------ thread mapping
+// An environment's drones occupy NP = next_pow2(N) consecutive lanes of ONE warp ("lane group"; lanes
+// n >= N idle), so every cross-drone exchange (downwash neighbours, CBF rows, the QP) needs only
+// group-level synchronisation: shared memory + __syncwarp(gmask) / shuffles.  No block barriers.
+#define MDS_BLOCK 256
+static inline int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+struct GroupMap {
+  int el, n, e, d;   // env slot in block, drone in env, global env, global drone
+  bool valid;        // lane maps to a real drone
+  bool env_valid;    // group maps to a real env
+  unsigned gmask;    // lanes of this group within the warp
+};
+MDS_DEV GroupMap group_map(int N, int NP, int E) {
+  GroupMap g;
+  const int tid = threadIdx.x, epb = MDS_BLOCK / NP;
+  g.el = tid / NP;
+  g.n = tid - g.el * NP;
+  g.e = blockIdx.x * epb + g.el;
+  g.env_valid = g.e < E;
+  g.valid = g.env_valid && g.n < N;
+  g.d = g.e * N + g.n;
+  const int lane0 = (tid & 31) & ~(NP - 1);
+  g.gmask = NP >= 32 ? 0xffffffffu : (((1u << NP) - 1u) << lane0);
+  return g;
+}
 
-// ------------------------------------------------------------------ block-cooperative pieces
-// Downwash sum for this thread's drone over its env mates, positions staged in smem.
-// All threads of the block must call (two barriers).
+// Downwash sum for this lane's drone over its env mates; positions staged in shared memory.
+// Called by every lane of the group (two group syncs).
 template <typename Real>
-MDS_DEV Real downwash_block(const DroneP<Real>& P, typename Vec4T<Real>::type* sm_pos, V3<Real> p, int n, int N, bool valid) {
+MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* sm_pos, V3<Real> p, const GroupMap& g, int N) {
   typename Vec4T<Real>::type me;
   me.x = p.x; me.y = p.y; me.z = p.z; me.w = Real(0);
   sm_pos[threadIdx.x] = me;
-  __syncthreads();
+  __syncwarp(g.gmask);
   Real dw = Real(0);
-  if (valid) {
-    int base = threadIdx.x - n;
+  if (g.valid) {
+    const int base = threadIdx.x - g.n;
     for (int j = 0; j < N; ++j) {
-      if (j == n) continue;
+      if (j == g.n) continue;
       auto q = sm_pos[base + j];
       dw += downwash_term(P, p, v3(q.x, q.y, q.z));
     }
   }
-  __syncthreads();
+  __syncwarp(g.gmask);
   return dw;
 }
 
-// shared-memory carve-up for the CBF stage (per block)
+// per-env shared-memory block of the CBF stage (Real words):
+//   [0, max(9N, WS)) agents (p, dv, da per drone) -- overlaid by the QP workspace once the rows exist
+//   rows  n_rows * MDS_ROW_W  |  x 4N  |  2 ints (status, iters)
 template <typename Real> struct CbfSmem {
-  int* qcount;   // [1]
-  int* flag;     // [epb]  bit0: needs QP, bit1: wz interval empty (infeasible)
-  int* status;   // [epb]
-  int* iters;    // [epb]
-  int* queue;    // [epb]
-  Real* env0;    // per-env block of `stride` Reals: agents[N*9] | rows[n_rows*4] | x[4N] | z[4N]
-  int stride, off_rows, off_x, off_z;
+  Real* env0;
+  int stride, off_rows, off_x, off_st;
 };
-static inline size_t cbf_smem_ints(int epb) { return (size_t)(1 + 4 * epb + 3) & ~(size_t)3; }
 static inline int cbf_env_stride(int N, int n_obs) {
-  int s = 9 * N + 4 * (N * (N - 1) / 2 + N * n_obs) + 8 * N;
-  return s | 1;  // odd stride: the per-env solver threads hit distinct banks
-}
-template <typename Real> static size_t cbf_smem_bytes(int epb, int N, int n_obs) {
-  return cbf_smem_ints(epb) * sizeof(int) + (size_t)epb * cbf_env_stride(N, n_obs) * sizeof(Real) + 16;
-}
-template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw, int epb, int N, int n_obs) {
-  CbfSmem<Real> s;
-  int* ip = reinterpret_cast<int*>(raw);
-  s.qcount = ip; s.flag = ip + 1; s.status = s.flag + epb; s.iters = s.status + epb; s.queue = s.iters + epb;
-  size_t ints = (size_t)(1 + 4 * epb + 3) & ~(size_t)3;
-  s.env0 = reinterpret_cast<Real*>(raw + ((ints * sizeof(int) + 15) & ~(size_t)15));
   int n_rows = N * (N - 1) / 2 + N * n_obs;
-  s.off_rows = 9 * N; s.off_x = s.off_rows + 4 * n_rows; s.off_z = s.off_x + 4 * N;
-  s.stride = (s.off_z + 4 * N) | 1;
+  int head = 9 * N > MDS_QP_WS_WORDS ? 9 * N : MDS_QP_WS_WORDS;
+  return (head + MDS_ROW_W * n_rows + 4 * N + 2) | 1;  // odd stride spreads the groups over the banks
+}
+template <typename Real> static size_t cbf_smem_bytes(int NP, int N, int n_obs) {
+  return (size_t)(MDS_BLOCK / NP) * cbf_env_stride(N, n_obs) * sizeof(Real) + 16;
+}
+template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw, int N, int n_obs) {
+  CbfSmem<Real> s;
+  s.env0 = reinterpret_cast<Real*>(raw);
+  int n_rows = N * (N - 1) / 2 + N * n_obs;
+  int head = 9 * N > MDS_QP_WS_WORDS ? 9 * N : MDS_QP_WS_WORDS;
+  s.off_rows = head; s.off_x = head + MDS_ROW_W * n_rows; s.off_st = s.off_x + 4 * N;
+  s.stride = (s.off_st + 2) | 1;
   return s;
 }
 
-// CBF safety filter for the whole block: every thread calls it (barriers inside).
-// u_nom -> u_safe for this thread's drone; per-env status/iters in smem (read via S).
+// CBF safety filter for one env by its lane group: u_nom -> u_safe for this lane's drone.
+// Every lane of a valid group calls it; returns the env's QP status, *iters_out its iteration count.
 template <typename Real>
-MDS_DEV void cbf_filter_block(const DroneP<Real>& P, const CbfP<Real>& C, const CbfSmem<Real>& S, const Real* obstacles,
-                              int n_obs, int el, int n, int N, int epb, bool valid, const CbfAgent<Real>& ag, Real F,
-                              const Real unom[4], Real usafe[4], Real* min_h) {
-  const int n_pairs = N * (N - 1) / 2, n_rows = n_pairs + N * n_obs;
-  Real* env = S.env0 + (size_t)el * S.stride;
-  if (threadIdx.x == 0) *S.qcount = 0;
-  if (valid) {
+MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const CbfSmem<Real>& S, const Real* obstacles, int n_obs,
+                             const GroupMap& g, int N, int NP, const CbfAgent<Real>& ag, Real F, const Real unom[4], Real usafe[4],
+                             Real* min_h, int* iters_out) {
+  const int n = g.n, n_pairs = N * (N - 1) / 2, n_rows = n_pairs + N * n_obs;
+  Real* env = S.env0 + (size_t)g.el * S.stride;
+  Real* rows = env + S.off_rows;
+  Real* x = env + S.off_x;
+  if (g.valid) {
     Real* a = env + 9 * n;
     a[0] = ag.p.x; a[1] = ag.p.y; a[2] = ag.p.z; a[3] = ag.dv.x; a[4] = ag.dv.y; a[5] = ag.dv.z;
     a[6] = ag.da.x; a[7] = ag.da.y; a[8] = ag.da.z;
-    Real* x = env + S.off_x + 4 * n;
-    x[0] = unom[0]; x[1] = unom[1]; x[2] = unom[2]; x[3] = unom[3];
-    if (n == 0) { S.flag[el] = 0; S.status[el] = MDS_QP_OPTIMAL; S.iters[el] = 0; }
+    x[4 * n] = unom[0]; x[4 * n + 1] = unom[1]; x[4 * n + 2] = unom[2]; x[4 * n + 3] = unom[3];
   }
-  __syncthreads();
+  __syncwarp(g.gmask);
+  const Real tol = sizeof(Real) == 4 ? Real(2e-6) : Real(1e-11);
+  int fl = 0;
   Real lo = Real(0), hi = Real(0);
-  if (valid) {
-    const Real tol = sizeof(Real) == 4 ? Real(2e-6) : Real(1e-11);
-    int fl = 0;
-    const Real* x = env + S.off_x;
-    for (int r = n; r < n_rows; r += N) {
-      int i, j;
-      CbfAgent<Real> ai, aj;
-      Real Ds;
-      if (r < n_pairs) {
-        pair_from_index(r, N, &i, &j);
-        const Real* b = env + 9 * j;
-        aj.p = {b[0], b[1], b[2]}; aj.dv = {b[3], b[4], b[5]}; aj.da = {b[6], b[7], b[8]};
-        Ds = Real(2) * C.rs;
-      } else {
-        i = (r - n_pairs) / n_obs;
-        int o = (r - n_pairs) - i * n_obs;
-        j = -1;
-        aj.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
-        aj.dv = {Real(0), Real(0), Real(0)}; aj.da = aj.dv;
-        Ds = C.rs + obstacles[4 * o + 3];
-      }
-      const Real* a = env + 9 * i;
-      ai.p = {a[0], a[1], a[2]}; ai.dv = {a[3], a[4], a[5]}; ai.da = {a[6], a[7], a[8]};
-      Real a3[3], rhs, h0;
-      cbf_row(P, C, ai, aj, Ds, a3, &rhs, &h0);
-      *min_h = min_(*min_h, h0);
-      Real* row = env + S.off_rows + 4 * r;
-      row[0] = a3[0]; row[1] = a3[1]; row[2] = a3[2]; row[3] = rhs;
-      // does u_nom violate this row?   G u = -a.u_i (+ a.u_j)
-      const Real* xi = x + 4 * i;
-      Real t0 = a3[0] * xi[0], t1 = a3[1] * xi[1], t2 = a3[2] * xi[2];
-      Real gx = -(t0 + t1 + t2), mag = abs_(t0) + abs_(t1) + abs_(t2);
-      if (j >= 0) {
-        const Real* xj = x + 4 * j;
-        Real u0 = a3[0] * xj[0], u1 = a3[1] * xj[1], u2 = a3[2] * xj[2];
-        gx += u0 + u1 + u2;
-        mag += abs_(u0) + abs_(u1) + abs_(u2);
-      }
-      if (rhs - gx < -tol * (abs_(rhs) + mag + Real(1e-12))) fl |= 1;
+  for (int r = n; r < n_rows; r += NP) {  // barrier rows strided over the group
+    int i, j;
+    CbfAgent<Real> ai, aj;
+    Real Ds;
+    if (r < n_pairs) {
+      pair_from_index(r, N, &i, &j);
+      const Real* b = env + 9 * j;
+      aj.p = {b[0], b[1], b[2]}; aj.dv = {b[3], b[4], b[5]}; aj.da = {b[6], b[7], b[8]};
+      Ds = Real(2) * C.rs;
+    } else {
+      i = (r - n_pairs) / n_obs;
+      int o = (r - n_pairs) - i * n_obs;
+      j = -1;
+      aj.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
+      aj.dv = {Real(0), Real(0), Real(0)}; aj.da = aj.dv;
+      Ds = C.rs + obstacles[4 * o + 3];
     }
+    const Real* a = env + 9 * i;
+    ai.p = {a[0], a[1], a[2]}; ai.dv = {a[3], a[4], a[5]}; ai.da = {a[6], a[7], a[8]};
+    Real a3[3], rhs, h0;
+    cbf_row(P, C, ai, aj, Ds, a3, &rhs, &h0);
+    *min_h = min_(*min_h, h0);
+    Real* row = rows + MDS_ROW_W * r;
+    Real g2 = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2];
+    row[0] = a3[0]; row[1] = a3[1]; row[2] = a3[2]; row[3] = rhs; row[4] = j >= 0 ? Real(2) * g2 : g2;
+    row[5] = int_as_real(i | ((j >= 0 ? j : 0xff) << 8), Real(0));
+    // does u_nom violate this row?   G u = -a.u_i (+ a.u_j)
+    const Real* xi = x + 4 * i;
+    Real t0 = a3[0] * xi[0], t1 = a3[1] * xi[1], t2 = a3[2] * xi[2];
+    Real gx = -(t0 + t1 + t2), mag = abs_(t0) + abs_(t1) + abs_(t2);
+    if (j >= 0) {
+      const Real* xj = x + 4 * j;
+      Real u0 = a3[0] * xj[0], u1 = a3[1] * xj[1], u2 = a3[2] * xj[2];
+      gx += u0 + u1 + u2;
+      mag += abs_(u0) + abs_(u1) + abs_(u2);
+    }
+    if (rhs - gx < -tol * (abs_(rhs) + mag + Real(1e-12))) fl |= 1;
+  }
+  if (g.valid) {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
       if (abs_(unom[c]) > C.umax[c] * (Real(1) + tol)) fl |= 1;
     if (!cbf_wz_bounds(C, F, &lo, &hi)) fl |= 2;
-    if (fl) atomicOr(&S.flag[el], fl);
   }
-  __syncthreads();
-  if (valid && n == 0) {
-    int fl = S.flag[el];
-    if (fl & 2) S.status[el] = MDS_QP_INFEASIBLE;
-    else if (fl & 1) S.queue[atomicAdd(S.qcount, 1)] = el;
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < *S.qcount) {  // compacted: one solver thread per env that needs it
-    int e2 = S.queue[threadIdx.x];
-    Real* env2 = S.env0 + (size_t)e2 * S.stride;
-    int it = 0;
-    int st = qp_solve(C, env2 + S.off_rows, env2 + S.off_x, env2 + S.off_z, N, n_pairs, n_rows, n_obs, &it);
-    S.status[e2] = st;
-    S.iters[e2] = it;
-  }
-  __syncthreads();
-  if (valid) {
-    if (S.status[el] == MDS_QP_OPTIMAL) {
-      const Real* x = env + S.off_x + 4 * n;
-      usafe[0] = x[0]; usafe[1] = x[1]; usafe[2] = x[2];
+  for (int off = NP >> 1; off > 0; off >>= 1) fl |= __shfl_xor_sync(g.gmask, fl, off);
+  __syncwarp(g.gmask);  // rows complete; agents no longer needed (their storage becomes the QP workspace)
+  int status = MDS_QP_OPTIMAL, iters = 0;
+  if (fl & 2) status = MDS_QP_INFEASIBLE;
+  else if (fl & 1) status = qp_solve_group(C, rows, x, env, N, NP, n_rows, n, g.valid, g.gmask, &iters);
+  if (g.valid) {
+    if (status == MDS_QP_OPTIMAL) {
+      usafe[0] = x[4 * n]; usafe[1] = x[4 * n + 1]; usafe[2] = x[4 * n + 2];
       usafe[3] = clamp_(unom[3], lo, hi);
     } else {  // reference falls back to the nominal input (cbf/qptracker.py:30-34)
       usafe[0] = unom[0]; usafe[1] = unom[1]; usafe[2] = unom[2]; usafe[3] = unom[3];
     }
   }
+  __syncwarp(g.gmask);  // the env block may be reused by the next step
+  *iters_out = iters;
+  return status;
 }
 
 // ------------------------------------------------------------------ kernels: env step
 template <typename Real>
-__global__ void __launch_bounds__(256) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
-                                                            const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N, int epb) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  auto* sm_pos = reinterpret_cast<typename Vec4T<Real>::type*>(smem_raw);
-  const int el = threadIdx.x / N, n = threadIdx.x - el * N;
-  const int e = blockIdx.x * epb + el;
-  const bool valid = (el < epb) && (e < E);
-  const int d = e * N + n;
+__global__ void __launch_bounds__(MDS_BLOCK) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
+                                                                  const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N, int NP) {
+  __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
+  const GroupMap g = group_map(N, NP, E);
+  if (!g.env_valid) return;  // whole groups leave together
   Drone<Real> s;
+  s.p = {Real(0), Real(0), Real(0)};
   Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
   V3<Real> fx = {Real(0), Real(0), Real(0)}, av = {Real(0), Real(0), Real(0)};
-  if (valid) {
-    s = load_drone(st, d);
-    auto a = reinterpret_cast<const typename Vec4T<Real>::type*>(action)[d];
+  if (g.valid) {
+    s = load_drone(st, g.d);
+    auto a = reinterpret_cast<const typename Vec4T<Real>::type*>(action)[g.d];
     rpm[0] = clamp_(a.x, Real(0), P.max_rpm); rpm[1] = clamp_(a.y, Real(0), P.max_rpm);
     rpm[2] = clamp_(a.z, Real(0), P.max_rpm); rpm[3] = clamp_(a.w, Real(0), P.max_rpm);
-    if (fext) fx = {fext[3 * d], fext[3 * d + 1], fext[3 * d + 2]};
-  } else {
-    s.p = {Real(0), Real(0), Real(0)};
+    if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
   }
   const bool dwash = (P.physics == MDS_PHYSICS_DYN_GND_DRAG_DW) && (N > 1);
   for (int k = 0; k < P.substeps; ++k) {
     Real dw = Real(0);
-    if (dwash) dw = downwash_block(P, sm_pos, s.p, n, N, valid);
-    if (valid) {
+    if (dwash) dw = downwash_group(P, sm_pos, s.p, g, N);
+    if (g.valid) {
       av = physics_substep(P, s, rpm, dw, fx);
 #pragma unroll
       for (int i = 0; i < 4; ++i) s.rpm[i] = rpm[i];
     }
   }
-  if (valid) {
-    store_drone(st, d, s);
-    if (obs) store_obs(obs, d, make_obs(s, av));
+  if (g.valid) {
+    store_drone(st, g.d, s);
+    if (obs) store_obs(obs, g.d, make_obs(s, av));
   }
 }
 
@@ -299,34 +303,33 @@ __global__ void lowlevel_kernel(DroneP<Real> P, int variant, const Real* __restr
 
 // ------------------------------------------------------------------ kernels: CBF
 template <typename Real>
-__global__ void __launch_bounds__(256) cbf_qp_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __restrict__ obs, const Real* __restrict__ xdes,
-                                                      const Real* __restrict__ unom_g, const Real* __restrict__ obstacles, int n_obs,
-                                                      Real* __restrict__ usafe_g, int* __restrict__ status, int* __restrict__ iters,
-                                                      int E, int N, int epb) {
+__global__ void __launch_bounds__(MDS_BLOCK) cbf_qp_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __restrict__ obs, const Real* __restrict__ xdes,
+                                                            const Real* __restrict__ unom_g, const Real* __restrict__ obstacles, int n_obs,
+                                                            Real* __restrict__ usafe_g, int* __restrict__ status, int* __restrict__ iters,
+                                                            int E, int N, int NP) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, epb, N, n_obs);
-  const int el = threadIdx.x / N, n = threadIdx.x - el * N;
-  const int e = blockIdx.x * epb + el;
-  const bool valid = (el < epb) && (e < E);
-  const int d = e * N + n;
+  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, N, n_obs);
+  const GroupMap g = group_map(N, NP, E);
+  if (!g.env_valid) return;
   const int xdim = C.order == 2 ? 9 : 10;
   CbfAgent<Real> ag;
   ag.p = {Real(0), Real(0), Real(0)}; ag.dv = ag.p; ag.da = ag.p;
   Real F = Real(0), unom[4] = {Real(0), Real(0), Real(0), Real(0)}, usafe[4];
-  if (valid) {
-    Obs<Real> o = load_obs(obs, d);
+  if (g.valid) {
+    Obs<Real> o = load_obs(obs, g.d);
     Real xd[10];
-    for (int k = 0; k < xdim; ++k) xd[k] = xdes[(size_t)d * xdim + k];
+    for (int k = 0; k < xdim; ++k) xd[k] = xdes[(size_t)g.d * xdim + k];
     ag = cbf_agent(P, C, o, xd, &F);
-    load4(unom_g, d, unom);
+    load4(unom_g, g.d, unom);
   }
   Real min_h = Real(1e30);
-  cbf_filter_block(P, C, S, obstacles, n_obs, el, n, N, epb, valid, ag, F, unom, usafe, &min_h);
-  if (valid) {
-    store4(usafe_g, d, usafe);
-    if (n == 0) {
-      status[e] = S.status[el];
-      if (iters) iters[e] = S.iters[el];
+  int it = 0;
+  int st = cbf_filter_group(P, C, S, obstacles, n_obs, g, N, NP, ag, F, unom, usafe, &min_h, &it);
+  if (g.valid) {
+    store4(usafe_g, g.d, usafe);
+    if (g.n == 0) {
+      status[g.e] = st;
+      if (iters) iters[g.e] = it;
     }
   }
 }
@@ -467,135 +470,106 @@ MDS_DEV void atomic_max_double(double* addr, double v) {
   } while (assumed != old);
 }
 
-template <typename Real>
-__global__ void __launch_bounds__(256) rollout_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
-                                                       StateP<Real> st, PidP<Real> pid,
-                                                       const typename TrajSpecT<Real>::spec* __restrict__ specs,
-                                                       const typename TrajSpecT<Real>::seg* __restrict__ segs, Real* __restrict__ obs,
-                                                       Real* __restrict__ obs_log, double* __restrict__ stats, double t0, int K, int E, int N, int epb) {
+// One control step of the controller stack for every drone: reference -> tracking controller ->
+// (CBF-QP) -> inner loop -> RPM action.  CTRL / USE_CBF are compile-time so that each instantiation
+// carries only its own stage code (the whole K-step loop in one kernel overflowed the instruction
+// cache: 55 % of the stall samples were "no instruction"; profiles/r1_rollout_fused_ncu.txt).
+template <typename Real, int CTRL, bool USE_CBF>
+__global__ void __launch_bounds__(MDS_BLOCK) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+                                                               PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
+                                                               const typename TrajSpecT<Real>::seg* __restrict__ segs,
+                                                               const Real* __restrict__ obs, Real* __restrict__ action,
+                                                               double* __restrict__ stats, double t, int E, int N, int NP) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  auto* sm_pos = reinterpret_cast<typename Vec4T<Real>::type*>(smem_raw);
-  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw + 256 * sizeof(typename Vec4T<Real>::type), epb, N, Rc.n_obs);
-  const int el = threadIdx.x / N, n = threadIdx.x - el * N;
-  const int e = blockIdx.x * epb + el;
-  const bool valid = (el < epb) && (e < E);
-  const int d = e * N + n;
-  const size_t Dtot = (size_t)E * N;
-
-  Drone<Real> s;
-  s.p = {Real(0), Real(0), Real(0)};
-  Pid<Real> ps;
-  typename TrajSpecT<Real>::spec sp;
-  V3<Real> av = {Real(0), Real(0), Real(0)};
-  const bool has_pid = (Rc.ctrl == MDS_CTRL_LQR_OMEGA || Rc.ctrl == MDS_CTRL_LQR_YANK);
-  if (valid) {
-    s = load_drone(st, d);
-    sp = specs[d];
-    if (has_pid) ps = load_pid(pid, d);
-    const Real* o = obs + (size_t)d * MDS_OBS_DIM;
-    av = {o[13], o[14], o[15]};
-  }
-  const bool dwash = (P.physics == MDS_PHYSICS_DYN_GND_DRAG_DW) && (N > 1);
-  double sum_err = 0.0, max_err = 0.0, min_h = 1e30;
+  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, N, Rc.n_obs);
+  const GroupMap g = group_map(N, NP, E);
+  constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
+  double err = 0.0, min_h = 1e30;
   int qp_solves = 0, qp_iters = 0, qp_infeas = 0, qp_cap = 0;
-
-  for (int k = 0; k < K; ++k) {
-    const double t = t0 + (double)k * (double)P.dt_ctrl;
+  if (g.env_valid) {
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
+    Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
     Ref<Real> ref;
     Obs<Real> o;
-    Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
-    if (valid) {
-      ref = eval_traj<Real>(sp, segs, t);
-      o = make_obs(s, av);
-      double ex = (double)(s.p.x - ref.p.x), ey = (double)(s.p.y - ref.p.y), ez = (double)(s.p.z - ref.p.z);
-      double er = sqrt(ex * ex + ey * ey + ez * ez);
-      sum_err += er;
-      max_err = er > max_err ? er : max_err;
-      if (Rc.ctrl == MDS_CTRL_GEOMETRIC) {
+    if (g.valid) {
+      ref = eval_traj<Real>(specs[g.d], segs, t);
+      o = load_obs(obs, g.d);
+      double ex = (double)(o.p.x - ref.p.x), ey = (double)(o.p.y - ref.p.y), ez = (double)(o.p.z - ref.p.z);
+      err = sqrt(ex * ex + ey * ey + ez * ez);
+      if (CTRL == MDS_CTRL_GEOMETRIC) {
         geometric_input(P, G, o, ref, u);
         input_to_action(P, u, rpm);
       } else {
-        lqr_input(P, L, Rc.ctrl, o, ref, u);
-        if (Rc.ctrl == MDS_CTRL_LQR_TORQUE) input_to_action(P, u, rpm);
+        lqr_input(P, L, CTRL, o, ref, u);
+        if (CTRL == MDS_CTRL_LQR_TORQUE) input_to_action(P, u, rpm);
       }
     }
-    if (has_pid) {
-      if (Rc.use_cbf) {  // block-uniform branch: barriers inside
+    if (HAS_PID) {
+      if (USE_CBF) {
         CbfAgent<Real> ag;
         ag.p = {Real(0), Real(0), Real(0)}; ag.dv = ag.p; ag.da = ag.p;
         Real F = Real(0), unom[4] = {Real(0), Real(0), Real(0), Real(0)}, usafe[4] = {Real(0), Real(0), Real(0), Real(0)};
-        if (valid) {
-          if (Rc.ctrl == MDS_CTRL_LQR_OMEGA) u[0] = cap_thrust(P, u[0]);  // skip_low_level=True returns cap_u(u)
+        if (g.valid) {
+          if (CTRL == MDS_CTRL_LQR_OMEGA) u[0] = cap_thrust(P, u[0]);  // skip_low_level=True returns cap_u(u)
           Real xd[10];
           xd[0] = Real(0); xd[1] = Real(0); xd[2] = ref.yaw;
-          if (C.order == 2) { xd[3] = ref.v.x; xd[4] = ref.v.y; xd[5] = ref.v.z; }
+          if (CTRL == MDS_CTRL_LQR_OMEGA) { xd[3] = ref.v.x; xd[4] = ref.v.y; xd[5] = ref.v.z; }
           else { xd[3] = P.g * P.m; xd[4] = ref.v.x; xd[5] = ref.v.y; xd[6] = ref.v.z; }
           ag = cbf_agent(P, C, o, xd, &F);
           unom[0] = u[0] - Rc.u0_pre; unom[1] = u[1]; unom[2] = u[2]; unom[3] = u[3];
         }
         Real mh = Real(1e30);
-        cbf_filter_block(P, C, S, Rc.obstacles, Rc.n_obs, el, n, N, epb, valid, ag, F, unom, usafe, &mh);
-        if (valid) {
-          min_h = fmin(min_h, (double)mh);
-          if (n == 0) {
-            int stt = S.status[el], it = S.iters[el];
-            qp_solves += (it > 0 || stt != MDS_QP_OPTIMAL);
-            qp_iters += it;
-            qp_infeas += (stt == MDS_QP_INFEASIBLE);
-            qp_cap += (stt == MDS_QP_ITER_CAP);
+        int it = 0;
+        int stt = cbf_filter_group(P, C, S, Rc.obstacles, Rc.n_obs, g, N, NP, ag, F, unom, usafe, &mh, &it);
+        if (g.valid) {
+          min_h = (double)mh;
+          if (g.n == 0) {
+            qp_solves = (it > 0 || stt != MDS_QP_OPTIMAL);
+            qp_iters = it;
+            qp_infeas = (stt == MDS_QP_INFEASIBLE);
+            qp_cap = (stt == MDS_QP_ITER_CAP);
           }
           u[0] = usafe[0] + Rc.u0_post; u[1] = usafe[1]; u[2] = usafe[2]; u[3] = usafe[3];
         }
-        __syncthreads();  // S.status/iters are re-initialised by the next step
       }
-      if (valid) low_level(P, Rc.ctrl, ps, u, o, rpm);
-    }
-    if (valid) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rpm[i] = clamp_(rpm[i], Real(0), P.max_rpm);
-    }
-    for (int ss = 0; ss < P.substeps; ++ss) {
-      Real dw = Real(0);
-      if (dwash) dw = downwash_block(P, sm_pos, s.p, n, N, valid);
-      if (valid) {
-        av = physics_substep(P, s, rpm, dw, v3(Real(0), Real(0), Real(0)));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s.rpm[i] = rpm[i];
+      if (g.valid) {
+        Pid<Real> ps = load_pid(pid, g.d);
+        low_level(P, CTRL, ps, u, o, rpm);
+        store_pid(pid, g.d, ps);
       }
     }
-    if (valid && obs_log && Rc.write_obs_every > 0 && ((k + 1) % Rc.write_obs_every) == 0) {
-      size_t slot = (size_t)((k + 1) / Rc.write_obs_every - 1);
-      store_obs(obs_log + slot * Dtot * MDS_OBS_DIM, d, make_obs(s, av));
-    }
+    if (g.valid) store4(action, g.d, rpm);
   }
-  if (valid) {
-    store_drone(st, d, s);
-    if (has_pid) store_pid(pid, d, ps);
-    store_obs(obs, d, make_obs(s, av));
-  }
-  if (stats) {
-    // warp reduce, then one atomic per warp
-    double cnt = valid ? (double)K : 0.0, qs = qp_solves, qi = qp_iters, qf = qp_infeas, qc = qp_cap;
+  if (stats) {  // warp shuffle reduce -> shared memory -> ONE set of atomics per block (same-address atomics
+                // from every warp cost more than the whole step: 1.6 ms vs 0.4 ms per step at 1M drones)
+    __shared__ double sm_stats[MDS_BLOCK / 32][MDS_STAT_COUNT];
+    double v[MDS_STAT_COUNT];
+    v[MDS_STAT_DRONE_STEPS] = g.valid ? 1.0 : 0.0; v[MDS_STAT_SUM_POS_ERR] = err; v[MDS_STAT_MAX_POS_ERR] = err;
+    v[MDS_STAT_MIN_BARRIER] = min_h; v[MDS_STAT_QP_SOLVES] = qp_solves; v[MDS_STAT_QP_ITERS] = qp_iters;
+    v[MDS_STAT_QP_INFEASIBLE] = qp_infeas; v[MDS_STAT_QP_ITER_CAP] = qp_cap;
+    __syncwarp();
     for (int off = 16; off > 0; off >>= 1) {
-      cnt += __shfl_down_sync(0xffffffffu, cnt, off);
-      sum_err += __shfl_down_sync(0xffffffffu, sum_err, off);
-      max_err = fmax(max_err, __shfl_down_sync(0xffffffffu, max_err, off));
-      min_h = fmin(min_h, __shfl_down_sync(0xffffffffu, min_h, off));
-      qs += __shfl_down_sync(0xffffffffu, qs, off);
-      qi += __shfl_down_sync(0xffffffffu, qi, off);
-      qf += __shfl_down_sync(0xffffffffu, qf, off);
-      qc += __shfl_down_sync(0xffffffffu, qc, off);
+#pragma unroll
+      for (int k = 0; k < MDS_STAT_COUNT; ++k) {
+        double o2 = __shfl_down_sync(0xffffffffu, v[k], off);
+        v[k] = (k == MDS_STAT_MAX_POS_ERR) ? fmax(v[k], o2) : ((k == MDS_STAT_MIN_BARRIER) ? fmin(v[k], o2) : v[k] + o2);
+      }
     }
     if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&stats[MDS_STAT_DRONE_STEPS], cnt);
-      atomicAdd(&stats[MDS_STAT_SUM_POS_ERR], sum_err);
-      atomic_max_double(&stats[MDS_STAT_MAX_POS_ERR], max_err);
-      atomic_min_double(&stats[MDS_STAT_MIN_BARRIER], min_h);
-      if (qs > 0) atomicAdd(&stats[MDS_STAT_QP_SOLVES], qs);
-      if (qi > 0) atomicAdd(&stats[MDS_STAT_QP_ITERS], qi);
-      if (qf > 0) atomicAdd(&stats[MDS_STAT_QP_INFEASIBLE], qf);
-      if (qc > 0) atomicAdd(&stats[MDS_STAT_QP_ITER_CAP], qc);
+#pragma unroll
+      for (int k = 0; k < MDS_STAT_COUNT; ++k) sm_stats[threadIdx.x >> 5][k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < MDS_STAT_COUNT) {
+      const int k = threadIdx.x;
+      double acc = sm_stats[0][k];
+      for (int w = 1; w < MDS_BLOCK / 32; ++w) {
+        double o2 = sm_stats[w][k];
+        acc = (k == MDS_STAT_MAX_POS_ERR) ? fmax(acc, o2) : ((k == MDS_STAT_MIN_BARRIER) ? fmin(acc, o2) : acc + o2);
+      }
+      if (k == MDS_STAT_MAX_POS_ERR) atomic_max_double(&stats[k], acc);
+      else if (k == MDS_STAT_MIN_BARRIER) { if (USE_CBF) atomic_min_double(&stats[k], acc); }
+      else if (acc != 0.0) atomicAdd(&stats[k], acc);
     }
   }
 }
@@ -619,9 +593,8 @@ static int physics_step_impl(const MdsDroneParams* prm, MdsState st, const Real*
   MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV, "physics_step: bad E or N");
   MDS_REQUIRE(prm->substeps >= 1, "physics_step: substeps must be >= 1");
   MDS_REQUIRE(prm->physics == MDS_PHYSICS_DYN || prm->physics == MDS_PHYSICS_DYN_GND_DRAG_DW, "physics_step: unknown physics mode");
-  int epb = envs_per_block(N), threads = epb * N, blocks = (E + epb - 1) / epb;
-  size_t smem = 256 * sizeof(typename Vec4T<Real>::type);
-  physics_step_kernel<Real><<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(st), action, fext, obs, E, N, epb);
+  int NP = next_pow2(N), epb = MDS_BLOCK / NP, blocks = (E + epb - 1) / epb;
+  physics_step_kernel<Real><<<blocks, MDS_BLOCK, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(st), action, fext, obs, E, N, NP);
   return check_launch("physics_step");
 }
 template <typename Real> static int obs_from_state_impl(const MdsDroneParams* prm, MdsState st, Real* obs, int D, void* stream) {
@@ -675,12 +648,12 @@ static int cbf_qp_impl(const MdsDroneParams* prm, const MdsCbfParams* c, const R
   if (rc) return rc;
   MDS_REQUIRE(prm && obs && xdes && unom && usafe && status && E > 0, "cbf_qp: bad argument");
   MDS_REQUIRE(n_obs == 0 || obstacles, "cbf_qp: obstacles pointer is null");
-  int epb = envs_per_block(N), threads = epb * N, blocks = (E + epb - 1) / epb;
-  size_t smem = cbf_smem_bytes<Real>(epb, N, n_obs);
+  int NP = next_pow2(N), epb = MDS_BLOCK / NP, blocks = (E + epb - 1) / epb;
+  size_t smem = cbf_smem_bytes<Real>(NP, N, n_obs);
   cudaError_t e = cudaFuncSetAttribute(cbf_qp_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "cbf_qp: shared memory opt-in failed: %s", cudaGetErrorString(e));
-  cbf_qp_kernel<Real><<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*c), obs, xdes, unom, obstacles, n_obs, usafe,
-                                                                        status, iters, E, N, epb);
+  cbf_qp_kernel<Real><<<blocks, MDS_BLOCK, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*c), obs, xdes, unom, obstacles, n_obs, usafe,
+                                                                          status, iters, E, N, NP);
   return check_launch("cbf_qp");
 }
 template <typename Real>
@@ -714,8 +687,8 @@ static int xdot_nonlinear_impl(const MdsDroneParams* prm, double jx, double jy, 
 template <typename Real>
 static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr, const MdsCbfParams* cbf,
                         MdsState st, MdsPidState pid, const typename TrajSpecT<Real>::spec* specs, const typename TrajSpecT<Real>::seg* segs,
-                        Real* obs, Real* obs_log, double* stats, double t0, int K, int E, int N, void* stream) {
-  MDS_REQUIRE(prm && cfg && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && specs && obs, "rollout: null pointer");
+                        Real* obs, Real* action, Real* obs_log, double* stats, double t0, int K, int E, int N, void* stream) {
+  MDS_REQUIRE(prm && cfg && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && specs && obs && action, "rollout: null pointer");
   MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV && K > 0, "rollout: bad E, N or K");
   MDS_REQUIRE(cfg->ctrl >= MDS_CTRL_GEOMETRIC && cfg->ctrl <= MDS_CTRL_LQR_YANK, "rollout: unknown controller");
   RolloutP<Real> R;
@@ -751,12 +724,48 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     R.n_obs = 0;
   }
   MDS_REQUIRE(!(cfg->write_obs_every > 0) || obs_log, "rollout: obs_log buffer missing");
-  int epb = envs_per_block(N), threads = epb * N, blocks = (E + epb - 1) / epb;
-  size_t smem = 256 * sizeof(typename Vec4T<Real>::type) + cbf_smem_bytes<Real>(epb, N, R.n_obs);
-  cudaError_t e = cudaFuncSetAttribute(rollout_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: shared memory opt-in failed: %s", cudaGetErrorString(e));
-  rollout_kernel<Real><<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), R, G, L, C, to_dev<Real>(st), to_dev<Real>(pid), specs, segs,
-                                                                         obs, obs_log, stats, t0, K, E, N, epb);
+  int NP = next_pow2(N), epb = MDS_BLOCK / NP, blocks = (E + epb - 1) / epb;
+  size_t smem = R.use_cbf ? cbf_smem_bytes<Real>(NP, N, R.n_obs) : 16;
+  cudaStream_t cs = (cudaStream_t)stream;
+  const DroneP<Real> Pd = to_dev<Real>(*prm);
+  const StateP<Real> Sd = to_dev<Real>(st);
+  const PidP<Real> Pi = to_dev<Real>(pid);
+  const size_t obs_elems = (size_t)E * N * MDS_OBS_DIM;
+#define MDS_CTRL_STEP(CT, CB)                                                                                                       \
+  do {                                                                                                                              \
+    auto kern = ctrl_step_kernel<Real, CT, CB>;                                                                                     \
+    if (k == 0) {                                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
+      if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: shared memory opt-in failed: %s", cudaGetErrorString(e));         \
+    }                                                                                                                               \
+    kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Pi, specs, segs, obs_in, action, stats, t, E, N, NP);                     \
+  } while (0)
+  const Real* obs_in = obs;
+  for (int k = 0; k < K; ++k) {
+    const double t = t0 + (double)k * prm->dt_ctrl;
+    switch (R.ctrl) {
+      case MDS_CTRL_GEOMETRIC: MDS_CTRL_STEP(MDS_CTRL_GEOMETRIC, false); break;
+      case MDS_CTRL_LQR_TORQUE: MDS_CTRL_STEP(MDS_CTRL_LQR_TORQUE, false); break;
+      case MDS_CTRL_LQR_OMEGA:
+        if (R.use_cbf) MDS_CTRL_STEP(MDS_CTRL_LQR_OMEGA, true);
+        else MDS_CTRL_STEP(MDS_CTRL_LQR_OMEGA, false);
+        break;
+      default:
+        if (R.use_cbf) MDS_CTRL_STEP(MDS_CTRL_LQR_YANK, true);
+        else MDS_CTRL_STEP(MDS_CTRL_LQR_YANK, false);
+        break;
+    }
+    // the observation after this step goes to its log slot when one is due, else to the env's obs buffer
+    Real* obs_out = obs;
+    if (R.write_obs_every > 0 && ((k + 1) % R.write_obs_every) == 0) obs_out = obs_log + (size_t)((k + 1) / R.write_obs_every - 1) * obs_elems;
+    physics_step_kernel<Real><<<blocks, MDS_BLOCK, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
+    obs_in = obs_out;
+  }
+#undef MDS_CTRL_STEP
+  if (obs_in != obs) {
+    cudaError_t e = cudaMemcpyAsync(obs, obs_in, obs_elems * sizeof(Real), cudaMemcpyDeviceToDevice, cs);
+    if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: %s", cudaGetErrorString(e));
+  }
   return check_launch("rollout");
 }
 
@@ -819,9 +828,9 @@ int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 *
     return xdot_nonlinear_impl<REAL>(prm, jx, jy, jz, obs, xdot, D, stream);                                                                       \
   }                                                                                                                                                \
   int mds_rollout_##SUF(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr,                       \
-                        const MdsCbfParams* cbf, MdsState st, MdsPidState pid, const SPEC* specs, const SEG* segs, REAL* obs, REAL* obs_log,       \
-                        double* stats, double t0, int K, int E, int N, void* stream) {                                                             \
-    return rollout_impl<REAL>(prm, cfg, geo, lqr, cbf, st, pid, specs, segs, obs, obs_log, stats, t0, K, E, N, stream);                            \
+                        const MdsCbfParams* cbf, MdsState st, MdsPidState pid, const SPEC* specs, const SEG* segs, REAL* obs, REAL* action,        \
+                        REAL* obs_log, double* stats, double t0, int K, int E, int N, void* stream) {                                              \
+    return rollout_impl<REAL>(prm, cfg, geo, lqr, cbf, st, pid, specs, segs, obs, action, obs_log, stats, t0, K, E, N, stream);                    \
   }
 
 MDS_DEFINE(f32, float, MdsTrajSpecF32, MdsTrajSegF32)

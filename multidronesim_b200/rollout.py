@@ -1,5 +1,6 @@
-"""Fused K-step rollout: trajectory -> controller -> (CBF-QP) -> inner loop -> physics, with
-each drone's state held in registers across the K control steps (``mds_rollout``).
+"""K-step rollout (``mds_rollout``): per control step one fused controller kernel (trajectory ->
+tracking controller -> CBF-QP -> inner loop) and one physics kernel (all sub-steps in registers),
+enqueued back to back with no host synchronisation.
 
 It is the device equivalent of the reference's per-step Python loops
 (simulations/EnvGeometric.py:434-479, simulations/CBFTest.py:302-358,
@@ -68,7 +69,7 @@ class FusedRollout:
         pid = self.controller._pid() if self.cfg.ctrl != _lib.CTRL_GEOMETRIC else _lib.PidState(None, None)
         cbf = self.qp.cbf.c_params() if self.qp is not None else None
         _lib.call("mds_rollout", env.dtype, env._prm, self.cfg, geo, lqr, cbf, env._state_struct(), pid,
-                  _lib.ptr(self.trajs.specs), _lib.ptr(self.trajs.segs), _lib.ptr(env._obs), _lib.ptr(obs_log),
+                  _lib.ptr(self.trajs.specs), _lib.ptr(self.trajs.segs), _lib.ptr(env._obs), _lib.ptr(env._action), _lib.ptr(obs_log),
                   _lib.ptr(self.stats), float(t0), int(K), env.NUM_ENVS, env.NUM_DRONES, _lib.stream_ptr(env.device))
         env.step_counter += K * env.PYB_STEPS_PER_CTRL
         self.t = t0 + K * env.CTRL_TIMESTEP
