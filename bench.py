@@ -39,6 +39,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_DRONES = 8
+SWARM_OBSTACLES = [[0.2, 0.0, 0.5, 0.1]]  # == multidronesim_b200.scenarios.SWARM_OBSTACLES (checked in run_gpu_arm)
 CBF_ORDER = 3
 # Algorithmic work per drone-step of the C5 path (DESIGN.md "Roofline"): FP32 operations of the closed-form
 # math (add/mul = 1, fma = 2, transcendental/div/sqrt = 1), hand-counted per stage and cross-checked against
@@ -95,7 +96,7 @@ def _cpu_worker_step(args):
         env, trajs = _oracle_env(env_index)
         _WORKER[key] = dict(env=env, trajs=trajs, ctrls=opl.make_controllers(env, "yank10"), t=0.0)
     w = _WORKER[key]
-    opl.run_cbf(w["env"], w["trajs"], CBF_ORDER, steps, obstacles=[[0.0, 0.0, 0.5, 0.1]], ctrls=w["ctrls"], t0=w["t"], log=False)
+    opl.run_cbf(w["env"], w["trajs"], CBF_ORDER, steps, obstacles=SWARM_OBSTACLES, ctrls=w["ctrls"], t0=w["t"], log=False)
     w["t"] += steps * w["env"].CTRL_TIMESTEP
     return N_DRONES * steps
 
@@ -149,7 +150,7 @@ def run_reference_arm(args):
 
 def workload_config(args, envs, per_gpu=True):
     return {"workload": "C5 swarm sweep: envs x 8 drones, Physics.DYN_GND_DRAG_DW 240 Hz, Lemniscate refs, LQR-yank-omega nominal, "
-                        "order-3 CBF-QP (r_safe 0.125, zscale 2, poles -3/-3.6/-5.6) + sphere obstacle r=0.1, YankOmega inner loop",
+                        "order-3 CBF-QP (r_safe 0.125, zscale 2, poles -3/-3.6/-5.6) + sphere obstacle r=0.1 at (0.2, 0, 0.5), YankOmega inner loop",
             "envs_per_gpu" if per_gpu else "envs": envs, "drones_per_env": N_DRONES, "drone_model": "cf2p", "cbf_order": CBF_ORDER,
             "control_steps_per_step": args.fuse if per_gpu else args.ref_steps_per_step, "parallelism": f"env-sharded x{args.gpus}",
             "l2": "working set (state+obs+traj specs+PID > 200 MB per GPU) exceeds the 126 MB L2; no flush needed"}
@@ -227,6 +228,7 @@ def run_gpu_arm(args):
     import multidronesim_b200 as mds
     from multidronesim_b200 import scenarios
 
+    assert scenarios.SWARM_OBSTACLES == SWARM_OBSTACLES
     rank, local_rank, world = mds.dist.init_from_env()
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")

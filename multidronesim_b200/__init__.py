@@ -7,7 +7,7 @@ from .enums import DroneModel, Physics
 from .constants import DroneConstants
 from .envs import BatchedCtrlAviary, CtrlAviary
 from .rollout import FusedRollout
-from . import control, model, cbf, trajectories, obstacles, utils, dist
+from . import control, model, cbf, trajectories, obstacles, utils, dist, scenarios
 
 __all__ = ["DroneModel", "Physics", "DroneConstants", "BatchedCtrlAviary", "CtrlAviary", "FusedRollout",
-           "control", "model", "cbf", "trajectories", "obstacles", "utils", "dist", "_lib"]
+           "control", "model", "cbf", "trajectories", "obstacles", "utils", "dist", "scenarios", "_lib"]

@@ -78,23 +78,41 @@ MDS_DEV void cbf_row(const DroneP<Real>& P, const CbfP<Real>& C, const CbfAgent<
   *rhs = C.k0 * h0 + C.k1 * h1 + C.k2 * h2 + Lf;
 }
 
-// pair index r in [0, N(N-1)/2) -> (i, j), i < j, lexicographic (cbf.py:342-346)
-MDS_DEV void pair_from_index(int r, int N, int* i, int* j) {
-  int a = 0;
-  while (r >= N - 1 - a) { r -= N - 1 - a; ++a; }
-  *i = a; *j = a + 1 + r;
+// ----------------------------------------------------------------------------------------
+// Row ownership.  The env's lane group (NP = next power of two >= N consecutive lanes of one warp, lane n
+// owns drone n) splits the barrier rows so that every row has its owner's drone as one end point:
+//   slot s <  K1 = (N-1)/2          : pair (n, n+s+1 mod N)          -- every lane
+//   slot s == K1, N even            : pair (n, n+N/2) for n < N/2    -- the "diameters"
+//   slot s >= S0 = K1 + (N even)    : obstacle s - S0 against drone n
+// RPL = S0 + n_obs slots per lane; row id r = n * RPL + s.  Each unordered pair appears exactly once and
+// is evaluated with i = min, j = max (cbf.py:342-346 orientation).  Unused slots hold a never-violated row.
+struct RowMap {
+  int K1, S0, RPL, half;  // half = N/2 if N even else 0
+};
+MDS_DEV RowMap row_map(int N, int n_obs) {
+  RowMap m;
+  m.K1 = (N - 1) >> 1;
+  m.half = (N & 1) ? 0 : (N >> 1);
+  m.S0 = m.K1 + (m.half ? 1 : 0);
+  m.RPL = m.S0 + n_obs;
+  return m;
+}
+// partner drone of (lane n, slot s): >= 0 pair partner, -1 obstacle row, -2 unused slot
+MDS_DEV int row_partner(const RowMap& M, int N, int n, int s) {
+  if (s < M.K1) { int m = n + s + 1; return m >= N ? m - N : m; }
+  if (s < M.S0) return (n < M.half) ? n + M.half : -2;
+  return -1;
 }
 
 // ----------------------------------------------------------------------------------------
 // Per-env QP over the coupled inputs x[4n + c], c in {0,1,2}, n < N (c == 3 is decoupled), solved
-// COOPERATIVELY by the env's lane group (NP = next power of two >= N consecutive lanes of one warp;
-// lane n owns drone n).  Only group-level synchronisation is used (__syncwarp / shuffles with the
-// group's lane mask), so groups of one warp iterate independently and no block barrier exists.
+// COOPERATIVELY by the env's lane group.  Only group-level synchronisation is used (__syncwarp /
+// shuffles with the group's lane mask), so the groups of a warp iterate independently; no block barrier.
 //
-// Constraint index space:  [0, n_rows): barrier rows (pairs, then obstacles i*n_obs + o)
-//                          [n_rows, n_rows + 6N): box  s * x[i,c] <= umax[c], k = i*6 + (s<0)*3 + c
-// Shared-memory row record (MDS_ROW_W words): a0, a1, a2, rhs, |g|^2, (i | j<<8 | active<<16) as int bits.
-#define MDS_ROW_W 6
+// Constraint ids:  [0, NP*RPL)          barrier rows (above);  smem record = (a0, a1, a2, rhs), G = -a on i, +a on j
+//                  MDS_QP_BOX0 + 6n + k  box  s * x[n,c] <= umax[c],  k = (s<0)*3 + c
+// An active-set entry packs (id | i << 16 | j << 24), j = 0x7f for single-block constraints.
+#define MDS_QP_BOX0 4096
 #define MDS_QP_WS_WORDS (4 * MDS_QP_QMAX + MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2 + 4)  // act, lam, d, r, chol, header
 
 template <typename Real> struct QpCon {
@@ -102,25 +120,22 @@ template <typename Real> struct QpCon {
   Real gi[3];    // coefficients on block i; block j carries -gi (pair rows)
   Real rhs, g2;
 };
-MDS_DEV int real_as_int(float v) { return __float_as_int(v); }
-MDS_DEV int real_as_int(double v) { return (int)__double2loint(v); }
-MDS_DEV float int_as_real(int v, float) { return __int_as_float(v); }
-MDS_DEV double int_as_real(int v, double) { return __hiloint2double(0, v); }
+MDS_DEV int pack_con(int id, int i, int j) { return id | (i << 16) | ((j < 0 ? 0x7f : j) << 24); }
 
 template <typename Real>
-MDS_DEV QpCon<Real> qp_get(const Real* rows, const CbfP<Real>& C, int idx, int n_rows) {
+MDS_DEV QpCon<Real> qp_get(const typename Vec4T<Real>::type* rows, const CbfP<Real>& C, int packed) {
   QpCon<Real> c;
-  if (idx < n_rows) {
-    const Real* r = rows + MDS_ROW_W * idx;
-    c.gi[0] = -r[0]; c.gi[1] = -r[1]; c.gi[2] = -r[2]; c.rhs = r[3]; c.g2 = r[4];
-    int ij = real_as_int(r[5]);
-    c.i = ij & 0xff;
-    c.j = (ij >> 8) & 0xff;
-    if (c.j == 0xff) c.j = -1;
+  const int id = packed & 0xffff;
+  c.i = (packed >> 16) & 0xff;
+  c.j = (packed >> 24) & 0x7f;
+  if (c.j == 0x7f) c.j = -1;
+  if (id < MDS_QP_BOX0) {
+    auto r = rows[id];
+    c.gi[0] = -r.x; c.gi[1] = -r.y; c.gi[2] = -r.z; c.rhs = r.w;
+    Real a2 = r.x * r.x + r.y * r.y + r.z * r.z;
+    c.g2 = c.j >= 0 ? Real(2) * a2 : a2;
   } else {
-    int k = idx - n_rows;
-    c.i = k / 6; c.j = -1;
-    int rem = k - 6 * c.i;
+    int rem = id - MDS_QP_BOX0 - 6 * c.i;
     int comp = rem >= 3 ? rem - 3 : rem;
     Real s = rem < 3 ? Real(1) : Real(-1);
     c.gi[0] = comp == 0 ? s : Real(0); c.gi[1] = comp == 1 ? s : Real(0); c.gi[2] = comp == 2 ? s : Real(0);
@@ -128,13 +143,13 @@ MDS_DEV QpCon<Real> qp_get(const Real* rows, const CbfP<Real>& C, int idx, int n
   }
   return c;
 }
-template <typename Real> MDS_DEV Real qp_dot_x(const QpCon<Real>& c, const Real* x, Real* mag) {
-  const Real* xi = x + 4 * c.i;
-  Real t0 = c.gi[0] * xi[0], t1 = c.gi[1] * xi[1], t2 = c.gi[2] * xi[2];
+template <typename Real> MDS_DEV Real qp_dot_x(const QpCon<Real>& c, const typename Vec4T<Real>::type* x, Real* mag) {
+  auto xi = x[c.i];
+  Real t0 = c.gi[0] * xi.x, t1 = c.gi[1] * xi.y, t2 = c.gi[2] * xi.z;
   Real s = t0 + t1 + t2, m = abs_(t0) + abs_(t1) + abs_(t2);
   if (c.j >= 0) {
-    const Real* xj = x + 4 * c.j;
-    Real u0 = c.gi[0] * xj[0], u1 = c.gi[1] * xj[1], u2 = c.gi[2] * xj[2];
+    auto xj = x[c.j];
+    Real u0 = c.gi[0] * xj.x, u1 = c.gi[1] * xj.y, u2 = c.gi[2] * xj.z;
     s -= u0 + u1 + u2;
     m += abs_(u0) + abs_(u1) + abs_(u2);
   }
@@ -155,19 +170,84 @@ template <typename Real> MDS_DEV Real qp_coef(const QpCon<Real>& c, int n, int k
   return (c.i == n) ? c.gi[k] : ((c.j == n) ? -c.gi[k] : Real(0));
 }
 
+// slack test shared by the row builder and the scans: violated <=> rhs - G x < -tol (|rhs| + sum |terms|)
+template <typename Real> MDS_DEV Real qp_tol() { return sizeof(Real) == 4 ? Real(2e-6) : Real(1e-11); }
+
+// Most violated inactive constraint among this lane's own rows (slots not in rowmask) and own box bounds
+// (not in boxmask) at the iterate x (own block xn in registers, partners' blocks from shared memory),
+// then the group-wide argmin.  Returns the packed constraint or -1 (none violated) / -2 (a zero row with
+// negative rhs: infeasible).
+template <typename Real>
+MDS_DEV int qp_scan(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows, const typename Vec4T<Real>::type* x, const Real xn[3],
+                    const RowMap& M, int N, int NP, int n, bool valid, unsigned rowmask, unsigned boxmask, unsigned gmask) {
+  const Real tol = qp_tol<Real>();
+  Real best = Real(0);
+  int bcon = 0x7fffffff;
+  if (valid) {
+    for (int s = 0; s < M.RPL; ++s) {
+      if (rowmask & (1u << s)) continue;
+      const int m = row_partner(M, N, n, s);
+      if (m == -2) continue;
+      auto r = rows[n * M.RPL + s];
+      // G x = -a.x_i + a.x_j ; own block enters with sign -1 when n == i (n < m or obstacle), +1 when n == j
+      const Real sg = (m >= 0 && m < n) ? Real(1) : Real(-1);
+      Real t0 = r.x * xn[0], t1 = r.y * xn[1], t2 = r.z * xn[2];
+      Real gx = sg * (t0 + t1 + t2), mag = abs_(t0) + abs_(t1) + abs_(t2);
+      Real a2 = r.x * r.x + r.y * r.y + r.z * r.z;
+      if (m >= 0) {
+        auto xm = x[m];
+        Real u0 = r.x * xm.x, u1 = r.y * xm.y, u2 = r.z * xm.z;
+        gx -= sg * (u0 + u1 + u2);
+        mag += abs_(u0) + abs_(u1) + abs_(u2);
+        a2 *= Real(2);
+      }
+      Real sl = r.w - gx;
+      if (sl < -tol * (abs_(r.w) + mag + Real(1e-12))) {
+        Real v = (a2 > Real(0)) ? sl * rsqrt_(a2) : Real(-1e30);  // zero row with rhs < 0: infeasible
+        int i = (m >= 0 && m < n) ? m : n, j = (m >= 0) ? ((m < n) ? n : m) : -1;
+        int con = pack_con(n * M.RPL + s, i, j);
+        if (v < best || (v == best && con < bcon)) { best = v; bcon = con; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (boxmask & (1u << k)) continue;
+      const int comp = k >= 3 ? k - 3 : k;
+      const Real sgn = k < 3 ? Real(1) : Real(-1);
+      Real sl = C.umax[comp] - sgn * xn[comp];
+      if (sl < -tol * (C.umax[comp] + abs_(xn[comp]) + Real(1e-12))) {
+        int con = pack_con(MDS_QP_BOX0 + 6 * n + k, n, -1);
+        if (sl < best || (sl == best && con < bcon)) { best = sl; bcon = con; }
+      }
+    }
+  }
+  for (int off = NP >> 1; off > 0; off >>= 1) {
+    Real ov = __shfl_xor_sync(gmask, best, off);
+    int oc = __shfl_xor_sync(gmask, bcon, off);
+    if (ov < best || (ov == best && oc < bcon)) { best = ov; bcon = oc; }
+  }
+  if (bcon == 0x7fffffff) return -1;
+  if (best <= Real(-1e30)) return -2;
+  return bcon;
+}
+
 // Goldfarb-Idnani dual active set, P = I, executed by the env's lane group.
-//   rows : smem barrier-row records;  x : smem iterate [4N] (u_nom on entry, minimiser on exit);
-//   ws   : smem workspace of MDS_QP_WS_WORDS Reals;  n : this lane's drone (valid = n < N).
-// Work split: the O(#constraints) scan for the most violated row and the O(N) primal update are spread
-// over the lanes (lane n owns drone n's inputs and box bounds); the O(q^2) scalar part (triangular solves
-// with the Cholesky factor of the active Gram matrix, step lengths, multiplier and factor updates) is done
-// by the group's lane 0 and published through shared memory between __syncwarp(gmask) points.
+//   rows : smem barrier rows;  x : smem iterate, one Vec4 per drone (u_nom on entry, minimiser on exit);
+//   ws   : smem workspace of MDS_QP_WS_WORDS Reals;  p0 : the most violated constraint at u_nom (packed),
+//   found by the row builder's own scan.
+// Work split: scans and the primal update are spread over the lanes (lane n owns drone n's inputs, rows and
+// box bounds).  The first iteration (empty active set: z = g_p, t = -s_p / |g_p|^2) is computed redundantly by
+// every lane with no workspace traffic -- in the C5 workload it is the only one for most environments.  From
+// the second iteration on, the O(q^2) scalar part (triangular solves with the Cholesky factor of the active
+// Gram matrix, step lengths, multiplier and factor updates) is done by the group's lane 0 and published
+// through shared memory between __syncwarp(gmask) points.
 enum { MDS_QP_ACT_FULL = 0, MDS_QP_ACT_DROP = 1, MDS_QP_ACT_STOP = 2 };
 
 template <typename Real>
-MDS_DEV int qp_solve_group(const CbfP<Real>& C, Real* rows, Real* x, Real* ws, int N, int NP, int n_rows, int n, bool valid,
-                           unsigned gmask, int* iters_out) {
-  const Real tol = sizeof(Real) == 4 ? Real(2e-6) : Real(1e-11);
+MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows, typename Vec4T<Real>::type* x, Real* ws,
+                           const RowMap& M, int N, int NP, int n, bool valid, unsigned gmask, int p0, int* iters_out) {
+  using R4 = typename Vec4T<Real>::type;
+  const Real tol = qp_tol<Real>();
   const Real zn_eps = sizeof(Real) == 4 ? Real(1e-5) : Real(1e-10);
   const Real INF = Real(1e30);
   // workspace: one int per Real slot for act / header ints
@@ -177,55 +257,50 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, Real* rows, Real* x, Real* ws, i
   Real* Lc = ws + 4 * MDS_QP_QMAX;  // packed lower-triangular Cholesky factor of the active Gram matrix
   Real* hdr = Lc + MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2;  // [0] t, [1] action, [2] dropped index, [3] status
   auto iref = [](Real* slot) -> int& { return *reinterpret_cast<int*>(slot); };
-  int q = 0, iters = 0, status = MDS_QP_OPTIMAL;
-  unsigned boxmask = 0;  // this lane's own active box constraints (6 bits)
+  unsigned rowmask = 0, boxmask = 0;  // this lane's own active rows (slots) / box bounds (6 bits)
+  auto set_active = [&](int con, bool on) {
+    const int id = con & 0xffff;
+    if (id >= MDS_QP_BOX0) {
+      const int k = id - MDS_QP_BOX0 - 6 * n;
+      if (k >= 0 && k < 6) boxmask = on ? (boxmask | (1u << k)) : (boxmask & ~(1u << k));
+    } else {
+      const int s = id - n * M.RPL;
+      if (s >= 0 && s < M.RPL) rowmask = on ? (rowmask | (1u << s)) : (rowmask & ~(1u << s));
+    }
+  };
   Real xn[3] = {Real(0), Real(0), Real(0)};
-  if (valid) { xn[0] = x[4 * n]; xn[1] = x[4 * n + 1]; xn[2] = x[4 * n + 2]; }
+  Real x3 = Real(0);
+  if (valid) { R4 v = x[n]; xn[0] = v.x; xn[1] = v.y; xn[2] = v.z; x3 = v.w; }
+  auto publish_x = [&]() {
+    if (valid) { R4 v; v.x = xn[0]; v.y = xn[1]; v.z = xn[2]; v.w = x3; x[n] = v; }
+  };
+  int q = 0, iters = 1, status = MDS_QP_OPTIMAL;
+  int p = p0;
+  QpCon<Real> cp = qp_get(rows, C, p);
+  Real lam_p = Real(0);  // meaningful on lane 0 only
+  // ---- first iteration, empty active set
+  {
+    Real mag, gx = qp_dot_x(cp, x, &mag);
+    Real t = -(cp.rhs - gx) / cp.g2;  // g2 > 0: zero rows are reported by the scan as infeasible
+    __syncwarp(gmask);                // every lane has read x before anyone overwrites it
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xn[k] -= t * qp_coef(cp, n, k);
+    publish_x();
+    if (n == 0) { iref(ws) = p; lam[0] = t; Lc[0] = sqrt_(cp.g2); }
+    set_active(p, true);
+    q = 1;
+    __syncwarp(gmask);
+  }
+  bool need_scan = true;
   // ONE flat loop (scan-if-needed -> scalar part -> primal step -> add or drop) instead of nested
   // outer/inner loops: the lane groups of a warp then stay converged on the same instructions even when
   // one group takes a full step and another a partial step (nested loops serialised the groups, ~4x).
-  bool need_scan = true;
-  int p = 0;
-  QpCon<Real> cp;
-  cp.i = 0; cp.j = -1; cp.gi[0] = cp.gi[1] = cp.gi[2] = Real(0); cp.rhs = Real(0); cp.g2 = Real(1);
-  Real lam_p = Real(0);  // meaningful on lane 0 only
   for (;;) {
     if (need_scan) {
-      // ---- most violated inactive constraint: barrier rows strided over the group, own box bounds
-      Real best = Real(0);
-      int bidx = 0x7fffffff;
-      for (int r = n; r < n_rows; r += NP) {
-        if (real_as_int(rows[MDS_ROW_W * r + 5]) & 0x10000) continue;
-        QpCon<Real> c = qp_get(rows, C, r, n_rows);
-        Real mag, gx = qp_dot_x(c, x, &mag);
-        Real sl = c.rhs - gx;
-        if (sl < -tol * (abs_(c.rhs) + mag + Real(1e-12))) {
-          Real v = (c.g2 > Real(0)) ? sl * rsqrt_(c.g2) : -INF;  // zero row with rhs < 0: infeasible
-          if (v < best || (v == best && r < bidx)) { best = v; bidx = r; }
-        }
-      }
-      if (valid) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          if (boxmask & (1u << k)) continue;
-          int comp = k >= 3 ? k - 3 : k;
-          Real sg = k < 3 ? Real(1) : Real(-1);
-          Real sl = C.umax[comp] - sg * xn[comp];
-          if (sl < -tol * (C.umax[comp] + abs_(xn[comp]) + Real(1e-12))) {
-            int idx = n_rows + 6 * n + k;
-            if (sl < best || (sl == best && idx < bidx)) { best = sl; bidx = idx; }
-          }
-        }
-      }
-      for (int off = NP >> 1; off > 0; off >>= 1) {
-        Real ov = __shfl_xor_sync(gmask, best, off);
-        int oi = __shfl_xor_sync(gmask, bidx, off);
-        if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
-      }
-      if (bidx == 0x7fffffff) break;  // optimal
-      if (best <= -INF) { status = MDS_QP_INFEASIBLE; break; }
-      p = bidx;
-      cp = qp_get(rows, C, p, n_rows);
+      p = qp_scan(C, rows, x, xn, M, N, NP, n, valid, rowmask, boxmask, gmask);
+      if (p == -1) break;  // optimal
+      if (p == -2) { status = MDS_QP_INFEASIBLE; break; }
+      cp = qp_get(rows, C, p);
       lam_p = Real(0);
     }
     ++iters;
@@ -238,7 +313,7 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, Real* rows, Real* x, Real* ws, i
       } else {
         Real dd = Real(0);
         for (int a = 0; a < q; ++a) {
-          QpCon<Real> ca = qp_get(rows, C, iref(ws + a), n_rows);
+          QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
           Real sacc = qp_dot_g(ca, cp);
           for (int k = 0; k < a; ++k) sacc -= Lc[a * (a + 1) / 2 + k] * dv[k];
           sacc /= Lc[a * (a + 1) / 2 + a];
@@ -292,14 +367,14 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, Real* rows, Real* x, Real* ws, i
 #pragma unroll
       for (int k = 0; k < 3; ++k) zk[k] = qp_coef(cp, n, k);
       for (int a = 0; a < q; ++a) {
-        QpCon<Real> ca = qp_get(rows, C, iref(ws + a), n_rows);
+        QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
         Real ra = rv[a];
 #pragma unroll
         for (int k = 0; k < 3; ++k) zk[k] -= ra * qp_coef(ca, n, k);
       }
 #pragma unroll
       for (int k = 0; k < 3; ++k) xn[k] -= t * zk[k];
-      x[4 * n] = xn[0]; x[4 * n + 1] = xn[1]; x[4 * n + 2] = xn[2];
+      publish_x();
     }
     const int pd = (action == MDS_QP_ACT_DROP) ? iref(ws + kdrop) : -1;
     __syncwarp(gmask);  // x updated; every lane has consumed act / r of this iteration
@@ -310,23 +385,21 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, Real* rows, Real* x, Real* ws, i
         Lc[q * (q + 1) / 2 + q] = sqrt_(cp.g2 - dd);
         iref(ws + q) = p;
         lam[q] = lam_p;
-        if (p < n_rows) rows[MDS_ROW_W * p + 5] = int_as_real(real_as_int(rows[MDS_ROW_W * p + 5]) | 0x10000, Real(0));
       }
-      if (p >= n_rows && valid && (p - n_rows) / 6 == n) boxmask |= 1u << ((p - n_rows) - 6 * n);
+      set_active(p, true);
       ++q;
       need_scan = true;
     } else {  // partial step: drop constraint kdrop, rebuild the (small) factor, keep working on p
-      if (pd >= n_rows && valid && (pd - n_rows) / 6 == n) boxmask &= ~(1u << ((pd - n_rows) - 6 * n));
+      set_active(pd, false);
       --q;
       need_scan = false;
       if (n == 0) {
-        if (pd < n_rows) rows[MDS_ROW_W * pd + 5] = int_as_real(real_as_int(rows[MDS_ROW_W * pd + 5]) & ~0x10000, Real(0));
         for (int a = kdrop; a < q; ++a) { iref(ws + a) = iref(ws + a + 1); lam[a] = lam[a + 1]; }
         int st = MDS_QP_OPTIMAL;
         for (int a = 0; a < q; ++a) {
-          QpCon<Real> ca = qp_get(rows, C, iref(ws + a), n_rows);
+          QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
           for (int b2 = 0; b2 <= a; ++b2) {
-            QpCon<Real> cb = qp_get(rows, C, iref(ws + b2), n_rows);
+            QpCon<Real> cb = qp_get(rows, C, iref(ws + b2));
             Real sacc = qp_dot_g(ca, cb);
             for (int k = 0; k < b2; ++k) sacc -= Lc[a * (a + 1) / 2 + k] * Lc[b2 * (b2 + 1) / 2 + k];
             if (a == b2) {
@@ -344,11 +417,11 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, Real* rows, Real* x, Real* ws, i
     if (action == MDS_QP_ACT_DROP && iref(hdr + 3) != MDS_QP_OPTIMAL) { status = iref(hdr + 3); break; }
   }
   __syncwarp(gmask);
-  if (status == MDS_QP_OPTIMAL && q > 0) {
+  if (status == MDS_QP_OPTIMAL && q > 1) {
     // certify: rows held active must still be satisfied (guards breakdown on nearly dependent active sets)
     const Real ctol = sizeof(Real) == 4 ? Real(1e-3) : Real(1e-7);
     for (int a = 0; a < q; ++a) {
-      QpCon<Real> ca = qp_get(rows, C, iref(ws + a), n_rows);
+      QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
       Real mag, gx = qp_dot_x(ca, x, &mag);
       if (ca.rhs - gx < -ctol * (abs_(ca.rhs) + mag + Real(1e-12))) status = MDS_QP_ITER_CAP;
     }

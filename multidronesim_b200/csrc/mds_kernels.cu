@@ -78,28 +78,30 @@ MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* s
   return dw;
 }
 
-// per-env shared-memory block of the CBF stage (Real words):
-//   [0, max(9N, WS)) agents (p, dv, da per drone) -- overlaid by the QP workspace once the rows exist
-//   rows  n_rows * MDS_ROW_W  |  x 4N  |  2 ints (status, iters)
+// per-env shared-memory block of the CBF stage (in Reals; every part is a multiple of 4 so that the Vec4
+// accesses stay aligned):
+//   head  max(12 NP, WS)  agents (p, dv, da per drone; 3 Vec4 each) -- overlaid by the QP workspace once the rows exist
+//   rows  4 NP RPL        one Vec4 (a0, a1, a2, rhs) per row, owner-major (mds_cbf.cuh "Row ownership")
+//   x     4 NP            the QP iterate, one Vec4 per drone
 template <typename Real> struct CbfSmem {
   Real* env0;
-  int stride, off_rows, off_x, off_st;
+  int stride, off_rows, off_x;
 };
-static inline int cbf_env_stride(int N, int n_obs) {
-  int n_rows = N * (N - 1) / 2 + N * n_obs;
-  int head = 9 * N > MDS_QP_WS_WORDS ? 9 * N : MDS_QP_WS_WORDS;
-  return (head + MDS_ROW_W * n_rows + 4 * N + 2) | 1;  // odd stride spreads the groups over the banks
+static inline int cbf_env_stride(int NP, int N, int n_obs) {
+  int rpl = (N - 1) / 2 + ((N & 1) ? 0 : 1) + n_obs;
+  int head = 12 * NP > MDS_QP_WS_WORDS ? 12 * NP : ((MDS_QP_WS_WORDS + 3) & ~3);
+  return head + 4 * NP * rpl + 4 * NP;
 }
 template <typename Real> static size_t cbf_smem_bytes(int NP, int N, int n_obs) {
-  return (size_t)(MDS_BLOCK / NP) * cbf_env_stride(N, n_obs) * sizeof(Real) + 16;
+  return (size_t)(MDS_BLOCK / NP) * cbf_env_stride(NP, N, n_obs) * sizeof(Real) + 32;
 }
-template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw, int N, int n_obs) {
+template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw, int NP, int N, int n_obs) {
   CbfSmem<Real> s;
   s.env0 = reinterpret_cast<Real*>(raw);
-  int n_rows = N * (N - 1) / 2 + N * n_obs;
-  int head = 9 * N > MDS_QP_WS_WORDS ? 9 * N : MDS_QP_WS_WORDS;
-  s.off_rows = head; s.off_x = head + MDS_ROW_W * n_rows; s.off_st = s.off_x + 4 * N;
-  s.stride = (s.off_st + 2) | 1;
+  const RowMap M = row_map(N, n_obs);
+  int head = 12 * NP > MDS_QP_WS_WORDS ? 12 * NP : ((MDS_QP_WS_WORDS + 3) & ~3);
+  s.off_rows = head; s.off_x = head + 4 * NP * M.RPL;
+  s.stride = s.off_x + 4 * NP;
   return s;
 }
 
@@ -109,72 +111,67 @@ template <typename Real>
 MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const CbfSmem<Real>& S, const Real* obstacles, int n_obs,
                              const GroupMap& g, int N, int NP, const CbfAgent<Real>& ag, Real F, const Real unom[4], Real usafe[4],
                              Real* min_h, int* iters_out) {
-  const int n = g.n, n_pairs = N * (N - 1) / 2, n_rows = n_pairs + N * n_obs;
+  using R4 = typename Vec4T<Real>::type;
+  const int n = g.n;
+  const RowMap M = row_map(N, n_obs);
   Real* env = S.env0 + (size_t)g.el * S.stride;
-  Real* rows = env + S.off_rows;
-  Real* x = env + S.off_x;
+  R4* agents = reinterpret_cast<R4*>(env);
+  R4* rows = reinterpret_cast<R4*>(env + S.off_rows);
+  R4* x = reinterpret_cast<R4*>(env + S.off_x);
   if (g.valid) {
-    Real* a = env + 9 * n;
-    a[0] = ag.p.x; a[1] = ag.p.y; a[2] = ag.p.z; a[3] = ag.dv.x; a[4] = ag.dv.y; a[5] = ag.dv.z;
-    a[6] = ag.da.x; a[7] = ag.da.y; a[8] = ag.da.z;
-    x[4 * n] = unom[0]; x[4 * n + 1] = unom[1]; x[4 * n + 2] = unom[2]; x[4 * n + 3] = unom[3];
+    R4 a0, a1, a2, xv;
+    a0.x = ag.p.x; a0.y = ag.p.y; a0.z = ag.p.z; a0.w = ag.dv.x;
+    a1.x = ag.dv.y; a1.y = ag.dv.z; a1.z = ag.da.x; a1.w = ag.da.y;
+    a2.x = ag.da.z; a2.y = Real(0); a2.z = Real(0); a2.w = Real(0);
+    agents[3 * n] = a0; agents[3 * n + 1] = a1; agents[3 * n + 2] = a2;
+    xv.x = unom[0]; xv.y = unom[1]; xv.z = unom[2]; xv.w = unom[3];
+    x[n] = xv;
   }
   __syncwarp(g.gmask);
-  const Real tol = sizeof(Real) == 4 ? Real(2e-6) : Real(1e-11);
   int fl = 0;
   Real lo = Real(0), hi = Real(0);
-  for (int r = n; r < n_rows; r += NP) {  // barrier rows strided over the group
-    int i, j;
-    CbfAgent<Real> ai, aj;
-    Real Ds;
-    if (r < n_pairs) {
-      pair_from_index(r, N, &i, &j);
-      const Real* b = env + 9 * j;
-      aj.p = {b[0], b[1], b[2]}; aj.dv = {b[3], b[4], b[5]}; aj.da = {b[6], b[7], b[8]};
-      Ds = Real(2) * C.rs;
-    } else {
-      i = (r - n_pairs) / n_obs;
-      int o = (r - n_pairs) - i * n_obs;
-      j = -1;
-      aj.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
-      aj.dv = {Real(0), Real(0), Real(0)}; aj.da = aj.dv;
-      Ds = C.rs + obstacles[4 * o + 3];
-    }
-    const Real* a = env + 9 * i;
-    ai.p = {a[0], a[1], a[2]}; ai.dv = {a[3], a[4], a[5]}; ai.da = {a[6], a[7], a[8]};
-    Real a3[3], rhs, h0;
-    cbf_row(P, C, ai, aj, Ds, a3, &rhs, &h0);
-    *min_h = min_(*min_h, h0);
-    Real* row = rows + MDS_ROW_W * r;
-    Real g2 = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2];
-    row[0] = a3[0]; row[1] = a3[1]; row[2] = a3[2]; row[3] = rhs; row[4] = j >= 0 ? Real(2) * g2 : g2;
-    row[5] = int_as_real(i | ((j >= 0 ? j : 0xff) << 8), Real(0));
-    // does u_nom violate this row?   G u = -a.u_i (+ a.u_j)
-    const Real* xi = x + 4 * i;
-    Real t0 = a3[0] * xi[0], t1 = a3[1] * xi[1], t2 = a3[2] * xi[2];
-    Real gx = -(t0 + t1 + t2), mag = abs_(t0) + abs_(t1) + abs_(t2);
-    if (j >= 0) {
-      const Real* xj = x + 4 * j;
-      Real u0 = a3[0] * xj[0], u1 = a3[1] * xj[1], u2 = a3[2] * xj[2];
-      gx += u0 + u1 + u2;
-      mag += abs_(u0) + abs_(u1) + abs_(u2);
-    }
-    if (rhs - gx < -tol * (abs_(rhs) + mag + Real(1e-12))) fl |= 1;
-  }
   if (g.valid) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      if (abs_(unom[c]) > C.umax[c] * (Real(1) + tol)) fl |= 1;
-    if (!cbf_wz_bounds(C, F, &lo, &hi)) fl |= 2;
+    for (int s = 0; s < M.RPL; ++s) {  // this lane's own rows
+      const int m = row_partner(M, N, n, s);
+      R4 row;
+      row.x = Real(0); row.y = Real(0); row.z = Real(0); row.w = Real(1e30);
+      if (m != -2) {
+        CbfAgent<Real> other;
+        Real Ds;
+        if (m >= 0) {
+          R4 b0 = agents[3 * m], b1 = agents[3 * m + 1], b2 = agents[3 * m + 2];
+          other.p = {b0.x, b0.y, b0.z}; other.dv = {b0.w, b1.x, b1.y}; other.da = {b1.z, b1.w, b2.x};
+          Ds = Real(2) * C.rs;
+        } else {
+          const int o = s - M.S0;
+          other.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
+          other.dv = {Real(0), Real(0), Real(0)}; other.da = other.dv;
+          Ds = C.rs + obstacles[4 * o + 3];
+        }
+        Real a3[3], rhs, h0;
+        if (m >= 0 && m < n) cbf_row(P, C, other, ag, Ds, a3, &rhs, &h0);  // i = min(n, m), j = max(n, m)
+        else cbf_row(P, C, ag, other, Ds, a3, &rhs, &h0);
+        *min_h = min_(*min_h, h0);
+        row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
+      }
+      rows[n * M.RPL + s] = row;
+    }
+    if (!cbf_wz_bounds(C, F, &lo, &hi)) fl = 1;
   }
   for (int off = NP >> 1; off > 0; off >>= 1) fl |= __shfl_xor_sync(g.gmask, fl, off);
   __syncwarp(g.gmask);  // rows complete; agents no longer needed (their storage becomes the QP workspace)
   int status = MDS_QP_OPTIMAL, iters = 0;
-  if (fl & 2) status = MDS_QP_INFEASIBLE;
-  else if (fl & 1) status = qp_solve_group(C, rows, x, env, N, NP, n_rows, n, g.valid, g.gmask, &iters);
+  if (fl) {
+    status = MDS_QP_INFEASIBLE;
+  } else {
+    const int p0 = qp_scan(C, rows, x, unom, M, N, NP, n, g.valid, 0u, 0u, g.gmask);
+    if (p0 == -2) status = MDS_QP_INFEASIBLE;
+    else if (p0 >= 0) status = qp_solve_group(C, rows, x, env, M, N, NP, n, g.valid, g.gmask, p0, &iters);
+  }
   if (g.valid) {
     if (status == MDS_QP_OPTIMAL) {
-      usafe[0] = x[4 * n]; usafe[1] = x[4 * n + 1]; usafe[2] = x[4 * n + 2];
+      R4 xv = x[n];
+      usafe[0] = xv.x; usafe[1] = xv.y; usafe[2] = xv.z;
       usafe[3] = clamp_(unom[3], lo, hi);
     } else {  // reference falls back to the nominal input (cbf/qptracker.py:30-34)
       usafe[0] = unom[0]; usafe[1] = unom[1]; usafe[2] = unom[2]; usafe[3] = unom[3];
@@ -307,8 +304,8 @@ __global__ void __launch_bounds__(MDS_BLOCK) cbf_qp_kernel(DroneP<Real> P, CbfP<
                                                             const Real* __restrict__ unom_g, const Real* __restrict__ obstacles, int n_obs,
                                                             Real* __restrict__ usafe_g, int* __restrict__ status, int* __restrict__ iters,
                                                             int E, int N, int NP) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, N, n_obs);
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, n_obs);
   const GroupMap g = group_map(N, NP, E);
   if (!g.env_valid) return;
   const int xdim = C.order == 2 ? 9 : 10;
@@ -480,8 +477,8 @@ __global__ void __launch_bounds__(MDS_BLOCK) ctrl_step_kernel(DroneP<Real> P, Ro
                                                                const typename TrajSpecT<Real>::seg* __restrict__ segs,
                                                                const Real* __restrict__ obs, Real* __restrict__ action,
                                                                double* __restrict__ stats, double t, int E, int N, int NP) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, N, Rc.n_obs);
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
   const GroupMap g = group_map(N, NP, E);
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
   double err = 0.0, min_h = 1e30;
@@ -494,8 +491,7 @@ __global__ void __launch_bounds__(MDS_BLOCK) ctrl_step_kernel(DroneP<Real> P, Ro
     if (g.valid) {
       ref = eval_traj<Real>(specs[g.d], segs, t);
       o = load_obs(obs, g.d);
-      double ex = (double)(o.p.x - ref.p.x), ey = (double)(o.p.y - ref.p.y), ez = (double)(o.p.z - ref.p.z);
-      err = sqrt(ex * ex + ey * ey + ez * ez);
+      err = (double)norm(o.p - ref.p);
       if (CTRL == MDS_CTRL_GEOMETRIC) {
         geometric_input(P, G, o, ref, u);
         input_to_action(P, u, rpm);
@@ -540,32 +536,45 @@ __global__ void __launch_bounds__(MDS_BLOCK) ctrl_step_kernel(DroneP<Real> P, Ro
     }
     if (g.valid) store4(action, g.d, rpm);
   }
-  if (stats) {  // warp shuffle reduce -> shared memory -> ONE set of atomics per block (same-address atomics
-                // from every warp cost more than the whole step: 1.6 ms vs 0.4 ms per step at 1M drones)
-    __shared__ double sm_stats[MDS_BLOCK / 32][MDS_STAT_COUNT];
-    double v[MDS_STAT_COUNT];
-    v[MDS_STAT_DRONE_STEPS] = g.valid ? 1.0 : 0.0; v[MDS_STAT_SUM_POS_ERR] = err; v[MDS_STAT_MAX_POS_ERR] = err;
-    v[MDS_STAT_MIN_BARRIER] = min_h; v[MDS_STAT_QP_SOLVES] = qp_solves; v[MDS_STAT_QP_ITERS] = qp_iters;
-    v[MDS_STAT_QP_INFEASIBLE] = qp_infeas; v[MDS_STAT_QP_ITER_CAP] = qp_cap;
-    __syncwarp();
-    for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-      for (int k = 0; k < MDS_STAT_COUNT; ++k) {
-        double o2 = __shfl_down_sync(0xffffffffu, v[k], off);
-        v[k] = (k == MDS_STAT_MAX_POS_ERR) ? fmax(v[k], o2) : ((k == MDS_STAT_MIN_BARRIER) ? fmin(v[k], o2) : v[k] + o2);
-      }
-    }
+  if (stats) {
+    // Per-warp reduction with redux.sync on integer images (counters; non-negative float bits order like
+    // unsigned ints; the barrier minimum goes through an order-preserving float -> int map) and five float
+    // shuffles for the error sum, then shared memory and ONE set of atomics per block: same-address atomics
+    // from every warp cost more than the whole step (1.6 ms vs 0.4 ms per step at 1M drones).
+    __shared__ float sm_f[MDS_BLOCK / 32][2];
+    __shared__ int sm_i[MDS_BLOCK / 32][6];
+    const unsigned full = 0xffffffffu;
+    const float errf = (float)err, mhf = (float)min_h;
+    int mh_i = __float_as_int(mhf);
+    mh_i = mh_i >= 0 ? mh_i : (mh_i ^ 0x7fffffff);
+    const int w_steps = __reduce_add_sync(full, g.valid ? 1 : 0), w_solves = __reduce_add_sync(full, qp_solves);
+    const int w_iters = __reduce_add_sync(full, qp_iters), w_inf = __reduce_add_sync(full, qp_infeas), w_cap = __reduce_add_sync(full, qp_cap);
+    const unsigned w_maxe = __reduce_max_sync(full, __float_as_uint(errf));
+    const int w_minh = __reduce_min_sync(full, mh_i);
+    float w_sum = errf;
+    for (int off = 16; off > 0; off >>= 1) w_sum += __shfl_xor_sync(full, w_sum, off);
+    const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-      for (int k = 0; k < MDS_STAT_COUNT; ++k) sm_stats[threadIdx.x >> 5][k] = v[k];
+      sm_f[w][0] = w_sum; sm_f[w][1] = __uint_as_float(w_maxe);
+      sm_i[w][0] = w_steps; sm_i[w][1] = w_solves; sm_i[w][2] = w_iters; sm_i[w][3] = w_inf; sm_i[w][4] = w_cap; sm_i[w][5] = w_minh;
     }
     __syncthreads();
     if (threadIdx.x < MDS_STAT_COUNT) {
       const int k = threadIdx.x;
-      double acc = sm_stats[0][k];
-      for (int w = 1; w < MDS_BLOCK / 32; ++w) {
-        double o2 = sm_stats[w][k];
-        acc = (k == MDS_STAT_MAX_POS_ERR) ? fmax(acc, o2) : ((k == MDS_STAT_MIN_BARRIER) ? fmin(acc, o2) : acc + o2);
+      double acc = 0.0;
+      if (k == MDS_STAT_SUM_POS_ERR) {
+        for (int i = 0; i < MDS_BLOCK / 32; ++i) acc += (double)sm_f[i][0];
+      } else if (k == MDS_STAT_MAX_POS_ERR) {
+        for (int i = 0; i < MDS_BLOCK / 32; ++i) acc = fmax(acc, (double)sm_f[i][1]);
+      } else if (k == MDS_STAT_MIN_BARRIER) {
+        int m = sm_i[0][5];
+        for (int i = 1; i < MDS_BLOCK / 32; ++i) m = min(m, sm_i[i][5]);
+        acc = (double)__int_as_float(m >= 0 ? m : (m ^ 0x7fffffff));
+      } else {
+        const int col = k == MDS_STAT_DRONE_STEPS ? 0 : (k == MDS_STAT_QP_SOLVES ? 1 : (k == MDS_STAT_QP_ITERS ? 2 : (k == MDS_STAT_QP_INFEASIBLE ? 3 : 4)));
+        long long t = 0;
+        for (int i = 0; i < MDS_BLOCK / 32; ++i) t += sm_i[i][col];
+        acc = (double)t;
       }
       if (k == MDS_STAT_MAX_POS_ERR) atomic_max_double(&stats[k], acc);
       else if (k == MDS_STAT_MIN_BARRIER) { if (USE_CBF) atomic_min_double(&stats[k], acc); }

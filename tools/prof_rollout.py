@@ -1,0 +1,21 @@
+"""Small driver for ncu: C5-style swarm, `pre` warm-up control steps then `n` more (2 kernels per control step).
+usage: python tools/prof_rollout.py [envs] [pre] [n] [f32|f64]"""
+import os
+import sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from multidronesim_b200 import scenarios  # noqa: E402
+E = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+pre = int(sys.argv[2]) if len(sys.argv) > 2 else 240
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+dt = torch.float64 if (len(sys.argv) > 4 and sys.argv[4] == "f64") else torch.float32
+sc = scenarios.cbf_swarm(E, 8, order=3, dtype=dt)
+ro = sc["rollout"]
+ro.run(pre)
+torch.cuda.synchronize()
+ro.reset_stats()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); ro.run(n); e1.record()
+torch.cuda.synchronize()
+print("ms/control-step %.4f" % (e0.elapsed_time(e1) / n), ro.stats_dict())
