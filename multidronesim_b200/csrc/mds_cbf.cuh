@@ -84,8 +84,10 @@ MDS_DEV void cbf_row(const DroneP<Real>& P, const CbfP<Real>& C, const CbfAgent<
 //   slot s <  K1 = (N-1)/2          : pair (n, n+s+1 mod N)          -- every lane
 //   slot s == K1, N even            : pair (n, n+N/2) for n < N/2    -- the "diameters"
 //   slot s >= S0 = K1 + (N even)    : obstacle s - S0 against drone n
-// RPL = S0 + n_obs slots per lane; row id r = n * RPL + s.  Each unordered pair appears exactly once and
-// is evaluated with i = min, j = max (cbf.py:342-346 orientation).  Unused slots hold a never-violated row.
+// RPL = S0 + n_obs slots per lane; row id r = n * RPL + s.  Each unordered pair appears exactly once, evaluated
+// as (owner - partner): a row is odd in (e, dv, da) in its coefficients and even in its right-hand side, and
+// negation is exact in floating point, so  G = -a on the owner's block, +a on the partner's  is bit-identical
+// to the reference's i < j orientation (cbf.py:342-346, 299-300).  Unused slots hold a never-violated row.
 struct RowMap {
   int K1, S0, RPL, half;  // half = N/2 if N even else 0
 };
@@ -173,62 +175,75 @@ template <typename Real> MDS_DEV Real qp_coef(const QpCon<Real>& c, int n, int k
 // slack test shared by the row builder and the scans: violated <=> rhs - G x < -tol (|rhs| + sum |terms|)
 template <typename Real> MDS_DEV Real qp_tol() { return sizeof(Real) == 4 ? Real(2e-6) : Real(1e-11); }
 
-// Most violated inactive constraint among this lane's own rows (slots not in rowmask) and own box bounds
-// (not in boxmask) at the iterate x (own block xn in registers, partners' blocks from shared memory),
-// then the group-wide argmin.  Returns the packed constraint or -1 (none violated) / -2 (a zero row with
-// negative rhs: infeasible).
+// running "most violated constraint" of one lane: (normalised slack, packed constraint), ties -> lowest id
+template <typename Real> struct QpWorst {
+  Real v;
+  int con;
+};
+// owner lane n tests its own barrier row (a0, a1, a2, rhs) with partner m (< 0: obstacle) at the iterate
+// (own block xn, partner block from shared memory):  G x = -a.x_n + a.x_m
+template <typename Real>
+MDS_DEV void qp_test_row(QpWorst<Real>& w, const typename Vec4T<Real>::type& r, const Real xn[3], const typename Vec4T<Real>::type* x,
+                         int n, int m, int id) {
+  Real t0 = r.x * xn[0], t1 = r.y * xn[1], t2 = r.z * xn[2];
+  Real gx = -(t0 + t1 + t2), mag = abs_(t0) + abs_(t1) + abs_(t2);
+  Real a2 = r.x * r.x + r.y * r.y + r.z * r.z;
+  if (m >= 0) {
+    auto xm = x[m];
+    Real u0 = r.x * xm.x, u1 = r.y * xm.y, u2 = r.z * xm.z;
+    gx += u0 + u1 + u2;
+    mag += abs_(u0) + abs_(u1) + abs_(u2);
+    a2 *= Real(2);
+  }
+  Real sl = r.w - gx;
+  if (sl < -qp_tol<Real>() * (abs_(r.w) + mag + Real(1e-12))) {
+    Real v = (a2 > Real(0)) ? sl * rsqrt_(a2) : Real(-1e30);  // zero row with rhs < 0: infeasible
+    int con = pack_con(id, n, m);
+    if (v < w.v || (v == w.v && con < w.con)) { w.v = v; w.con = con; }
+  }
+}
+// own box bounds not in boxmask
+template <typename Real> MDS_DEV void qp_test_box(QpWorst<Real>& w, const CbfP<Real>& C, const Real xn[3], int n, unsigned boxmask) {
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    if (boxmask & (1u << k)) continue;
+    const int comp = k >= 3 ? k - 3 : k;
+    const Real sgn = k < 3 ? Real(1) : Real(-1);
+    Real sl = C.umax[comp] - sgn * xn[comp];
+    if (sl < -qp_tol<Real>() * (C.umax[comp] + abs_(xn[comp]) + Real(1e-12))) {
+      int con = pack_con(MDS_QP_BOX0 + 6 * n + k, n, -1);
+      if (sl < w.v || (sl == w.v && con < w.con)) { w.v = sl; w.con = con; }
+    }
+  }
+}
+// group-wide argmin -> packed constraint, or -1 (none violated) / -2 (a zero row with negative rhs: infeasible)
+template <typename Real> MDS_DEV int qp_worst_of_group(QpWorst<Real> w, int NP, unsigned gmask) {
+  for (int off = NP >> 1; off > 0; off >>= 1) {
+    Real ov = __shfl_xor_sync(gmask, w.v, off);
+    int oc = __shfl_xor_sync(gmask, w.con, off);
+    if (ov < w.v || (ov == w.v && oc < w.con)) { w.v = ov; w.con = oc; }
+  }
+  if (w.con == 0x7fffffff) return -1;
+  if (w.v <= Real(-1e30)) return -2;
+  return w.con;
+}
+
+// Most violated inactive constraint among every lane's own rows (slots not in rowmask) and own box bounds
+// (not in boxmask) at the iterate x.
 template <typename Real>
 MDS_DEV int qp_scan(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows, const typename Vec4T<Real>::type* x, const Real xn[3],
                     const RowMap& M, int N, int NP, int n, bool valid, unsigned rowmask, unsigned boxmask, unsigned gmask) {
-  const Real tol = qp_tol<Real>();
-  Real best = Real(0);
-  int bcon = 0x7fffffff;
+  QpWorst<Real> w = {Real(0), 0x7fffffff};
   if (valid) {
     for (int s = 0; s < M.RPL; ++s) {
       if (rowmask & (1u << s)) continue;
       const int m = row_partner(M, N, n, s);
       if (m == -2) continue;
-      auto r = rows[n * M.RPL + s];
-      // G x = -a.x_i + a.x_j ; own block enters with sign -1 when n == i (n < m or obstacle), +1 when n == j
-      const Real sg = (m >= 0 && m < n) ? Real(1) : Real(-1);
-      Real t0 = r.x * xn[0], t1 = r.y * xn[1], t2 = r.z * xn[2];
-      Real gx = sg * (t0 + t1 + t2), mag = abs_(t0) + abs_(t1) + abs_(t2);
-      Real a2 = r.x * r.x + r.y * r.y + r.z * r.z;
-      if (m >= 0) {
-        auto xm = x[m];
-        Real u0 = r.x * xm.x, u1 = r.y * xm.y, u2 = r.z * xm.z;
-        gx -= sg * (u0 + u1 + u2);
-        mag += abs_(u0) + abs_(u1) + abs_(u2);
-        a2 *= Real(2);
-      }
-      Real sl = r.w - gx;
-      if (sl < -tol * (abs_(r.w) + mag + Real(1e-12))) {
-        Real v = (a2 > Real(0)) ? sl * rsqrt_(a2) : Real(-1e30);  // zero row with rhs < 0: infeasible
-        int i = (m >= 0 && m < n) ? m : n, j = (m >= 0) ? ((m < n) ? n : m) : -1;
-        int con = pack_con(n * M.RPL + s, i, j);
-        if (v < best || (v == best && con < bcon)) { best = v; bcon = con; }
-      }
+      qp_test_row(w, rows[n * M.RPL + s], xn, x, n, m, n * M.RPL + s);
     }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      if (boxmask & (1u << k)) continue;
-      const int comp = k >= 3 ? k - 3 : k;
-      const Real sgn = k < 3 ? Real(1) : Real(-1);
-      Real sl = C.umax[comp] - sgn * xn[comp];
-      if (sl < -tol * (C.umax[comp] + abs_(xn[comp]) + Real(1e-12))) {
-        int con = pack_con(MDS_QP_BOX0 + 6 * n + k, n, -1);
-        if (sl < best || (sl == best && con < bcon)) { best = sl; bcon = con; }
-      }
-    }
+    qp_test_box(w, C, xn, n, boxmask);
   }
-  for (int off = NP >> 1; off > 0; off >>= 1) {
-    Real ov = __shfl_xor_sync(gmask, best, off);
-    int oc = __shfl_xor_sync(gmask, bcon, off);
-    if (ov < best || (ov == best && oc < bcon)) { best = ov; bcon = oc; }
-  }
-  if (bcon == 0x7fffffff) return -1;
-  if (best <= Real(-1e30)) return -2;
-  return bcon;
+  return qp_worst_of_group(w, NP, gmask);
 }
 
 // Goldfarb-Idnani dual active set, P = I, executed by the env's lane group.

@@ -94,6 +94,8 @@ MDS_DEV float exp_(float x) { return expf(x); }
 MDS_DEV double exp_(double x) { return exp(x); }
 MDS_DEV float tan_(float x) { return tanf(x); }
 MDS_DEV double tan_(double x) { return tan(x); }
+MDS_DEV float rint_(float x) { return rintf(x); }
+MDS_DEV double rint_(double x) { return rint(x); }
 MDS_DEV float abs_(float x) { return fabsf(x); }
 MDS_DEV double abs_(double x) { return fabs(x); }
 MDS_DEV float min_(float a, float b) { return fminf(a, b); }

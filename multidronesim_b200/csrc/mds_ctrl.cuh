@@ -113,38 +113,24 @@ MDS_DEV void geometric_input(const DroneP<Real>& P, const GeoP<Real>& G, const O
   u[3] = P.izz * t0.z - gy.z;
 }
 
-// scipy from_euler('xyz') extrinsic = Rz(yaw) Ry(pitch) Rx(roll)
-template <typename Real> MDS_DEV M3<Real> euler_xyz_to_rot(V3<Real> e) {
-  Real sa, ca, sb, cb, sc, cc;
-  sincos_(e.x, &sa, &ca);
-  sincos_(e.y, &sb, &cb);
-  sincos_(e.z, &sc, &cc);
-  M3<Real> R;
-  R.m[0] = cb * cc; R.m[1] = sa * sb * cc - ca * sc; R.m[2] = ca * sb * cc + sa * sc;
-  R.m[3] = cb * sc; R.m[4] = sa * sb * sc + ca * cc; R.m[5] = ca * sb * sc - sa * cc;
-  R.m[6] = -sb; R.m[7] = sa * cb; R.m[8] = ca * cb;
-  return R;
-}
-
 // LQR error state + u = -K e (+ hover) for the three parametrisations (B8-B10).
 // variant: MDS_CTRL_LQR_TORQUE (dim 12), _OMEGA (9), _YANK (10).  Returns the UN-capped u.
 template <typename Real>
 MDS_DEV void lqr_input(const DroneP<Real>& P, const LqrP<Real>& L, int variant, const Obs<Real>& o, const Ref<Real>& r, Real u[4]) {
   Real sy, cy;
   sincos_(r.yaw, &sy, &cy);
-  // R_err = Rz(yaw_d)^T R(rpy); its xyz-extrinsic Euler angles
-  M3<Real> R = euler_xyz_to_rot(o.rpy);
-  M3<Real> Re;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    Re.m[j] = cy * R.m[j] + sy * R.m[3 + j];
-    Re.m[3 + j] = -sy * R.m[j] + cy * R.m[3 + j];
-    Re.m[6 + j] = R.m[6 + j];
-  }
+  // Error attitude (lqr_omega_controller.py:97-104): as_euler('xyz') of R_eq^T R with R = from_euler('xyz', rpy)
+  // = Rz(yaw) Ry(pitch) Rx(roll) and R_eq = Rz(yaw_d).  Rz(yaw_d)^T Rz(yaw) = Rz(yaw - yaw_d), and the obs pitch is
+  // an asin() in [-pi/2, pi/2], so the Euler angles of the product are (roll, pitch, wrap(yaw - yaw_d)) in closed
+  // form -- no rotation matrix, sincos or atan2 round trip (it was ~10 % of the controller kernel's instructions).
   Real e[12];
-  e[0] = atan2_(Re.m[7], Re.m[8]);
-  e[1] = asin_(clamp_(-Re.m[6], Real(-1), Real(1)));
-  e[2] = atan2_(Re.m[3], Re.m[0]);
+  e[0] = o.rpy.x;
+  e[1] = o.rpy.y;
+  {
+    const Real two_pi = Real(6.283185307179586476925286766559), inv_two_pi = Real(0.15915494309189533576888376337251);
+    Real d = o.rpy.z - r.yaw;
+    e[2] = d - two_pi * rint_(d * inv_two_pi);
+  }
   V3<Real> dp = o.p - r.p, dv = o.v - r.v;
   V3<Real> ep = {cy * dp.x + sy * dp.y, -sy * dp.x + cy * dp.y, dp.z};
   V3<Real> ev = {cy * dv.x + sy * dv.y, -sy * dv.x + cy * dv.y, dv.z};

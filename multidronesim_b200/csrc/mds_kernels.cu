@@ -45,10 +45,10 @@ struct GroupMap {
 };
 MDS_DEV GroupMap group_map(int N, int NP, int E) {
   GroupMap g;
-  const int tid = threadIdx.x, epb = MDS_BLOCK / NP;
-  g.el = tid / NP;
-  g.n = tid - g.el * NP;
-  g.e = blockIdx.x * epb + g.el;
+  const int tid = threadIdx.x, lg = __ffs(NP) - 1;  // NP is a power of two
+  g.el = tid >> lg;
+  g.n = tid & (NP - 1);
+  g.e = blockIdx.x * (MDS_BLOCK >> lg) + g.el;
   g.env_valid = g.e < E;
   g.valid = g.env_valid && g.n < N;
   g.d = g.e * N + g.n;
@@ -130,8 +130,9 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
   __syncwarp(g.gmask);
   int fl = 0;
   Real lo = Real(0), hi = Real(0);
+  QpWorst<Real> worst = {Real(0), 0x7fffffff};
   if (g.valid) {
-    for (int s = 0; s < M.RPL; ++s) {  // this lane's own rows
+    for (int s = 0; s < M.RPL; ++s) {  // this lane's own rows, each tested against u_nom as it is built
       const int m = row_partner(M, N, n, s);
       R4 row;
       row.x = Real(0); row.y = Real(0); row.z = Real(0); row.w = Real(1e30);
@@ -149,25 +150,22 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
           Ds = C.rs + obstacles[4 * o + 3];
         }
         Real a3[3], rhs, h0;
-        if (m >= 0 && m < n) cbf_row(P, C, other, ag, Ds, a3, &rhs, &h0);  // i = min(n, m), j = max(n, m)
-        else cbf_row(P, C, ag, other, Ds, a3, &rhs, &h0);
+        cbf_row(P, C, ag, other, Ds, a3, &rhs, &h0);  // owner - partner (mds_cbf.cuh "Row ownership")
         *min_h = min_(*min_h, h0);
         row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
+        qp_test_row(worst, row, unom, x, n, m, n * M.RPL + s);
       }
       rows[n * M.RPL + s] = row;
     }
+    qp_test_box(worst, C, unom, n, 0u);
     if (!cbf_wz_bounds(C, F, &lo, &hi)) fl = 1;
   }
   for (int off = NP >> 1; off > 0; off >>= 1) fl |= __shfl_xor_sync(g.gmask, fl, off);
+  const int p0 = qp_worst_of_group(worst, NP, g.gmask);
   __syncwarp(g.gmask);  // rows complete; agents no longer needed (their storage becomes the QP workspace)
   int status = MDS_QP_OPTIMAL, iters = 0;
-  if (fl) {
-    status = MDS_QP_INFEASIBLE;
-  } else {
-    const int p0 = qp_scan(C, rows, x, unom, M, N, NP, n, g.valid, 0u, 0u, g.gmask);
-    if (p0 == -2) status = MDS_QP_INFEASIBLE;
-    else if (p0 >= 0) status = qp_solve_group(C, rows, x, env, M, N, NP, n, g.valid, g.gmask, p0, &iters);
-  }
+  if (fl || p0 == -2) status = MDS_QP_INFEASIBLE;
+  else if (p0 >= 0) status = qp_solve_group(C, rows, x, env, M, N, NP, n, g.valid, g.gmask, p0, &iters);
   if (g.valid) {
     if (status == MDS_QP_OPTIMAL) {
       R4 xv = x[n];

@@ -36,9 +36,13 @@ MDS_DEV V3<Real> physics_substep(const DroneP<Real>& P, Drone<Real>& s, const Re
   V3<Real> extra = fext;
   if (P.physics == MDS_PHYSICS_DYN_GND_DRAG_DW) {
     // ground effect: per-prop height above the plane, gated on |roll|, |pitch| < pi/2
-    V3<Real> rpy = quat_to_rpy(s.qx, s.qy, s.qz, s.qw);
-    const Real half_pi = Real(1.5707963267948966);
-    if (abs_(rpy.x) < half_pi && abs_(rpy.y) < half_pi) {
+    // |roll| < pi/2 and |pitch| < pi/2 of Bullet's getEulerFromQuaternion without the atan2/asin: pitch is
+    // asin(sarg) (+-pi/2 exactly inside the +-0.99999 gimbal branches), roll = atan2(A, B) is inside (-pi/2, pi/2)
+    // iff B > 0 (or A = B = 0).
+    const Real sarg = Real(-2) * (s.qx * s.qz - s.qw * s.qy);
+    const Real rollA = Real(2) * (s.qy * s.qz + s.qw * s.qx);
+    const Real rollB = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz;
+    if (abs_(sarg) < Real(0.99999) && (rollB > Real(0) || (rollB == Real(0) && rollA == Real(0)))) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         Real h = s.p.z + R.m[6] * P.prop_x[i] + R.m[7] * P.prop_y[i];

@@ -18,8 +18,8 @@ template <typename Real> struct Ref {
 };
 
 MDS_DEV double reduce_2pi(double th) {
-  const double two_pi = 6.283185307179586476925286766559;
-  return th - two_pi * floor(th / two_pi);
+  const double two_pi = 6.283185307179586476925286766559, inv_two_pi = 0.15915494309189533576888376337251;
+  return th - two_pi * floor(th * inv_two_pi);  // multiply: the fp64 divide is a ~40-instruction subroutine
 }
 
 // Circle.py:24-45.  p = {r, v, cx, cy, cz, yaw_rate}.  Quirk B18: yaw in [pi, 3pi).

@@ -17,6 +17,12 @@ cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 sass = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+want_k = os.environ.get("NCU_KERNEL", "")
+for a, b in zip(starts[:-1], starts[1:]):  # a report may hold several kernels: take the first whose name matches
+    if want_k in rows[a][1]:
+        rows = rows[a:b]
+        break
 kname = rows[0][1]
 hdr = rows[1]
 body = [dict(zip(hdr, r)) for r in rows[2:] if len(r) == len(hdr)]
