@@ -9,13 +9,17 @@ Workload (config.workload): SURVEY.md 8(d) C5 -- per GPU 125 000 independent env
 CBF-QP (28 pair rows + 8 obstacle rows + box/force bounds per env) -> YankOmega inner loop ->
 DYN_GND_DRAG_DW physics (ground effect, drag, pairwise downwash) -> 20-float observation.
 
-One bench "step" = one launch of the fused rollout kernel = ``--fuse`` control steps of every drone.
-``value``  : drone-steps/s, state resident in HBM, CUDA events on the launching stream, max over ranks.
-``e2e``    : the same metric through the per-call API with HOST buffers: every control step copies the
-             step's references (host -> device, pinned) in and the observations (device -> host) out.
-``roofline``: FP32 pipe (no tensor cores on this path; nothing is a dense contraction) for the fused
-             kernel, peak measured live with an FMA-chain microbenchmark; plus ``roofline_hbm`` for the
-             per-call physics-step kernel against MEASURED_PEAKS.json's HBM copy bandwidth.
+One bench "step" = one ``mds_rollout`` call = ``--fuse`` control steps of every drone (two kernel launches per
+control step: the controller-stack kernel and the physics kernel, enqueued back to back, no host sync).
+``value``   : drone-steps/s, state resident in HBM, CUDA events on the launching stream, max over ranks.
+``e2e``     : the same metric through the per-call API with HOST buffers (multidronesim_b200.HostPipeline): every
+              control step copies the step's references host -> device from pinned memory and the new observation
+              device -> host, copies overlapped with the neighbouring steps' kernels on their own streams.
+``roofline``: the dominant kernel (controller stack incl. the CBF-QP) against the measured HBM copy bandwidth
+              (MEASURED_PEAKS.json): algorithmic bytes per launch / its mean launch duration from per-launch CUDA
+              events over a replay of the timed region; ``roofline_physics`` the same for the physics kernel,
+              ``roofline_step`` for both together; each carries the FP32-pipe view (FMA-chain peak measured live).
+              No tensor cores on this path: nothing is a dense contraction.
 ``cpu_baseline``: oracle/ (numpy restatement of the reference's algorithms) on all host cores, bounded sample.
 """
 from __future__ import annotations
@@ -44,15 +48,17 @@ CBF_ORDER = 3
 # Algorithmic work per drone-step of the C5 path (DESIGN.md "Roofline"): FP32 operations of the closed-form
 # math (add/mul = 1, fma = 2, transcendental/div/sqrt = 1), hand-counted per stage and cross-checked against
 # ncu's smsp__sass_thread_inst_executed_op_f{add,mul,fma} for the QP-inactive path.
-ALGO_FLOP_PER_DRONE_STEP = {"traj": 70, "lqr_yank": 330, "cbf_rows": 520, "cbf_check": 60, "lowlevel": 110,
+ALGO_FLOP_PER_DRONE_STEP = {"traj": 70, "lqr_yank": 130, "cbf_rows": 680, "cbf_check": 110, "qp_iteration": 90, "lowlevel": 110,
                             "physics_gnd_drag_dw_n8": 640, "obs": 60}
-ALGO_BYTES_PER_DRONE_STEP_PERCALL_F32 = 232  # read state 17 + action 4, write state 17 + obs 20 floats
+# Algorithmic HBM bytes per drone-step (fp32), per kernel of the rollout (DESIGN.md "Roofline"):
+ALGO_BYTES_CTRL_F32 = {"read_obs": 80, "read_traj_spec": 48, "read_pid": 24, "write_pid": 24, "write_action": 16}
+ALGO_BYTES_PHYS_F32 = {"read_state": 68, "read_action": 16, "write_state": 68, "write_obs": 80}  # 232 B
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=125000, help="environments per GPU (weak scaling)")
@@ -216,6 +222,32 @@ def measured_peaks():
         return None
 
 
+def snapshot(env, ctrl, ro):
+    return (env.state_dict(), ctrl.low_level._a.clone(), ctrl.low_level._b.clone(), ro.t, ro.stats.clone())
+
+
+def restore(env, ctrl, ro, snap):
+    env.load_state_dict(snap[0])
+    ctrl.low_level._a.copy_(snap[1])
+    ctrl.low_level._b.copy_(snap[2])
+    ro.t = snap[3]
+    ro.stats.copy_(snap[4])
+
+
+def ncu_traffic(kernel, envs, dtype):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/ncu_traffic.json: written by tools/ncu_traffic.py from the .ncu-rep), or None if no capture
+    of this kernel at this size exists."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        return None
+    for row in tab.get("kernels", []):
+        if row["kernel"].startswith(kernel) and row["envs"] == envs and row["dtype"] == dtype:
+            return row["dram_bytes_per_launch"]
+    return None
+
+
 def run_gpu_arm(args):
     cpu = None
     rank_env = int(os.environ.get("RANK", "0"))
@@ -235,11 +267,12 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    esz = 4 if dtype == torch.float32 else 8
     E, N, F, K, W = args.envs, N_DRONES, args.fuse, args.steps, max(3, args.warmup)
     D = E * N
 
     sc = scenarios.cbf_swarm(E, N, order=CBF_ORDER, dtype=dtype, device=dev, env_offset=rank * E)
-    env, ro = sc["env"], sc["rollout"]
+    env, ro, ctrl = sc["env"], sc["rollout"], sc["ctrl"]
     fma_peak = mds._lib.fma_peak_tflops(use_f64=(dtype == torch.float64))
 
     def barrier():
@@ -251,6 +284,7 @@ def run_gpu_arm(args):
         ro.run(F)
     torch.cuda.synchronize()
     ro.reset_stats()
+    snap = snapshot(env, ctrl, ro)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
@@ -271,37 +305,50 @@ def run_gpu_arm(args):
     stats = dict(zip(mds._lib.STAT_NAMES, mds.dist.reduce_stats(stats_all).tolist()))
     clocks = clk.summary()
 
-    # ---- roofline of the dominant kernel (this rank) -------------------------------------------
-    flop_unit = sum(ALGO_FLOP_PER_DRONE_STEP.values())
-    launch_ms = ms / K
-    achieved_tf = flop_unit * D * F / (launch_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp32", "kernel": "rollout_kernel<float>" if dtype == torch.float32 else "rollout_kernel<double>",
-                "achieved": achieved_tf, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved_tf / fma_peak,
-                "peak_source": "measured live: mds_fma_peak dependent-FMA chains, 2 x 1024 threads per SM (no FP32 figure in MEASURED_PEAKS.json)",
-                "algorithmic_flop_per_drone_step": flop_unit, "launch_ms": launch_ms, "traffic": None,
-                "note": "QP-inactive path flops; active-set iterations (stats.qp_iters) are extra work not counted"}
-
-    # per-call physics-step kernel: HBM roofline (232 B per drone-step)
-    act = torch.full((E, N, 4), float(env.HOVER_RPM), device=dev, dtype=dtype)
-    for _ in range(3):
-        env.step(act)
+    # ---- per-kernel durations over the SAME K*F control steps (this rank) ------------------------------------
+    # Replay the timed region from its snapshot one launch at a time (MdsRolloutCfg.stages) with a CUDA event
+    # pair around every launch on the launching stream: the rollout is deterministic, so each kernel does
+    # exactly the work it did in the timed region.
+    restore(env, ctrl, ro, snap)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
-    e0.record()
-    for _ in range(reps):
-        env.step(act)
-    e1.record()
+    n_steps = K * F
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_steps)]
+    for k in range(n_steps):
+        evs[k][0].record()
+        ro.run(1, stages=1)
+        evs[k][1].record()
+        ro.run(1, stages=2)
+        evs[k][2].record()
     torch.cuda.synchronize()
-    step_ms = e0.elapsed_time(e1) / reps
+    ctrl_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / n_steps
+    phys_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / n_steps
+    step_ms = ms / n_steps
     peaks = measured_peaks()
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
-    bytes_unit = ALGO_BYTES_PER_DRONE_STEP_PERCALL_F32 * (1 if dtype == torch.float32 else 2)
-    hbm_gbs = bytes_unit * D / (step_ms * 1e-3) / 1e9
-    roofline_hbm = {"bound": "hbm", "kernel": "physics_step_kernel", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": hbm_gbs / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
-                    "algorithmic_bytes_per_drone_step": bytes_unit, "launch_ms": step_ms, "traffic": None,
-                    "drone_steps_per_s": D / (step_ms * 1e-3)}
+    peak_src = "MEASURED_PEAKS.json hbm_gbs, of measured (sustained copy)" if peaks else "fallback 6.65 TB/s, of fallback"
+    sfx = "float" if dtype == torch.float32 else "double"
+    b_ctrl, b_phys = sum(ALGO_BYTES_CTRL_F32.values()) * esz // 4, sum(ALGO_BYTES_PHYS_F32.values()) * esz // 4
+    flop_ctrl = sum(v for k, v in ALGO_FLOP_PER_DRONE_STEP.items() if k not in ("physics_gnd_drag_dw_n8", "obs"))
+    flop_phys = ALGO_FLOP_PER_DRONE_STEP["physics_gnd_drag_dw_n8"] + ALGO_FLOP_PER_DRONE_STEP["obs"]
+
+    def roof(kernel, bytes_unit, flop_unit, launch_ms):
+        gbs = bytes_unit * D / (launch_ms * 1e-3) / 1e9
+        tf = flop_unit * D / (launch_ms * 1e-3) / 1e12
+        return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "peak_source": peak_src, "algorithmic_bytes_per_drone_step": bytes_unit, "launch_ms": launch_ms,
+                "share_of_step": launch_ms / (ctrl_ms + phys_ms), "traffic": ncu_traffic(kernel.split("<")[0], E, args.dtype),
+                "fp32_pipe": {"achieved_tflops": tf, "peak_tflops": fma_peak, "frac": tf / fma_peak, "algorithmic_flop_per_drone_step": flop_unit,
+                              "peak_source": "measured live: mds_fma_peak dependent-FMA chains (no non-tensor FP32 figure in MEASURED_PEAKS.json)"}}
+
+    roofline = roof(f"ctrl_step_kernel<{sfx}, MDS_CTRL_LQR_YANK, true>", b_ctrl, flop_ctrl, ctrl_ms)
+    roofline["note"] = ("dominant kernel of the step (reference -> LQR -> CBF rows -> QP -> inner loop); arithmetic intensity "
+                        f"{flop_ctrl / b_ctrl:.1f} flop/B is below the ridge ({fma_peak * 1e3 / hbm_peak:.1f} flop/B), so HBM is the bound; "
+                        "durations from per-launch CUDA events over a replay of the timed region")
+    roofline_physics = roof(f"physics_step_kernel<{sfx}>", b_phys, flop_phys, phys_ms)
+    gbs_step = (b_ctrl + b_phys) * D / (step_ms * 1e-3) / 1e9
+    roofline_step = {"bound": "hbm", "achieved": gbs_step, "peak": hbm_peak, "unit": "GB/s", "frac": gbs_step / hbm_peak,
+                     "algorithmic_bytes_per_drone_step": b_ctrl + b_phys, "ms_per_control_step": step_ms,
+                     "sum_of_kernel_ms": ctrl_ms + phys_ms, "note": "both kernels back to back inside the timed region (this rank)"}
 
     # ---- end to end through the per-call API with host buffers --------------------------------
     e2e = None
@@ -312,17 +359,18 @@ def run_gpu_arm(args):
         line = {"metric": "drone-steps/sec (DYN_GND_DRAG_DW + LQR + order-3 CBF-QP, 8 drones/env)", "value": value, "unit": "drone-steps/s",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, E),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "roofline_hbm": roofline_hbm,
-                "cpu_baseline": cpu, "rollout_stats": stats, "sm_count": mds._lib.device_info()["sm_count"]}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * F * K, "roofline": roofline, "roofline_physics": roofline_physics,
+                "roofline_step": roofline_step, "cpu_baseline": cpu, "rollout_stats": stats, "sm_count": mds._lib.device_info()["sm_count"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def run_e2e(args, mds, sc, dev, dtype, world, barrier):
-    """Reference-facing per-call sequence with HOST buffers, every control step:
+    """Reference-facing per-call sequence with HOST buffers (multidronesim_b200.HostPipeline), every control step:
        H2D refs (what the reference passes to set_desired_trajectory) -> LQR (skip_low_level) -> caller glue
-       (nominal -= mg, xdes) -> CBF-QP -> inner loop -> env.step -> D2H observations."""
+       (nominal -= mg, xdes) -> CBF-QP -> inner loop -> env.step -> D2H observations; the copies of neighbouring
+       steps overlap the kernels on their own streams."""
     import torch
     import torch.distributed as dist
     env, ctrl, trk, trajs = sc["env"], sc["ctrl"], sc["tracker"], sc["trajs"]
@@ -336,22 +384,20 @@ def run_e2e(args, mds, sc, dev, dtype, world, barrier):
     for k in range(S):
         ref_host[k].copy_(trajs.eval(k * env.CTRL_TIMESTEP))
     torch.cuda.synchronize()
-    obs_host = torch.empty(E, N, 20, dtype=dtype).pin_memory()
-    ref_dev = torch.empty(D, 11, device=dev, dtype=dtype)
-    pipe = mds.rollout.PerCallPipeline(env, ctrl, trk, sc["obstacles"])
-    for k in range(3):
-        ref_dev.copy_(ref_host[k], non_blocking=True)
-        pipe.step(ref_dev)
-        obs_host.copy_(env.obs, non_blocking=True)
-    torch.cuda.synchronize()
+    obs_host = [torch.empty(E, N, 20, dtype=dtype).pin_memory() for _ in range(2)]
+    pipe = mds.HostPipeline(env, ctrl, trk, sc["obstacles"])
+    for k in range(4):
+        pipe.step(ref_host[k], obs_host[k & 1])
+    pipe.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
+    cs = torch.cuda.current_stream(dev)
     ev0.record()
     for k in range(S):
-        ref_dev.copy_(ref_host[k], non_blocking=True)
-        pipe.step(ref_dev)
-        obs_host.copy_(env.obs, non_blocking=True)
+        pipe.step(ref_host[k], obs_host[k & 1])
+    cs.wait_stream(pipe.s_out)  # the last observation has landed in host memory
+    cs.wait_stream(pipe.s_in)
     ev1.record()
     torch.cuda.synchronize()
     barrier()
@@ -362,7 +408,8 @@ def run_e2e(args, mds, sc, dev, dtype, world, barrier):
     esz = 4 if dtype == torch.float32 else 8
     return {"value": world * D * S / (ms * 1e-3), "unit": "drone-steps/s", "h2d_bytes_per_step": D * 11 * esz, "d2h_bytes_per_step": D * 20 * esz,
             "control_steps": S, "ms_per_control_step": ms / S, "kernels_per_control_step": pipe.launches_per_step,
-            "path": "H2D refs -> mds_lqr_ctrl -> mds_cbf_prepare -> mds_cbf_qp -> mds_lowlevel -> mds_physics_step -> D2H obs (one stream)"}
+            "path": "pinned host refs -> H2D (copy stream) -> mds_lqr_ctrl -> mds_cbf_prepare -> mds_cbf_qp -> mds_lowlevel -> mds_physics_step "
+                    "-> D2H obs to pinned host (copy stream); two slots, copies overlap the next step's kernels"}
 
 
 def main():

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MDS_ABI_VERSION 1
+#define MDS_ABI_VERSION 2
 #define MDS_MAX_DRONES_PER_ENV 32
 #define MDS_MAX_OBSTACLES 8
 #define MDS_OBS_DIM 20
@@ -144,6 +144,10 @@ typedef struct MdsRolloutCfg {
   int use_cbf;         /* 0/1; requires ctrl LQR_OMEGA (order 2) or LQR_YANK (order 3) */
   int num_obstacles;   /* spheres shared by all envs (<= N, reference quirk B14)        */
   int write_obs_every; /* 0 = only after the last step; k>0 = log obs every k steps     */
+  int stages;          /* 0 or 3 = controller kernel + physics kernel per step; 1 = controller kernel only
+                          (action_dev <- controller stack at obs_dev; the env does not advance); 2 = physics
+                          kernel only (env advances under action_dev).  1 and 2 exist so that a caller can
+                          bracket each kernel with its own CUDA events (bench.py roofline).            */
   double obstacles[MDS_MAX_OBSTACLES * 4]; /* cx, cy, cz, r */
 } MdsRolloutCfg;
 

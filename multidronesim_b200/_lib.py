@@ -66,7 +66,7 @@ class CbfParams(C.Structure):
 
 class RolloutCfg(C.Structure):
     _fields_ = [("ctrl", C.c_int), ("use_cbf", C.c_int), ("num_obstacles", C.c_int),
-                ("write_obs_every", C.c_int), ("obstacles", C.c_double * (MAX_OBSTACLES * 4))]
+                ("write_obs_every", C.c_int), ("stages", C.c_int), ("obstacles", C.c_double * (MAX_OBSTACLES * 4))]
 
 
 # numpy dtypes of the device-side trajectory tables (must match the C structs)

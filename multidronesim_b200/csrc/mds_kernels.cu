@@ -698,6 +698,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   MDS_REQUIRE(prm && cfg && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && specs && obs && action, "rollout: null pointer");
   MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV && K > 0, "rollout: bad E, N or K");
   MDS_REQUIRE(cfg->ctrl >= MDS_CTRL_GEOMETRIC && cfg->ctrl <= MDS_CTRL_LQR_YANK, "rollout: unknown controller");
+  MDS_REQUIRE(cfg->stages >= 0 && cfg->stages <= 3, "rollout: stages must be 0..3");
   RolloutP<Real> R;
   memset(&R, 0, sizeof(R));
   R.ctrl = cfg->ctrl; R.use_cbf = cfg->use_cbf; R.n_obs = cfg->num_obstacles; R.write_obs_every = cfg->write_obs_every;
@@ -748,9 +749,10 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Pi, specs, segs, obs_in, action, stats, t, E, N, NP);                     \
   } while (0)
   const Real* obs_in = obs;
+  const bool do_ctrl = cfg->stages != 2, do_phys = cfg->stages != 1;
   for (int k = 0; k < K; ++k) {
     const double t = t0 + (double)k * prm->dt_ctrl;
-    switch (R.ctrl) {
+    if (do_ctrl) switch (R.ctrl) {
       case MDS_CTRL_GEOMETRIC: MDS_CTRL_STEP(MDS_CTRL_GEOMETRIC, false); break;
       case MDS_CTRL_LQR_TORQUE: MDS_CTRL_STEP(MDS_CTRL_LQR_TORQUE, false); break;
       case MDS_CTRL_LQR_OMEGA:
@@ -762,6 +764,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
         else MDS_CTRL_STEP(MDS_CTRL_LQR_YANK, false);
         break;
     }
+    if (!do_phys) continue;
     // the observation after this step goes to its log slot when one is due, else to the env's obs buffer
     Real* obs_out = obs;
     if (R.write_obs_every > 0 && ((k + 1) % R.write_obs_every) == 0) obs_out = obs_log + (size_t)((k + 1) / R.write_obs_every - 1) * obs_elems;

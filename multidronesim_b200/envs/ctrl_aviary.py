@@ -138,9 +138,14 @@ class BatchedCtrlAviary(DroneConstants):
             self._ext_force = torch.zeros(self.NUM_ENVS, self.NUM_DRONES, 3, device=self.device, dtype=self.dtype)
         self._stage(force, self._ext_force, "force")
 
-    def step(self, action):
+    def step(self, action, obs_out=None):
         """action: RPM [E,N,4] (or [N,4] when E == 1), device tensor or host array.
-        Returns (obs [E,N,20], reward [E], terminated [E], truncated [E], info)."""
+        Returns (obs [E,N,20], reward [E], terminated [E], truncated [E], info).
+        ``obs_out``: optional device buffer [E,N,20] that receives the new observation and BECOMES the env's obs
+        buffer (lets a caller alternate two buffers so that a device->host copy of step k overlaps step k+1)."""
+        if obs_out is not None:
+            _lib.require_cuda(obs_out, "obs_out", self.dtype, (self.NUM_ENVS, self.NUM_DRONES, _lib.OBS_DIM))
+            self._obs = obs_out
         if isinstance(action, torch.Tensor) and action.is_cuda and action.dtype == self.dtype and action.is_contiguous() \
                 and action.numel() == self._action.numel():
             act = action

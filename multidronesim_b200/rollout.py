@@ -52,13 +52,18 @@ class FusedRollout:
         self.stats.zero_()
         self.stats[3] = 1e30  # MDS_STAT_MIN_BARRIER
 
-    def run(self, K, t0=None, obs_log=None, log_every=0):
+    def run(self, K, t0=None, obs_log=None, log_every=0, stages=3):
         """Advance every environment K control steps.  ``obs_log`` [K//log_every, E, N, 20] receives the
         observation after every ``log_every``-th step (the reference's ``observations.append(obs)``).
+        ``stages``: 3 = controller kernel + physics kernel (default); 1 = controller kernel only (fills the
+        env's action buffer, time does not advance); 2 = physics kernel only (consumes that action buffer).
         Returns the env's obs buffer (observation after the last step)."""
         env = self.env
         if t0 is None:
             t0 = self.t
+        if stages not in (1, 2, 3):
+            raise ValueError("stages must be 1, 2 or 3")
+        self.cfg.stages = int(stages)
         self.cfg.write_obs_every = int(log_every) if obs_log is not None else 0
         if obs_log is not None:
             _lib.require_cuda(obs_log, "obs_log", env.dtype)
@@ -71,8 +76,9 @@ class FusedRollout:
         _lib.call("mds_rollout", env.dtype, env._prm, self.cfg, geo, lqr, cbf, env._state_struct(), pid,
                   _lib.ptr(self.trajs.specs), _lib.ptr(self.trajs.segs), _lib.ptr(env._obs), _lib.ptr(env._action), _lib.ptr(obs_log),
                   _lib.ptr(self.stats), float(t0), int(K), env.NUM_ENVS, env.NUM_DRONES, _lib.stream_ptr(env.device))
-        env.step_counter += K * env.PYB_STEPS_PER_CTRL
-        self.t = t0 + K * env.CTRL_TIMESTEP
+        if stages != 1:
+            env.step_counter += K * env.PYB_STEPS_PER_CTRL
+            self.t = t0 + K * env.CTRL_TIMESTEP
         return env._obs
 
     def stats_dict(self):
@@ -95,7 +101,9 @@ class PerCallPipeline:
         self.mg = env.M * env.G
         self.launches_per_step = 5 if qp_tracker is not None else 2
 
-    def step(self, ref):
+    def step(self, ref, obs_out=None):
+        """ref: device tensor [D, 11] (pos, vel, acc, yaw, yaw_rate per drone).  Returns the new observation
+        (written to ``obs_out`` when given, see BatchedCtrlAviary.step)."""
         env, c = self.env, self.ctrl
         c.set_reference(ref)
         obs = env.obs
@@ -110,4 +118,54 @@ class PerCallPipeline:
             if self.qp.order == 2:
                 us[..., 0] += self.mg
             action = c.compute_low_level(us, obs)
-        return env.step(action)[0]
+        return env.step(action, obs_out)[0]
+
+
+class HostPipeline:
+    """Host-buffer form of the per-call path: every control step takes that step's references from PINNED host
+    memory and delivers the new observation into PINNED host memory, as a host-side caller of the reference's
+    loop would see it (obs out of ``env.step``, set-points in through ``set_desired_trajectory``).
+
+    Three streams, two slots: the H2D copy of step k+1's references and the D2H copy of step k's observation
+    run on their own streams while the kernels of step k+1 run on the caller's stream; events order the reuse
+    of the two device reference buffers and the two device observation buffers.  ``step`` is asynchronous;
+    the returned event fires when ``obs_host`` holds the step's observation."""
+
+    def __init__(self, env, controller, qp_tracker=None, obstacles=None):
+        self.env = env
+        self.pipe = PerCallPipeline(env, controller, qp_tracker, obstacles)
+        dev, dt = env.device, env.dtype
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.ref_dev = [torch.empty(env.NUM_TOTAL, _lib.REF_DIM, device=dev, dtype=dt) for _ in range(2)]
+        self.obs_dev = [torch.empty(env.NUM_ENVS, env.NUM_DRONES, _lib.OBS_DIM, device=dev, dtype=dt) for _ in range(2)]
+        mk = lambda: [torch.cuda.Event() for _ in range(2)]
+        self.ref_ready, self.ref_free, self.obs_ready, self.obs_free = mk(), mk(), mk(), mk()
+        self.k = 0
+        self.launches_per_step = self.pipe.launches_per_step
+
+    def step(self, ref_host, obs_host):
+        env, slot = self.env, self.k & 1
+        cs = torch.cuda.current_stream(env.device)
+        first = self.k < 2
+        with torch.cuda.stream(self.s_in):
+            if not first:
+                self.s_in.wait_event(self.ref_free[slot])
+            self.ref_dev[slot].copy_(ref_host.reshape(self.ref_dev[slot].shape), non_blocking=True)
+            self.ref_ready[slot].record(self.s_in)
+        cs.wait_event(self.ref_ready[slot])
+        if not first:
+            cs.wait_event(self.obs_free[slot])
+        self.pipe.step(self.ref_dev[slot], obs_out=self.obs_dev[slot])
+        self.ref_free[slot].record(cs)
+        self.obs_ready[slot].record(cs)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.obs_ready[slot])
+            obs_host.copy_(self.obs_dev[slot].reshape(obs_host.shape), non_blocking=True)
+            self.obs_free[slot].record(self.s_out)
+        self.k += 1
+        return self.obs_free[slot]
+
+    def synchronize(self):
+        self.s_in.synchronize()
+        self.s_out.synchronize()
+        torch.cuda.current_stream(self.env.device).synchronize()

@@ -34,6 +34,37 @@ def lemniscate_pos(a, theta, center):
     return np.stack([center[0] + a * s * c / den, center[1] + a * c / den, np.full_like(theta, center[2])], axis=-1)
 
 
+def counter_normal(seed, env_ids, per_env):
+    """Standard normals [len(env_ids), per_env] that depend only on (seed, absolute env index, slot): a splitmix64
+    counter hash -> two uniforms -> Box-Muller.  Env e draws the same numbers however the envs are sharded over
+    GPUs, so an N-GPU run reproduces the 1-GPU run env for env."""
+    def mix(z):
+        z = (z + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        e = np.asarray(env_ids, dtype=np.uint64)[:, None]
+        k = np.arange(per_env, dtype=np.uint64)[None, :]
+        base = mix(mix(np.uint64(seed) + np.uint64(0x1234567)) ^ (e * np.uint64(0xD1342543DE82EF95))) ^ (k * np.uint64(0x2545F4914F6CDD1D))
+        a, b = mix(base), mix(base ^ np.uint64(0xA5A5A5A5A5A5A5A5))
+    u1 = ((a >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740993.0   # (0, 1)
+    u2 = (b >> np.uint64(11)).astype(np.float64) / 9007199254740992.0           # [0, 1)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def cbf_swarm_init(num_envs, num_drones=8, seed=3, env_offset=0, a=1.0, center=(0.0, 0.0, 0.5), jitter=0.02, z_step=0.04):
+    """Initial positions [E, N, 3] of the C3 / C5 swarm for the env range [env_offset, env_offset + E): drone k at
+    phase 2 pi k / (N + 0.25) of the lemniscate, N(0, jitter^2) per coordinate, plus k * z_step in z."""
+    E, N = int(num_envs), int(num_drones)
+    phase = (2 * np.pi / (N + 0.25)) * np.arange(N)
+    base = lemniscate_pos(a, phase, np.asarray(center, dtype=float))
+    noise = counter_normal(seed, env_offset + np.arange(E), 3 * N).reshape(E, N, 3)
+    init = base[None] + jitter * noise
+    init[..., 2] += z_step * np.arange(N)[None, :]
+    return init
+
+
 def cbf_swarm(num_envs, num_drones=8, order=3, dtype=torch.float32, device="cuda", seed=3, env_offset=0,
               omega=0.5, obstacle=True, physics=Physics.DYN_GND_DRAG_DW, pyb_freq=240, ctrl_freq=240):
     """C3 / C5: N drones per env on one lemniscate (a=1, centre (0,0,0.5)) with phase shifts
@@ -44,15 +75,7 @@ def cbf_swarm(num_envs, num_drones=8, order=3, dtype=torch.float32, device="cuda
     E, N = int(num_envs), int(num_drones)
     center = np.array([0.0, 0.0, 0.5])
     phase = (2 * np.pi / (N + 0.25)) * np.arange(N)
-    init = np.empty((E, N, 3))
-    base = lemniscate_pos(1.0, phase, center)
-    # counter-based per-env streams: env e always draws the same jitter, whatever the sharding
-    for lo in range(0, E, 65536):
-        hi = min(E, lo + 65536)
-        ss = np.random.SeedSequence([seed, env_offset + lo])
-        rng = np.random.default_rng(ss)
-        init[lo:hi] = base[None] + rng.normal(0, 0.02, (hi - lo, N, 3))
-    init[..., 2] += 0.04 * np.arange(N)[None, :]
+    init = cbf_swarm_init(E, N, seed=seed, env_offset=env_offset)
     env = BatchedCtrlAviary(drone_model=DroneModel.CF2P, num_drones=N, initial_xyzs=init, physics=physics,
                             pyb_freq=pyb_freq, ctrl_freq=ctrl_freq, num_envs=E, device=device, dtype=dtype)
     if order == 3:
@@ -78,16 +101,17 @@ def tracking_swarm(num_envs, dtype=torch.float32, device="cuda", seed=1, env_off
     centre (0,0,1)), odd envs Lemniscate(a=1, omega=1.5, centre (0,0,0.5)) with a random phase shift;
     initial position = traj(0) + N(0, 0.05^2), z >= 0.1."""
     E = int(num_envs)
-    rng = np.random.default_rng(np.random.SeedSequence([seed, env_offset]))
-    kind = np.where(np.arange(E) % 2 == 0, _lib.TRAJ_CIRCLE, _lib.TRAJ_LEMNISCATE)
-    phase = rng.uniform(0, 2 * np.pi, E)
+    ids = env_offset + np.arange(E)
+    kind = np.where(ids % 2 == 0, _lib.TRAJ_CIRCLE, _lib.TRAJ_LEMNISCATE)
+    # a uniform phase from the same per-env counter stream (Phi of a standard normal)
+    phase = 2 * np.pi * 0.5 * (1.0 + np.vectorize(math.erf)(counter_normal(seed + 1000, ids, 1)[:, 0] / math.sqrt(2.0)))
     params = np.zeros((E, 7))
     circ = kind == _lib.TRAJ_CIRCLE
     params[circ, 0:6] = [1.0, 0.5, 0.0, 0.0, 1.0, 0.0]
     params[~circ, 0:5] = [1.0, 1.5, 0.0, 0.0, 0.5]
     params[~circ, 6] = phase[~circ]
     p0 = np.where(circ[:, None], np.array([1.0, 0.0, 1.0])[None], lemniscate_pos(1.0, phase, np.array([0.0, 0.0, 0.5])))
-    init = p0 + rng.normal(0, 0.05, (E, 3))
+    init = p0 + 0.05 * counter_normal(seed, ids, 3)
     init[:, 2] = np.maximum(init[:, 2], 0.1)
     env = BatchedCtrlAviary(drone_model=DroneModel.CF2P, num_drones=1, initial_xyzs=init.reshape(E, 1, 3), physics=physics,
                             num_envs=E, device=device, dtype=dtype)
