@@ -156,6 +156,14 @@ int mds_abi_version(void);
 const char* mds_last_error(void);
 int mds_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes);
 
+/* ---- plain-host helpers (for callers without a CUDA-aware array library; the reference is numpy-only) ---- */
+#include <stddef.h>
+int mds_device_alloc(size_t bytes, void** out_dev); /* zero-filled device buffer */
+int mds_device_free(void* dev);
+int mds_copy_to_device(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int mds_copy_to_host(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+int mds_stream_synchronize(void* stream);
+
 /* ---- env step: replaces CtrlAviary.step (call sites EnvGeometric.py:431,469) ----- */
 /* clip RPM to [0, max_rpm]; `substeps` explicit DYN / DYN_GND_DRAG_DW updates; write obs.
  * ext_force_dev: optional [D*3] world-frame force per drone (wind, EnvGeometric.py:463-467). */
@@ -163,6 +171,13 @@ int mds_physics_step_f32(const MdsDroneParams* prm, MdsState st, const float* ac
                          const float* ext_force_dev, float* obs_dev, int E, int N, void* stream);
 int mds_physics_step_f64(const MdsDroneParams* prm, MdsState st, const double* action_dev,
                          const double* ext_force_dev, double* obs_dev, int E, int N, void* stream);
+/* HOST-array form of the same call, the literal `obs = env.step(action)` of the reference's loops
+ * (EnvGeometric.py:469): action_host [D*4] -> H2D -> step -> D2H -> obs_host [D*20]; synchronous on `stream`.
+ * action_dev / obs_dev are the library-side device staging buffers (caller-owned). */
+int mds_physics_step_host_f32(const MdsDroneParams* prm, MdsState st, const float* action_host, float* action_dev,
+                              float* obs_dev, float* obs_host, int E, int N, void* stream);
+int mds_physics_step_host_f64(const MdsDroneParams* prm, MdsState st, const double* action_host, double* action_dev,
+                              double* obs_dev, double* obs_host, int E, int N, void* stream);
 /* (re)build obs from state without stepping (reset(); ang vel = R w) */
 int mds_obs_from_state_f32(const MdsDroneParams* prm, MdsState st, float* obs_dev, int D, void* stream);
 int mds_obs_from_state_f64(const MdsDroneParams* prm, MdsState st, double* obs_dev, int D, void* stream);

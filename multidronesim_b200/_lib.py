@@ -89,6 +89,7 @@ _PRM = C.POINTER(DroneParams)
 # name -> argtypes (suffix-less); each exists as _f32 and _f64
 _SIGS = {
     "mds_physics_step": [_PRM, State, _P, _P, _P, _I, _I, _P],
+    "mds_physics_step_host": [_PRM, State, _P, _P, _P, _P, _I, _I, _P],
     "mds_obs_from_state": [_PRM, State, _P, _I, _P],
     "mds_traj_eval": [_P, _P, _D, _P, _I, _P],
     "mds_geometric_ctrl": [_PRM, C.POINTER(GeoGains), _P, _P, _P, _P, _I, _P],
@@ -108,6 +109,11 @@ _PLAIN = {
     "mds_device_info": ([C.POINTER(_I)] * 4, _I),
     "mds_cbf_num_rows": ([_I, _I, _I], _I),
     "mds_fma_peak": ([_I, _I, C.POINTER(_D), _P], _I),
+    "mds_device_alloc": ([C.c_size_t, C.POINTER(C.c_void_p)], _I),
+    "mds_device_free": ([_P], _I),
+    "mds_copy_to_device": ([_P, _P, C.c_size_t, _P], _I),
+    "mds_copy_to_host": ([_P, _P, C.c_size_t, _P], _I),
+    "mds_stream_synchronize": ([_P], _I),
 }
 
 EXPORTED_SYMBOLS = tuple(sorted([f"{k}_{s}" for k in _SIGS for s in ("f32", "f64")] + list(_PLAIN)))

@@ -796,11 +796,55 @@ int mds_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes) 
   if (l2_bytes) *l2_bytes = p.l2CacheSize;
   return MDS_OK;
 }
+// ---- plain-host helpers: let a caller without a CUDA-aware array library (the reference is numpy-only) own
+// device buffers and move host arrays across the boundary
+int mds_device_alloc(size_t bytes, void** out_dev) {
+  MDS_REQUIRE(out_dev && bytes > 0, "device_alloc: bad argument");
+  cudaError_t e = cudaMalloc(out_dev, bytes);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "device_alloc: %s", cudaGetErrorString(e));
+  e = cudaMemset(*out_dev, 0, bytes);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "device_alloc: %s", cudaGetErrorString(e));
+  return MDS_OK;
+}
+int mds_device_free(void* dev) {
+  cudaError_t e = cudaFree(dev);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "device_free: %s", cudaGetErrorString(e));
+  return MDS_OK;
+}
+int mds_copy_to_device(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+  MDS_REQUIRE(dst_dev && src_host, "copy_to_device: null pointer");
+  cudaError_t e = cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "copy_to_device: %s", cudaGetErrorString(e));
+  return MDS_OK;
+}
+int mds_copy_to_host(void* dst_host, const void* src_dev, size_t bytes, void* stream) {
+  MDS_REQUIRE(dst_host && src_dev, "copy_to_host: null pointer");
+  cudaError_t e = cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "copy_to_host: %s", cudaGetErrorString(e));
+  return MDS_OK;
+}
+int mds_stream_synchronize(void* stream) {
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "stream_synchronize: %s", cudaGetErrorString(e));
+  return MDS_OK;
+}
 int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 * N + (order == 3 ? 2 * N : 0) + N * n_obs; }
 
 #define MDS_DEFINE(SUF, REAL, SPEC, SEG)                                                                                                          \
   int mds_physics_step_##SUF(const MdsDroneParams* prm, MdsState st, const REAL* action, const REAL* fext, REAL* obs, int E, int N, void* stream) { \
     return physics_step_impl<REAL>(prm, st, action, fext, obs, E, N, stream);                                                                      \
+  }                                                                                                                                                \
+  int mds_physics_step_host_##SUF(const MdsDroneParams* prm, MdsState st, const REAL* action_host, REAL* action_dev, REAL* obs_dev,              \
+                                  REAL* obs_host, int E, int N, void* stream) {                                                                   \
+    MDS_REQUIRE(action_host && action_dev && obs_dev && obs_host && E > 0 && N > 0, "physics_step_host: bad argument");                             \
+    const size_t D = (size_t)E * N;                                                                                                                \
+    int rc = mds_copy_to_device(action_dev, action_host, D * 4 * sizeof(REAL), stream);                                                            \
+    if (rc) return rc;                                                                                                                             \
+    rc = physics_step_impl<REAL>(prm, st, action_dev, (const REAL*)nullptr, obs_dev, E, N, stream);                                                \
+    if (rc) return rc;                                                                                                                             \
+    rc = mds_copy_to_host(obs_host, obs_dev, D * MDS_OBS_DIM * sizeof(REAL), stream);                                                              \
+    if (rc) return rc;                                                                                                                             \
+    return mds_stream_synchronize(stream);                                                                                                         \
   }                                                                                                                                                \
   int mds_obs_from_state_##SUF(const MdsDroneParams* prm, MdsState st, REAL* obs, int D, void* stream) {                                           \
     return obs_from_state_impl<REAL>(prm, st, obs, D, stream);                                                                                     \

@@ -138,3 +138,41 @@ def test_external_force(lib_built):
         obs = env.step(act)[0]
         want = o.step(act[0])[0]
     assert obs_err(obs[0].cpu().numpy(), want) < 1e-9 and want[0, 0] > 0
+
+
+@pytest.mark.gpu
+def test_plain_host_abi_numpy_only(lib_built):
+    """The boundary as a numpy-only caller (the reference has no torch) would use it: device buffers from
+    mds_device_alloc, state uploaded with mds_copy_to_device, `obs = step(action)` with HOST arrays through
+    mds_physics_step_host_f64 -- compared with the oracle env step by step (INTEGRATION.md stub)."""
+    import ctypes as C
+    from multidronesim_b200 import _lib
+    from multidronesim_b200.constants import DroneConstants
+    from multidronesim_b200.enums import DroneModel, Physics
+    lib = lib_built
+    N, steps = 3, 12
+    rng = np.random.default_rng(5)
+    o = OracleCtrlAviary(ODM.CF2P, N, initial_xyzs=np.array([[0, 0, 0.5], [0.3, 0, 0.9], [0.1, 0.05, 1.4]]), physics=OPH.DYN_GND_DRAG_DW)
+    prm = DroneConstants(DroneModel.CF2P, Physics.DYN_GND_DRAG_DW, 240, 240).c_params()
+
+    def dev(nbytes):
+        p = C.c_void_p()
+        assert lib.mds_device_alloc(nbytes, C.byref(p)) == 0
+        return p
+    bufs = {k: dev(N * w * 8) for k, w in (("pos_wx", 4), ("quat", 4), ("vel_wy", 4), ("rpm", 4), ("wz", 1), ("action", 4), ("obs", 20))}
+    pos_wx = np.zeros((N, 4)); pos_wx[:, :3] = o.pos
+    quat = np.tile([0.0, 0, 0, 1], (N, 1))
+    for name, arr in (("pos_wx", pos_wx), ("quat", quat)):
+        assert lib.mds_copy_to_device(bufs[name], arr.ctypes.data_as(C.c_void_p), arr.nbytes, None) == 0
+    assert lib.mds_stream_synchronize(None) == 0
+    st = _lib.State(*(bufs[k].value for k in ("pos_wx", "quat", "vel_wy", "rpm", "wz")))
+    obs = np.zeros((N, 20))
+    for k in range(steps):
+        action = rng.uniform(12000, 16000, (N, 4))
+        rc = lib.mds_physics_step_host_f64(C.byref(prm), st, action.ctypes.data_as(C.c_void_p), bufs["action"], bufs["obs"],
+                                           obs.ctypes.data_as(C.c_void_p), 1, N, None)
+        assert rc == 0, lib.mds_last_error()
+        want = o.step(action)[0]
+        assert np.max(np.abs(obs - want) / (1 + np.abs(want))) < 1e-9
+    for p in bufs.values():
+        assert lib.mds_device_free(p) == 0
