@@ -151,7 +151,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "drone-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "drone-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, envs, per_gpu=True):
@@ -361,7 +361,7 @@ def run_gpu_arm(args):
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, E),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * F * K, "roofline": roofline, "roofline_physics": roofline_physics,
                 "roofline_step": roofline_step, "cpu_baseline": cpu, "rollout_stats": stats, "sm_count": mds._lib.device_info()["sm_count"]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -412,8 +412,21 @@ def run_e2e(args, mds, sc, dev, dtype, world, barrier):
                     "-> D2H obs to pinned host (copy stream); two slots, copies overlap the next step's kernels"}
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the process's original stdout; everything else (NCCL banners, warnings) to stderr"""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    global _JSON_FD
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)  # libraries that print to stdout (e.g. "NCCL version ...") must not pollute the JSON line
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -235,12 +235,13 @@ MDS_DEV int qp_scan(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows,
                     const RowMap& M, int N, int NP, int n, bool valid, unsigned rowmask, unsigned boxmask, unsigned gmask) {
   QpWorst<Real> w = {Real(0), 0x7fffffff};
   if (valid) {
-    for (int s = 0; s < M.RPL; ++s) {
-      if (rowmask & (1u << s)) continue;
+#pragma unroll
+    for (int s = 0; s < M.S0; ++s) {  // pair slots
       const int m = row_partner(M, N, n, s);
-      if (m == -2) continue;
-      qp_test_row(w, rows[n * M.RPL + s], xn, x, n, m, n * M.RPL + s);
+      if (m >= 0 && !(rowmask & (1u << s))) qp_test_row(w, rows[n * M.RPL + s], xn, x, n, m, n * M.RPL + s);
     }
+    for (int s = M.S0; s < M.RPL; ++s)  // obstacle slots
+      if (!(rowmask & (1u << s))) qp_test_row(w, rows[n * M.RPL + s], xn, x, n, -1, n * M.RPL + s);
     qp_test_box(w, C, xn, n, boxmask);
   }
   return qp_worst_of_group(w, NP, gmask);

@@ -68,8 +68,10 @@ MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* s
   Real dw = Real(0);
   if (g.valid) {
     const int base = threadIdx.x - g.n;
-    for (int j = 0; j < N; ++j) {
-      if (j == g.n) continue;
+#pragma unroll
+    for (int k = 1; k < N; ++k) {  // partners in circular order: no self test, unrolls when N is a compile-time constant
+      int j = g.n + k;
+      j = j >= N ? j - N : j;
       auto q = sm_pos[base + j];
       dw += downwash_term(P, p, v3(q.x, q.y, q.z));
     }
@@ -132,30 +134,36 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
   Real lo = Real(0), hi = Real(0);
   QpWorst<Real> worst = {Real(0), 0x7fffffff};
   if (g.valid) {
-    for (int s = 0; s < M.RPL; ++s) {  // this lane's own rows, each tested against u_nom as it is built
+    // this lane's own rows, each tested against u_nom as it is built: pair slots (compile-time count when N is),
+    // then obstacle slots
+#pragma unroll
+    for (int s = 0; s < M.S0; ++s) {
       const int m = row_partner(M, N, n, s);
       R4 row;
       row.x = Real(0); row.y = Real(0); row.z = Real(0); row.w = Real(1e30);
-      if (m != -2) {
+      if (m >= 0) {
         CbfAgent<Real> other;
-        Real Ds;
-        if (m >= 0) {
-          R4 b0 = agents[3 * m], b1 = agents[3 * m + 1], b2 = agents[3 * m + 2];
-          other.p = {b0.x, b0.y, b0.z}; other.dv = {b0.w, b1.x, b1.y}; other.da = {b1.z, b1.w, b2.x};
-          Ds = Real(2) * C.rs;
-        } else {
-          const int o = s - M.S0;
-          other.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
-          other.dv = {Real(0), Real(0), Real(0)}; other.da = other.dv;
-          Ds = C.rs + obstacles[4 * o + 3];
-        }
+        R4 b0 = agents[3 * m], b1 = agents[3 * m + 1], b2 = agents[3 * m + 2];
+        other.p = {b0.x, b0.y, b0.z}; other.dv = {b0.w, b1.x, b1.y}; other.da = {b1.z, b1.w, b2.x};
         Real a3[3], rhs, h0;
-        cbf_row(P, C, ag, other, Ds, a3, &rhs, &h0);  // owner - partner (mds_cbf.cuh "Row ownership")
+        cbf_row(P, C, ag, other, Real(2) * C.rs, a3, &rhs, &h0);  // owner - partner (mds_cbf.cuh "Row ownership")
         *min_h = min_(*min_h, h0);
         row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
         qp_test_row(worst, row, unom, x, n, m, n * M.RPL + s);
       }
       rows[n * M.RPL + s] = row;
+    }
+    for (int o = 0; o < n_obs; ++o) {
+      CbfAgent<Real> other;
+      other.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
+      other.dv = {Real(0), Real(0), Real(0)}; other.da = other.dv;
+      Real a3[3], rhs, h0;
+      cbf_row(P, C, ag, other, C.rs + obstacles[4 * o + 3], a3, &rhs, &h0);
+      *min_h = min_(*min_h, h0);
+      R4 row;
+      row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
+      qp_test_row(worst, row, unom, x, n, -1, n * M.RPL + M.S0 + o);
+      rows[n * M.RPL + M.S0 + o] = row;
     }
     qp_test_box(worst, C, unom, n, 0u);
     if (!cbf_wz_bounds(C, F, &lo, &hi)) fl = 1;
@@ -181,10 +189,20 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
 }
 
 // ------------------------------------------------------------------ kernels: env step
-template <typename Real>
+// NT > 0: drones per env as a compile-time constant (the rollout's specialisation for the 8-drone swarms: partner
+// loops unroll, lane maps fold to shifts); NT == 0: run-time N.
+template <int NT> MDS_DEV int ct_n(int n_rt) { return NT > 0 ? NT : n_rt; }
+template <int NT> MDS_DEV int ct_np(int np_rt) {
+  if (NT <= 0) return np_rt;
+  int p = 1;
+  while (p < NT) p <<= 1;
+  return p;
+}
+template <typename Real, int NT>
 __global__ void __launch_bounds__(MDS_BLOCK) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
-                                                                  const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N, int NP) {
+                                                                  const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N_rt, int NP_rt) {
   __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
+  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   const GroupMap g = group_map(N, NP, E);
   if (!g.env_valid) return;  // whole groups leave together
   Drone<Real> s;
@@ -469,13 +487,14 @@ MDS_DEV void atomic_max_double(double* addr, double v) {
 // (CBF-QP) -> inner loop -> RPM action.  CTRL / USE_CBF are compile-time so that each instantiation
 // carries only its own stage code (the whole K-step loop in one kernel overflowed the instruction
 // cache: 55 % of the stall samples were "no instruction"; profiles/r1_rollout_fused_ncu.txt).
-template <typename Real, int CTRL, bool USE_CBF>
+template <typename Real, int CTRL, bool USE_CBF, int NT>
 __global__ void __launch_bounds__(MDS_BLOCK) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
                                                                PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                const typename TrajSpecT<Real>::seg* __restrict__ segs,
                                                                const Real* __restrict__ obs, Real* __restrict__ action,
-                                                               double* __restrict__ stats, double t, int E, int N, int NP) {
+                                                               double* __restrict__ stats, double t, int E, int N_rt, int NP_rt) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
+  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
   const GroupMap g = group_map(N, NP, E);
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
@@ -601,7 +620,8 @@ static int physics_step_impl(const MdsDroneParams* prm, MdsState st, const Real*
   MDS_REQUIRE(prm->substeps >= 1, "physics_step: substeps must be >= 1");
   MDS_REQUIRE(prm->physics == MDS_PHYSICS_DYN || prm->physics == MDS_PHYSICS_DYN_GND_DRAG_DW, "physics_step: unknown physics mode");
   int NP = next_pow2(N), epb = MDS_BLOCK / NP, blocks = (E + epb - 1) / epb;
-  physics_step_kernel<Real><<<blocks, MDS_BLOCK, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(st), action, fext, obs, E, N, NP);
+  if (N == 8) physics_step_kernel<Real, 8><<<blocks, MDS_BLOCK, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(st), action, fext, obs, E, N, NP);
+  else physics_step_kernel<Real, 0><<<blocks, MDS_BLOCK, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(st), action, fext, obs, E, N, NP);
   return check_launch("physics_step");
 }
 template <typename Real> static int obs_from_state_impl(const MdsDroneParams* prm, MdsState st, Real* obs, int D, void* stream) {
@@ -741,7 +761,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   const size_t obs_elems = (size_t)E * N * MDS_OBS_DIM;
 #define MDS_CTRL_STEP(CT, CB)                                                                                                       \
   do {                                                                                                                              \
-    auto kern = ctrl_step_kernel<Real, CT, CB>;                                                                                     \
+    auto kern = (N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>;                                   \
     if (k == 0) {                                                                                                                   \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
       if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: shared memory opt-in failed: %s", cudaGetErrorString(e));         \
@@ -768,7 +788,8 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     // the observation after this step goes to its log slot when one is due, else to the env's obs buffer
     Real* obs_out = obs;
     if (R.write_obs_every > 0 && ((k + 1) % R.write_obs_every) == 0) obs_out = obs_log + (size_t)((k + 1) / R.write_obs_every - 1) * obs_elems;
-    physics_step_kernel<Real><<<blocks, MDS_BLOCK, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
+    if (N == 8) physics_step_kernel<Real, 8><<<blocks, MDS_BLOCK, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
+    else physics_step_kernel<Real, 0><<<blocks, MDS_BLOCK, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
     obs_in = obs_out;
   }
 #undef MDS_CTRL_STEP
