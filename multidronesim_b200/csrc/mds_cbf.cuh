@@ -185,21 +185,23 @@ template <typename Real> struct QpWorst {
 template <typename Real>
 MDS_DEV void qp_test_row(QpWorst<Real>& w, const typename Vec4T<Real>::type& r, const Real xn[3], const typename Vec4T<Real>::type* x,
                          int n, int m, int id) {
-  Real t0 = r.x * xn[0], t1 = r.y * xn[1], t2 = r.z * xn[2];
-  Real gx = -(t0 + t1 + t2), mag = abs_(t0) + abs_(t1) + abs_(t2);
-  Real a2 = r.x * r.x + r.y * r.y + r.z * r.z;
+  Real gx = -(r.x * xn[0] + r.y * xn[1] + r.z * xn[2]);
+  typename Vec4T<Real>::type xm;
+  xm.x = Real(0); xm.y = Real(0); xm.z = Real(0); xm.w = Real(0);
   if (m >= 0) {
-    auto xm = x[m];
-    Real u0 = r.x * xm.x, u1 = r.y * xm.y, u2 = r.z * xm.z;
-    gx += u0 + u1 + u2;
-    mag += abs_(u0) + abs_(u1) + abs_(u2);
-    a2 *= Real(2);
+    xm = x[m];
+    gx += r.x * xm.x + r.y * xm.y + r.z * xm.z;
   }
   Real sl = r.w - gx;
-  if (sl < -qp_tol<Real>() * (abs_(r.w) + mag + Real(1e-12))) {
-    Real v = (a2 > Real(0)) ? sl * rsqrt_(a2) : Real(-1e30);  // zero row with rhs < 0: infeasible
-    int con = pack_con(id, n, m);
-    if (v < w.v || (v == w.v && con < w.con)) { w.v = v; w.con = con; }
+  if (sl < Real(0)) {  // the magnitude of the terms (for the relative tolerance) only when the slack is negative
+    Real mag = abs_(r.x * xn[0]) + abs_(r.y * xn[1]) + abs_(r.z * xn[2]) + abs_(r.x * xm.x) + abs_(r.y * xm.y) + abs_(r.z * xm.z);
+    if (sl < -qp_tol<Real>() * (abs_(r.w) + mag + Real(1e-12))) {
+      Real a2 = r.x * r.x + r.y * r.y + r.z * r.z;
+      if (m >= 0) a2 *= Real(2);
+      Real v = (a2 > Real(0)) ? sl * rsqrt_(a2) : Real(-1e30);  // zero row with rhs < 0: infeasible
+      int con = pack_con(id, n, m);
+      if (v < w.v || (v == w.v && con < w.con)) { w.v = v; w.con = con; }
+    }
   }
 }
 // own box bounds not in boxmask

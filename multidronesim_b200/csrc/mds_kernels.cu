@@ -488,7 +488,7 @@ MDS_DEV void atomic_max_double(double* addr, double v) {
 // carries only its own stage code (the whole K-step loop in one kernel overflowed the instruction
 // cache: 55 % of the stall samples were "no instruction"; profiles/r1_rollout_fused_ncu.txt).
 template <typename Real, int CTRL, bool USE_CBF, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+__global__ void __launch_bounds__(MDS_BLOCK, 4) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
                                                                PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                const typename TrajSpecT<Real>::seg* __restrict__ segs,
                                                                const Real* __restrict__ obs, Real* __restrict__ action,
