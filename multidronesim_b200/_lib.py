@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmds_b200.so")
+LIB_PATH = os.environ.get("MDS_B200_LIB") or os.path.join(_HERE, "csrc", "libmds_b200.so")  # override: kernel-variant experiments
 
 MAX_DRONES_PER_ENV = 32
 MAX_OBSTACLES = 8

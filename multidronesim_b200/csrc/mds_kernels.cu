@@ -36,6 +36,12 @@ static int check_launch(const char* what) {
 // n >= N idle), so every cross-drone exchange (downwash neighbours, CBF rows, the QP) needs only
 // group-level synchronisation: shared memory + __syncwarp(gmask) / shuffles.  No block barriers.
 #define MDS_BLOCK 256
+#ifndef MDS_CTRL_MINB
+#define MDS_CTRL_MINB 4  // resident blocks per SM the controller kernel is compiled for (64 registers)
+#endif
+#ifndef MDS_PHYS_MINB
+#define MDS_PHYS_MINB 5
+#endif
 static inline int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 struct GroupMap {
   int el, n, e, d;   // env slot in block, drone in env, global env, global drone
@@ -199,7 +205,7 @@ template <int NT> MDS_DEV int ct_np(int np_rt) {
   return p;
 }
 template <typename Real, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
+__global__ void __launch_bounds__(MDS_BLOCK, MDS_PHYS_MINB) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
                                                                   const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N_rt, int NP_rt) {
   __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
@@ -488,7 +494,7 @@ MDS_DEV void atomic_max_double(double* addr, double v) {
 // carries only its own stage code (the whole K-step loop in one kernel overflowed the instruction
 // cache: 55 % of the stall samples were "no instruction"; profiles/r1_rollout_fused_ncu.txt).
 template <typename Real, int CTRL, bool USE_CBF, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, 4) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+__global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_MINB) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
                                                                PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                const typename TrajSpecT<Real>::seg* __restrict__ segs,
                                                                const Real* __restrict__ obs, Real* __restrict__ action,
