@@ -312,6 +312,8 @@ def run_gpu_arm(args):
     restore(env, ctrl, ro, snap)
     torch.cuda.synchronize()
     n_steps = K * F
+    if ro.plan() != 4:
+        raise SystemExit("bench.py's per-kernel replay assumes the two-launch plan (swarms above 2^18 drones)")
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_steps)]
     for k in range(n_steps):
         evs[k][0].record()

@@ -144,10 +144,15 @@ typedef struct MdsRolloutCfg {
   int use_cbf;         /* 0/1; requires ctrl LQR_OMEGA (order 2) or LQR_YANK (order 3) */
   int num_obstacles;   /* spheres shared by all envs (<= N, reference quirk B14)        */
   int write_obs_every; /* 0 = only after the last step; k>0 = log obs every k steps     */
-  int stages;          /* 0 or 3 = controller kernel + physics kernel per step; 1 = controller kernel only
-                          (action_dev <- controller stack at obs_dev; the env does not advance); 2 = physics
-                          kernel only (env advances under action_dev).  1 and 2 exist so that a caller can
-                          bracket each kernel with its own CUDA events (bench.py roofline).            */
+  int stages;          /* launch plan for the K control steps:
+                          0      whole steps, plan chosen by mds_rollout_plan(E, N) (3 for small swarms, 4 for large)
+                          3      whole steps, fused: ctrl | K-1 x [physics + ctrl in one launch] | physics
+                          4      whole steps as two launches each (controller kernel, physics kernel)
+                          1      controller kernel only (action_dev <- controller stack at obs_dev; env does not advance)
+                          2      physics kernel only (env advances under action_dev)
+                          5      K fused launches: physics under the current action_dev, then the controller at
+                                 t0 + k dt_ctrl on the new observation (t0 = time AFTER the first physics step)
+                          1, 2 and 5 let a caller replay a rollout launch by launch with its own CUDA events. */
   double obstacles[MDS_MAX_OBSTACLES * 4]; /* cx, cy, cz, r */
 } MdsRolloutCfg;
 
@@ -239,9 +244,11 @@ int mds_xdot_linear_f64(const MdsDroneParams* prm, int kind, const double* obs_d
 int mds_xdot_nonlinear_f32(const MdsDroneParams* prm, double jx, double jy, double jz, const float* obs_dev, float* xdot_dev, int D, void* stream);
 int mds_xdot_nonlinear_f64(const MdsDroneParams* prm, double jx, double jy, double jz, const double* obs_dev, double* xdot_dev, int D, void* stream);
 
-/* ---- K-step rollout: per control step ONE fused controller kernel (reference -> tracking controller ->
- * CBF-QP -> inner loop, all in registers / shared memory) and ONE physics kernel (all sub-steps in registers),
- * enqueued back to back on `stream` with no host synchronisation (capturable in a CUDA graph).
+/* ---- K-step rollout: ONE launch per control step in the steady state -- the env advances under the previous
+ * action (all sub-steps in registers) and the controller stack (reference -> tracking controller -> CBF-QP -> inner
+ * loop, registers / shared memory) runs on the new observation before it leaves the registers; a controller-only
+ * launch opens and a physics-only launch closes the sequence (MdsRolloutCfg.stages).  Everything is enqueued on
+ * `stream` with no host synchronisation (capturable in a CUDA graph).
  * obs_dev [D*20] in/out (observation before the first / after the last step); action_dev [D*4] scratch;
  * obs_log_dev optional [K/write_obs_every][D*20]; stats_dev optional [MDS_STAT_COUNT] doubles (accumulated). */
 int mds_rollout_f32(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
@@ -252,6 +259,9 @@ int mds_rollout_f64(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const M
                     const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
                     const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double* obs_dev, double* action_dev,
                     double* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
+
+/* launch plan (MdsRolloutCfg.stages value 3 or 4) that stages == 0 selects for E envs of N drones */
+int mds_rollout_plan(int E, int N);
 
 /* ---- measurement aid: dependent-FMA-chain peak of the FP32 / FP64 pipes (TFLOP/s) ---- */
 int mds_fma_peak(int use_f64, int iters, double* tflops_out, void* stream);

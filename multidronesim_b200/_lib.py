@@ -108,6 +108,7 @@ _PLAIN = {
     "mds_last_error": ([], C.c_char_p),
     "mds_device_info": ([C.POINTER(_I)] * 4, _I),
     "mds_cbf_num_rows": ([_I, _I, _I], _I),
+    "mds_rollout_plan": ([_I, _I], _I),
     "mds_fma_peak": ([_I, _I, C.POINTER(_D), _P], _I),
     "mds_device_alloc": ([C.c_size_t, C.POINTER(C.c_void_p)], _I),
     "mds_device_free": ([_P], _I),

@@ -35,9 +35,14 @@ static int check_launch(const char* what) {
 // An environment's drones occupy NP = next_pow2(N) consecutive lanes of ONE warp ("lane group"; lanes
 // n >= N idle), so every cross-drone exchange (downwash neighbours, CBF rows, the QP) needs only
 // group-level synchronisation: shared memory + __syncwarp(gmask) / shuffles.  No block barriers.
+#ifndef MDS_BLOCK
 #define MDS_BLOCK 256
+#endif
 #ifndef MDS_CTRL_MINB
 #define MDS_CTRL_MINB 4  // resident blocks per SM the controller kernel is compiled for (64 registers)
+#endif
+#ifndef MDS_FUSED_MINB
+#define MDS_FUSED_MINB 4
 #endif
 #ifndef MDS_PHYS_MINB
 #define MDS_PHYS_MINB 5
@@ -204,13 +209,12 @@ template <int NT> MDS_DEV int ct_np(int np_rt) {
   while (p < NT) p <<= 1;
   return p;
 }
-template <typename Real, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, MDS_PHYS_MINB) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
-                                                                  const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N_rt, int NP_rt) {
-  __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
-  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
-  const GroupMap g = group_map(N, NP, E);
-  if (!g.env_valid) return;  // whole groups leave together
+// One control period of the env for this lane's drone (every lane of a valid group calls it): loads the state and
+// the action, runs the sub-steps with the state in registers, stores the state and (if obs != nullptr) the
+// observation, and returns the observation in registers.
+template <typename Real>
+MDS_DEV Obs<Real> physics_body(const DroneP<Real>& P, const StateP<Real>& st, const Real* __restrict__ action, const Real* __restrict__ fext,
+                               Real* __restrict__ obs, typename Vec4T<Real>::type* sm_pos, const GroupMap& g, int N) {
   Drone<Real> s;
   s.p = {Real(0), Real(0), Real(0)};
   Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
@@ -232,10 +236,23 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_PHYS_MINB) physics_step_kernel(
       for (int i = 0; i < 4; ++i) s.rpm[i] = rpm[i];
     }
   }
+  Obs<Real> o;
   if (g.valid) {
     store_drone(st, g.d, s);
-    if (obs) store_obs(obs, g.d, make_obs(s, av));
+    o = make_obs(s, av);
+    if (obs) store_obs(obs, g.d, o);
   }
+  return o;
+}
+
+template <typename Real, int NT>
+__global__ void __launch_bounds__(MDS_BLOCK, MDS_PHYS_MINB) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
+                                                                  const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N_rt, int NP_rt) {
+  __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
+  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
+  const GroupMap g = group_map(N, NP, E);
+  if (!g.env_valid) return;  // whole groups leave together
+  physics_body(P, st, action, fext, obs, sm_pos, g, N);
 }
 
 template <typename Real>
@@ -489,10 +506,122 @@ MDS_DEV void atomic_max_double(double* addr, double v) {
   } while (assumed != old);
 }
 
-// One control step of the controller stack for every drone: reference -> tracking controller ->
-// (CBF-QP) -> inner loop -> RPM action.  CTRL / USE_CBF are compile-time so that each instantiation
-// carries only its own stage code (the whole K-step loop in one kernel overflowed the instruction
-// cache: 55 % of the stall samples were "no instruction"; profiles/r1_rollout_fused_ncu.txt).
+// L1 prefetch of the lines a thread will load much later (PID state after the QP, trajectory spec after the
+// physics step): the three global-load latencies of a thread then overlap instead of adding up.
+MDS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// per-lane contributions to the rollout statistics
+struct StepStats {
+  float err, min_h;
+  int qp_solves, qp_iters, qp_infeas, qp_cap;
+};
+
+// One control step of the controller stack for this lane's drone (every lane of a valid group calls it):
+// reference -> tracking controller -> (CBF-QP) -> inner loop -> RPM action.  CTRL / USE_CBF are compile-time so
+// that each instantiation carries only its own stage code (one kernel with run-time switches overflowed the
+// instruction cache: 55 % of the stall samples were "no instruction").
+template <typename Real, int CTRL, bool USE_CBF>
+MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const GeoP<Real>& G, const LqrP<Real>& L, const CbfP<Real>& C,
+                       const CbfSmem<Real>& S, const PidP<Real>& pid, const typename TrajSpecT<Real>::spec& spec,
+                       const typename TrajSpecT<Real>::seg* __restrict__ segs, const Obs<Real>& o, const GroupMap& g, int N, int NP,
+                       double t, Real rpm[4], StepStats& ss) {
+  constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
+  Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
+  Ref<Real> ref;
+  if (g.valid) {
+    ref = eval_traj<Real>(spec, segs, t);
+    ss.err = (float)norm(o.p - ref.p);
+    if (CTRL == MDS_CTRL_GEOMETRIC) {
+      geometric_input(P, G, o, ref, u);
+      input_to_action(P, u, rpm);
+    } else {
+      lqr_input(P, L, CTRL, o, ref, u);
+      if (CTRL == MDS_CTRL_LQR_TORQUE) input_to_action(P, u, rpm);
+    }
+  }
+  if (HAS_PID) {
+    if (USE_CBF) {
+      CbfAgent<Real> ag;
+      ag.p = {Real(0), Real(0), Real(0)}; ag.dv = ag.p; ag.da = ag.p;
+      Real F = Real(0), unom[4] = {Real(0), Real(0), Real(0), Real(0)}, usafe[4] = {Real(0), Real(0), Real(0), Real(0)};
+      if (g.valid) {
+        if (CTRL == MDS_CTRL_LQR_OMEGA) u[0] = cap_thrust(P, u[0]);  // skip_low_level=True returns cap_u(u)
+        Real xd[10];
+        xd[0] = Real(0); xd[1] = Real(0); xd[2] = ref.yaw;
+        if (CTRL == MDS_CTRL_LQR_OMEGA) { xd[3] = ref.v.x; xd[4] = ref.v.y; xd[5] = ref.v.z; }
+        else { xd[3] = P.g * P.m; xd[4] = ref.v.x; xd[5] = ref.v.y; xd[6] = ref.v.z; }
+        ag = cbf_agent(P, C, o, xd, &F);
+        unom[0] = u[0] - Rc.u0_pre; unom[1] = u[1]; unom[2] = u[2]; unom[3] = u[3];
+      }
+      Real mh = Real(1e30);
+      int it = 0;
+      int stt = cbf_filter_group(P, C, S, Rc.obstacles, Rc.n_obs, g, N, NP, ag, F, unom, usafe, &mh, &it);
+      if (g.valid) {
+        ss.min_h = (float)mh;
+        if (g.n == 0) {
+          ss.qp_solves = (it > 0 || stt != MDS_QP_OPTIMAL);
+          ss.qp_iters = it;
+          ss.qp_infeas = (stt == MDS_QP_INFEASIBLE);
+          ss.qp_cap = (stt == MDS_QP_ITER_CAP);
+        }
+        u[0] = usafe[0] + Rc.u0_post; u[1] = usafe[1]; u[2] = usafe[2]; u[3] = usafe[3];
+      }
+    }
+    if (g.valid) {
+      Pid<Real> ps = load_pid(pid, g.d);
+      low_level(P, CTRL, ps, u, o, rpm);
+      store_pid(pid, g.d, ps);
+    }
+  }
+}
+
+// Block-wide accumulation of the statistics (called by EVERY thread of the block).
+// Per-warp reduction with redux.sync on integer images (counters; non-negative float bits order like unsigned
+// ints; the barrier minimum goes through an order-preserving float -> int map) and five float shuffles for the
+// error sum, then shared memory and ONE set of atomics per block: same-address atomics from every warp cost
+// more than the whole step (1.6 ms vs 0.4 ms per step at 1M drones).
+template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ stats, bool valid, const StepStats& ss) {
+  __shared__ float sm_f[MDS_BLOCK / 32][2];
+  __shared__ int sm_i[MDS_BLOCK / 32][6];
+  const unsigned full = 0xffffffffu;
+  int mh_i = __float_as_int(ss.min_h);
+  mh_i = mh_i >= 0 ? mh_i : (mh_i ^ 0x7fffffff);
+  const int w_steps = __reduce_add_sync(full, valid ? 1 : 0), w_solves = __reduce_add_sync(full, ss.qp_solves);
+  const int w_iters = __reduce_add_sync(full, ss.qp_iters), w_inf = __reduce_add_sync(full, ss.qp_infeas), w_cap = __reduce_add_sync(full, ss.qp_cap);
+  const unsigned w_maxe = __reduce_max_sync(full, __float_as_uint(ss.err));
+  const int w_minh = __reduce_min_sync(full, mh_i);
+  float w_sum = ss.err;
+  for (int off = 16; off > 0; off >>= 1) w_sum += __shfl_xor_sync(full, w_sum, off);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    sm_f[w][0] = w_sum; sm_f[w][1] = __uint_as_float(w_maxe);
+    sm_i[w][0] = w_steps; sm_i[w][1] = w_solves; sm_i[w][2] = w_iters; sm_i[w][3] = w_inf; sm_i[w][4] = w_cap; sm_i[w][5] = w_minh;
+  }
+  __syncthreads();
+  if (threadIdx.x < MDS_STAT_COUNT) {
+    const int k = threadIdx.x;
+    double acc = 0.0;
+    if (k == MDS_STAT_SUM_POS_ERR) {
+      for (int i = 0; i < MDS_BLOCK / 32; ++i) acc += (double)sm_f[i][0];
+    } else if (k == MDS_STAT_MAX_POS_ERR) {
+      for (int i = 0; i < MDS_BLOCK / 32; ++i) acc = fmax(acc, (double)sm_f[i][1]);
+    } else if (k == MDS_STAT_MIN_BARRIER) {
+      int m = sm_i[0][5];
+      for (int i = 1; i < MDS_BLOCK / 32; ++i) m = min(m, sm_i[i][5]);
+      acc = (double)__int_as_float(m >= 0 ? m : (m ^ 0x7fffffff));
+    } else {
+      const int col = k == MDS_STAT_DRONE_STEPS ? 0 : (k == MDS_STAT_QP_SOLVES ? 1 : (k == MDS_STAT_QP_ITERS ? 2 : (k == MDS_STAT_QP_INFEASIBLE ? 3 : 4)));
+      long long t = 0;
+      for (int i = 0; i < MDS_BLOCK / 32; ++i) t += sm_i[i][col];
+      acc = (double)t;
+    }
+    if (k == MDS_STAT_MAX_POS_ERR) atomic_max_double(&stats[k], acc);
+    else if (k == MDS_STAT_MIN_BARRIER) { if (USE_CBF) atomic_min_double(&stats[k], acc); }
+    else if (acc != 0.0) atomicAdd(&stats[k], acc);
+  }
+}
+
+// controller stack alone: obs (HBM) -> action (HBM)
 template <typename Real, int CTRL, bool USE_CBF, int NT>
 __global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_MINB) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
                                                                PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
@@ -503,107 +632,55 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_MINB) ctrl_step_kernel(Dro
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
   const GroupMap g = group_map(N, NP, E);
-  constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
-  double err = 0.0, min_h = 1e30;
-  int qp_solves = 0, qp_iters = 0, qp_infeas = 0, qp_cap = 0;
+  StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
   if (g.env_valid) {
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
-    Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
-    Ref<Real> ref;
     Obs<Real> o;
-    if (g.valid) {
-      ref = eval_traj<Real>(specs[g.d], segs, t);
+    typename TrajSpecT<Real>::spec spec;
+    spec.kind = MDS_TRAJ_WAIT;
+    if (g.valid) {  // every global load of this thread is issued here, before the first dependent instruction
       o = load_obs(obs, g.d);
-      err = (double)norm(o.p - ref.p);
-      if (CTRL == MDS_CTRL_GEOMETRIC) {
-        geometric_input(P, G, o, ref, u);
-        input_to_action(P, u, rpm);
-      } else {
-        lqr_input(P, L, CTRL, o, ref, u);
-        if (CTRL == MDS_CTRL_LQR_TORQUE) input_to_action(P, u, rpm);
-      }
+      spec = specs[g.d];
+      if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
     }
-    if (HAS_PID) {
-      if (USE_CBF) {
-        CbfAgent<Real> ag;
-        ag.p = {Real(0), Real(0), Real(0)}; ag.dv = ag.p; ag.da = ag.p;
-        Real F = Real(0), unom[4] = {Real(0), Real(0), Real(0), Real(0)}, usafe[4] = {Real(0), Real(0), Real(0), Real(0)};
-        if (g.valid) {
-          if (CTRL == MDS_CTRL_LQR_OMEGA) u[0] = cap_thrust(P, u[0]);  // skip_low_level=True returns cap_u(u)
-          Real xd[10];
-          xd[0] = Real(0); xd[1] = Real(0); xd[2] = ref.yaw;
-          if (CTRL == MDS_CTRL_LQR_OMEGA) { xd[3] = ref.v.x; xd[4] = ref.v.y; xd[5] = ref.v.z; }
-          else { xd[3] = P.g * P.m; xd[4] = ref.v.x; xd[5] = ref.v.y; xd[6] = ref.v.z; }
-          ag = cbf_agent(P, C, o, xd, &F);
-          unom[0] = u[0] - Rc.u0_pre; unom[1] = u[1]; unom[2] = u[2]; unom[3] = u[3];
-        }
-        Real mh = Real(1e30);
-        int it = 0;
-        int stt = cbf_filter_group(P, C, S, Rc.obstacles, Rc.n_obs, g, N, NP, ag, F, unom, usafe, &mh, &it);
-        if (g.valid) {
-          min_h = (double)mh;
-          if (g.n == 0) {
-            qp_solves = (it > 0 || stt != MDS_QP_OPTIMAL);
-            qp_iters = it;
-            qp_infeas = (stt == MDS_QP_INFEASIBLE);
-            qp_cap = (stt == MDS_QP_ITER_CAP);
-          }
-          u[0] = usafe[0] + Rc.u0_post; u[1] = usafe[1]; u[2] = usafe[2]; u[3] = usafe[3];
-        }
-      }
-      if (g.valid) {
-        Pid<Real> ps = load_pid(pid, g.d);
-        low_level(P, CTRL, ps, u, o, rpm);
-        store_pid(pid, g.d, ps);
-      }
-    }
+    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
     if (g.valid) store4(action, g.d, rpm);
   }
-  if (stats) {
-    // Per-warp reduction with redux.sync on integer images (counters; non-negative float bits order like
-    // unsigned ints; the barrier minimum goes through an order-preserving float -> int map) and five float
-    // shuffles for the error sum, then shared memory and ONE set of atomics per block: same-address atomics
-    // from every warp cost more than the whole step (1.6 ms vs 0.4 ms per step at 1M drones).
-    __shared__ float sm_f[MDS_BLOCK / 32][2];
-    __shared__ int sm_i[MDS_BLOCK / 32][6];
-    const unsigned full = 0xffffffffu;
-    const float errf = (float)err, mhf = (float)min_h;
-    int mh_i = __float_as_int(mhf);
-    mh_i = mh_i >= 0 ? mh_i : (mh_i ^ 0x7fffffff);
-    const int w_steps = __reduce_add_sync(full, g.valid ? 1 : 0), w_solves = __reduce_add_sync(full, qp_solves);
-    const int w_iters = __reduce_add_sync(full, qp_iters), w_inf = __reduce_add_sync(full, qp_infeas), w_cap = __reduce_add_sync(full, qp_cap);
-    const unsigned w_maxe = __reduce_max_sync(full, __float_as_uint(errf));
-    const int w_minh = __reduce_min_sync(full, mh_i);
-    float w_sum = errf;
-    for (int off = 16; off > 0; off >>= 1) w_sum += __shfl_xor_sync(full, w_sum, off);
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) {
-      sm_f[w][0] = w_sum; sm_f[w][1] = __uint_as_float(w_maxe);
-      sm_i[w][0] = w_steps; sm_i[w][1] = w_solves; sm_i[w][2] = w_iters; sm_i[w][3] = w_inf; sm_i[w][4] = w_cap; sm_i[w][5] = w_minh;
+  if (stats) stats_block_reduce<USE_CBF>(stats, g.valid, ss);
+}
+
+// One launch per control step inside a rollout: the env advances under the PREVIOUS step's action, and the
+// controller stack runs on the new observation while it is still in registers (the observation is written for the
+// caller / the log but never read back; the action buffer is read and rewritten by the same thread).  Blocks of
+// one grid are in different phases (HBM-heavy physics, issue-heavy controller), which overlap on an SM.
+template <typename Real, int CTRL, bool USE_CBF, int NT>
+__global__ void __launch_bounds__(MDS_BLOCK, MDS_FUSED_MINB) step_fused_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+                                                                StateP<Real> st, PidP<Real> pid,
+                                                                const typename TrajSpecT<Real>::spec* __restrict__ specs,
+                                                                const typename TrajSpecT<Real>::seg* __restrict__ segs,
+                                                                Real* __restrict__ action, Real* __restrict__ obs_out,
+                                                                double* __restrict__ stats, double t, int E, int N_rt, int NP_rt) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
+  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
+  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
+  const GroupMap g = group_map(N, NP, E);
+  StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
+  if (g.env_valid) {
+    if (g.valid) {
+      prefetch_l1(specs + g.d);
+      prefetch_l1(reinterpret_cast<const char*>(specs + g.d) + 32);
+      if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
     }
-    __syncthreads();
-    if (threadIdx.x < MDS_STAT_COUNT) {
-      const int k = threadIdx.x;
-      double acc = 0.0;
-      if (k == MDS_STAT_SUM_POS_ERR) {
-        for (int i = 0; i < MDS_BLOCK / 32; ++i) acc += (double)sm_f[i][0];
-      } else if (k == MDS_STAT_MAX_POS_ERR) {
-        for (int i = 0; i < MDS_BLOCK / 32; ++i) acc = fmax(acc, (double)sm_f[i][1]);
-      } else if (k == MDS_STAT_MIN_BARRIER) {
-        int m = sm_i[0][5];
-        for (int i = 1; i < MDS_BLOCK / 32; ++i) m = min(m, sm_i[i][5]);
-        acc = (double)__int_as_float(m >= 0 ? m : (m ^ 0x7fffffff));
-      } else {
-        const int col = k == MDS_STAT_DRONE_STEPS ? 0 : (k == MDS_STAT_QP_SOLVES ? 1 : (k == MDS_STAT_QP_ITERS ? 2 : (k == MDS_STAT_QP_INFEASIBLE ? 3 : 4)));
-        long long t = 0;
-        for (int i = 0; i < MDS_BLOCK / 32; ++i) t += sm_i[i][col];
-        acc = (double)t;
-      }
-      if (k == MDS_STAT_MAX_POS_ERR) atomic_max_double(&stats[k], acc);
-      else if (k == MDS_STAT_MIN_BARRIER) { if (USE_CBF) atomic_min_double(&stats[k], acc); }
-      else if (acc != 0.0) atomicAdd(&stats[k], acc);
-    }
+    const Obs<Real> o = physics_body(P, st, action, (const Real*)nullptr, obs_out, sm_pos, g, N);
+    Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
+    typename TrajSpecT<Real>::spec spec;
+    spec.kind = MDS_TRAJ_WAIT;
+    if (g.valid) spec = specs[g.d];
+    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
+    if (g.valid) store4(action, g.d, rpm);
   }
+  if (stats) stats_block_reduce<USE_CBF>(stats, g.valid, ss);
 }
 
 // ------------------------------------------------------------------ FMA-chain peak microbenchmark
@@ -717,6 +794,7 @@ static int xdot_nonlinear_impl(const MdsDroneParams* prm, double jx, double jy, 
   xdot_nonlinear_kernel<Real><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), Real(jx), Real(jy), Real(jz), obs, xdot, D);
   return check_launch("xdot_nonlinear");
 }
+extern "C" int mds_rollout_plan(int E, int N);
 template <typename Real>
 static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr, const MdsCbfParams* cbf,
                         MdsState st, MdsPidState pid, const typename TrajSpecT<Real>::spec* specs, const typename TrajSpecT<Real>::seg* segs,
@@ -724,7 +802,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   MDS_REQUIRE(prm && cfg && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && specs && obs && action, "rollout: null pointer");
   MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV && K > 0, "rollout: bad E, N or K");
   MDS_REQUIRE(cfg->ctrl >= MDS_CTRL_GEOMETRIC && cfg->ctrl <= MDS_CTRL_LQR_YANK, "rollout: unknown controller");
-  MDS_REQUIRE(cfg->stages >= 0 && cfg->stages <= 3, "rollout: stages must be 0..3");
+  MDS_REQUIRE(cfg->stages >= 0 && cfg->stages <= 5, "rollout: stages must be 0..5");
   RolloutP<Real> R;
   memset(&R, 0, sizeof(R));
   R.ctrl = cfg->ctrl; R.use_cbf = cfg->use_cbf; R.n_obs = cfg->num_obstacles; R.write_obs_every = cfg->write_obs_every;
@@ -765,42 +843,72 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   const StateP<Real> Sd = to_dev<Real>(st);
   const PidP<Real> Pi = to_dev<Real>(pid);
   const size_t obs_elems = (size_t)E * N * MDS_OBS_DIM;
-#define MDS_CTRL_STEP(CT, CB)                                                                                                       \
+  // launch plan.  stages 0: mds_rollout_plan(E, N) picks 3 or 4; 3: the whole step, fused wherever a physics step is
+  // followed by a controller step (ctrl | K-1 x [physics + ctrl] | physics); 4: two launches (ctrl, physics) per step;
+  // 1: controller kernel only; 2: physics kernel only; 5: K fused launches [physics under the current action
+  // buffer + controller at t0 + k dt] -- with 1 and 2 it lets a caller replay a rollout launch by launch.
+  const int mode = cfg->stages == 0 ? mds_rollout_plan(E, N) : cfg->stages;
+  auto obs_slot = [&](int j) -> Real* {  // where the observation after physics step j (1-based) goes
+    if (R.write_obs_every > 0 && (j % R.write_obs_every) == 0) return obs_log + (size_t)(j / R.write_obs_every - 1) * obs_elems;
+    return obs;
+  };
+  cudaError_t attr_err = cudaSuccess;
+#define MDS_LAUNCH_CTRL(CT, CB, FUSED, T, OBS_PTR)                                                                                  \
   do {                                                                                                                              \
-    auto kern = (N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>;                                   \
-    if (k == 0) {                                                                                                                   \
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
-      if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: shared memory opt-in failed: %s", cudaGetErrorString(e));         \
+    if (FUSED) {                                                                                                                    \
+      auto kern = (N == 8) ? step_fused_kernel<Real, CT, CB, 8> : step_fused_kernel<Real, CT, CB, 0>;                               \
+      if (first_fused) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+      kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Sd, Pi, specs, segs, action, OBS_PTR, stats, T, E, N, NP);              \
+    } else {                                                                                                                        \
+      auto kern = (N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>;                                 \
+      if (first_ctrl) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
+      kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Pi, specs, segs, (const Real*)(OBS_PTR), action, stats, T, E, N, NP);   \
     }                                                                                                                               \
-    kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Pi, specs, segs, obs_in, action, stats, t, E, N, NP);                     \
   } while (0)
-  const Real* obs_in = obs;
-  const bool do_ctrl = cfg->stages != 2, do_phys = cfg->stages != 1;
-  for (int k = 0; k < K; ++k) {
-    const double t = t0 + (double)k * prm->dt_ctrl;
-    if (do_ctrl) switch (R.ctrl) {
-      case MDS_CTRL_GEOMETRIC: MDS_CTRL_STEP(MDS_CTRL_GEOMETRIC, false); break;
-      case MDS_CTRL_LQR_TORQUE: MDS_CTRL_STEP(MDS_CTRL_LQR_TORQUE, false); break;
+  bool first_ctrl = true, first_fused = true;
+  auto launch_ctrl = [&](bool fused, double t, Real* obs_ptr) {
+    switch (R.ctrl) {
+      case MDS_CTRL_GEOMETRIC: MDS_LAUNCH_CTRL(MDS_CTRL_GEOMETRIC, false, fused, t, obs_ptr); break;
+      case MDS_CTRL_LQR_TORQUE: MDS_LAUNCH_CTRL(MDS_CTRL_LQR_TORQUE, false, fused, t, obs_ptr); break;
       case MDS_CTRL_LQR_OMEGA:
-        if (R.use_cbf) MDS_CTRL_STEP(MDS_CTRL_LQR_OMEGA, true);
-        else MDS_CTRL_STEP(MDS_CTRL_LQR_OMEGA, false);
+        if (R.use_cbf) MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, true, fused, t, obs_ptr);
+        else MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, false, fused, t, obs_ptr);
         break;
       default:
-        if (R.use_cbf) MDS_CTRL_STEP(MDS_CTRL_LQR_YANK, true);
-        else MDS_CTRL_STEP(MDS_CTRL_LQR_YANK, false);
+        if (R.use_cbf) MDS_LAUNCH_CTRL(MDS_CTRL_LQR_YANK, true, fused, t, obs_ptr);
+        else MDS_LAUNCH_CTRL(MDS_CTRL_LQR_YANK, false, fused, t, obs_ptr);
         break;
     }
-    if (!do_phys) continue;
-    // the observation after this step goes to its log slot when one is due, else to the env's obs buffer
-    Real* obs_out = obs;
-    if (R.write_obs_every > 0 && ((k + 1) % R.write_obs_every) == 0) obs_out = obs_log + (size_t)((k + 1) / R.write_obs_every - 1) * obs_elems;
+    if (fused) first_fused = false; else first_ctrl = false;
+  };
+  auto launch_phys = [&](Real* obs_out) {
     if (N == 8) physics_step_kernel<Real, 8><<<blocks, MDS_BLOCK, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
     else physics_step_kernel<Real, 0><<<blocks, MDS_BLOCK, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
-    obs_in = obs_out;
+  };
+  const double dt = prm->dt_ctrl;
+  Real* obs_last = obs;  // buffer holding the newest observation
+  if (mode == 1) {
+    for (int k = 0; k < K; ++k) launch_ctrl(false, t0 + k * dt, obs);
+  } else if (mode == 2) {
+    for (int k = 0; k < K; ++k) { obs_last = obs_slot(k + 1); launch_phys(obs_last); }
+  } else if (mode == 4) {
+    for (int k = 0; k < K; ++k) {
+      launch_ctrl(false, t0 + k * dt, obs_last);
+      obs_last = obs_slot(k + 1);
+      launch_phys(obs_last);
+    }
+  } else if (mode == 5) {
+    for (int k = 0; k < K; ++k) { obs_last = obs_slot(k + 1); launch_ctrl(true, t0 + k * dt, obs_last); }
+  } else {
+    launch_ctrl(false, t0, obs);
+    for (int k = 1; k < K; ++k) { obs_last = obs_slot(k); launch_ctrl(true, t0 + k * dt, obs_last); }
+    obs_last = obs_slot(K);
+    launch_phys(obs_last);
   }
-#undef MDS_CTRL_STEP
-  if (obs_in != obs) {
-    cudaError_t e = cudaMemcpyAsync(obs, obs_in, obs_elems * sizeof(Real), cudaMemcpyDeviceToDevice, cs);
+#undef MDS_LAUNCH_CTRL
+  if (attr_err != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: shared memory opt-in failed: %s", cudaGetErrorString(attr_err));
+  if (obs_last != obs) {
+    cudaError_t e = cudaMemcpyAsync(obs, obs_last, obs_elems * sizeof(Real), cudaMemcpyDeviceToDevice, cs);
     if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: %s", cudaGetErrorString(e));
   }
   return check_launch("rollout");
@@ -855,6 +963,10 @@ int mds_stream_synchronize(void* stream) {
   if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "stream_synchronize: %s", cudaGetErrorString(e));
   return MDS_OK;
 }
+// Measured on B200 (tools/exp_plans.py, C5 swarm): one fused launch per step is ~20 % faster up to ~1.3e5 drones
+// (launch- and tail-bound regime), two launches per step ~2-5 % faster from ~1e6 drones (the leaner kernels keep
+// more warps resident); the crossover is taken at 2^18 drones.
+int mds_rollout_plan(int E, int N) { return ((long long)E * N <= (1 << 18)) ? 3 : 4; }
 int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 * N + (order == 3 ? 2 * N : 0) + N * n_obs; }
 
 #define MDS_DEFINE(SUF, REAL, SPEC, SEG)                                                                                                          \

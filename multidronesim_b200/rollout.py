@@ -52,17 +52,25 @@ class FusedRollout:
         self.stats.zero_()
         self.stats[3] = 1e30  # MDS_STAT_MIN_BARRIER
 
-    def run(self, K, t0=None, obs_log=None, log_every=0, stages=3):
+    def plan(self):
+        """launch plan ``run`` uses by default: 3 (one fused launch per step) or 4 (two launches per step)"""
+        return _lib.load_library().mds_rollout_plan(self.env.NUM_ENVS, self.env.NUM_DRONES)
+
+    def run(self, K, t0=None, obs_log=None, log_every=0, stages=0):
         """Advance every environment K control steps.  ``obs_log`` [K//log_every, E, N, 20] receives the
         observation after every ``log_every``-th step (the reference's ``observations.append(obs)``).
-        ``stages``: 3 = controller kernel + physics kernel (default); 1 = controller kernel only (fills the
-        env's action buffer, time does not advance); 2 = physics kernel only (consumes that action buffer).
+        ``stages`` (MdsRolloutCfg.stages): 0 = whole steps, plan 3 or 4 chosen from the swarm size (default, ``plan()``);
+        3 = whole steps, one fused launch per step in the steady state;
+        4 = whole steps as two launches each; 1 = controller kernel only (fills the env's action buffer, time does
+        not advance); 2 = physics kernel only (consumes that action buffer); 5 = fused launches only (physics under
+        the current action buffer, then the controller at the new time).
         Returns the env's obs buffer (observation after the last step)."""
         env = self.env
         if t0 is None:
             t0 = self.t
-        if stages not in (1, 2, 3):
-            raise ValueError("stages must be 1, 2 or 3")
+        if stages not in (0, 1, 2, 3, 4, 5):
+            raise ValueError("stages must be 0..5")
+        t_call = t0 + env.CTRL_TIMESTEP if stages == 5 else t0  # 5: the controller runs after the physics step
         self.cfg.stages = int(stages)
         self.cfg.write_obs_every = int(log_every) if obs_log is not None else 0
         if obs_log is not None:
@@ -75,7 +83,7 @@ class FusedRollout:
         cbf = self.qp.cbf.c_params() if self.qp is not None else None
         _lib.call("mds_rollout", env.dtype, env._prm, self.cfg, geo, lqr, cbf, env._state_struct(), pid,
                   _lib.ptr(self.trajs.specs), _lib.ptr(self.trajs.segs), _lib.ptr(env._obs), _lib.ptr(env._action), _lib.ptr(obs_log),
-                  _lib.ptr(self.stats), float(t0), int(K), env.NUM_ENVS, env.NUM_DRONES, _lib.stream_ptr(env.device))
+                  _lib.ptr(self.stats), float(t_call), int(K), env.NUM_ENVS, env.NUM_DRONES, _lib.stream_ptr(env.device))
         if stages != 1:
             env.step_counter += K * env.PYB_STEPS_PER_CTRL
             self.t = t0 + K * env.CTRL_TIMESTEP

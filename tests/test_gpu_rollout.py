@@ -158,3 +158,38 @@ def test_cbf_closed_loop_vs_oracle(order, N, dtype, tol, lib_built):
     st = ro.stats_dict()
     assert worst < tol, worst
     assert st["qp_solves"] > 0 and n_active > 0
+
+
+@pytest.mark.parametrize("ctrl,cbf_order,N", [("yank10", 3, 8), ("omega9", 2, 3), ("geometric", None, 1)])
+def test_launch_plans_agree(ctrl, cbf_order, N, lib_built):
+    """MdsRolloutCfg.stages: the fused plan (one launch per step), the two-launch plan and a launch-by-launch
+    replay (1, then 5 x (K-1), then 2) are the same computation: bit-identical observations and statistics,
+    including the observation log."""
+    import multidronesim_b200.trajectories as T
+    E, K, dtype = 5, 9, torch.float32
+    rng = np.random.default_rng(11)
+    specs = [dict(a=1.0, center=np.array([0, 0, 0.5]), omega=0.5, yaw_rate=0.1, phase_shift=float(2 * np.pi / (N + 0.25) * k)) for k in range(N)]
+    init = np.zeros((E, N, 3))
+    for e in range(E):
+        for j, sp in enumerate(specs):
+            init[e, j] = otj.Lemniscate(**sp)(0.0)[0] + rng.normal(0, 0.02, 3) + np.array([0, 0, 0.04 * j])
+    obstacles = [[0.2, 0.0, 0.5, 0.1]] if cbf_order is not None else None
+    outs = []
+    for plan in ("fused", "two", "replay"):
+        mds, env, c, trk, ts, ro = build(E, N, dtype, "dyn_gnd_drag_dw", [T.Lemniscate(**sp) for sp in specs] * E, ctrl, cbf_order, obstacles, init)
+        log = torch.zeros(K // 3, E, N, 20, device="cuda", dtype=dtype)
+        if plan == "fused":
+            assert ro.plan() == 3  # small swarm
+            ro.run(K, obs_log=log, log_every=3, stages=3)
+        elif plan == "two":
+            ro.run(K, obs_log=log, log_every=3, stages=4)
+        else:
+            ro.run(1, stages=1)
+            for k in range(K - 1):
+                ro.run(1, stages=5)
+            ro.run(1, stages=2)
+        assert abs(ro.t - K * env.CTRL_TIMESTEP) < 1e-12
+        outs.append((env.obs.cpu().numpy().copy(), log.cpu().numpy().copy(), ro.stats.cpu().numpy().copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.abs(outs[0][1]).max() > 0
+    assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][2], outs[2][2])
