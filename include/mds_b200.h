@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MDS_ABI_VERSION 2
+#define MDS_ABI_VERSION 3
 #define MDS_MAX_DRONES_PER_ENV 32
 #define MDS_MAX_OBSTACLES 8
 #define MDS_OBS_DIM 20
@@ -57,7 +57,8 @@ enum {
   MDS_CTRL_GEOMETRIC = 0,   /* control/geometric.py -> input_to_action              */
   MDS_CTRL_LQR_TORQUE = 1,  /* control/lqr/lqr_controller.py (12-dim) -> mixer     */
   MDS_CTRL_LQR_OMEGA = 2,   /* lqr_omega_controller.py (9-dim) + ThrustOmega PID   */
-  MDS_CTRL_LQR_YANK = 3     /* lqr_YO_controller.py (10-dim) + YankOmega PID       */
+  MDS_CTRL_LQR_YANK = 3,    /* lqr_YO_controller.py (10-dim) + YankOmega PID       */
+  MDS_CTRL_DSLPID = 4       /* upstream DSLPIDControl (MultiDroneExample.py:85-114): target = reference pos / vel / yaw / yaw rate */
 };
 
 /* trajectory generator kinds (reference trajectories/ package) */
@@ -100,6 +101,18 @@ typedef struct MdsPidState {
   void* a; /* Real4[D] = (last_wx, last_wy, last_wz, integral_x) */
   void* b; /* Real2[D] = (integral_y, integral_z) */
 } MdsPidState;
+
+/* upstream DSLPIDControl state: integral_pos_e, last_rpy, integral_rpy_e */
+typedef struct MdsDslPidState {
+  void* a; /* Real4[D] = (integral_pos_e xyz, last_roll)                              */
+  void* b; /* Real4[D] = (last_pitch, last_yaw, integral_rpy_e x, integral_rpy_e y)   */
+  void* c; /* Real [D] = integral_rpy_e z                                             */
+} MdsDslPidState;
+/* upstream DSLPIDControl gains (P/I/D of the position loop "FOR" and the attitude loop "TOR"; MultiDroneExample.py:87-92
+ * overrides them with half of the upstream defaults) */
+typedef struct MdsDslPidGains {
+  double p_for[3], i_for[3], d_for[3], p_tor[3], i_tor[3], d_tor[3];
+} MdsDslPidGains;
 
 /* control/geometric.py:14-23 */
 typedef struct MdsGeoGains {
@@ -199,6 +212,12 @@ int mds_geometric_ctrl_f32(const MdsDroneParams* prm, const MdsGeoGains* gains, 
                            const float* ref_dev, float* action_dev, float* u_dev, int D, void* stream);
 int mds_geometric_ctrl_f64(const MdsDroneParams* prm, const MdsGeoGains* gains, const double* obs_dev,
                            const double* ref_dev, double* action_dev, double* u_dev, int D, void* stream);
+/* upstream DSLPIDControl.computeControlFromState (call site MultiDroneExample.py:111-114), one drone per thread.
+ * target_dev [D*12] = target_pos3, target_rpy3, target_vel3, target_rpy_rates3; pos_e_dev optional [D*3]. */
+int mds_dslpid_ctrl_f32(const MdsDroneParams* prm, const MdsDslPidGains* gains, const float* obs_dev, const float* target_dev,
+                        MdsDslPidState state, float* action_dev, float* pos_e_dev, int D, void* stream);
+int mds_dslpid_ctrl_f64(const MdsDroneParams* prm, const MdsDslPidGains* gains, const double* obs_dev, const double* target_dev,
+                        MdsDslPidState state, double* action_dev, double* pos_e_dev, int D, void* stream);
 /* LQR*.compute(obs, skip_low_level): u = -K e (+ hover), capped as each variant does.
  * variant = MDS_CTRL_LQR_*; action_dev may be NULL (skip_low_level=True).  For LQR_TORQUE the
  * action is the mixer output; for LQR_OMEGA / LQR_YANK it runs the inner PID (pid required). */
@@ -253,11 +272,11 @@ int mds_xdot_nonlinear_f64(const MdsDroneParams* prm, double jx, double jy, doub
  * obs_log_dev optional [K/write_obs_every][D*20]; stats_dev optional [MDS_STAT_COUNT] doubles (accumulated). */
 int mds_rollout_f32(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
                     const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
-                    const MdsTrajSpecF32* specs_dev, const MdsTrajSegF32* segs_dev, float* obs_dev, float* action_dev,
+                    const MdsDslPidGains* dsl, MdsDslPidState dsl_state, const MdsTrajSpecF32* specs_dev, const MdsTrajSegF32* segs_dev, float* obs_dev, float* action_dev,
                     float* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
 int mds_rollout_f64(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
                     const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
-                    const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double* obs_dev, double* action_dev,
+                    const MdsDslPidGains* dsl, MdsDslPidState dsl_state, const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double* obs_dev, double* action_dev,
                     double* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
 
 /* launch plan (MdsRolloutCfg.stages value 3 or 4) that stages == 0 selects for E envs of N drones */

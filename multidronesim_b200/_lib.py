@@ -23,7 +23,7 @@ STAT_NAMES = ("drone_steps", "sum_pos_err", "max_pos_err", "min_barrier",
 DRONE_CF2X, DRONE_CF2P = 0, 1
 PHYSICS_DYN, PHYSICS_DYN_GND_DRAG_DW = 0, 1
 QP_OPTIMAL, QP_INFEASIBLE, QP_ITER_CAP = 0, 1, 2
-CTRL_GEOMETRIC, CTRL_LQR_TORQUE, CTRL_LQR_OMEGA, CTRL_LQR_YANK = 0, 1, 2, 3
+CTRL_GEOMETRIC, CTRL_LQR_TORQUE, CTRL_LQR_OMEGA, CTRL_LQR_YANK, CTRL_DSLPID = 0, 1, 2, 3, 4
 TRAJ_WAIT, TRAJ_CIRCLE, TRAJ_LEMNISCATE, TRAJ_TABLE = 0, 1, 2, 3
 SEG_WAIT, SEG_CIRCLE, SEG_LEMNISCATE, SEG_LINE = 0, 1, 2, 3
 
@@ -48,6 +48,14 @@ class State(C.Structure):
 
 class PidState(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p)]
+
+
+class DslPidState(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p)]
+
+
+class DslPidGains(C.Structure):
+    _fields_ = [(n, C.c_double * 3) for n in ("p_for", "i_for", "d_for", "p_tor", "i_tor", "d_tor")]
 
 
 class GeoGains(C.Structure):
@@ -93,6 +101,7 @@ _SIGS = {
     "mds_obs_from_state": [_PRM, State, _P, _I, _P],
     "mds_traj_eval": [_P, _P, _D, _P, _I, _P],
     "mds_geometric_ctrl": [_PRM, C.POINTER(GeoGains), _P, _P, _P, _P, _I, _P],
+    "mds_dslpid_ctrl": [_PRM, C.POINTER(DslPidGains), _P, _P, DslPidState, _P, _P, _I, _P],
     "mds_lqr_ctrl": [_PRM, C.POINTER(LqrGains), _I, _P, _P, _P, _P, PidState, _I, _P],
     "mds_lowlevel": [_PRM, _I, _P, _P, PidState, _P, _I, _P],
     "mds_cbf_qp": [_PRM, C.POINTER(CbfParams), _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P],
@@ -101,7 +110,7 @@ _SIGS = {
     "mds_xdot_linear": [_PRM, _I, _P, _P, _I, _P],
     "mds_xdot_nonlinear": [_PRM, _D, _D, _D, _P, _P, _I, _P],
     "mds_rollout": [_PRM, C.POINTER(RolloutCfg), C.POINTER(GeoGains), C.POINTER(LqrGains), C.POINTER(CbfParams),
-                    State, PidState, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _P],
+                    State, PidState, C.POINTER(DslPidGains), DslPidState, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _P],
 }
 _PLAIN = {
     "mds_abi_version": ([], _I),

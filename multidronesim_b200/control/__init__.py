@@ -1,7 +1,8 @@
 from .base_controller import BaseController
+from .dslpid import DSLPIDControl
 from .geometric import GeometricControl
 from .low_level import ThrustOmegaController, YankOmegaController
 from .lqr import LQRController, LQROmegaController, LQRYankOmegaController
 
-__all__ = ["BaseController", "GeometricControl", "ThrustOmegaController", "YankOmegaController",
+__all__ = ["BaseController", "GeometricControl", "DSLPIDControl", "ThrustOmegaController", "YankOmegaController",
            "LQRController", "LQROmegaController", "LQRYankOmegaController"]

@@ -217,6 +217,93 @@ MDS_DEV void thrust_omega_pid(const DroneP<Real>& P, Pid<Real>& s, Real thrust, 
   for (int i = 0; i < 4; ++i) rpm[i] = Real(MDS_PWM2RPM_SCALE) * clamp_(pw[i], Real(MDS_MIN_PWM), Real(MDS_MAX_PWM)) + Real(MDS_PWM2RPM_CONST);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Upstream gym-pybullet-drones DSLPIDControl.computeControlFromState (external to the reference; call site
+// MultiDroneExample.py:111-114, gains halved at :85-92; SURVEY.md App. A.5 -- PARITY UNPINNED like the env step):
+// Crazyflie position PID -> thrust + desired attitude -> attitude PID -> PWM mixer -> RPM.
+template <typename Real> struct DslP { Real pf[3], if_[3], df[3], pt[3], it[3], dtq[3]; };
+template <typename Real> inline DslP<Real> to_dev(const MdsDslPidGains& g) {
+  DslP<Real> d;
+  for (int i = 0; i < 3; ++i) {
+    d.pf[i] = Real(g.p_for[i]); d.if_[i] = Real(g.i_for[i]); d.df[i] = Real(g.d_for[i]);
+    d.pt[i] = Real(g.p_tor[i]); d.it[i] = Real(g.i_tor[i]); d.dtq[i] = Real(g.d_tor[i]);
+  }
+  return d;
+}
+template <typename Real> struct DslState {
+  V3<Real> ipos, last_rpy, irpy;
+};
+// SoA planes: a Real4 = (ipos, last_roll), b Real4 = (last_pitch, last_yaw, irpy.x, irpy.y), c Real = irpy.z
+template <typename Real> struct DslStateP {
+  typename Vec4T<Real>::type *a, *b;
+  Real* c;
+};
+template <typename Real> inline DslStateP<Real> to_dev(const MdsDslPidState& s) {
+  using R4 = typename Vec4T<Real>::type;
+  return DslStateP<Real>{(R4*)s.a, (R4*)s.b, (Real*)s.c};
+}
+template <typename Real> MDS_DEV DslState<Real> load_dsl(const DslStateP<Real>& p, int d) {
+  auto a = p.a[d]; auto b = p.b[d];
+  return DslState<Real>{{a.x, a.y, a.z}, {a.w, b.x, b.y}, {b.z, b.w, p.c[d]}};
+}
+template <typename Real> MDS_DEV void store_dsl(const DslStateP<Real>& p, int d, const DslState<Real>& s) {
+  typename Vec4T<Real>::type a, b;
+  a.x = s.ipos.x; a.y = s.ipos.y; a.z = s.ipos.z; a.w = s.last_rpy.x;
+  b.x = s.last_rpy.y; b.y = s.last_rpy.z; b.z = s.irpy.x; b.w = s.irpy.y;
+  p.a[d] = a; p.b[d] = b; p.c[d] = s.irpy.z;
+}
+template <typename Real>
+MDS_DEV void dslpid_control(const DroneP<Real>& P, const DslP<Real>& G, DslState<Real>& s, const Obs<Real>& o, V3<Real> tpos, V3<Real> trpy,
+                            V3<Real> tvel, V3<Real> trates, Real rpm[4], V3<Real>* pos_e_out) {
+  const Real dt = P.dt_ctrl;
+  M3<Real> R = quat_to_rot_scipy(o.qx, o.qy, o.qz, o.qw);
+  // position loop: PID on position / velocity error + gravity feed-forward; integral clamps +-2 and +-0.15 on z
+  V3<Real> pe = tpos - o.p, ve = tvel - o.v;
+  s.ipos.x = clamp_(s.ipos.x + pe.x * dt, Real(-2), Real(2));
+  s.ipos.y = clamp_(s.ipos.y + pe.y * dt, Real(-2), Real(2));
+  s.ipos.z = clamp_(clamp_(s.ipos.z + pe.z * dt, Real(-2), Real(2)), Real(-0.15), Real(0.15));
+  V3<Real> tt = {G.pf[0] * pe.x + G.if_[0] * s.ipos.x + G.df[0] * ve.x, G.pf[1] * pe.y + G.if_[1] * s.ipos.y + G.df[1] * ve.y,
+                 G.pf[2] * pe.z + G.if_[2] * s.ipos.z + G.df[2] * ve.z + P.g * P.m};
+  Real scalar_thrust = max_(Real(0), tt.x * R.m[2] + tt.y * R.m[5] + tt.z * R.m[8]);
+  Real thrust = (sqrt_(scalar_thrust / (Real(4) * P.kf)) - Real(MDS_PWM2RPM_CONST)) / Real(MDS_PWM2RPM_SCALE);
+  V3<Real> zax = (Real(1) / norm(tt)) * tt;
+  Real sy, cy;
+  sincos_(trpy.z, &sy, &cy);
+  V3<Real> xc = {cy, sy, Real(0)};
+  V3<Real> yc = cross(zax, xc);
+  V3<Real> yax = (Real(1) / norm(yc)) * yc;
+  V3<Real> xax = cross(yax, zax);
+  M3<Real> Rd = from_cols(xax, yax, zax);
+  // attitude loop: rot_e = vee(Rd^T R - R^T Rd), rate error from finite-differenced rpy
+  M3<Real> A = matmulTN(Rd, R);  // Rd^T R; R^T Rd is its transpose
+  V3<Real> rot_e = {A.m[7] - A.m[5], A.m[2] - A.m[6], A.m[3] - A.m[1]};
+  Real inv_dt = Real(1) / dt;
+  V3<Real> rate_e = {trates.x - (o.rpy.x - s.last_rpy.x) * inv_dt, trates.y - (o.rpy.y - s.last_rpy.y) * inv_dt,
+                     trates.z - (o.rpy.z - s.last_rpy.z) * inv_dt};
+  s.last_rpy = o.rpy;
+  s.irpy.x = clamp_(clamp_(s.irpy.x - rot_e.x * dt, Real(-1500), Real(1500)), Real(-1), Real(1));
+  s.irpy.y = clamp_(clamp_(s.irpy.y - rot_e.y * dt, Real(-1500), Real(1500)), Real(-1), Real(1));
+  s.irpy.z = clamp_(s.irpy.z - rot_e.z * dt, Real(-1500), Real(1500));
+  V3<Real> tq = {clamp_(-G.pt[0] * rot_e.x + G.dtq[0] * rate_e.x + G.it[0] * s.irpy.x, Real(-3200), Real(3200)),
+                 clamp_(-G.pt[1] * rot_e.y + G.dtq[1] * rate_e.y + G.it[1] * s.irpy.y, Real(-3200), Real(3200)),
+                 clamp_(-G.pt[2] * rot_e.z + G.dtq[2] * rate_e.z + G.it[2] * s.irpy.z, Real(-3200), Real(3200))};
+  Real pw[4];
+  if (P.drone_model == MDS_DRONE_CF2X) {
+    pw[0] = thrust + (Real(-0.5) * tq.x - Real(0.5) * tq.y - tq.z);
+    pw[1] = thrust + (Real(-0.5) * tq.x + Real(0.5) * tq.y + tq.z);
+    pw[2] = thrust + (Real(0.5) * tq.x + Real(0.5) * tq.y - tq.z);
+    pw[3] = thrust + (Real(0.5) * tq.x - Real(0.5) * tq.y + tq.z);
+  } else {
+    pw[0] = thrust + (-tq.y - tq.z);
+    pw[1] = thrust + (tq.x + tq.z);
+    pw[2] = thrust + (tq.y - tq.z);
+    pw[3] = thrust + (-tq.x + tq.z);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rpm[i] = Real(MDS_PWM2RPM_SCALE) * clamp_(pw[i], Real(MDS_MIN_PWM), Real(MDS_MAX_PWM)) + Real(MDS_PWM2RPM_CONST);
+  *pos_e_out = pe;
+}
+
 // compute_low_level (lqr_omega_controller.py:78-88, lqr_YO_controller.py:87-98): world ->
 // body rates with scipy's normalised R, then the inner loop.
 template <typename Real>

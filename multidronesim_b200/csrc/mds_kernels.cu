@@ -325,6 +325,20 @@ __global__ void lqr_ctrl_kernel(DroneP<Real> P, LqrP<Real> L, int variant, const
   store4(u_out, d, u);
 }
 template <typename Real>
+__global__ void dslpid_ctrl_kernel(DroneP<Real> P, DslP<Real> G, const Real* __restrict__ obs, const Real* __restrict__ target,
+                                   DslStateP<Real> st, Real* __restrict__ action, Real* __restrict__ pos_e, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const Real* t = target + (size_t)d * 12;
+  DslState<Real> s = load_dsl(st, d);
+  Real rpm[4];
+  V3<Real> pe;
+  dslpid_control(P, G, s, load_obs(obs, d), v3(t[0], t[1], t[2]), v3(t[3], t[4], t[5]), v3(t[6], t[7], t[8]), v3(t[9], t[10], t[11]), rpm, &pe);
+  store_dsl(st, d, s);
+  store4(action, d, rpm);
+  if (pos_e) { pos_e[3 * d] = pe.x; pos_e[3 * d + 1] = pe.y; pos_e[3 * d + 2] = pe.z; }
+}
+template <typename Real>
 __global__ void lowlevel_kernel(DroneP<Real> P, int variant, const Real* __restrict__ u_in, const Real* __restrict__ obs,
                                 PidP<Real> pid, Real* __restrict__ action, int D) {
   int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,7 +536,8 @@ struct StepStats {
 // instruction cache: 55 % of the stall samples were "no instruction").
 template <typename Real, int CTRL, bool USE_CBF>
 MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const GeoP<Real>& G, const LqrP<Real>& L, const CbfP<Real>& C,
-                       const CbfSmem<Real>& S, const PidP<Real>& pid, const typename TrajSpecT<Real>::spec& spec,
+                       const DslP<Real>& Dg, const DslStateP<Real>& dst, const CbfSmem<Real>& S, const PidP<Real>& pid,
+                       const typename TrajSpecT<Real>::spec& spec,
                        const typename TrajSpecT<Real>::seg* __restrict__ segs, const Obs<Real>& o, const GroupMap& g, int N, int NP,
                        double t, Real rpm[4], StepStats& ss) {
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
@@ -534,6 +549,11 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
     if (CTRL == MDS_CTRL_GEOMETRIC) {
       geometric_input(P, G, o, ref, u);
       input_to_action(P, u, rpm);
+    } else if (CTRL == MDS_CTRL_DSLPID) {
+      DslState<Real> ds = load_dsl(dst, g.d);
+      V3<Real> pe;
+      dslpid_control(P, Dg, ds, o, ref.p, v3(Real(0), Real(0), ref.yaw), ref.v, v3(Real(0), Real(0), ref.yaw_rate), rpm, &pe);
+      store_dsl(dst, g.d, ds);
     } else {
       lqr_input(P, L, CTRL, o, ref, u);
       if (CTRL == MDS_CTRL_LQR_TORQUE) input_to_action(P, u, rpm);
@@ -624,7 +644,7 @@ template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ sta
 // controller stack alone: obs (HBM) -> action (HBM)
 template <typename Real, int CTRL, bool USE_CBF, int NT>
 __global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_MINB) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
-                                                               PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
+                                                               DslP<Real> Dg, DslStateP<Real> dst, PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                const typename TrajSpecT<Real>::seg* __restrict__ segs,
                                                                const Real* __restrict__ obs, Real* __restrict__ action,
                                                                double* __restrict__ stats, double t, int E, int N_rt, int NP_rt) {
@@ -643,7 +663,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_MINB) ctrl_step_kernel(Dro
       spec = specs[g.d];
       if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
     }
-    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
+    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
     if (g.valid) store4(action, g.d, rpm);
   }
   if (stats) stats_block_reduce<USE_CBF>(stats, g.valid, ss);
@@ -655,7 +675,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_MINB) ctrl_step_kernel(Dro
 // one grid are in different phases (HBM-heavy physics, issue-heavy controller), which overlap on an SM.
 template <typename Real, int CTRL, bool USE_CBF, int NT>
 __global__ void __launch_bounds__(MDS_BLOCK, MDS_FUSED_MINB) step_fused_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
-                                                                StateP<Real> st, PidP<Real> pid,
+                                                                DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
                                                                 const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                 const typename TrajSpecT<Real>::seg* __restrict__ segs,
                                                                 Real* __restrict__ action, Real* __restrict__ obs_out,
@@ -677,7 +697,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_FUSED_MINB) step_fused_kernel(D
     typename TrajSpecT<Real>::spec spec;
     spec.kind = MDS_TRAJ_WAIT;
     if (g.valid) spec = specs[g.d];
-    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
+    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
     if (g.valid) store4(action, g.d, rpm);
   }
   if (stats) stats_block_reduce<USE_CBF>(stats, g.valid, ss);
@@ -723,6 +743,14 @@ static int geometric_impl(const MdsDroneParams* prm, const MdsGeoGains* g, const
   MDS_REQUIRE(prm && g && obs && ref && action && D > 0, "geometric_ctrl: bad argument");
   geometric_ctrl_kernel<Real><<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*g), obs, ref, action, u, D);
   return check_launch("geometric_ctrl");
+}
+template <typename Real>
+static int dslpid_impl(const MdsDroneParams* prm, const MdsDslPidGains* g, const Real* obs, const Real* target, MdsDslPidState st, Real* action,
+                       Real* pos_e, int D, void* stream) {
+  MDS_REQUIRE(prm && g && obs && target && st.a && st.b && st.c && action && D > 0, "dslpid_ctrl: bad argument");
+  dslpid_ctrl_kernel<Real><<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*g), obs, target, to_dev<Real>(st), action,
+                                                                                pos_e, D);
+  return check_launch("dslpid_ctrl");
 }
 static bool lqr_dim_ok(int variant, int dim) {
   return (variant == MDS_CTRL_LQR_TORQUE && dim == 12) || (variant == MDS_CTRL_LQR_OMEGA && dim == 9) || (variant == MDS_CTRL_LQR_YANK && dim == 10);
@@ -797,11 +825,12 @@ static int xdot_nonlinear_impl(const MdsDroneParams* prm, double jx, double jy, 
 extern "C" int mds_rollout_plan(int E, int N);
 template <typename Real>
 static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr, const MdsCbfParams* cbf,
-                        MdsState st, MdsPidState pid, const typename TrajSpecT<Real>::spec* specs, const typename TrajSpecT<Real>::seg* segs,
+                        MdsState st, MdsPidState pid, const MdsDslPidGains* dsl, MdsDslPidState dsl_state,
+                        const typename TrajSpecT<Real>::spec* specs, const typename TrajSpecT<Real>::seg* segs,
                         Real* obs, Real* action, Real* obs_log, double* stats, double t0, int K, int E, int N, void* stream) {
   MDS_REQUIRE(prm && cfg && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && specs && obs && action, "rollout: null pointer");
   MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV && K > 0, "rollout: bad E, N or K");
-  MDS_REQUIRE(cfg->ctrl >= MDS_CTRL_GEOMETRIC && cfg->ctrl <= MDS_CTRL_LQR_YANK, "rollout: unknown controller");
+  MDS_REQUIRE(cfg->ctrl >= MDS_CTRL_GEOMETRIC && cfg->ctrl <= MDS_CTRL_DSLPID, "rollout: unknown controller");
   MDS_REQUIRE(cfg->stages >= 0 && cfg->stages <= 5, "rollout: stages must be 0..5");
   RolloutP<Real> R;
   memset(&R, 0, sizeof(R));
@@ -813,9 +842,16 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   CbfP<Real> C;
   memset(&C, 0, sizeof(C));
   C.order = 2;
+  DslP<Real> Dg;
+  memset(&Dg, 0, sizeof(Dg));
+  DslStateP<Real> Ds = to_dev<Real>(dsl_state);
   if (cfg->ctrl == MDS_CTRL_GEOMETRIC) {
     MDS_REQUIRE(geo, "rollout: geometric gains missing");
     G = to_dev<Real>(*geo);
+  } else if (cfg->ctrl == MDS_CTRL_DSLPID) {
+    MDS_REQUIRE(dsl && dsl_state.a && dsl_state.b && dsl_state.c, "rollout: DSL PID gains or state missing");
+    MDS_REQUIRE(!cfg->use_cbf, "rollout: the CBF filter needs an LQR_OMEGA / LQR_YANK nominal controller");
+    Dg = to_dev<Real>(*dsl);
   } else {
     MDS_REQUIRE(lqr && lqr_dim_ok(cfg->ctrl, lqr->dim), "rollout: LQR gains missing or of the wrong dimension");
     L = to_dev<Real>(*lqr);
@@ -858,11 +894,11 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     if (FUSED) {                                                                                                                    \
       auto kern = (N == 8) ? step_fused_kernel<Real, CT, CB, 8> : step_fused_kernel<Real, CT, CB, 0>;                               \
       if (first_fused) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-      kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Sd, Pi, specs, segs, action, OBS_PTR, stats, T, E, N, NP);              \
+      kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, OBS_PTR, stats, T, E, N, NP);              \
     } else {                                                                                                                        \
       auto kern = (N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>;                                 \
       if (first_ctrl) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
-      kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Pi, specs, segs, (const Real*)(OBS_PTR), action, stats, T, E, N, NP);   \
+      kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Pi, specs, segs, (const Real*)(OBS_PTR), action, stats, T, E, N, NP);   \
     }                                                                                                                               \
   } while (0)
   bool first_ctrl = true, first_fused = true;
@@ -870,6 +906,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     switch (R.ctrl) {
       case MDS_CTRL_GEOMETRIC: MDS_LAUNCH_CTRL(MDS_CTRL_GEOMETRIC, false, fused, t, obs_ptr); break;
       case MDS_CTRL_LQR_TORQUE: MDS_LAUNCH_CTRL(MDS_CTRL_LQR_TORQUE, false, fused, t, obs_ptr); break;
+      case MDS_CTRL_DSLPID: MDS_LAUNCH_CTRL(MDS_CTRL_DSLPID, false, fused, t, obs_ptr); break;
       case MDS_CTRL_LQR_OMEGA:
         if (R.use_cbf) MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, true, fused, t, obs_ptr);
         else MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, false, fused, t, obs_ptr);
@@ -995,6 +1032,10 @@ int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 *
                                void* stream) {                                                                                                     \
     return geometric_impl<REAL>(prm, g, obs, ref, action, u, D, stream);                                                                           \
   }                                                                                                                                                \
+  int mds_dslpid_ctrl_##SUF(const MdsDroneParams* prm, const MdsDslPidGains* g, const REAL* obs, const REAL* target, MdsDslPidState st,          \
+                            REAL* action, REAL* pos_e, int D, void* stream) {                                                                    \
+    return dslpid_impl<REAL>(prm, g, obs, target, st, action, pos_e, D, stream);                                                                  \
+  }                                                                                                                                                \
   int mds_lqr_ctrl_##SUF(const MdsDroneParams* prm, const MdsLqrGains* g, int variant, const REAL* obs, const REAL* ref, REAL* u, REAL* action,    \
                          MdsPidState pid, int D, void* stream) {                                                                                   \
     return lqr_impl<REAL>(prm, g, variant, obs, ref, u, action, pid, D, stream);                                                                   \
@@ -1021,9 +1062,10 @@ int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 *
     return xdot_nonlinear_impl<REAL>(prm, jx, jy, jz, obs, xdot, D, stream);                                                                       \
   }                                                                                                                                                \
   int mds_rollout_##SUF(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr,                       \
-                        const MdsCbfParams* cbf, MdsState st, MdsPidState pid, const SPEC* specs, const SEG* segs, REAL* obs, REAL* action,        \
-                        REAL* obs_log, double* stats, double t0, int K, int E, int N, void* stream) {                                              \
-    return rollout_impl<REAL>(prm, cfg, geo, lqr, cbf, st, pid, specs, segs, obs, action, obs_log, stats, t0, K, E, N, stream);                    \
+                        const MdsCbfParams* cbf, MdsState st, MdsPidState pid, const MdsDslPidGains* dsl, MdsDslPidState dsl_state,                \
+                        const SPEC* specs, const SEG* segs, REAL* obs, REAL* action, REAL* obs_log, double* stats, double t0, int K, int E,        \
+                        int N, void* stream) {                                                                                                     \
+    return rollout_impl<REAL>(prm, cfg, geo, lqr, cbf, st, pid, dsl, dsl_state, specs, segs, obs, action, obs_log, stats, t0, K, E, N, stream);    \
   }
 
 MDS_DEFINE(f32, float, MdsTrajSpecF32, MdsTrajSegF32)

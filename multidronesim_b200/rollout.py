@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from .control.dslpid import DSLPIDControl
 from .control.geometric import GeometricControl
 from .control.lqr import LQRController, LQROmegaController, LQRYankOmegaController
 
@@ -26,6 +27,8 @@ class FusedRollout:
         cfg = _lib.RolloutCfg()
         if isinstance(controller, GeometricControl):
             cfg.ctrl = _lib.CTRL_GEOMETRIC
+        elif isinstance(controller, DSLPIDControl):
+            cfg.ctrl = _lib.CTRL_DSLPID
         elif isinstance(controller, LQROmegaController):
             cfg.ctrl = _lib.CTRL_LQR_OMEGA
         elif isinstance(controller, LQRYankOmegaController):
@@ -77,11 +80,14 @@ class FusedRollout:
             _lib.require_cuda(obs_log, "obs_log", env.dtype)
             if obs_log.numel() < (K // max(1, log_every)) * env.NUM_TOTAL * _lib.OBS_DIM:
                 raise ValueError("obs_log too small")
+        is_lqr = self.cfg.ctrl in (_lib.CTRL_LQR_TORQUE, _lib.CTRL_LQR_OMEGA, _lib.CTRL_LQR_YANK)
         geo = self.controller.c_gains() if self.cfg.ctrl == _lib.CTRL_GEOMETRIC else None
-        lqr = self.controller.c_gains() if self.cfg.ctrl != _lib.CTRL_GEOMETRIC else None
-        pid = self.controller._pid() if self.cfg.ctrl != _lib.CTRL_GEOMETRIC else _lib.PidState(None, None)
+        lqr = self.controller.c_gains() if is_lqr else None
+        pid = self.controller._pid() if is_lqr else _lib.PidState(None, None)
+        dsl = self.controller.c_gains() if self.cfg.ctrl == _lib.CTRL_DSLPID else None
+        dsl_state = self.controller.state_struct() if self.cfg.ctrl == _lib.CTRL_DSLPID else _lib.DslPidState(None, None, None)
         cbf = self.qp.cbf.c_params() if self.qp is not None else None
-        _lib.call("mds_rollout", env.dtype, env._prm, self.cfg, geo, lqr, cbf, env._state_struct(), pid,
+        _lib.call("mds_rollout", env.dtype, env._prm, self.cfg, geo, lqr, cbf, env._state_struct(), pid, dsl, dsl_state,
                   _lib.ptr(self.trajs.specs), _lib.ptr(self.trajs.segs), _lib.ptr(env._obs), _lib.ptr(env._action), _lib.ptr(obs_log),
                   _lib.ptr(self.stats), float(t_call), int(K), env.NUM_ENVS, env.NUM_DRONES, _lib.stream_ptr(env.device))
         if stages != 1:

@@ -26,7 +26,7 @@ def test_header_symbols_exported(lib_built):
     for n in names:
         assert hasattr(lib_built, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names  # the ctypes table covers exactly the header
-    assert lib_built.mds_abi_version() == 2
+    assert lib_built.mds_abi_version() == 3
     assert lib_built.mds_cbf_num_rows(2, 8, 1) == 100 and lib_built.mds_cbf_num_rows(3, 8, 1) == 116  # SURVEY App. C row counts
     assert lib_built.mds_cbf_num_rows(2, 2, 1) == 19 and lib_built.mds_cbf_num_rows(3, 7, 0) == 91
 
@@ -37,7 +37,7 @@ def test_struct_sizes_match_c():
 #include <stdio.h>
 #include "mds_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(MdsDroneParams), sizeof(MdsState), sizeof(MdsPidState),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(MdsDslPidState), sizeof(MdsDslPidGains), sizeof(MdsDroneParams), sizeof(MdsState), sizeof(MdsPidState),
          sizeof(MdsGeoGains), sizeof(MdsLqrGains), sizeof(MdsCbfParams), sizeof(MdsRolloutCfg), sizeof(MdsTrajSpecF32),
          sizeof(MdsTrajSpecF64), sizeof(MdsTrajSegF32), sizeof(MdsTrajSegF64));
   return 0;
@@ -48,7 +48,7 @@ int main(void) {
         exe = os.path.join(d, "s")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)  # header is plain C
         sizes = [int(x) for x in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
-    py = [ctypes.sizeof(t) for t in (_lib.DroneParams, _lib.State, _lib.PidState, _lib.GeoGains, _lib.LqrGains, _lib.CbfParams, _lib.RolloutCfg)]
+    py = [ctypes.sizeof(t) for t in (_lib.DslPidState, _lib.DslPidGains, _lib.DroneParams, _lib.State, _lib.PidState, _lib.GeoGains, _lib.LqrGains, _lib.CbfParams, _lib.RolloutCfg)]
     py += [_lib.traj_spec_dtype("f4").itemsize, _lib.traj_spec_dtype("f8").itemsize, _lib.traj_seg_dtype("f4").itemsize, _lib.traj_seg_dtype("f8").itemsize]
     assert py == sizes
 

@@ -144,3 +144,43 @@ def test_models(golden, dtype, lib_built):
     assert scaled_err(U.obs_to_lin_model(obs, 10, env).cpu().numpy(), g["lin10"]) < TOL[dtype]
     assert scaled_err(U.obs_to_geo_model(obs).cpu().numpy(), g["geo18"]) < TOL[dtype]
     assert rel_err(U.input_to_action(env, torch.as_tensor(g["input_to_action_in"], device="cuda", dtype=dtype)).cpu().numpy(), g["input_to_action"]) < 10 * TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-4)])
+def test_dslpid_config1_closed_loop(dtype, tol, lib_built):
+    """BASELINE config 1 on the device: 2 CF2X drones, Physics.DYN, 240 Hz, upstream DSL PID with the halved gains of
+    MultiDroneExample.py:85-92 climbing 1 m -- step for step against the oracle's DslPid + env (both restated from
+    upstream, parity unpinned), 2 s closed loop, several environments with different starts."""
+    import multidronesim_b200 as mds
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel as ODM, Physics as OPH
+    from oracle.controllers import DslPid
+    E, N, steps = 3, 2, 480
+    rng = np.random.default_rng(2)
+    init = np.array([[[1.0, 0, 0.05], [-1.0, 0, 0.05]]]) + rng.normal(0, 0.05, (E, N, 3)) * np.array([1, 1, 0])
+    target = init + np.array([0, 0, 1.0])
+    env = mds.CtrlAviary(drone_model=mds.DroneModel.CF2X, num_drones=N, physics=mds.Physics.DYN, pyb_freq=240, ctrl_freq=240,
+                         initial_xyzs=init, num_envs=E, dtype=dtype)
+    ctrl = mds.control.DSLPIDControl(env, gain_scale=0.5)
+    obs = env.step(torch.zeros(E, N, 4, device="cuda", dtype=dtype))[0]
+    tgt = torch.as_tensor(target, device="cuda", dtype=dtype)
+    for _ in range(steps):
+        rpm, pos_e, _ = ctrl.computeControlFromState(env.CTRL_TIMESTEP, obs, tgt, torch.zeros(3))
+        obs = env.step(rpm)[0]
+    got = obs.double().cpu().numpy()
+    for e in range(E):
+        o = OracleCtrlAviary(ODM.CF2X, N, initial_xyzs=init[e], physics=OPH.DYN)
+        cs = [DslPid(o, gain_scale=0.5) for _ in range(N)]
+        ob = o.step(np.zeros((N, 4)))[0]
+        for _ in range(steps):
+            ob = o.step(np.array([cs[j].compute_from_state(o.CTRL_TIMESTEP, ob[j], target[e, j])[0] for j in range(N)]))[0]
+        assert np.max(np.abs(got[e, :, 0:3] - ob[:, 0:3])) < tol
+        assert np.max(np.abs(ob[:, 2] - target[e, :, 2])) < 0.6  # it is climbing towards the target
+    # the same closed loop as ONE rollout call (MDS_CTRL_DSLPID, WaitTrajectory targets): identical to the per-call loop
+    env2 = mds.CtrlAviary(drone_model=mds.DroneModel.CF2X, num_drones=N, physics=mds.Physics.DYN, initial_xyzs=init, num_envs=E, dtype=dtype)
+    ctrl2 = mds.control.DSLPIDControl(env2, gain_scale=0.5)
+    waits = [mds.trajectories.WaitTrajectory(target[e, j], 1e6) for e in range(E) for j in range(N)]
+    ro = mds.FusedRollout(env2, mds.trajectories.TrajectorySet(waits, dtype=dtype), ctrl2)
+    env2.step(torch.zeros(E, N, 4, device="cuda", dtype=dtype))
+    obs2 = ro.run(steps).double().cpu().numpy()
+    assert np.max(np.abs(obs2 - got)) < 1e-12 * (1 + np.max(np.abs(got)))
