@@ -166,7 +166,7 @@ typedef struct MdsRolloutCfg {
                           5      K fused launches: physics under the current action_dev, then the controller at
                                  t0 + k dt_ctrl on the new observation (t0 = time AFTER the first physics step)
                           1, 2 and 5 let a caller replay a rollout launch by launch with its own CUDA events. */
-  double obstacles[MDS_MAX_OBSTACLES * 4]; /* cx, cy, cz, r */
+  double obstacles[MDS_MAX_OBSTACLES * 4]; /* cx, cy, cz, r (r < 0: vertical cylinder of radius |r|) */
 } MdsRolloutCfg;
 
 /* ---- library ------------------------------------------------------------------ */
@@ -233,7 +233,8 @@ int mds_lowlevel_f64(const MdsDroneParams* prm, int variant, const double* u_dev
 
 /* ---- CBF-QP: replaces DroneQPTracker.compute_control (cbf/qptracker.py:22-34) ------ */
 /* xdes_dev [E*N*xdim]; u_nom_dev / u_safe_dev [E*N*4]; obstacles_dev [n_obs*4] = cx,cy,cz,r
- * (shared by all envs) ; status_dev [E] int32 ; iters_dev [E] int32 (may be NULL). */
+ * (shared by all envs; r > 0: sphere as cbf/cbf.py:380-383; r < 0: vertical cylinder of radius |r|, unbounded
+ * height, through (cx, cy) -- builder extension, the reference has spheres only) ; status_dev [E] int32 ; iters_dev [E] int32 (may be NULL). */
 int mds_cbf_qp_f32(const MdsDroneParams* prm, const MdsCbfParams* cbf, const float* obs_dev,
                    const float* xdes_dev, const float* u_nom_dev, const float* obstacles_dev, int n_obs,
                    float* u_safe_dev, int* status_dev, int* iters_dev, int E, int N, void* stream);

@@ -12,7 +12,8 @@ from .. import _lib
 
 def pack_obstacles(x_obs, obs_r_list, device, dtype):
     """Reference obstacle lists (x_obs [N_obs, order, 3] with row 0 = centre, radii list;
-    simulations/CBFTest.py:421-424) -> device [N_obs, 4] = cx, cy, cz, r."""
+    simulations/CBFTest.py:421-424) -> device [N_obs, 4] = cx, cy, cz, r.  A negative radius marks a vertical
+    cylinder of radius |r| (obstacles.Cylinder.as_row(); builder extension)."""
     if x_obs is None or obs_r_list is None:
         return None
     assert len(x_obs) == len(obs_r_list), \

@@ -47,18 +47,19 @@ MDS_DEV CbfAgent<Real> cbf_agent(const DroneP<Real>& P, const CbfP<Real>& C, con
 
 // One ECBF row between agent i and agent/obstacle j (obstacle: dv = da = 0).  a3 = LgLf^{r-1}h on
 // i's block (columns u0, wx, wy); rhs = Kcbf.[h, hdot, (hddot)] + Lf^r h; h0 = barrier value.
+// c4inv = 1 / zscale^4 for agents and sphere obstacles; 0 for a vertical-cylinder obstacle (the z terms vanish).
 template <typename Real>
 MDS_DEV void cbf_row(const DroneP<Real>& P, const CbfP<Real>& C, const CbfAgent<Real>& ai, const CbfAgent<Real>& aj,
-                     Real Ds, Real a3[3], Real* rhs, Real* h0_out) {
+                     Real Ds, Real c4inv, Real a3[3], Real* rhs, Real* h0_out) {
   V3<Real> e = ai.p - aj.p, dv = ai.dv - aj.dv, da = ai.da - aj.da;
   Real ex2 = e.x * e.x, ey2 = e.y * e.y, ez2 = e.z * e.z;
   Real rho = ex2 + ey2;
-  V3<Real> d = {Real(4) * e.x * rho, Real(4) * e.y * rho, Real(4) * e.z * ez2 * C.c4inv};
+  V3<Real> d = {Real(4) * e.x * rho, Real(4) * e.y * rho, Real(4) * e.z * ez2 * c4inv};
   Real Hxx = Real(12) * ex2 + Real(4) * ey2, Hxy = Real(8) * e.x * e.y, Hyy = Real(4) * ex2 + Real(12) * ey2;
-  Real Hzz = Real(12) * ez2 * C.c4inv;
+  Real Hzz = Real(12) * ez2 * c4inv;
   V3<Real> Hdv = {Hxx * dv.x + Hxy * dv.y, Hxy * dv.x + Hyy * dv.y, Hzz * dv.z};
   Real Ds2 = Ds * Ds;
-  Real h0 = rho * rho + ez2 * ez2 * C.c4inv - Ds2 * Ds2;
+  Real h0 = rho * rho + ez2 * ez2 * c4inv - Ds2 * Ds2;
   Real h1 = dot(d, dv);
   Real inv_m = Real(1) / P.m;
   *h0_out = h0;
@@ -72,7 +73,7 @@ MDS_DEV void cbf_row(const DroneP<Real>& P, const CbfP<Real>& C, const CbfAgent<
   Real h2 = d.y * da.x + d.z * da.y + Hxx * da.z * da.z + Real(2) * Hxy * da.z * dv.x + Hyy * dv.x * dv.x + Hzz * dv.y * dv.y;
   V3<Real> q = {Real(24) * e.x * dv.x * dv.x + Real(16) * e.y * dv.x * dv.y + Real(8) * e.x * dv.y * dv.y,
                 Real(8) * e.y * dv.x * dv.x + Real(16) * e.x * dv.x * dv.y + Real(24) * e.y * dv.y * dv.y,
-                Real(24) * e.z * C.c4inv * dv.z * dv.z};
+                Real(24) * e.z * c4inv * dv.z * dv.z};
   Real Lf = Real(3) * dot(da, Hdv) + dot(q, dv);
   a3[0] = d.z * inv_m; a3[1] = -P.g * d.y; a3[2] = P.g * d.x;
   *rhs = C.k0 * h0 + C.k1 * h1 + C.k2 * h2 + Lf;
@@ -251,6 +252,7 @@ MDS_DEV int qp_scan(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows,
 
 // Goldfarb-Idnani dual active set, P = I, executed by the env's lane group.
 //   rows : smem barrier rows;  x : smem iterate, one Vec4 per drone (u_nom on entry, minimiser on exit);
+//   xnom : smem copy of u_nom that stays untouched (fp32 polish);
 //   ws   : smem workspace of MDS_QP_WS_WORDS Reals;  p0 : the most violated constraint at u_nom (packed),
 //   found by the row builder's own scan.
 // Work split: scans and the primal update are spread over the lanes (lane n owns drone n's inputs, rows and
@@ -262,8 +264,9 @@ MDS_DEV int qp_scan(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows,
 enum { MDS_QP_ACT_FULL = 0, MDS_QP_ACT_DROP = 1, MDS_QP_ACT_STOP = 2 };
 
 template <typename Real>
-MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows, typename Vec4T<Real>::type* x, Real* ws,
-                           const RowMap& M, int N, int NP, int n, bool valid, unsigned gmask, int p0, int* iters_out) {
+MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows, typename Vec4T<Real>::type* x,
+                           const typename Vec4T<Real>::type* xnom, Real* ws, const RowMap& M, int N, int NP, int n, bool valid,
+                           unsigned gmask, int p0, int* iters_out) {
   using R4 = typename Vec4T<Real>::type;
   const Real tol = qp_tol<Real>();
   const Real zn_eps = sizeof(Real) == 4 ? Real(1e-5) : Real(1e-10);
@@ -435,6 +438,65 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
     if (action == MDS_QP_ACT_DROP && iref(hdr + 3) != MDS_QP_OPTIMAL) { status = iref(hdr + 3); break; }
   }
   __syncwarp(gmask);
+  if (sizeof(Real) == 4 && status == MDS_QP_OPTIMAL && q >= 3) {
+    // fp32 polish: the iterate has been moved by `iters` incremental steps and the factor grown row by row, which
+    // loses ~1e-4 on long solves.  With the final active set A the minimiser is u_nom - A' lam, (A A') lam = A u_nom - b;
+    // lane 0 solves this small system once in double and every lane rebuilds its own block from u_nom.
+    if (n == 0) {
+      double Lm[MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2], y[MDS_QP_QMAX];
+      bool ok = true;
+      for (int a = 0; a < q && ok; ++a) {
+        QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
+        for (int b2 = 0; b2 <= a; ++b2) {
+          QpCon<Real> cb = qp_get(rows, C, iref(ws + b2));
+          double ab = (double)ca.gi[0] * cb.gi[0] + (double)ca.gi[1] * cb.gi[1] + (double)ca.gi[2] * cb.gi[2], sacc = 0.0;
+          if (ca.i == cb.i) sacc += ab;
+          if (ca.j >= 0 && ca.j == cb.j) sacc += ab;
+          if (ca.j >= 0 && ca.j == cb.i) sacc -= ab;
+          if (cb.j >= 0 && cb.j == ca.i) sacc -= ab;
+          for (int k = 0; k < b2; ++k) sacc -= Lm[a * (a + 1) / 2 + k] * Lm[b2 * (b2 + 1) / 2 + k];
+          if (a == b2) {
+            if (sacc <= 0.0) { ok = false; break; }
+            Lm[a * (a + 1) / 2 + a] = sqrt(sacc);
+          } else {
+            Lm[a * (a + 1) / 2 + b2] = sacc / Lm[b2 * (b2 + 1) / 2 + b2];
+          }
+        }
+        // right-hand side A u_nom - b from the nominal inputs kept in the 4th ... see below: unom is passed in xnom
+        auto ui = xnom[ca.i];
+        double r = (double)ca.gi[0] * ui.x + (double)ca.gi[1] * ui.y + (double)ca.gi[2] * ui.z;
+        if (ca.j >= 0) { auto uj = xnom[ca.j]; r -= (double)ca.gi[0] * uj.x + (double)ca.gi[1] * uj.y + (double)ca.gi[2] * uj.z; }
+        y[a] = r - (double)ca.rhs;
+      }
+      if (ok) {
+        for (int a = 0; a < q; ++a) {  // forward, then backward substitution
+          double sacc = y[a];
+          for (int k = 0; k < a; ++k) sacc -= Lm[a * (a + 1) / 2 + k] * y[k];
+          y[a] = sacc / Lm[a * (a + 1) / 2 + a];
+        }
+        for (int a = q - 1; a >= 0; --a) {
+          double sacc = y[a];
+          for (int k = a + 1; k < q; ++k) sacc -= Lm[k * (k + 1) / 2 + a] * y[k];
+          y[a] = sacc / Lm[a * (a + 1) / 2 + a];
+        }
+        for (int a = 0; a < q; ++a) lam[a] = (Real)y[a];
+      }
+      iref(hdr + 1) = ok ? 1 : 0;
+    }
+    __syncwarp(gmask);
+    if (iref(hdr + 1) && valid) {
+      auto un = xnom[n];
+      double z0 = un.x, z1 = un.y, z2 = un.z;
+      for (int a = 0; a < q; ++a) {
+        QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
+        const double la = (double)lam[a];
+        z0 -= la * (double)qp_coef(ca, n, 0); z1 -= la * (double)qp_coef(ca, n, 1); z2 -= la * (double)qp_coef(ca, n, 2);
+      }
+      xn[0] = (Real)z0; xn[1] = (Real)z1; xn[2] = (Real)z2;
+      publish_x();
+    }
+    __syncwarp(gmask);
+  }
   if (status == MDS_QP_OPTIMAL && q > 1) {
     // certify: rows held active must still be satisfied (guards breakdown on nearly dependent active sets)
     const Real ctol = sizeof(Real) == 4 ? Real(1e-3) : Real(1e-7);
@@ -446,6 +508,15 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
   }
   *iters_out = iters;
   return status;
+}
+
+// Obstacle record (cx, cy, cz, r): r > 0 is the reference's sphere (super-ellipsoid barrier with the agents' zscale,
+// Ds = r_safe + r; cbf.py:380-383); r < 0 encodes a VERTICAL CYLINDER of radius |r| and unbounded height through
+// (cx, cy) -- the zscale -> infinity limit of the same barrier, h = (ex^2 + ey^2)^2 - Ds^4 (builder extension:
+// the reference has no cylinder primitive; parity is against oracle/cbf.py only).
+template <typename Real> MDS_DEV void obstacle_shape(const CbfP<Real>& C, Real r, Real* Ds, Real* c4inv) {
+  *Ds = C.rs + abs_(r);
+  *c4inv = r < Real(0) ? Real(0) : C.c4inv;
 }
 
 // decoupled 4th input (wz): box +-umax[3] merged with the order-3 force-bound rows, which the

@@ -96,6 +96,7 @@ MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* s
 //   head  max(12 NP, WS)  agents (p, dv, da per drone; 3 Vec4 each) -- overlaid by the QP workspace once the rows exist
 //   rows  4 NP RPL        one Vec4 (a0, a1, a2, rhs) per row, owner-major (mds_cbf.cuh "Row ownership")
 //   x     4 NP            the QP iterate, one Vec4 per drone
+//   xnom  4 NP            u_nom, kept for the fp32 polish of long solves
 template <typename Real> struct CbfSmem {
   Real* env0;
   int stride, off_rows, off_x;
@@ -103,7 +104,7 @@ template <typename Real> struct CbfSmem {
 static inline int cbf_env_stride(int NP, int N, int n_obs) {
   int rpl = (N - 1) / 2 + ((N & 1) ? 0 : 1) + n_obs;
   int head = 12 * NP > MDS_QP_WS_WORDS ? 12 * NP : ((MDS_QP_WS_WORDS + 3) & ~3);
-  return head + 4 * NP * rpl + 4 * NP;
+  return head + 4 * NP * rpl + 8 * NP;
 }
 template <typename Real> static size_t cbf_smem_bytes(int NP, int N, int n_obs) {
   return (size_t)(MDS_BLOCK / NP) * cbf_env_stride(NP, N, n_obs) * sizeof(Real) + 32;
@@ -114,7 +115,7 @@ template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw
   const RowMap M = row_map(N, n_obs);
   int head = 12 * NP > MDS_QP_WS_WORDS ? 12 * NP : ((MDS_QP_WS_WORDS + 3) & ~3);
   s.off_rows = head; s.off_x = head + 4 * NP * M.RPL;
-  s.stride = s.off_x + 4 * NP;
+  s.stride = s.off_x + 8 * NP;  // x, then the untouched copy of u_nom
   return s;
 }
 
@@ -131,6 +132,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
   R4* agents = reinterpret_cast<R4*>(env);
   R4* rows = reinterpret_cast<R4*>(env + S.off_rows);
   R4* x = reinterpret_cast<R4*>(env + S.off_x);
+  R4* xnom = x + NP;
   if (g.valid) {
     R4 a0, a1, a2, xv;
     a0.x = ag.p.x; a0.y = ag.p.y; a0.z = ag.p.z; a0.w = ag.dv.x;
@@ -139,6 +141,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
     agents[3 * n] = a0; agents[3 * n + 1] = a1; agents[3 * n + 2] = a2;
     xv.x = unom[0]; xv.y = unom[1]; xv.z = unom[2]; xv.w = unom[3];
     x[n] = xv;
+    xnom[n] = xv;
   }
   __syncwarp(g.gmask);
   int fl = 0;
@@ -157,7 +160,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
         R4 b0 = agents[3 * m], b1 = agents[3 * m + 1], b2 = agents[3 * m + 2];
         other.p = {b0.x, b0.y, b0.z}; other.dv = {b0.w, b1.x, b1.y}; other.da = {b1.z, b1.w, b2.x};
         Real a3[3], rhs, h0;
-        cbf_row(P, C, ag, other, Real(2) * C.rs, a3, &rhs, &h0);  // owner - partner (mds_cbf.cuh "Row ownership")
+        cbf_row(P, C, ag, other, Real(2) * C.rs, C.c4inv, a3, &rhs, &h0);  // owner - partner (mds_cbf.cuh "Row ownership")
         *min_h = min_(*min_h, h0);
         row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
         qp_test_row(worst, row, unom, x, n, m, n * M.RPL + s);
@@ -168,8 +171,9 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
       CbfAgent<Real> other;
       other.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
       other.dv = {Real(0), Real(0), Real(0)}; other.da = other.dv;
-      Real a3[3], rhs, h0;
-      cbf_row(P, C, ag, other, C.rs + obstacles[4 * o + 3], a3, &rhs, &h0);
+      Real a3[3], rhs, h0, Ds, c4inv;
+      obstacle_shape(C, obstacles[4 * o + 3], &Ds, &c4inv);
+      cbf_row(P, C, ag, other, Ds, c4inv, a3, &rhs, &h0);
       *min_h = min_(*min_h, h0);
       R4 row;
       row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
@@ -184,7 +188,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
   __syncwarp(g.gmask);  // rows complete; agents no longer needed (their storage becomes the QP workspace)
   int status = MDS_QP_OPTIMAL, iters = 0;
   if (fl || p0 == -2) status = MDS_QP_INFEASIBLE;
-  else if (p0 >= 0) status = qp_solve_group(C, rows, x, env, M, N, NP, n, g.valid, g.gmask, p0, &iters);
+  else if (p0 >= 0) status = qp_solve_group(C, rows, x, xnom, env, M, N, NP, n, g.valid, g.gmask, p0, &iters);
   if (g.valid) {
     if (status == MDS_QP_OPTIMAL) {
       R4 xv = x[n];
@@ -422,7 +426,7 @@ __global__ void cbf_rows_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __rest
   for (int i = 0; i < N - 1; ++i)
     for (int j = i + 1; j < N; ++j) {
       CbfAgent<Real> ai = agent(i, &F), aj = agent(j, &F);
-      cbf_row(P, C, ai, aj, Real(2) * C.rs, a3, &rhs, &h0);
+      cbf_row(P, C, ai, aj, Real(2) * C.rs, C.c4inv, a3, &rhs, &h0);
       for (int c = 0; c < 3; ++c) { G[(size_t)row * W + 4 * i + c] = -a3[c]; G[(size_t)row * W + 4 * j + c] = a3[c]; }
       h[row++] = rhs;
     }
@@ -439,7 +443,9 @@ __global__ void cbf_rows_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __rest
       CbfAgent<Real> ai = agent(i, &F), aj;
       aj.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
       aj.dv = {Real(0), Real(0), Real(0)}; aj.da = aj.dv;
-      cbf_row(P, C, ai, aj, C.rs + obstacles[4 * o + 3], a3, &rhs, &h0);
+      Real Ds, c4inv;
+      obstacle_shape(C, obstacles[4 * o + 3], &Ds, &c4inv);
+      cbf_row(P, C, ai, aj, Ds, c4inv, a3, &rhs, &h0);
       for (int c = 0; c < 3; ++c) G[(size_t)row * W + 4 * i + c] = -a3[c];
       h[row++] = rhs;
     }

@@ -1,3 +1,3 @@
-from .urdf_generator import generate_sphere, Sphere
+from .urdf_generator import Cylinder, Sphere, generate_cylinder, generate_sphere
 
-__all__ = ["generate_sphere", "Sphere"]
+__all__ = ["generate_sphere", "generate_cylinder", "Sphere", "Cylinder"]

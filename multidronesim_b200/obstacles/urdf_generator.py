@@ -16,6 +16,18 @@ class Sphere:
         return [float(self.center[0]), float(self.center[1]), float(self.center[2]), float(self.radius)]
 
 
+@dataclass(frozen=True)
+class Cylinder:
+    """Vertical cylinder through (center[0], center[1]) of unbounded height for the CBF (builder extension: the
+    reference has spheres only); ``height`` is used by the URDF (render / collision shape) alone."""
+    center: tuple
+    radius: float
+    height: float = 2.0
+
+    def as_row(self):
+        return [float(self.center[0]), float(self.center[1]), float(self.center[2]), -float(self.radius)]
+
+
 _TEMPLATE = """<?xml version="1.0"?>
 <robot name="sphere_obstacle">
   <link name="base_link">
@@ -32,4 +44,13 @@ def generate_sphere(radius, folder="/tmp"):
     path = os.path.join(folder, f"sphere_{radius}.urdf")
     with open(path, "w") as f:
         f.write(_TEMPLATE.format(r=radius))
+    return path
+
+
+def generate_cylinder(radius, height=2.0, folder="/tmp"):
+    """Write ``cylinder_<radius>_<height>.urdf`` (z-axis cylinder) and return its path."""
+    path = os.path.join(folder, f"cylinder_{radius}_{height}.urdf")
+    geom = f'<cylinder radius="{radius}" length="{height}"/>'
+    with open(path, "w") as f:
+        f.write(_TEMPLATE.replace("sphere_obstacle", "cylinder_obstacle").replace('<sphere radius="{r}"/>', geom))
     return path

@@ -5,8 +5,8 @@ reference materialises dense 2*xdim Jacobians / Hessians / a 20x20x20 tensor per
 pair (cbf/cbf.py:194-283); only the three position components and the rows of
 the hover-linearised A, B that touch them survive, so this file evaluates the
 same Lie derivatives in closed form (derivation in DESIGN.md section "CBF rows").
-Pinned row-for-row against the imported reference's ``_build_ineq_const`` by
-tests/test_oracle_vs_reference.py and tests/golden/cbf_rows.npz.
+Pinned row-for-row against the imported reference's ``_build_ineq_const`` through
+tests/golden/cbf_rows.npz (oracle/make_golden.py; tests/test_oracle_golden.py).
 
 Row order of G u <= h (cbf/cbf.py:308-367):
   pairs (i<j, lexicographic) | +I box, -I box (2*4N) | force bound (2N, order 3) | obstacles (i*N_obs + j)
@@ -53,13 +53,13 @@ def _split(prm, x):
     return x[0], x[1], x[3], x[4:7], x[7:10]
 
 
-def pair_row(prm, xi, xj, xi_des, xj_des, Ds):
+def pair_row(prm, xi, xj, xi_des, xj_des, Ds, cylinder=False):
     """One ECBF row: returns (a3, rhs) with a = LgL_f^{r-1}h[:3] on drone i's
     input block (columns [u0, wx, wy]) and rhs = Kcbf . [h, hdot, ..] + L_f^r h.
 
     Follows cbf/cbf.py:135-178 (custom_hdots, incl. quirk B12) and :194-283
     (custom_control_affine_terms)."""
-    c4 = prm.c ** 4
+    c4 = math.inf if cylinder else prm.c ** 4   # vertical cylinder = zscale -> infinity (builder extension, parity unpinned)
     g, m = prm.g, prm.m
     ri, pi_, Fi, vi, pi3 = _split(prm, xi)
     rj, pj_, Fj, vj, pj3 = _split(prm, xj)
@@ -74,7 +74,7 @@ def pair_row(prm, xi, xj, xi_des, xj_des, Ds):
     d = np.array([4 * ex * rho, 4 * ey * rho, 4 * ez ** 3 / c4])
     Hxx, Hxy, Hyy, Hzz = 12 * ex * ex + 4 * ey * ey, 8 * ex * ey, 4 * ex * ex + 12 * ey * ey, 12 * ez * ez / c4
     Hdv = np.array([Hxx * dv[0] + Hxy * dv[1], Hxy * dv[0] + Hyy * dv[1], Hzz * dv[2]])
-    h0 = rho * rho + (ez / prm.c) ** 4 - Ds ** 4
+    h0 = rho * rho + (0.0 if cylinder else (ez / prm.c) ** 4) - Ds ** 4
     h1 = d @ dv
     if prm.order == 2:
         Lf = d @ da + dv @ Hdv
@@ -122,7 +122,7 @@ def build_ineq(prm, x, xdes, x_obs=None, obs_r=None):
             for j in range(len(x_obs)):
                 xo = np.zeros(prm.xdim)
                 xo[-3:] = np.asarray(x_obs[j], float).reshape(-1, 3)[0]
-                a, rhs = pair_row(prm, x[i], xo, xdes[i], xo, prm.rs + obs_r[j])
+                a, rhs = pair_row(prm, x[i], xo, xdes[i], xo, prm.rs + abs(obs_r[j]), cylinder=obs_r[j] < 0)
                 g_row = np.zeros(4 * N)
                 g_row[4 * i:4 * i + 3] = -a
                 rows_G.append(g_row)

@@ -115,3 +115,42 @@ def test_anchor_and_status_codes(lib_built):
         assert torch.equal(u[1], unom[1]) and torch.equal(u[2], unom[2])
         with pytest.raises(mds._lib.MdsError):  # N_obs > N is rejected like the reference's IndexError (quirk B14)
             trk.compute_control(obs, xdes, unom, x_obs=torch.zeros(3, 4, device="cuda", dtype=dtype))
+
+
+@pytest.mark.parametrize("order,dtype,tol", [(2, torch.float64, 1e-9), (3, torch.float64, 1e-9), (3, torch.float32, 1e-4)])
+def test_cylinder_obstacles_vs_oracle(golden, order, dtype, tol, lib_built):
+    """Builder extension (the reference has spheres only; parity unpinned): a sphere and a vertical cylinder
+    (obstacles.Cylinder -> negative radius) in one obstacle set; device rows and QP answers against oracle/cbf.py."""
+    import multidronesim_b200 as mds
+    from multidronesim_b200.obstacles import Cylinder, Sphere
+    from oracle import cbf as ocbf
+    from oracle import conversions as cv
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel as ODM, Physics as OPH
+    name, N = ("o2_n8_obs1", 8) if order == 2 else ("o3_n8_obs1", 8)
+    g, env, cbf, trk, obs, xdes, _, unom = setup(golden, name, order, N, dtype)
+    prims = [Sphere((0.0, 0.0, 0.5), 0.1), Cylinder((0.4, -0.3, 0.0), 0.15, height=3.0)]
+    obst = torch.tensor([p.as_row() for p in prims], device="cuda", dtype=dtype)
+    Gd, hd = cbf.build_ineq_const(obs, xdes, obst)
+    u = trk.compute_control(obs, xdes, unom, x_obs=obst).double().cpu().numpy()
+    st = trk.status.cpu().numpy()
+    oenv = OracleCtrlAviary(ODM.CF2P, N, physics=OPH.DYN)
+    prm = ocbf.CbfParams(oenv, order, 1.0 if order == 2 else 2.0, 0.1 if order == 2 else 0.125, (-2.2, -2.4) if order == 2 else (-3.0, -3.6, -5.6))
+    obs_h, xdes_h, unom_h = g[f"{name}_obs"], g[f"{name}_xdes"], g[f"{name}_unom"]
+    solved = 0
+    for e in range(obs_h.shape[0]):
+        x = np.array([cv.obs_to_lin_model(obs_h[e, i], prm.xdim, oenv) for i in range(N)])
+        Gr, hr = ocbf.build_ineq(prm, x, xdes_h[e], [np.array(p.center) for p in prims], [p.as_row()[3] for p in prims])
+        assert scaled_err(Gd[e].double().cpu().numpy(), Gr) < max(tol, 1e-5 if dtype == torch.float32 else 0)
+        assert scaled_err(hd[e].double().cpu().numpy(), hr) < max(tol, 1e-5 if dtype == torch.float32 else 0)
+        uo, _, so, _ = solve_qp(np.eye(4 * N), -unom_h[e].reshape(-1), Gr, hr)
+        if so == 0 and st[e] == 0:
+            # per input column, relative to that column's bound (as test_qp_fp32_within_1e4)
+            err = np.abs(u[e] - uo.reshape(N, 4)) / np.maximum(1.0, np.abs(np.asarray(cbf.umax))[None, :])
+            assert np.max(err) < max(tol, 1e-8), (e, np.max(err))
+            solved += 1
+    assert solved >= (1 if order == 2 else 2)   # order-2 rows vanish at ez = 0: most random order-2 cases are infeasible
+    import os
+    from multidronesim_b200.obstacles import generate_cylinder
+    path = generate_cylinder(0.15, 3.0)
+    assert os.path.isfile(path) and 'cylinder radius="0.15" length="3.0"' in open(path).read()

@@ -179,3 +179,24 @@ def test_qp_infeasible_detected():
     h = np.array([-1.0, -1.0])  # x <= -1 and x >= 1
     _, _, st, _ = solve_qp(np.eye(2), np.zeros(2), G, h)
     assert st == 1
+
+
+def test_cylinder_row_is_the_zscale_limit():
+    """Builder extension (parity unpinned: the reference has spheres only): a vertical-cylinder obstacle row equals the
+    sphere row of the same radius in the limit zscale -> infinity, and differs from it at the reference's zscale."""
+    from oracle import cbf as ocbf
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel, Physics
+    env = OracleCtrlAviary(DroneModel.CF2P, 2, physics=Physics.DYN)
+    rng = np.random.default_rng(9)
+    for order, xdim in ((2, 9), (3, 10)):
+        x, xdes = rng.normal(0, 0.4, (2, xdim)), rng.normal(0, 0.4, (2, xdim))
+        xo = [np.array([0.3, -0.2, 0.7])]
+        prm = ocbf.CbfParams(env, order, 2.0, 0.125, (-2.2, -2.4) if order == 2 else (-3.0, -3.6, -5.6))
+        Gc, hc = ocbf.build_ineq(prm, x, xdes, xo, [-0.1])
+        Gs, hs = ocbf.build_ineq(prm, x, xdes, xo, [0.1])
+        big = ocbf.CbfParams(env, order, 1e9, 0.125, (-2.2, -2.4) if order == 2 else (-3.0, -3.6, -5.6))
+        Gl, hl = ocbf.build_ineq(big, x, xdes, xo, [0.1])
+        assert np.allclose(Gc[-2:], Gl[-2:], rtol=1e-12, atol=1e-15) and np.allclose(hc[-2:], hl[-2:], rtol=1e-12, atol=1e-15)
+        assert not np.allclose(hc[-2:], hs[-2:])
+        assert np.array_equal(Gc[:-2], Gs[:-2]) and np.array_equal(hc[:-2], hs[:-2])  # only the obstacle rows change
