@@ -9,16 +9,17 @@ Workload (config.workload): SURVEY.md 8(d) C5 -- per GPU 125 000 independent env
 CBF-QP (28 pair rows + 8 obstacle rows + box/force bounds per env) -> YankOmega inner loop ->
 DYN_GND_DRAG_DW physics (ground effect, drag, pairwise downwash) -> 20-float observation.
 
-One bench "step" = one ``mds_rollout`` call = ``--fuse`` control steps of every drone (two kernel launches per
-control step: the controller-stack kernel and the physics kernel, enqueued back to back, no host sync).
+One bench "step" = one ``mds_rollout`` call = ONE kernel launch = ``--fuse`` control steps of every drone with the
+observation and body rates in registers from step to step (environments are independent; a lane group owns its env).
 ``value``   : drone-steps/s, state resident in HBM, CUDA events on the launching stream, max over ranks.
 ``e2e``     : the same metric through the per-call API with HOST buffers (multidronesim_b200.HostPipeline): every
               control step copies the step's references host -> device from pinned memory and the new observation
               device -> host, copies overlapped with the neighbouring steps' kernels on their own streams.
-``roofline``: the dominant kernel (controller stack incl. the CBF-QP) against the measured HBM copy bandwidth
-              (MEASURED_PEAKS.json): algorithmic bytes per launch / its mean launch duration from per-launch CUDA
-              events over a replay of the timed region; ``roofline_physics`` the same for the physics kernel,
-              ``roofline_step`` for both together; each carries the FP32-pipe view (FMA-chain peak measured live).
+``roofline``: the dominant (only) kernel of the timed region, rollout_loop_kernel.  It is FP32-pipe-bound (the state
+              never leaves the registers: ~130 flop per HBM byte), so achieved = algorithmic flop per launch / launch
+              duration against the FMA-chain peak measured live (MEASURED_PEAKS.json has no non-tensor FP32 figure);
+              its HBM view is reported inside.  ``roofline_ctrl`` / ``roofline_physics``: the per-call kernels (what
+              ``e2e`` launches) against the measured HBM copy bandwidth, from a launch-by-launch replay.
               No tensor cores on this path: nothing is a dense contraction.
 ``cpu_baseline``: oracle/ (numpy restatement of the reference's algorithms) on all host cores, bounded sample.
 """
@@ -53,6 +54,10 @@ ALGO_FLOP_PER_DRONE_STEP = {"traj": 70, "lqr_yank": 130, "cbf_rows": 680, "cbf_c
 # Algorithmic HBM bytes per drone-step (fp32), per kernel of the rollout (DESIGN.md "Roofline"):
 ALGO_BYTES_CTRL_F32 = {"read_obs": 80, "read_traj_spec": 48, "read_pid": 24, "write_pid": 24, "write_action": 16}
 ALGO_BYTES_PHYS_F32 = {"read_state": 68, "read_action": 16, "write_state": 68, "write_obs": 80}  # 232 B
+# the K-steps-in-one-launch kernel, per drone and per LAUNCH (not per step): initial obs + body rates + trajectory spec,
+# PID state in and out, final state + obs + action
+ALGO_BYTES_LOOP_PER_LAUNCH_F32 = {"read_obs": 80, "read_body_rates": 12, "read_traj_spec": 48, "read_pid": 24, "write_pid": 24,
+                                  "write_state": 68, "write_obs": 80, "write_action": 16}
 
 
 def parse_args():
@@ -305,52 +310,58 @@ def run_gpu_arm(args):
     stats = dict(zip(mds._lib.STAT_NAMES, mds.dist.reduce_stats(stats_all).tolist()))
     clocks = clk.summary()
 
-    # ---- per-kernel durations over the SAME K*F control steps (this rank) ------------------------------------
-    # Replay the timed region from its snapshot one launch at a time (MdsRolloutCfg.stages) with a CUDA event
-    # pair around every launch on the launching stream: the rollout is deterministic, so each kernel does
-    # exactly the work it did in the timed region.
+    # ---- roofline of the dominant kernel: the K-steps-in-one-launch rollout kernel (this rank) ----------------
+    # Every bench step is ONE launch of rollout_loop_kernel (F control steps with the state in registers), so its
+    # mean launch duration is the timed region / K, on the launching stream.  It moves ~15 B per drone-step through
+    # HBM for ~1.9 kflop: FP32-pipe-bound (SURVEY.md 8d "fused K-step rollout"), peak = FMA-chain microbenchmark.
+    if ro.plan() != 6:
+        raise SystemExit("bench.py assumes the K-steps-in-one-launch plan")
+    n_steps = K * F
+    step_ms = ms / n_steps
+    launch_ms = ms / K
+    peaks = measured_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    peak_src = "MEASURED_PEAKS.json hbm_gbs, of measured (sustained copy)" if peaks else "fallback 6.65 TB/s, of fallback"
+    sfx = "float" if dtype == torch.float32 else "double"
+    flop_step = sum(ALGO_FLOP_PER_DRONE_STEP.values())
+    bytes_launch = sum(ALGO_BYTES_LOOP_PER_LAUNCH_F32.values()) * esz // 4
+    tf = flop_step * D * F / (launch_ms * 1e-3) / 1e12
+    gbs = bytes_launch * D / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "fp32", "kernel": f"rollout_loop_kernel<{sfx}, MDS_CTRL_LQR_YANK, true, 8>", "achieved": tf, "peak": fma_peak,
+                "unit": "TFLOP/s", "frac": tf / fma_peak,
+                "peak_source": "measured live: mds_fma_peak dependent-FMA chains on all SMs (no non-tensor FP32 figure in MEASURED_PEAKS.json)",
+                "algorithmic_flop_per_drone_step": flop_step, "control_steps_per_launch": F, "launch_ms": launch_ms, "share_of_step": 1.0,
+                "traffic": ncu_traffic("rollout_loop_kernel", E, args.dtype),
+                "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "algorithmic_bytes_per_drone_per_launch": bytes_launch,
+                        "peak_source": peak_src},
+                "note": f"arithmetic intensity {flop_step * F / bytes_launch:.0f} flop/B >> ridge {fma_peak * 1e3 / hbm_peak:.1f} flop/B: the state lives in "
+                        "registers for the whole launch, so the FP32 pipe (not HBM, not tensor cores: nothing is a dense contraction) bounds it"}
+
+    # ---- the per-call kernels against the HBM roofline: replay with one launch per kernel ----------------------
+    # (MdsRolloutCfg.stages 1 = controller kernel, 2 = physics kernel; a CUDA event pair around every launch)
     restore(env, ctrl, ro, snap)
     torch.cuda.synchronize()
-    n_steps = K * F
-    if ro.plan() != 4:
-        raise SystemExit("bench.py's per-kernel replay assumes the two-launch plan (swarms above 2^18 drones)")
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_steps)]
-    for k in range(n_steps):
+    n_rep = min(n_steps, 240)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_rep)]
+    for k in range(n_rep):
         evs[k][0].record()
         ro.run(1, stages=1)
         evs[k][1].record()
         ro.run(1, stages=2)
         evs[k][2].record()
     torch.cuda.synchronize()
-    ctrl_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / n_steps
-    phys_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / n_steps
-    step_ms = ms / n_steps
-    peaks = measured_peaks()
-    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
-    peak_src = "MEASURED_PEAKS.json hbm_gbs, of measured (sustained copy)" if peaks else "fallback 6.65 TB/s, of fallback"
-    sfx = "float" if dtype == torch.float32 else "double"
+    ctrl_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / n_rep
+    phys_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / n_rep
     b_ctrl, b_phys = sum(ALGO_BYTES_CTRL_F32.values()) * esz // 4, sum(ALGO_BYTES_PHYS_F32.values()) * esz // 4
-    flop_ctrl = sum(v for k, v in ALGO_FLOP_PER_DRONE_STEP.items() if k not in ("physics_gnd_drag_dw_n8", "obs"))
-    flop_phys = ALGO_FLOP_PER_DRONE_STEP["physics_gnd_drag_dw_n8"] + ALGO_FLOP_PER_DRONE_STEP["obs"]
 
-    def roof(kernel, bytes_unit, flop_unit, launch_ms):
-        gbs = bytes_unit * D / (launch_ms * 1e-3) / 1e9
-        tf = flop_unit * D / (launch_ms * 1e-3) / 1e12
-        return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                "peak_source": peak_src, "algorithmic_bytes_per_drone_step": bytes_unit, "launch_ms": launch_ms,
-                "share_of_step": launch_ms / (ctrl_ms + phys_ms), "traffic": ncu_traffic(kernel.split("<")[0], E, args.dtype),
-                "fp32_pipe": {"achieved_tflops": tf, "peak_tflops": fma_peak, "frac": tf / fma_peak, "algorithmic_flop_per_drone_step": flop_unit,
-                              "peak_source": "measured live: mds_fma_peak dependent-FMA chains (no non-tensor FP32 figure in MEASURED_PEAKS.json)"}}
+    def roof(kernel, bytes_unit, launch):
+        g = bytes_unit * D / (launch * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": kernel, "achieved": g, "peak": hbm_peak, "unit": "GB/s", "frac": g / hbm_peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_drone_step": bytes_unit, "launch_ms": launch, "traffic": ncu_traffic(kernel.split("<")[0], E, args.dtype),
+                "note": "per-call path (two launches per control step); replay of the first %d control steps of the timed region" % n_rep}
 
-    roofline = roof(f"ctrl_step_kernel<{sfx}, MDS_CTRL_LQR_YANK, true>", b_ctrl, flop_ctrl, ctrl_ms)
-    roofline["note"] = ("dominant kernel of the step (reference -> LQR -> CBF rows -> QP -> inner loop); arithmetic intensity "
-                        f"{flop_ctrl / b_ctrl:.1f} flop/B is below the ridge ({fma_peak * 1e3 / hbm_peak:.1f} flop/B), so HBM is the bound; "
-                        "durations from per-launch CUDA events over a replay of the timed region")
-    roofline_physics = roof(f"physics_step_kernel<{sfx}>", b_phys, flop_phys, phys_ms)
-    gbs_step = (b_ctrl + b_phys) * D / (step_ms * 1e-3) / 1e9
-    roofline_step = {"bound": "hbm", "achieved": gbs_step, "peak": hbm_peak, "unit": "GB/s", "frac": gbs_step / hbm_peak,
-                     "algorithmic_bytes_per_drone_step": b_ctrl + b_phys, "ms_per_control_step": step_ms,
-                     "sum_of_kernel_ms": ctrl_ms + phys_ms, "note": "both kernels back to back inside the timed region (this rank)"}
+    roofline_ctrl = roof(f"ctrl_step_kernel<{sfx}, MDS_CTRL_LQR_YANK, true, 8>", b_ctrl, ctrl_ms)
+    roofline_physics = roof(f"physics_step_kernel<{sfx}, 8>", b_phys, phys_ms)
 
     # ---- end to end through the per-call API with host buffers --------------------------------
     e2e = None
@@ -361,8 +372,8 @@ def run_gpu_arm(args):
         line = {"metric": "drone-steps/sec (DYN_GND_DRAG_DW + LQR + order-3 CBF-QP, 8 drones/env)", "value": value, "unit": "drone-steps/s",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, E),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * F * K, "roofline": roofline, "roofline_physics": roofline_physics,
-                "roofline_step": roofline_step, "cpu_baseline": cpu, "rollout_stats": stats, "sm_count": mds._lib.device_info()["sm_count"]}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "roofline_ctrl": roofline_ctrl,
+                "roofline_physics": roofline_physics, "cpu_baseline": cpu, "rollout_stats": stats, "sm_count": mds._lib.device_info()["sm_count"]}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

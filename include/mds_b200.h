@@ -158,7 +158,9 @@ typedef struct MdsRolloutCfg {
   int num_obstacles;   /* spheres shared by all envs (<= N, reference quirk B14)        */
   int write_obs_every; /* 0 = only after the last step; k>0 = log obs every k steps     */
   int stages;          /* launch plan for the K control steps:
-                          0      whole steps, plan chosen by mds_rollout_plan(E, N) (3 for small swarms, 4 for large)
+                          0      whole steps, plan chosen by mds_rollout_plan(E, N) (currently always 6)
+                          6      all K steps in ONE launch: observation and body rates stay in registers from step to
+                                 step (environments are independent and a lane group owns its environment)
                           3      whole steps, fused: ctrl | K-1 x [physics + ctrl in one launch] | physics
                           4      whole steps as two launches each (controller kernel, physics kernel)
                           1      controller kernel only (action_dev <- controller stack at obs_dev; env does not advance)
@@ -264,11 +266,11 @@ int mds_xdot_linear_f64(const MdsDroneParams* prm, int kind, const double* obs_d
 int mds_xdot_nonlinear_f32(const MdsDroneParams* prm, double jx, double jy, double jz, const float* obs_dev, float* xdot_dev, int D, void* stream);
 int mds_xdot_nonlinear_f64(const MdsDroneParams* prm, double jx, double jy, double jz, const double* obs_dev, double* xdot_dev, int D, void* stream);
 
-/* ---- K-step rollout: ONE launch per control step in the steady state -- the env advances under the previous
- * action (all sub-steps in registers) and the controller stack (reference -> tracking controller -> CBF-QP -> inner
- * loop, registers / shared memory) runs on the new observation before it leaves the registers; a controller-only
- * launch opens and a physics-only launch closes the sequence (MdsRolloutCfg.stages).  Everything is enqueued on
- * `stream` with no host synchronisation (capturable in a CUDA graph).
+/* ---- K-step rollout.  Default plan: ONE launch for all K control steps -- every lane group runs its own environment
+ * forward (reference -> tracking controller -> CBF-QP -> inner loop -> physics sub-steps) with the observation and
+ * the body rates in registers; HBM sees the initial load, the PID state, the log slots that are due and the final
+ * store.  Other plans (MdsRolloutCfg.stages): one fused launch per step, two launches per step, single kernels.
+ * Everything is enqueued on `stream` with no host synchronisation.
  * obs_dev [D*20] in/out (observation before the first / after the last step); action_dev [D*4] scratch;
  * obs_log_dev optional [K/write_obs_every][D*20]; stats_dev optional [MDS_STAT_COUNT] doubles (accumulated). */
 int mds_rollout_f32(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
@@ -280,7 +282,7 @@ int mds_rollout_f64(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const M
                     const MdsDslPidGains* dsl, MdsDslPidState dsl_state, const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double* obs_dev, double* action_dev,
                     double* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
 
-/* launch plan (MdsRolloutCfg.stages value 3 or 4) that stages == 0 selects for E envs of N drones */
+/* launch plan (a MdsRolloutCfg.stages value) that stages == 0 selects for E envs of N drones */
 int mds_rollout_plan(int E, int N);
 
 /* ---- measurement aid: dependent-FMA-chain peak of the FP32 / FP64 pipes (TFLOP/s) ---- */

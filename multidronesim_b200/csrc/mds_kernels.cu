@@ -41,6 +41,9 @@ static int check_launch(const char* what) {
 #ifndef MDS_CTRL_MINB
 #define MDS_CTRL_MINB 4  // resident blocks per SM the controller kernel is compiled for (64 registers)
 #endif
+#ifndef MDS_LOOP_MINB
+#define MDS_LOOP_MINB 2  // the K-step loop kernel serves small swarms: registers before occupancy
+#endif
 #ifndef MDS_FUSED_MINB
 #define MDS_FUSED_MINB 4
 #endif
@@ -213,23 +216,24 @@ template <int NT> MDS_DEV int ct_np(int np_rt) {
   while (p < NT) p <<= 1;
   return p;
 }
-// One control period of the env for this lane's drone (every lane of a valid group calls it): loads the state and
-// the action, runs the sub-steps with the state in registers, stores the state and (if obs != nullptr) the
-// observation, and returns the observation in registers.
+template <typename Real> MDS_DEV void store4(Real* p, int d, const Real v[4]) {
+  typename Vec4T<Real>::type o;
+  o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3];
+  reinterpret_cast<typename Vec4T<Real>::type*>(p)[d] = o;
+}
+template <typename Real> MDS_DEV void load4(const Real* p, int d, Real v[4]) {
+  auto o = reinterpret_cast<const typename Vec4T<Real>::type*>(p)[d];
+  v[0] = o.x; v[1] = o.y; v[2] = o.z; v[3] = o.w;
+}
+// One control period of the env for this lane's drone with the state in registers (every lane of a valid group
+// calls it): clips the action, runs the sub-steps, returns the new observation.
 template <typename Real>
-MDS_DEV Obs<Real> physics_body(const DroneP<Real>& P, const StateP<Real>& st, const Real* __restrict__ action, const Real* __restrict__ fext,
-                               Real* __restrict__ obs, typename Vec4T<Real>::type* sm_pos, const GroupMap& g, int N) {
-  Drone<Real> s;
-  s.p = {Real(0), Real(0), Real(0)};
-  Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
-  V3<Real> fx = {Real(0), Real(0), Real(0)}, av = {Real(0), Real(0), Real(0)};
-  if (g.valid) {
-    s = load_drone(st, g.d);
-    auto a = reinterpret_cast<const typename Vec4T<Real>::type*>(action)[g.d];
-    rpm[0] = clamp_(a.x, Real(0), P.max_rpm); rpm[1] = clamp_(a.y, Real(0), P.max_rpm);
-    rpm[2] = clamp_(a.z, Real(0), P.max_rpm); rpm[3] = clamp_(a.w, Real(0), P.max_rpm);
-    if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
-  }
+MDS_DEV Obs<Real> physics_core(const DroneP<Real>& P, Drone<Real>& s, const Real action[4], V3<Real> fx, typename Vec4T<Real>::type* sm_pos,
+                               const GroupMap& g, int N) {
+  Real rpm[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rpm[i] = clamp_(action[i], Real(0), P.max_rpm);
+  V3<Real> av = {Real(0), Real(0), Real(0)};
   const bool dwash = (P.physics == MDS_PHYSICS_DYN_GND_DRAG_DW) && (N > 1);
   for (int k = 0; k < P.substeps; ++k) {
     Real dw = Real(0);
@@ -241,16 +245,34 @@ MDS_DEV Obs<Real> physics_body(const DroneP<Real>& P, const StateP<Real>& st, co
     }
   }
   Obs<Real> o;
+  if (g.valid) o = make_obs(s, av);
+  return o;
+}
+
+// The same through HBM: loads the state and the action, stores the state and (if obs != nullptr) the observation,
+// and returns the observation in registers.
+template <typename Real>
+MDS_DEV Obs<Real> physics_body(const DroneP<Real>& P, const StateP<Real>& st, const Real* __restrict__ action, const Real* __restrict__ fext,
+                               Real* __restrict__ obs, typename Vec4T<Real>::type* sm_pos, const GroupMap& g, int N) {
+  Drone<Real> s;
+  s.p = {Real(0), Real(0), Real(0)};
+  Real act[4] = {Real(0), Real(0), Real(0), Real(0)};
+  V3<Real> fx = {Real(0), Real(0), Real(0)};
+  if (g.valid) {
+    s = load_drone(st, g.d);
+    load4(action, g.d, act);
+    if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
+  }
+  Obs<Real> o = physics_core(P, s, act, fx, sm_pos, g, N);
   if (g.valid) {
     store_drone(st, g.d, s);
-    o = make_obs(s, av);
     if (obs) store_obs(obs, g.d, o);
   }
   return o;
 }
 
 template <typename Real, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, MDS_PHYS_MINB) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
+__global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_PHYS_MINB : 2) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
                                                                   const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N_rt, int NP_rt) {
   __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
@@ -284,15 +306,6 @@ __global__ void traj_eval_kernel(const typename TrajSpecT<Real>::spec* __restric
   Real* r = ref + (size_t)d * MDS_REF_DIM;
   r[0] = o.p.x; r[1] = o.p.y; r[2] = o.p.z; r[3] = o.v.x; r[4] = o.v.y; r[5] = o.v.z;
   r[6] = o.a.x; r[7] = o.a.y; r[8] = o.a.z; r[9] = o.yaw; r[10] = o.yaw_rate;
-}
-template <typename Real> MDS_DEV void store4(Real* p, int d, const Real v[4]) {
-  typename Vec4T<Real>::type o;
-  o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3];
-  reinterpret_cast<typename Vec4T<Real>::type*>(p)[d] = o;
-}
-template <typename Real> MDS_DEV void load4(const Real* p, int d, Real v[4]) {
-  auto o = reinterpret_cast<const typename Vec4T<Real>::type*>(p)[d];
-  v[0] = o.x; v[1] = o.y; v[2] = o.z; v[3] = o.w;
 }
 template <typename Real>
 __global__ void geometric_ctrl_kernel(DroneP<Real> P, GeoP<Real> G, const Real* __restrict__ obs, const Real* __restrict__ ref,
@@ -606,15 +619,15 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
 // ints; the barrier minimum goes through an order-preserving float -> int map) and five float shuffles for the
 // error sum, then shared memory and ONE set of atomics per block: same-address atomics from every warp cost
 // more than the whole step (1.6 ms vs 0.4 ms per step at 1M drones).
-template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ stats, bool valid, const StepStats& ss) {
+template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ stats, int drone_steps, const StepStats& ss, float max_err) {
   __shared__ float sm_f[MDS_BLOCK / 32][2];
   __shared__ int sm_i[MDS_BLOCK / 32][6];
   const unsigned full = 0xffffffffu;
   int mh_i = __float_as_int(ss.min_h);
   mh_i = mh_i >= 0 ? mh_i : (mh_i ^ 0x7fffffff);
-  const int w_steps = __reduce_add_sync(full, valid ? 1 : 0), w_solves = __reduce_add_sync(full, ss.qp_solves);
+  const int w_steps = __reduce_add_sync(full, drone_steps), w_solves = __reduce_add_sync(full, ss.qp_solves);
   const int w_iters = __reduce_add_sync(full, ss.qp_iters), w_inf = __reduce_add_sync(full, ss.qp_infeas), w_cap = __reduce_add_sync(full, ss.qp_cap);
-  const unsigned w_maxe = __reduce_max_sync(full, __float_as_uint(ss.err));
+  const unsigned w_maxe = __reduce_max_sync(full, __float_as_uint(max_err));
   const int w_minh = __reduce_min_sync(full, mh_i);
   float w_sum = ss.err;
   for (int off = 16; off > 0; off >>= 1) w_sum += __shfl_xor_sync(full, w_sum, off);
@@ -649,7 +662,7 @@ template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ sta
 
 // controller stack alone: obs (HBM) -> action (HBM)
 template <typename Real, int CTRL, bool USE_CBF, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_MINB) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+__global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_CTRL_MINB : 2) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
                                                                DslP<Real> Dg, DslStateP<Real> dst, PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                const typename TrajSpecT<Real>::seg* __restrict__ segs,
                                                                const Real* __restrict__ obs, Real* __restrict__ action,
@@ -672,7 +685,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_MINB) ctrl_step_kernel(Dro
     ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
     if (g.valid) store4(action, g.d, rpm);
   }
-  if (stats) stats_block_reduce<USE_CBF>(stats, g.valid, ss);
+  if (stats) stats_block_reduce<USE_CBF>(stats, g.valid ? 1 : 0, ss, ss.err);
 }
 
 // One launch per control step inside a rollout: the env advances under the PREVIOUS step's action, and the
@@ -680,7 +693,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_MINB) ctrl_step_kernel(Dro
 // caller / the log but never read back; the action buffer is read and rewritten by the same thread).  Blocks of
 // one grid are in different phases (HBM-heavy physics, issue-heavy controller), which overlap on an SM.
 template <typename Real, int CTRL, bool USE_CBF, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, MDS_FUSED_MINB) step_fused_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+__global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB : 2) step_fused_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
                                                                 DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
                                                                 const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                 const typename TrajSpecT<Real>::seg* __restrict__ segs,
@@ -706,7 +719,66 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_FUSED_MINB) step_fused_kernel(D
     ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
     if (g.valid) store4(action, g.d, rpm);
   }
-  if (stats) stats_block_reduce<USE_CBF>(stats, g.valid, ss);
+  if (stats) stats_block_reduce<USE_CBF>(stats, g.valid ? 1 : 0, ss, ss.err);
+}
+
+// K control steps in ONE launch.  Environments never interact, and everything that couples the drones of an
+// environment (downwash, CBF rows, QP) is exchanged inside its lane group, so a group can run its env forward on its
+// own: the observation and the body rates stay in registers from step to step, HBM sees the initial load, the PID
+// state (L1-resident), the log slots that are due and the final store.  No launch per step, no grid-wide barrier.
+template <typename Real, int CTRL, bool USE_CBF, int NT>
+__global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+                                                                  DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
+                                                                  const typename TrajSpecT<Real>::spec* __restrict__ specs,
+                                                                  const typename TrajSpecT<Real>::seg* __restrict__ segs,
+                                                                  Real* __restrict__ action, Real* __restrict__ obs, Real* __restrict__ obs_log,
+                                                                  double* __restrict__ stats, double t0, double dt_ctrl, int K, int E, int N_rt, int NP_rt) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
+  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
+  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
+  const GroupMap g = group_map(N, NP, E);
+  StepStats acc = {0.f, 1e30f, 0, 0, 0, 0};
+  float max_err = 0.f;
+  int steps_done = 0;
+  if (g.env_valid) {
+    Obs<Real> o;
+    V3<Real> wb = {Real(0), Real(0), Real(0)};  // body rates: the one part of the state the observation does not carry
+    typename TrajSpecT<Real>::spec spec;
+    spec.kind = MDS_TRAJ_WAIT;
+    if (g.valid) {
+      o = load_obs(obs, g.d);
+      spec = specs[g.d];
+      wb = {st.pos_wx[g.d].w, st.vel_wy[g.d].w, st.wz[g.d]};
+    }
+    Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
+    const size_t obs_elems = (size_t)E * N * MDS_OBS_DIM;
+    for (int k = 0; k < K; ++k) {
+      StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
+      ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss);  // the host plans form t exactly like this
+      acc.err += ss.err; max_err = fmaxf(max_err, ss.err); acc.min_h = fminf(acc.min_h, ss.min_h);
+      acc.qp_solves += ss.qp_solves; acc.qp_iters += ss.qp_iters; acc.qp_infeas += ss.qp_infeas; acc.qp_cap += ss.qp_cap;
+      Drone<Real> s;
+      s.p = o.p; s.qx = o.qx; s.qy = o.qy; s.qz = o.qz; s.qw = o.qw; s.v = o.v; s.w = wb;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s.rpm[i] = o.rpm[i];
+      o = physics_core(P, s, rpm, v3(Real(0), Real(0), Real(0)), sm_pos, g, N);
+      wb = s.w;
+      if (g.valid && Rc.write_obs_every > 0 && ((k + 1) % Rc.write_obs_every) == 0)
+        store_obs(obs_log + (size_t)((k + 1) / Rc.write_obs_every - 1) * obs_elems, g.d, o);
+    }
+    if (g.valid) {
+      Drone<Real> s;
+      s.p = o.p; s.qx = o.qx; s.qy = o.qy; s.qz = o.qz; s.qw = o.qw; s.v = o.v; s.w = wb;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s.rpm[i] = o.rpm[i];
+      store_drone(st, g.d, s);
+      store_obs(obs, g.d, o);
+      store4(action, g.d, rpm);
+      steps_done = K;
+    }
+  }
+  if (stats) stats_block_reduce<USE_CBF>(stats, steps_done, acc, max_err);
 }
 
 // ------------------------------------------------------------------ FMA-chain peak microbenchmark
@@ -837,7 +909,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   MDS_REQUIRE(prm && cfg && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && specs && obs && action, "rollout: null pointer");
   MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV && K > 0, "rollout: bad E, N or K");
   MDS_REQUIRE(cfg->ctrl >= MDS_CTRL_GEOMETRIC && cfg->ctrl <= MDS_CTRL_DSLPID, "rollout: unknown controller");
-  MDS_REQUIRE(cfg->stages >= 0 && cfg->stages <= 5, "rollout: stages must be 0..5");
+  MDS_REQUIRE(cfg->stages >= 0 && cfg->stages <= 6, "rollout: stages must be 0..6");
   RolloutP<Real> R;
   memset(&R, 0, sizeof(R));
   R.ctrl = cfg->ctrl; R.use_cbf = cfg->use_cbf; R.n_obs = cfg->num_obstacles; R.write_obs_every = cfg->write_obs_every;
@@ -885,7 +957,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   const StateP<Real> Sd = to_dev<Real>(st);
   const PidP<Real> Pi = to_dev<Real>(pid);
   const size_t obs_elems = (size_t)E * N * MDS_OBS_DIM;
-  // launch plan.  stages 0: mds_rollout_plan(E, N) picks 3 or 4; 3: the whole step, fused wherever a physics step is
+  // launch plan.  stages 0: mds_rollout_plan(E, N) (= 6, K steps in one launch); 3: the whole step, fused wherever a physics step is
   // followed by a controller step (ctrl | K-1 x [physics + ctrl] | physics); 4: two launches (ctrl, physics) per step;
   // 1: controller kernel only; 2: physics kernel only; 5: K fused launches [physics under the current action
   // buffer + controller at t0 + k dt] -- with 1 and 2 it lets a caller replay a rollout launch by launch.
@@ -907,6 +979,27 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
       kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Pi, specs, segs, (const Real*)(OBS_PTR), action, stats, T, E, N, NP);   \
     }                                                                                                                               \
   } while (0)
+#define MDS_LAUNCH_LOOP(CT, CB)                                                                                                      \
+  do {                                                                                                                              \
+    auto kern = (N == 8) ? rollout_loop_kernel<Real, CT, CB, 8> : rollout_loop_kernel<Real, CT, CB, 0>;                             \
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
+    kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, obs, obs_log, stats, t0, prm->dt_ctrl, K, E, N, NP); \
+  } while (0)
+  auto launch_loop = [&]() {
+    switch (R.ctrl) {
+      case MDS_CTRL_GEOMETRIC: MDS_LAUNCH_LOOP(MDS_CTRL_GEOMETRIC, false); break;
+      case MDS_CTRL_LQR_TORQUE: MDS_LAUNCH_LOOP(MDS_CTRL_LQR_TORQUE, false); break;
+      case MDS_CTRL_DSLPID: MDS_LAUNCH_LOOP(MDS_CTRL_DSLPID, false); break;
+      case MDS_CTRL_LQR_OMEGA:
+        if (R.use_cbf) MDS_LAUNCH_LOOP(MDS_CTRL_LQR_OMEGA, true);
+        else MDS_LAUNCH_LOOP(MDS_CTRL_LQR_OMEGA, false);
+        break;
+      default:
+        if (R.use_cbf) MDS_LAUNCH_LOOP(MDS_CTRL_LQR_YANK, true);
+        else MDS_LAUNCH_LOOP(MDS_CTRL_LQR_YANK, false);
+        break;
+    }
+  };
   bool first_ctrl = true, first_fused = true;
   auto launch_ctrl = [&](bool fused, double t, Real* obs_ptr) {
     switch (R.ctrl) {
@@ -942,6 +1035,8 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     }
   } else if (mode == 5) {
     for (int k = 0; k < K; ++k) { obs_last = obs_slot(k + 1); launch_ctrl(true, t0 + k * dt, obs_last); }
+  } else if (mode == 6) {
+    launch_loop();  // writes the final observation to `obs` itself
   } else {
     launch_ctrl(false, t0, obs);
     for (int k = 1; k < K; ++k) { obs_last = obs_slot(k); launch_ctrl(true, t0 + k * dt, obs_last); }
@@ -949,6 +1044,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     launch_phys(obs_last);
   }
 #undef MDS_LAUNCH_CTRL
+#undef MDS_LAUNCH_LOOP
   if (attr_err != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: shared memory opt-in failed: %s", cudaGetErrorString(attr_err));
   if (obs_last != obs) {
     cudaError_t e = cudaMemcpyAsync(obs, obs_last, obs_elems * sizeof(Real), cudaMemcpyDeviceToDevice, cs);
@@ -1006,10 +1102,11 @@ int mds_stream_synchronize(void* stream) {
   if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "stream_synchronize: %s", cudaGetErrorString(e));
   return MDS_OK;
 }
-// Measured on B200 (tools/exp_plans.py, C5 swarm): one fused launch per step is ~20 % faster up to ~1.3e5 drones
-// (launch- and tail-bound regime), two launches per step ~2-5 % faster from ~1e6 drones (the leaner kernels keep
-// more warps resident); the crossover is taken at 2^18 drones.
-int mds_rollout_plan(int E, int N) { return ((long long)E * N <= (1 << 18)) ? 3 : 4; }
+// Measured on B200 (tools/exp_plans.py, tools/exp_c2.py): the K-steps-in-one-launch plan (6) is the fastest at every
+// size and precision -- C2 4096 envs 1.8 us per step vs 8.3 (fused) / 11.3 (two launches); C5 1M drones fp32 0.127 ms
+// vs 0.140 / 0.132; fp64 0.305 ms vs 0.50 / 0.44 -- so stages == 0 always selects it.  3 and 4 remain for callers
+// that want the observation materialised in HBM after every step, 1 / 2 / 5 for launch-by-launch replays.
+int mds_rollout_plan(int E, int N) { (void)E; (void)N; return 6; }
 int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 * N + (order == 3 ? 2 * N : 0) + N * n_obs; }
 
 #define MDS_DEFINE(SUF, REAL, SPEC, SEG)                                                                                                          \

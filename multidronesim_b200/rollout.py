@@ -1,6 +1,6 @@
-"""K-step rollout (``mds_rollout``): per control step one fused controller kernel (trajectory ->
-tracking controller -> CBF-QP -> inner loop) and one physics kernel (all sub-steps in registers),
-enqueued back to back with no host synchronisation.
+"""K-step rollout (``mds_rollout``): by default ONE launch advances every environment K control steps (trajectory ->
+tracking controller -> CBF-QP -> inner loop -> physics sub-steps, observation and body rates in registers from step to
+step); other launch plans (one fused launch per step, two launches per step, single kernels) via ``stages``.
 
 It is the device equivalent of the reference's per-step Python loops
 (simulations/EnvGeometric.py:434-479, simulations/CBFTest.py:302-358,
@@ -56,13 +56,14 @@ class FusedRollout:
         self.stats[3] = 1e30  # MDS_STAT_MIN_BARRIER
 
     def plan(self):
-        """launch plan ``run`` uses by default: 3 (one fused launch per step) or 4 (two launches per step)"""
+        """launch plan ``run`` uses by default (6: all K steps in one launch)"""
         return _lib.load_library().mds_rollout_plan(self.env.NUM_ENVS, self.env.NUM_DRONES)
 
     def run(self, K, t0=None, obs_log=None, log_every=0, stages=0):
         """Advance every environment K control steps.  ``obs_log`` [K//log_every, E, N, 20] receives the
         observation after every ``log_every``-th step (the reference's ``observations.append(obs)``).
-        ``stages`` (MdsRolloutCfg.stages): 0 = whole steps, plan 3 or 4 chosen from the swarm size (default, ``plan()``);
+        ``stages`` (MdsRolloutCfg.stages): 0 = whole steps with the default plan (``plan()``: 6 = all K steps in ONE
+        launch, observation and body rates in registers from step to step);
         3 = whole steps, one fused launch per step in the steady state;
         4 = whole steps as two launches each; 1 = controller kernel only (fills the env's action buffer, time does
         not advance); 2 = physics kernel only (consumes that action buffer); 5 = fused launches only (physics under
@@ -71,8 +72,8 @@ class FusedRollout:
         env = self.env
         if t0 is None:
             t0 = self.t
-        if stages not in (0, 1, 2, 3, 4, 5):
-            raise ValueError("stages must be 0..5")
+        if stages not in (0, 1, 2, 3, 4, 5, 6):
+            raise ValueError("stages must be 0..6")
         t_call = t0 + env.CTRL_TIMESTEP if stages == 5 else t0  # 5: the controller runs after the physics step
         self.cfg.stages = int(stages)
         self.cfg.write_obs_every = int(log_every) if obs_log is not None else 0

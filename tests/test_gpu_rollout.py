@@ -175,14 +175,16 @@ def test_launch_plans_agree(ctrl, cbf_order, N, lib_built):
             init[e, j] = otj.Lemniscate(**sp)(0.0)[0] + rng.normal(0, 0.02, 3) + np.array([0, 0, 0.04 * j])
     obstacles = [[0.2, 0.0, 0.5, 0.1]] if cbf_order is not None else None
     outs = []
-    for plan in ("fused", "two", "replay"):
+    for plan in ("fused", "two", "replay", "loop"):
         mds, env, c, trk, ts, ro = build(E, N, dtype, "dyn_gnd_drag_dw", [T.Lemniscate(**sp) for sp in specs] * E, ctrl, cbf_order, obstacles, init)
         log = torch.zeros(K // 3, E, N, 20, device="cuda", dtype=dtype)
         if plan == "fused":
-            assert ro.plan() == 3  # small swarm
+            assert ro.plan() == 6  # the default is the K-steps-in-one-launch plan
             ro.run(K, obs_log=log, log_every=3, stages=3)
         elif plan == "two":
             ro.run(K, obs_log=log, log_every=3, stages=4)
+        elif plan == "loop":
+            ro.run(K, obs_log=log, log_every=3, stages=6)
         else:
             ro.run(1, stages=1)
             for k in range(K - 1):
@@ -193,3 +195,8 @@ def test_launch_plans_agree(ctrl, cbf_order, N, lib_built):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
     assert np.array_equal(outs[0][1], outs[1][1]) and np.abs(outs[0][1]).max() > 0
     assert np.array_equal(outs[0][2], outs[1][2]) and np.array_equal(outs[0][2], outs[2][2])
+    # the K-steps-in-one-launch plan is the same arithmetic compiled as one loop body: nvcc may contract a*b+c into
+    # an FMA differently there, so it agrees to fp32 rounding (amplified over K closed-loop steps), not bit for bit;
+    # its per-thread float accumulation of the error sum rounds differently, the counters are exact
+    assert np.allclose(outs[0][0], outs[3][0], rtol=2e-4, atol=2e-4) and np.allclose(outs[0][1], outs[3][1], rtol=2e-4, atol=2e-4)
+    assert np.allclose(outs[0][2], outs[3][2], rtol=1e-3) and outs[0][2][0] == outs[3][2][0]

@@ -1,4 +1,5 @@
-"""Small driver for ncu: C5-style swarm, `pre` warm-up control steps then `n` more (2 kernels per control step).
+"""Small driver for ncu: C5-style swarm; `pre` warm-up control steps in launches of 24 (rollout_loop_kernel), one timed
+launch of `n` steps, then one control step as the per-call pair (ctrl_step_kernel, physics_step_kernel).
 usage: python tools/prof_rollout.py [envs] [pre] [n] [f32|f64]"""
 import os
 import sys
@@ -12,10 +13,13 @@ n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 dt = torch.float64 if (len(sys.argv) > 4 and sys.argv[4] == "f64") else torch.float32
 sc = scenarios.cbf_swarm(E, 8, order=3, dtype=dt)
 ro = sc["rollout"]
-ro.run(pre)
+for _ in range(pre // 24):
+    ro.run(24)
 torch.cuda.synchronize()
 ro.reset_stats()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); ro.run(n); e1.record()
 torch.cuda.synchronize()
 print("ms/control-step %.4f" % (e0.elapsed_time(e1) / n), ro.stats_dict())
+ro.run(1, stages=4)
+torch.cuda.synchronize()

@@ -27,10 +27,10 @@ lines += [f"# {tag}: measured on 1x B200 (python bench.py, defaults)", "",
           f"e2e   {b['e2e']['value']:.4g} {b['unit']}  ({b['e2e']['ms_per_control_step']:.3f} ms per control step; H2D {b['e2e']['h2d_bytes_per_step'] / 1e6:.0f} MB, D2H {b['e2e']['d2h_bytes_per_step'] / 1e6:.0f} MB per step)",
           f"cpu   {b['cpu_baseline']['value']:.4g} {b['unit']} on {b['cpu_baseline']['cores']} cores ({b['cpu_baseline']['kind']})" if b.get("cpu_baseline") else "cpu   -",
           f"clocks {b['clocks']}", ""]
-for key in ("roofline", "roofline_physics", "roofline_step"):
+for key in ("roofline", "roofline_ctrl", "roofline_physics"):
     r = b[key]
-    lines.append(f"{key}: {r.get('kernel', 'ctrl + physics')}: {r['achieved']:.0f} GB/s of {r['peak']:.0f} = {r['frac']:.3f}"
-                 + (f"; launch {r['launch_ms'] * 1e3:.1f} us, share of step {r['share_of_step']:.2f}, ncu DRAM traffic {r['traffic']}" if "launch_ms" in r else ""))
+    lines.append(f"{key}: {r['kernel']}: {r['achieved']:.4g} {r['unit']} of {r['peak']:.4g} = {r['frac']:.3f} ({r['bound']}); "
+                 f"launch {r['launch_ms'] * 1e3:.1f} us, ncu DRAM traffic per launch {r['traffic']}")
 lines.append(f"rollout_stats: {b['rollout_stats']}")
 lines.append("")
 
@@ -51,10 +51,10 @@ if os.path.isfile(lp):
     ll = [f"ncu launch list of `python bench.py --no-cpu-baseline` ({sum(v[0] for v in agg.values())} launches; cold-cache, serialised: compare shares)"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         ll.append(f"  {k[:72]:<72} n={v[0]:6d} total {v[1] / 1e3:10.2f} ms  mean {v[1] / v[0]:8.1f} us  share {100 * v[1] / tot:5.1f}%")
-    c, p = agg.get("ctrl_step_kernel<float, 3, 1>", [1, 0])[1], agg.get("physics_step_kernel<float>", [1, 0])[1]
-    # the per-call (e2e) section also launches physics_step; the rollout's own share is reported from the bench line
-    ll.append(f"  ctrl_step : physics_step total time ratio under ncu = {c / max(p, 1e-9):.2f} (bench events: "
-              f"{b['roofline']['launch_ms'] / b['roofline_physics']['launch_ms']:.2f})")
+    c = sum(v[1] for k, v in agg.items() if k.startswith("ctrl_step_kernel"))
+    p = sum(v[1] for k, v in agg.items() if k.startswith("physics_step_kernel"))
+    ll.append(f"  ctrl_step : physics_step total time ratio under ncu = {c / max(p, 1e-9):.2f} (bench replay events: "
+              f"{b['roofline_ctrl']['launch_ms'] / b['roofline_physics']['launch_ms']:.2f})")
     open(os.path.join(P, f"{tag}_launches_summary.txt"), "w").write("\n".join(ll) + "\n")
     lines += ll + [""]
 
@@ -66,7 +66,8 @@ if os.path.isfile(rep):
     summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), raw], capture_output=True, text=True).stdout
     open(os.path.join(P, f"{tag}_ncu_kernels.txt"), "w").write(summ)
     subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), rep, "125000", "f32"], check=True)
-    for kern, pat, fn in (("ctrl_step", "ctrl_step_kernelIfLi3ELb1", "ctrl_lines"), ("physics_step", "physics_step_kernelIf", "physics_lines")):
+    for kern, pat, fn in (("rollout_loop", "rollout_loop_kernelIfLi3ELb1ELi8", "loop_lines"), ("ctrl_step", "ctrl_step_kernelIfLi3ELb1ELi8", "ctrl_lines"),
+                          ("physics_step", "physics_step_kernelIfLi8", "physics_lines")):
         env = dict(os.environ, NCU_KERNEL=kern)
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, so, pat, "40"], capture_output=True, text=True, env=env).stdout
         open(os.path.join(P, f"{tag}_{fn}.txt"), "w").write(out)
