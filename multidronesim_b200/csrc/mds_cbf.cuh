@@ -205,17 +205,18 @@ MDS_DEV void qp_test_row(QpWorst<Real>& w, const typename Vec4T<Real>::type& r, 
     }
   }
 }
-// own box bounds not in boxmask
+// own box bounds not in boxmask: per component only the bound on the side x is on can be violated
 template <typename Real> MDS_DEV void qp_test_box(QpWorst<Real>& w, const CbfP<Real>& C, const Real xn[3], int n, unsigned boxmask) {
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    if (boxmask & (1u << k)) continue;
-    const int comp = k >= 3 ? k - 3 : k;
-    const Real sgn = k < 3 ? Real(1) : Real(-1);
-    Real sl = C.umax[comp] - sgn * xn[comp];
-    if (sl < -qp_tol<Real>() * (C.umax[comp] + abs_(xn[comp]) + Real(1e-12))) {
-      int con = pack_con(MDS_QP_BOX0 + 6 * n + k, n, -1);
-      if (sl < w.v || (sl == w.v && con < w.con)) { w.v = sl; w.con = con; }
+  for (int comp = 0; comp < 3; ++comp) {
+    const Real ax = abs_(xn[comp]);
+    const Real sl = C.umax[comp] - ax;
+    if (sl < -qp_tol<Real>() * (C.umax[comp] + ax + Real(1e-12))) {
+      const int k = (xn[comp] < Real(0) ? 3 : 0) + comp;
+      if (!(boxmask & (1u << k))) {
+        int con = pack_con(MDS_QP_BOX0 + 6 * n + k, n, -1);
+        if (sl < w.v || (sl == w.v && con < w.con)) { w.v = sl; w.con = con; }
+      }
     }
   }
 }
