@@ -28,6 +28,12 @@ static int check_launch(const char* what) {
   }
   return MDS_OK;
 }
+// a failed runtime call leaves its error for the next cudaGetLastError(): report it and clear it
+static int cuda_fail(const char* what, cudaError_t e) {
+  (void)cudaGetLastError();
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return MDS_ERR_LAUNCH;
+}
 #define MDS_REQUIRE(cond, msg) \
   if (!(cond)) return fail(MDS_ERR_ARG, "%s", msg)
 
@@ -62,7 +68,7 @@ MDS_DEV GroupMap group_map(int N, int NP, int E) {
   const int tid = threadIdx.x, lg = __ffs(NP) - 1;  // NP is a power of two
   g.el = tid >> lg;
   g.n = tid & (NP - 1);
-  g.e = blockIdx.x * (MDS_BLOCK >> lg) + g.el;
+  g.e = blockIdx.x * (blockDim.x >> lg) + g.el;  // blockDim.x <= MDS_BLOCK (launch_geometry)
   g.env_valid = g.e < E;
   g.valid = g.env_valid && g.n < N;
   g.d = g.e * N + g.n;
@@ -109,8 +115,17 @@ static inline int cbf_env_stride(int NP, int N, int n_obs) {
   int head = 12 * NP > MDS_QP_WS_WORDS ? 12 * NP : ((MDS_QP_WS_WORDS + 3) & ~3);
   return head + 4 * NP * rpl + 8 * NP;
 }
-template <typename Real> static size_t cbf_smem_bytes(int NP, int N, int n_obs) {
-  return (size_t)(MDS_BLOCK / NP) * cbf_env_stride(NP, N, n_obs) * sizeof(Real) + 32;
+template <typename Real> static size_t cbf_smem_bytes(int threads, int NP, int N, int n_obs) {
+  return (size_t)(threads / NP) * cbf_env_stride(NP, N, n_obs) * sizeof(Real) + 32;
+}
+// Threads per block (a power of two in [NP or 32, MDS_BLOCK]) such that the CBF stage's shared memory stays under
+// ~100 KB per block (two blocks per SM): only small lane groups in fp64 (many envs per block, each with its own QP
+// workspace) and 32-drone groups with many obstacles ever need fewer than MDS_BLOCK threads.
+template <typename Real> static int cbf_block_threads(int NP, int N, int n_obs) {
+  int threads = MDS_BLOCK;
+  const int floor_threads = NP > 32 ? NP : 32;
+  while (threads > floor_threads && cbf_smem_bytes<Real>(threads, NP, N, n_obs) > 100 * 1024) threads >>= 1;
+  return threads;
 }
 template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw, int NP, int N, int n_obs) {
   CbfSmem<Real> s;
@@ -622,6 +637,7 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
 template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ stats, int drone_steps, const StepStats& ss, float max_err) {
   __shared__ float sm_f[MDS_BLOCK / 32][2];
   __shared__ int sm_i[MDS_BLOCK / 32][6];
+  const int n_warps = blockDim.x >> 5;
   const unsigned full = 0xffffffffu;
   int mh_i = __float_as_int(ss.min_h);
   mh_i = mh_i >= 0 ? mh_i : (mh_i ^ 0x7fffffff);
@@ -641,17 +657,17 @@ template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ sta
     const int k = threadIdx.x;
     double acc = 0.0;
     if (k == MDS_STAT_SUM_POS_ERR) {
-      for (int i = 0; i < MDS_BLOCK / 32; ++i) acc += (double)sm_f[i][0];
+      for (int i = 0; i < n_warps; ++i) acc += (double)sm_f[i][0];
     } else if (k == MDS_STAT_MAX_POS_ERR) {
-      for (int i = 0; i < MDS_BLOCK / 32; ++i) acc = fmax(acc, (double)sm_f[i][1]);
+      for (int i = 0; i < n_warps; ++i) acc = fmax(acc, (double)sm_f[i][1]);
     } else if (k == MDS_STAT_MIN_BARRIER) {
       int m = sm_i[0][5];
-      for (int i = 1; i < MDS_BLOCK / 32; ++i) m = min(m, sm_i[i][5]);
+      for (int i = 1; i < n_warps; ++i) m = min(m, sm_i[i][5]);
       acc = (double)__int_as_float(m >= 0 ? m : (m ^ 0x7fffffff));
     } else {
       const int col = k == MDS_STAT_DRONE_STEPS ? 0 : (k == MDS_STAT_QP_SOLVES ? 1 : (k == MDS_STAT_QP_ITERS ? 2 : (k == MDS_STAT_QP_INFEASIBLE ? 3 : 4)));
       long long t = 0;
-      for (int i = 0; i < MDS_BLOCK / 32; ++i) t += sm_i[i][col];
+      for (int i = 0; i < n_warps; ++i) t += sm_i[i][col];
       acc = (double)t;
     }
     if (k == MDS_STAT_MAX_POS_ERR) atomic_max_double(&stats[k], acc);
@@ -864,11 +880,11 @@ static int cbf_qp_impl(const MdsDroneParams* prm, const MdsCbfParams* c, const R
   if (rc) return rc;
   MDS_REQUIRE(prm && obs && xdes && unom && usafe && status && E > 0, "cbf_qp: bad argument");
   MDS_REQUIRE(n_obs == 0 || obstacles, "cbf_qp: obstacles pointer is null");
-  int NP = next_pow2(N), epb = MDS_BLOCK / NP, blocks = (E + epb - 1) / epb;
-  size_t smem = cbf_smem_bytes<Real>(NP, N, n_obs);
+  const int NP = next_pow2(N), threads = cbf_block_threads<Real>(NP, N, n_obs), epb = threads / NP, blocks = (E + epb - 1) / epb;
+  size_t smem = cbf_smem_bytes<Real>(threads, NP, N, n_obs);
   cudaError_t e = cudaFuncSetAttribute(cbf_qp_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "cbf_qp: shared memory opt-in failed: %s", cudaGetErrorString(e));
-  cbf_qp_kernel<Real><<<blocks, MDS_BLOCK, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*c), obs, xdes, unom, obstacles, n_obs, usafe,
+  if (e != cudaSuccess) return cuda_fail("cbf_qp: shared memory opt-in failed", e);
+  cbf_qp_kernel<Real><<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*c), obs, xdes, unom, obstacles, n_obs, usafe,
                                                                           status, iters, E, N, NP);
   return check_launch("cbf_qp");
 }
@@ -950,8 +966,9 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     R.n_obs = 0;
   }
   MDS_REQUIRE(!(cfg->write_obs_every > 0) || obs_log, "rollout: obs_log buffer missing");
-  int NP = next_pow2(N), epb = MDS_BLOCK / NP, blocks = (E + epb - 1) / epb;
-  size_t smem = R.use_cbf ? cbf_smem_bytes<Real>(NP, N, R.n_obs) : 16;
+  const int NP = next_pow2(N), threads = R.use_cbf ? cbf_block_threads<Real>(NP, N, R.n_obs) : MDS_BLOCK, epb = threads / NP;
+  const int blocks = (E + epb - 1) / epb;
+  size_t smem = R.use_cbf ? cbf_smem_bytes<Real>(threads, NP, N, R.n_obs) : 32;
   cudaStream_t cs = (cudaStream_t)stream;
   const DroneP<Real> Pd = to_dev<Real>(*prm);
   const StateP<Real> Sd = to_dev<Real>(st);
@@ -972,18 +989,18 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     if (FUSED) {                                                                                                                    \
       auto kern = (N == 8) ? step_fused_kernel<Real, CT, CB, 8> : step_fused_kernel<Real, CT, CB, 0>;                               \
       if (first_fused) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-      kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, OBS_PTR, stats, T, E, N, NP);              \
+      kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, OBS_PTR, stats, T, E, N, NP);              \
     } else {                                                                                                                        \
       auto kern = (N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>;                                 \
       if (first_ctrl) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
-      kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Pi, specs, segs, (const Real*)(OBS_PTR), action, stats, T, E, N, NP);   \
+      kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Pi, specs, segs, (const Real*)(OBS_PTR), action, stats, T, E, N, NP);   \
     }                                                                                                                               \
   } while (0)
 #define MDS_LAUNCH_LOOP(CT, CB)                                                                                                      \
   do {                                                                                                                              \
     auto kern = (N == 8) ? rollout_loop_kernel<Real, CT, CB, 8> : rollout_loop_kernel<Real, CT, CB, 0>;                             \
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
-    kern<<<blocks, MDS_BLOCK, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, obs, obs_log, stats, t0, prm->dt_ctrl, K, E, N, NP); \
+    kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, obs, obs_log, stats, t0, prm->dt_ctrl, K, E, N, NP); \
   } while (0)
   auto launch_loop = [&]() {
     switch (R.ctrl) {
@@ -1018,8 +1035,8 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     if (fused) first_fused = false; else first_ctrl = false;
   };
   auto launch_phys = [&](Real* obs_out) {
-    if (N == 8) physics_step_kernel<Real, 8><<<blocks, MDS_BLOCK, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
-    else physics_step_kernel<Real, 0><<<blocks, MDS_BLOCK, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
+    if (N == 8) physics_step_kernel<Real, 8><<<blocks, threads, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
+    else physics_step_kernel<Real, 0><<<blocks, threads, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
   };
   const double dt = prm->dt_ctrl;
   Real* obs_last = obs;  // buffer holding the newest observation
@@ -1045,7 +1062,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   }
 #undef MDS_LAUNCH_CTRL
 #undef MDS_LAUNCH_LOOP
-  if (attr_err != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: shared memory opt-in failed: %s", cudaGetErrorString(attr_err));
+  if (attr_err != cudaSuccess) return cuda_fail("rollout: shared memory opt-in failed", attr_err);
   if (obs_last != obs) {
     cudaError_t e = cudaMemcpyAsync(obs, obs_last, obs_elems * sizeof(Real), cudaMemcpyDeviceToDevice, cs);
     if (e != cudaSuccess) return fail(MDS_ERR_LAUNCH, "rollout: %s", cudaGetErrorString(e));

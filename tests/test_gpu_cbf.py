@@ -154,3 +154,52 @@ def test_cylinder_obstacles_vs_oracle(golden, order, dtype, tol, lib_built):
     from multidronesim_b200.obstacles import generate_cylinder
     path = generate_cylinder(0.15, 3.0)
     assert os.path.isfile(path) and 'cylinder radius="0.15" length="3.0"' in open(path).read()
+
+
+@pytest.mark.parametrize("N,n_obs,order", [(5, 2, 3), (16, 1, 3), (32, 2, 3), (3, 0, 2), (1, 1, 3), (6, 3, 2)])
+def test_qp_other_group_sizes_vs_oracle(N, n_obs, order, lib_built):
+    """Lane-group sizes other than the swarm's 8 (NP = 1, 4, 8 with idle lanes, 16, 32; odd N has no 'diameter' slot):
+    dense rows and QP answers in fp64 against oracle/cbf.py + oracle/qp.py on random states."""
+    import multidronesim_b200 as mds
+    from oracle import cbf as ocbf
+    from oracle import conversions as cv
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel as ODM, Physics as OPH
+    from scipy.spatial.transform import Rotation
+    E, dtype = 9, torch.float64
+    rng = np.random.default_rng(100 + N)
+    env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=N, num_envs=E, dtype=dtype)
+    Mdl = mds.model.LinearizedOmegaModel if order == 2 else mds.model.LinearizedYankOmegaModel
+    poles = np.array([-2.2, -2.4]) if order == 2 else np.array([-3.0, -3.6, -5.6])
+    rs, zs = (0.1, 1.0) if order == 2 else (0.125, 2.0)
+    cbf = mds.cbf.DroneCBF(env, [Mdl(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=order, cbf_poles=poles)
+    trk = mds.cbf.DroneQPTracker(cbf, order=order, num_robots=N, xdim=cbf.xdim, env=env)
+    oenv = OracleCtrlAviary(ODM.CF2P, N, physics=OPH.DYN)
+    prm = ocbf.CbfParams(oenv, order, zs, rs, tuple(poles))
+    spread = 0.6 * N ** (1 / 3) * (2.5 if N >= 16 else 1.0)   # big groups: sparse enough that active sets stay under the cap of 12
+    rpy = rng.uniform(-0.3, 0.3, (E, N, 3))
+    obs = np.concatenate([rng.uniform(-spread, spread, (E, N, 3)), Rotation.from_euler("xyz", rpy.reshape(-1, 3)).as_quat().reshape(E, N, 4), rpy,
+                          rng.normal(0, 0.5, (E, N, 3)), rng.normal(0, 0.5, (E, N, 3)), rng.uniform(12000, 17000, (E, N, 4))], axis=-1)
+    xdes = np.zeros((E, N, cbf.xdim))
+    xdes[..., -3:] = obs[..., 0:3] + rng.normal(0, 0.2, (E, N, 3))
+    if order == 3:
+        xdes[..., 3] = oenv.M * oenv.G
+    unom = rng.normal(0, 1.0, (E, N, 4)) * np.array([0.5, 2.0, 2.0, 2.0])
+    obst = np.concatenate([rng.uniform(-spread, spread, (n_obs, 3)), rng.uniform(0.05, 0.2, (n_obs, 1))], axis=1) if n_obs else None
+    dev = lambda a: None if a is None else torch.as_tensor(a, device="cuda", dtype=dtype).contiguous()
+    Gd, hd = cbf.build_ineq_const(dev(obs), dev(xdes), dev(obst))
+    u = trk.compute_control(dev(obs), dev(xdes), dev(unom), x_obs=dev(obst)).cpu().numpy()
+    st, solved = trk.status.cpu().numpy(), 0
+    for e in range(E):
+        x = np.array([cv.obs_to_lin_model(obs[e, i], prm.xdim, oenv) for i in range(N)])
+        Gr, hr = ocbf.build_ineq(prm, x, xdes[e], None if obst is None else [o[:3] for o in obst], None if obst is None else [o[3] for o in obst])
+        assert scaled_err(Gd[e].cpu().numpy(), Gr) < 1e-9 and scaled_err(hd[e].cpu().numpy(), hr) < 1e-9
+        uo, _, so, _ = solve_qp(np.eye(4 * N), -unom[e].reshape(-1), Gr, hr)
+        if so == 0 and st[e] == 0:
+            assert np.max(np.abs(u[e].reshape(-1) - uo)) < 1e-7 * (1 + np.max(np.abs(uo))), (e, np.max(np.abs(u[e].reshape(-1) - uo)))
+            solved += 1
+        elif so == 1:
+            assert st[e] != 0
+        if st[e] != 0:
+            assert np.array_equal(u[e], unom[e])
+    assert solved >= (1 if order == 2 else 3), (solved, st.tolist())
