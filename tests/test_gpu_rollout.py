@@ -127,7 +127,7 @@ def test_c2_tracking_vs_oracle_1s(dtype, tol, lib_built):
     assert ro.stats_dict()["max_pos_err"] < 0.5
 
 
-@pytest.mark.parametrize("order,N,dtype,tol", [(2, 2, torch.float64, 1e-6), (3, 4, torch.float64, 1e-6), (3, 8, torch.float32, 2e-3)])
+@pytest.mark.parametrize("order,N,dtype,tol", [(2, 2, torch.float64, 1e-6), (3, 4, torch.float64, 1e-6), (3, 5, torch.float64, 1e-6), (3, 8, torch.float32, 2e-3)])
 def test_cbf_closed_loop_vs_oracle(order, N, dtype, tol, lib_built):
     """config C3 in miniature: LQR nominal -> CBF-QP -> inner loop -> DYN_GND_DRAG_DW, drones on one
     lemniscate through a sphere obstacle at its centre (simulations/CBFTest.py:418-424)."""
