@@ -262,6 +262,11 @@ int mds_cbf_prepare_f64(const MdsDroneParams* prm, int order, double u0_offset, 
 /* kind 12: LinearizedModel.calc_xdot_from_obs; 9 / 10: builder-defined (quirk B23) */
 int mds_xdot_linear_f32(const MdsDroneParams* prm, int kind, const float* obs_dev, float* xdot_dev, int D, void* stream);
 int mds_xdot_linear_f64(const MdsDroneParams* prm, int kind, const double* obs_dev, double* xdot_dev, int D, void* stream);
+/* roll_out_linear_system (simulations/CompareModels.py:82-95): the 12-dim linear model driven by the logged RPMs as
+ * zero-order-hold inputs, advanced exactly over each log interval dt (the reference uses scipy RK45).
+ * obs_log_dev [T][D*20] (e.g. the obs_log of mds_rollout) -> x_dev [T][D*12], x_dev[0] = first logged state. */
+int mds_linear_rollout_f32(const MdsDroneParams* prm, const float* obs_log_dev, double dt, float* x_dev, int T, int D, void* stream);
+int mds_linear_rollout_f64(const MdsDroneParams* prm, const double* obs_log_dev, double dt, double* x_dev, int T, int D, void* stream);
 /* QuadrotorDynamics.dynamics via action_to_input / obs_to_geo_model / geo_x_dot_to_linear; J = diag(jx,jy,jz) */
 int mds_xdot_nonlinear_f32(const MdsDroneParams* prm, double jx, double jy, double jz, const float* obs_dev, float* xdot_dev, int D, void* stream);
 int mds_xdot_nonlinear_f64(const MdsDroneParams* prm, double jx, double jy, double jz, const double* obs_dev, double* xdot_dev, int D, void* stream);

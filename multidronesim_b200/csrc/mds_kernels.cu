@@ -528,6 +528,35 @@ __global__ void xdot_nonlinear_kernel(DroneP<Real> P, Real jx, Real jy, Real jz,
   out[9] = o.v.x; out[10] = o.v.y; out[11] = o.v.z;
 }
 
+// Roll-out of the 12-dim hover-linearised model along a logged flight (simulations/CompareModels.py:82-95): the reference
+// integrates x' = A (x - x_eq) + B (u(t) - u_eq) with scipy's RK45 and the logged RPMs as zero-order-hold inputs.  With a
+// constant input the chain  u -> w -> rpy -> (vx, vy) -> (px, py)  integrates to polynomials in t, so each log interval
+// is advanced EXACTLY (to rounding); one thread per drone walks its T samples.  obs_log [T, D, 20] -> x_out [T, D, 12],
+// x = [rpy, w, v, p] (utils/model_conversions.py:41-45), x_out[0] = the first logged state.
+template <typename Real>
+__global__ void linear_rollout_kernel(DroneP<Real> P, const Real* __restrict__ obs_log, Real dt, Real* __restrict__ x_out, int T, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Obs<Real> o = load_obs(obs_log, d);
+  V3<Real> rpy = o.rpy, w = o.av, v = o.v, p = o.p;
+  const Real t = dt, t2 = t * t * Real(0.5), t3 = t * t * t / Real(6), t4 = t * t * t * t / Real(24);
+  for (int k = 0;; ++k) {
+    Real* x = x_out + ((size_t)k * D + d) * 12;
+    x[0] = rpy.x; x[1] = rpy.y; x[2] = rpy.z; x[3] = w.x; x[4] = w.y; x[5] = w.z;
+    x[6] = v.x; x[7] = v.y; x[8] = v.z; x[9] = p.x; x[10] = p.y; x[11] = p.z;
+    if (k == T - 1) break;
+    Real u[4];
+    action_to_input(P, o.rpm, u);  // the input logged with sample k holds until sample k + 1
+    const V3<Real> al = {u[1] / P.ixx, u[2] / P.iyy, u[3] / P.izz};
+    const Real az = (u[0] - P.m * P.g) / P.m;
+    p = {p.x + v.x * t + P.g * (rpy.y * t2 + w.y * t3 + al.y * t4), p.y + v.y * t - P.g * (rpy.x * t2 + w.x * t3 + al.x * t4), p.z + v.z * t + az * t2};
+    v = {v.x + P.g * (rpy.y * t + w.y * t2 + al.y * t3), v.y - P.g * (rpy.x * t + w.x * t2 + al.x * t3), v.z + az * t};
+    rpy = {rpy.x + w.x * t + al.x * t2, rpy.y + w.y * t + al.y * t2, rpy.z + w.z * t + al.z * t2};
+    w = {w.x + al.x * t, w.y + al.y * t, w.z + al.z * t};
+    o = load_obs(obs_log + (size_t)(k + 1) * D * MDS_OBS_DIM, d);  // only its RPMs are used
+  }
+}
+
 // ------------------------------------------------------------------ kernel: fused K-step rollout
 template <typename Real> struct RolloutP {
   int ctrl, use_cbf, n_obs, write_obs_every;
@@ -910,6 +939,11 @@ template <typename Real> static int xdot_linear_impl(const MdsDroneParams* prm, 
   xdot_linear_kernel<Real><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), kind, obs, xdot, D);
   return check_launch("xdot_linear");
 }
+template <typename Real> static int linear_rollout_impl(const MdsDroneParams* prm, const Real* obs_log, double dt, Real* x_out, int T, int D, void* stream) {
+  MDS_REQUIRE(prm && obs_log && x_out && T > 0 && D > 0 && dt > 0, "linear_rollout: bad argument");
+  linear_rollout_kernel<Real><<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), obs_log, Real(dt), x_out, T, D);
+  return check_launch("linear_rollout");
+}
 template <typename Real>
 static int xdot_nonlinear_impl(const MdsDroneParams* prm, double jx, double jy, double jz, const Real* obs, Real* xdot, int D, void* stream) {
   MDS_REQUIRE(prm && obs && xdot && D > 0 && jx > 0 && jy > 0 && jz > 0, "xdot_nonlinear: bad argument");
@@ -1177,6 +1211,9 @@ int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 *
   }                                                                                                                                                \
   int mds_xdot_linear_##SUF(const MdsDroneParams* prm, int kind, const REAL* obs, REAL* xdot, int D, void* stream) {                               \
     return xdot_linear_impl<REAL>(prm, kind, obs, xdot, D, stream);                                                                                \
+  }                                                                                                                                                \
+  int mds_linear_rollout_##SUF(const MdsDroneParams* prm, const REAL* obs_log, double dt, REAL* x_out, int T, int D, void* stream) {               \
+    return linear_rollout_impl<REAL>(prm, obs_log, dt, x_out, T, D, stream);                                                                       \
   }                                                                                                                                                \
   int mds_xdot_nonlinear_##SUF(const MdsDroneParams* prm, double jx, double jy, double jz, const REAL* obs, REAL* xdot, int D, void* stream) {     \
     return xdot_nonlinear_impl<REAL>(prm, jx, jy, jz, obs, xdot, D, stream);                                                                       \

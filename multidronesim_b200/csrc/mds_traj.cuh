@@ -136,14 +136,10 @@ template <typename Real, typename Seg> MDS_DEV Ref<Real> eval_segment(const Seg&
 
 // Stateless equivalent of CompoundTrajectory.__call__ for a forward-running clock:
 // segment = first k with t <= t_end[k]; past the end -> last segment at its own end.
+// Out of line: the closed-form generators are the hot path of the swarm workloads, and keeping the segment-table
+// walk (and the Line / Rotate code it pulls in) out of the callers' instruction stream keeps their hot loop compact.
 template <typename Real>
-MDS_DEV Ref<Real> eval_traj(const typename TrajSpecT<Real>::spec& sp, const typename TrajSpecT<Real>::seg* __restrict__ segs, double t) {
-  switch (sp.kind) {
-    case MDS_TRAJ_CIRCLE: return eval_circle<Real>(sp.p, t);
-    case MDS_TRAJ_LEMNISCATE: return eval_lemniscate<Real>(sp.p, t);
-    case MDS_TRAJ_WAIT: return eval_wait<Real>(sp.p);
-    default: break;
-  }
+__device__ __noinline__ Ref<Real> eval_traj_table(const typename TrajSpecT<Real>::spec& sp, const typename TrajSpecT<Real>::seg* __restrict__ segs, double t) {
   int b = sp.seg_begin, n = sp.seg_count;
   if (sp.pad) return eval_segment<Real>(segs[b], t);  // stand-alone generator: no compound end clamp
   double total = (double)segs[b + n - 1].t_end;
@@ -155,6 +151,17 @@ MDS_DEV Ref<Real> eval_traj(const typename TrajSpecT<Real>::spec& sp, const type
     ++k;
   }
   return eval_segment<Real>(segs[b + k], t - t0);
+}
+
+template <typename Real>
+MDS_DEV Ref<Real> eval_traj(const typename TrajSpecT<Real>::spec& sp, const typename TrajSpecT<Real>::seg* __restrict__ segs, double t) {
+  switch (sp.kind) {
+    case MDS_TRAJ_CIRCLE: return eval_circle<Real>(sp.p, t);
+    case MDS_TRAJ_LEMNISCATE: return eval_lemniscate<Real>(sp.p, t);
+    case MDS_TRAJ_WAIT: return eval_wait<Real>(sp.p);
+    default: break;
+  }
+  return eval_traj_table<Real>(sp, segs, t);
 }
 
 }  // namespace mds

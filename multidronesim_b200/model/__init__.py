@@ -42,6 +42,21 @@ class LinearizedModel(_LinearBase):
     """x = [rpy, rates, v, p], u = [f, tx, ty, tz] (model/linearized.py:24-104)."""
     DIM = 12
 
+    def roll_out(self, obs_log, dt=None, out=None):
+        """simulations/CompareModels.py:82-95 (``roll_out_linear_system``) for every drone of a logged flight:
+        obs_log [T, E, N, 20] (e.g. ``FusedRollout.run(..., obs_log=...)``) -> x [T, E, N, 12], the linear model driven by
+        the logged RPMs as zero-order-hold inputs from the first logged state.  Each log interval ``dt`` (default: the
+        env's control period) is advanced exactly; the reference integrates the same ODE with scipy's RK45."""
+        env = self.env
+        obs_log = _lib.require_cuda(obs_log, "obs_log", env.dtype)
+        T = int(obs_log.shape[0])
+        D = obs_log[0].numel() // _lib.OBS_DIM
+        if out is None:
+            out = torch.empty(*obs_log.shape[:-1], 12, device=obs_log.device, dtype=obs_log.dtype)
+        _lib.call("mds_linear_rollout", env.dtype, env._prm, _lib.ptr(obs_log), float(env.CTRL_TIMESTEP if dt is None else dt), _lib.ptr(out), T, D,
+                  _lib.stream_ptr(obs_log.device))
+        return out
+
     def __init__(self, env, debug=False):
         self.Ixx, self.Iyy, self.Izz = env.J[0, 0], env.J[1, 1], env.J[2, 2]
         super().__init__(env, debug)

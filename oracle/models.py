@@ -100,3 +100,26 @@ def xdot_nonlinear_from_obs(env, obs, use_env_inertia=False):
     """simulations/CompareModels.py:52-54: action_to_input -> dynamics -> geo_x_dot_to_linear."""
     u = cv.action_to_input(env, obs[16:20])
     return cv.geo_x_dot_to_linear(xdot_nonlinear(env, cv.obs_to_geo_model(obs), u, use_env_inertia))
+
+
+def roll_out_linear_system(env, observations, obs_ts, rtol=1e-11, atol=1e-13):
+    """simulations/CompareModels.py:82-95: integrate the 12-dim linear model from the first logged state with the logged
+    RPMs as inputs ("closest observation in the past", i.e. zero-order hold), sampled at ``obs_ts``.  The reference calls
+    ``solve_ivp`` with its default tolerances (rtol 1e-3); the oracle integrates interval by interval with tight
+    tolerances so that it can pin the device kernel's exact per-interval update.  -> y [T, 12]."""
+    from scipy.integrate import solve_ivp
+    A, B, _, _ = linear_model_matrices(env, "torque12")
+    ueq = np.array([env.M * env.G, 0, 0, 0])
+    x = cv.obs_to_lin_model(observations[0], 12)
+    out = [x.copy()]
+    for k in range(len(obs_ts) - 1):
+        u = cv.action_to_input(env, observations[k][16:20]) - ueq
+
+        def f(t, xx):
+            xe = np.zeros(12)
+            xe[9:] = xx[9:]
+            return A @ (xx - xe) + B @ u
+        res = solve_ivp(f, [obs_ts[k], obs_ts[k + 1]], x, rtol=rtol, atol=atol)
+        x = res.y[:, -1]
+        out.append(x.copy())
+    return np.array(out)

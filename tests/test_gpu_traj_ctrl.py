@@ -184,3 +184,32 @@ def test_dslpid_config1_closed_loop(dtype, tol, lib_built):
     env2.step(torch.zeros(E, N, 4, device="cuda", dtype=dtype))
     obs2 = ro.run(steps).double().cpu().numpy()
     assert np.max(np.abs(obs2 - got)) < 1e-12 * (1 + np.max(np.abs(got)))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-5)])
+def test_linear_roll_out(dtype, tol, lib_built):
+    """roll_out_linear_system (simulations/CompareModels.py:82-95) on device along a logged closed-loop flight: the exact
+    per-interval update vs the oracle's tight-tolerance integration of the same ODE."""
+    import multidronesim_b200 as mds
+    from oracle import models as om
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel as ODM, Physics as OPH
+    E, N, T = 3, 2, 60
+    env = mds.CtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=N, physics=mds.Physics.DYN, num_envs=E, dtype=dtype,
+                         initial_xyzs=np.array([[0.0, 0, 1.0], [0.5, 0.2, 1.2]]))
+    ctrl = mds.control.GeometricControl(env)
+    trajs = mds.trajectories.TrajectorySet([mds.trajectories.CircleTrajectory(r=0.5, v=0.4, center=np.array([0.0, 0.0, 1.0]), yaw_rate=0.0),
+                                            mds.trajectories.Lemniscate(a=0.5, center=np.array([0.5, 0.2, 1.2]), omega=1.0)] * E, dtype=dtype)
+    log = torch.zeros(T, E, N, 20, device="cuda", dtype=dtype)
+    mds.FusedRollout(env, trajs, ctrl).run(T, obs_log=log, log_every=1)
+    x = mds.model.LinearizedModel(env).roll_out(log).double().cpu().numpy()
+    obs = log.double().cpu().numpy()
+    oenv = OracleCtrlAviary(ODM.CF2P, 1, physics=OPH.DYN)
+    ts = env.CTRL_TIMESTEP * np.arange(T)
+    worst = 0.0
+    for e in range(E):
+        for n in range(N):
+            want = om.roll_out_linear_system(oenv, obs[:, e, n], ts)
+            worst = max(worst, float(np.max(np.abs(x[:, e, n] - want) / (1 + np.abs(want)))))
+    assert worst < tol, worst
+    assert np.abs(x[-1] - x[0]).max() > 1e-3  # the roll-out moved

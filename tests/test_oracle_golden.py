@@ -200,3 +200,35 @@ def test_cylinder_row_is_the_zscale_limit():
         assert np.allclose(Gc[-2:], Gl[-2:], rtol=1e-12, atol=1e-15) and np.allclose(hc[-2:], hl[-2:], rtol=1e-12, atol=1e-15)
         assert not np.allclose(hc[-2:], hs[-2:])
         assert np.array_equal(Gc[:-2], Gs[:-2]) and np.array_equal(hc[:-2], hs[:-2])  # only the obstacle rows change
+
+
+def test_linear_roll_out_matches_reference_style_integration():
+    """CompareModels.py:82-95: the oracle's interval-by-interval roll-out equals one solve_ivp call over the whole log
+    with the reference's 'closest observation in the past' input lookup (tight tolerances), and stays within the
+    reference's own default-tolerance integration error."""
+    from scipy.integrate import solve_ivp
+    from oracle import conversions as cv
+    from oracle import models as om
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel, Physics
+    env = OracleCtrlAviary(DroneModel.CF2P, 1, physics=Physics.DYN)
+    rng = np.random.default_rng(4)
+    T, dt = 40, 1.0 / 240
+    obs = np.zeros((T, 20))
+    obs[:, 0:3] = rng.normal(0, 1, (T, 3)); obs[:, 6] = 1.0
+    obs[0, 7:10] = rng.uniform(-0.2, 0.2, 3); obs[0, 10:16] = rng.normal(0, 0.3, 6)
+    ts = dt * np.arange(T)
+    obs[:, 16:20] = env.HOVER_RPM + 300 * np.sin(2 * np.pi * 3 * ts[:, None] + rng.uniform(0, 6, 4)[None, :])  # a smooth logged flight
+    y = om.roll_out_linear_system(env, obs, ts)
+    A, B, _, _ = om.linear_model_matrices(env, "torque12")
+
+    def f(t, x):  # the reference's closure, CompareModels.py:85-92
+        idx = int(np.argmin(np.abs(ts - t)))
+        if ts[idx] > t:
+            idx -= 1
+        xe = np.zeros(12); xe[9:] = x[9:]
+        return A @ (x - xe) + B @ (cv.action_to_input(env, obs[idx][16:20]) - np.array([env.M * env.G, 0, 0, 0]))
+    ref_default = solve_ivp(f, [0, ts[-1]], cv.obs_to_lin_model(obs[0], 12), t_eval=ts).y.T
+    assert np.max(np.abs(y - ref_default)) < 2e-2 * (1 + np.max(np.abs(y)))   # the reference's own rtol = 1e-3 across input jumps
+    tight = solve_ivp(f, [0, ts[-1]], cv.obs_to_lin_model(obs[0], 12), t_eval=ts, rtol=1e-10, atol=1e-12, max_step=dt).y.T
+    assert np.max(np.abs(y - tight)) < 1e-7 * (1 + np.max(np.abs(y)))
