@@ -182,7 +182,7 @@ class ClockSampler:
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -192,7 +192,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -202,9 +202,18 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """clocks over the samples that arrived inside [t0, t1] (the timed region); if the region is too short for two
+        samples, over everything since the sampler started (settle + warm-up + timed: the same kernels, same load)"""
+        rows, window = self.rows, "all samples"
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[0] <= t1 + 0.12]
+            if len(inside) >= 2:
+                rows, window = inside, "timed region"
+            else:
+                window = "settle + warm-up + timed region (timed region shorter than two sampling periods)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for _, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -217,7 +226,7 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -288,23 +297,26 @@ def run_gpu_arm(args):
             dist.barrier()
 
     # ---- device-resident headline -------------------------------------------------------------
-    for _ in range(args.settle // F):
-        ro.run(F)
-    for _ in range(W):
-        ro.run(F)
-    torch.cuda.synchronize()
-    ro.reset_stats()
-    snap = snapshot(env, ctrl, ro)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    torch.cuda.synchronize()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:  # sampling starts with the settle phase: nvidia-smi needs ~0.2 s to deliver its first line
+        for _ in range(args.settle // F):
+            ro.run(F)
+        for _ in range(W):
+            ro.run(F)
+        torch.cuda.synchronize()
+        ro.reset_stats()
+        snap = snapshot(env, ctrl, ro)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        t_wall0 = time.perf_counter()
         ev0.record()
         for _ in range(K):
             ro.run(F)
         ev1.record()
         torch.cuda.synchronize()
-    barrier()
+        t_wall1 = time.perf_counter()
+        barrier()
+        time.sleep(0.12)  # let the sample that covers the end of the region arrive
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -313,7 +325,7 @@ def run_gpu_arm(args):
     value = world * D * F * K / (ms_max * 1e-3)
     stats_all = mds.dist.gather_stats(ro.stats)  # the path's only collective (NCCL all-gather of 8 doubles per rank)
     stats = dict(zip(mds._lib.STAT_NAMES, mds.dist.reduce_stats(stats_all).tolist()))
-    clocks = clk.summary()
+    clocks = clk.summary(t_wall0, t_wall1)
 
     # ---- roofline of the dominant kernel: the K-steps-in-one-launch rollout kernel (this rank) ----------------
     # Every bench step is ONE launch of rollout_loop_kernel (F control steps with the state in registers), so its
