@@ -10,13 +10,14 @@ CBF-QP (28 pair rows + 8 obstacle rows + box/force bounds per env) -> YankOmega 
 DYN_GND_DRAG_DW physics (ground effect, drag, pairwise downwash) -> 20-float observation.
 
 One bench "step" = one ``mds_rollout`` call = ONE kernel launch = ``--fuse`` control steps of every drone with the
-observation and body rates in registers from step to step (environments are independent; a lane group owns its env).
+observation and body rates in registers from step to step (environments are independent; a lane group owns its env);
+every step's observation is also written to HBM (obs log), as the reference's loop keeps every obs.
 ``value``   : drone-steps/s, state resident in HBM, CUDA events on the launching stream, max over ranks.
 ``e2e``     : the same metric through the per-call API with HOST buffers (multidronesim_b200.HostPipeline): every
               control step copies the step's references host -> device from pinned memory and the new observation
               device -> host, copies overlapped with the neighbouring steps' kernels on their own streams.
 ``roofline``: the dominant (only) kernel of the timed region, rollout_loop_kernel.  It is FP32-pipe-bound (the state
-              never leaves the registers: ~130 flop per HBM byte), so achieved = algorithmic flop per launch / launch
+              never leaves the registers: ~20 flop per HBM byte with the per-step obs log, ridge 9.8), so achieved = algorithmic flop per launch / launch
               duration against the FMA-chain peak measured live (MEASURED_PEAKS.json has no non-tensor FP32 figure);
               its HBM view is reported inside.  ``roofline_ctrl`` / ``roofline_physics``: the per-call kernels (what
               ``e2e`` launches) against the measured HBM copy bandwidth, from a launch-by-launch replay.
@@ -56,6 +57,7 @@ ALGO_BYTES_CTRL_F32 = {"read_obs": 80, "read_traj_spec": 48, "read_pid": 24, "wr
 ALGO_BYTES_PHYS_F32 = {"read_state": 68, "read_action": 16, "write_state": 68, "write_obs": 80}  # 232 B
 # the K-steps-in-one-launch kernel, per drone and per LAUNCH (not per step): initial obs + body rates + trajectory spec,
 # PID state in and out, final state + obs + action
+ALGO_BYTES_OBS_LOG_PER_STEP_F32 = 80  # the observation of every control step, written to its log slot
 ALGO_BYTES_LOOP_PER_LAUNCH_F32 = {"read_obs": 80, "read_body_rates": 12, "read_traj_spec": 48, "read_pid": 24, "write_pid": 24,
                                   "write_state": 68, "write_obs": 80, "write_action": 16}
 
@@ -167,7 +169,8 @@ def workload_config(args, envs, per_gpu=True):
                         "order-3 CBF-QP (r_safe 0.125, zscale 2, poles -3/-3.6/-5.6) + sphere obstacle r=0.1 at (0.2, 0, 0.5), YankOmega inner loop",
             "envs_per_gpu" if per_gpu else "envs": envs, "drones_per_env": N_DRONES, "drone_model": "cf2p", "cbf_order": CBF_ORDER,
             "control_steps_per_step": args.fuse if per_gpu else args.ref_steps_per_step, "settle_steps": args.settle, "parallelism": f"env-sharded x{args.gpus}",
-            "l2": "working set (state+obs+traj specs+PID > 200 MB per GPU) exceeds the 126 MB L2; no flush needed"}
+            "obs": "every control step's observation is written to HBM (log ring of control_steps_per_step slots)",
+            "l2": "working set (state+obs+traj specs+PID+obs log > 2 GB per GPU) exceeds the 126 MB L2; no flush needed"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -297,11 +300,15 @@ def run_gpu_arm(args):
             dist.barrier()
 
     # ---- device-resident headline -------------------------------------------------------------
+    # every control step's observation is materialised in HBM (a ring of F log slots, reused by each launch), as the
+    # reference's loop does (observations.append(obs)); a drone-step therefore includes its 80 B observation write
+    obs_ring = torch.empty(F, E, N, 20, device=dev, dtype=dtype)
+    step = lambda: ro.run(F, obs_log=obs_ring, log_every=1)
     with ClockSampler(local_rank) as clk:  # sampling starts with the settle phase: nvidia-smi needs ~0.2 s to deliver its first line
         for _ in range(args.settle // F):
-            ro.run(F)
+            step()
         for _ in range(W):
-            ro.run(F)
+            step()
         torch.cuda.synchronize()
         ro.reset_stats()
         snap = snapshot(env, ctrl, ro)
@@ -311,7 +318,7 @@ def run_gpu_arm(args):
         t_wall0 = time.perf_counter()
         ev0.record()
         for _ in range(K):
-            ro.run(F)
+            step()
         ev1.record()
         torch.cuda.synchronize()
         t_wall1 = time.perf_counter()
@@ -341,7 +348,7 @@ def run_gpu_arm(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs, of measured (sustained copy)" if peaks else "fallback 6.65 TB/s, of fallback"
     sfx = "float" if dtype == torch.float32 else "double"
     flop_step = sum(ALGO_FLOP_PER_DRONE_STEP.values())
-    bytes_launch = sum(ALGO_BYTES_LOOP_PER_LAUNCH_F32.values()) * esz // 4
+    bytes_launch = (sum(ALGO_BYTES_LOOP_PER_LAUNCH_F32.values()) + F * ALGO_BYTES_OBS_LOG_PER_STEP_F32) * esz // 4
     tf = flop_step * D * F / (launch_ms * 1e-3) / 1e12
     gbs = bytes_launch * D / (launch_ms * 1e-3) / 1e9
     roofline = {"bound": "fp32", "kernel": f"rollout_loop_kernel<{sfx}, MDS_CTRL_LQR_YANK, true, 8>", "achieved": tf, "peak": fma_peak,
@@ -351,8 +358,9 @@ def run_gpu_arm(args):
                 "traffic": ncu_traffic("rollout_loop_kernel", E, args.dtype),
                 "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "algorithmic_bytes_per_drone_per_launch": bytes_launch,
                         "peak_source": peak_src},
-                "note": f"arithmetic intensity {flop_step * F / bytes_launch:.0f} flop/B >> ridge {fma_peak * 1e3 / hbm_peak:.1f} flop/B: the state lives in "
-                        "registers for the whole launch, so the FP32 pipe (not HBM, not tensor cores: nothing is a dense contraction) bounds it"}
+                "note": f"arithmetic intensity {flop_step * F / bytes_launch:.0f} flop/B > ridge {fma_peak * 1e3 / hbm_peak:.1f} flop/B: the state lives in "
+                        "registers for the whole launch and HBM sees the per-step observation log plus one state load/store per launch, so the "
+                        "FP32 pipe (not HBM, not tensor cores: nothing is a dense contraction) bounds it"}
 
     # ---- the per-call kernels against the HBM roofline: replay with one launch per kernel ----------------------
     # (MdsRolloutCfg.stages 1 = controller kernel, 2 = physics kernel; a CUDA event pair around every launch)

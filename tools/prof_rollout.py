@@ -13,12 +13,13 @@ n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 dt = torch.float64 if (len(sys.argv) > 4 and sys.argv[4] == "f64") else torch.float32
 sc = scenarios.cbf_swarm(E, 8, order=3, dtype=dt)
 ro = sc["rollout"]
+ring = torch.empty(max(n, 24), E, 8, 20, device="cuda", dtype=dt)  # as bench.py: every step's observation goes to HBM
 for _ in range(pre // 24):
-    ro.run(24)
+    ro.run(24, obs_log=ring, log_every=1)
 torch.cuda.synchronize()
 ro.reset_stats()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); ro.run(n); e1.record()
+e0.record(); ro.run(n, obs_log=ring, log_every=1); e1.record()
 torch.cuda.synchronize()
 print("ms/control-step %.4f" % (e0.elapsed_time(e1) / n), ro.stats_dict())
 ro.run(1, stages=4)
