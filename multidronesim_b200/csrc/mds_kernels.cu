@@ -798,6 +798,8 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
     }
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
     const size_t obs_elems = (size_t)E * N * MDS_OBS_DIM;
+    int log_countdown = Rc.write_obs_every;  // steps until the next log slot is due (no division in the loop)
+    Real* log_slot = obs_log;
     for (int k = 0; k < K; ++k) {
       StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
       ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss);  // the host plans form t exactly like this
@@ -809,8 +811,11 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
       for (int i = 0; i < 4; ++i) s.rpm[i] = o.rpm[i];
       o = physics_core(P, s, rpm, v3(Real(0), Real(0), Real(0)), sm_pos, g, N);
       wb = s.w;
-      if (g.valid && Rc.write_obs_every > 0 && ((k + 1) % Rc.write_obs_every) == 0)
-        store_obs(obs_log + (size_t)((k + 1) / Rc.write_obs_every - 1) * obs_elems, g.d, o);
+      if (Rc.write_obs_every > 0 && --log_countdown == 0) {
+        if (g.valid) store_obs(log_slot, g.d, o);
+        log_slot += obs_elems;
+        log_countdown = Rc.write_obs_every;
+      }
     }
     if (g.valid) {
       Drone<Real> s;
