@@ -70,8 +70,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=125000, help="environments per GPU (weak scaling)")
     ap.add_argument("--fuse", type=int, default=24, help="control steps per fused launch (one bench step)")
-    ap.add_argument("--settle", type=int, default=240, help="untimed control steps that take the swarm from its start at rest into steady "
-                                                              "flight before warm-up (both arms); the start-up transient has heavy-tailed QP iteration counts")
+    ap.add_argument("--settle", type=int, default=3024, help="untimed control steps that take the swarm from its start at rest into its steady "
+                                                               "lap before warm-up, in both arms (default: one lemniscate period); the start-up "
+                                                               "transient has heavy-tailed QP iteration counts")
     ap.add_argument("--e2e-steps", type=int, default=48, help="control steps timed on the host-buffer path")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="wall budget of the cpu_baseline sample")
     ap.add_argument("--ref-steps-per-step", type=int, default=48, help="control steps per reference-arm step and worker")
@@ -116,7 +117,7 @@ def _cpu_worker_step(args):
     return N_DRONES * steps
 
 
-def cpu_baseline(seconds, steps_per_task=24, settle=240):
+def cpu_baseline(seconds, steps_per_task=24, settle=3024):
     """bounded sample: every host core advances its own C5 environment in 24-step tasks for ~`seconds`"""
     cores = os.cpu_count() or 1
     ctx = mp.get_context("fork")
