@@ -51,6 +51,12 @@ if os.path.isfile(lp):
     ll = [f"ncu launch list of `python bench.py --no-cpu-baseline` ({sum(v[0] for v in agg.values())} launches; cold-cache, serialised: compare shares)"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         ll.append(f"  {k[:72]:<72} n={v[0]:6d} total {v[1] / 1e3:10.2f} ms  mean {v[1] / v[0]:8.1f} us  share {100 * v[1] / tot:5.1f}%")
+    loop = [v for k, v in agg.items() if k.startswith("rollout_loop_kernel")]
+    if loop:
+        ll.append(f"  timed region of bench.py = {b['steps']} consecutive rollout_loop_kernel launches and nothing else: share of the step 1.00 "
+                  f"(bench roofline.share_of_step {b['roofline']['share_of_step']:.2f}); ncu mean {loop[0][1] / loop[0][0]:.0f} us per launch (cold, serialised) vs "
+                  f"{b['roofline']['launch_ms'] * 1e3:.0f} us from the bench's CUDA events; the other launches are settle / warm-up, the per-kernel "
+                  "replay (ctrl_step, physics_step), the e2e per-call pipeline and the FMA-peak microbenchmark")
     c = sum(v[1] for k, v in agg.items() if k.startswith("ctrl_step_kernel"))
     p = sum(v[1] for k, v in agg.items() if k.startswith("physics_step_kernel"))
     ll.append(f"  ctrl_step : physics_step total time ratio under ncu = {c / max(p, 1e-9):.2f} (bench replay events: "
