@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MDS_ABI_VERSION 3
+#define MDS_ABI_VERSION 4
 #define MDS_MAX_DRONES_PER_ENV 32
 #define MDS_MAX_OBSTACLES 8
 #define MDS_OBS_DIM 20
@@ -277,15 +277,16 @@ int mds_xdot_nonlinear_f64(const MdsDroneParams* prm, double jx, double jy, doub
  * store.  Other plans (MdsRolloutCfg.stages): one fused launch per step, two launches per step, single kernels.
  * Everything is enqueued on `stream` with no host synchronisation.
  * obs_dev [D*20] in/out (observation before the first / after the last step); action_dev [D*4] scratch;
+ * ext_force_dev optional [D*3] constant world-frame force per drone (wind, EnvGeometric.py:463-467);
  * obs_log_dev optional [K/write_obs_every][D*20]; stats_dev optional [MDS_STAT_COUNT] doubles (accumulated). */
 int mds_rollout_f32(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
                     const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
                     const MdsDslPidGains* dsl, MdsDslPidState dsl_state, const MdsTrajSpecF32* specs_dev, const MdsTrajSegF32* segs_dev, float* obs_dev, float* action_dev,
-                    float* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
+                    const float* ext_force_dev, float* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
 int mds_rollout_f64(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
                     const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
                     const MdsDslPidGains* dsl, MdsDslPidState dsl_state, const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double* obs_dev, double* action_dev,
-                    double* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
+                    const double* ext_force_dev, double* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
 
 /* launch plan (a MdsRolloutCfg.stages value) that stages == 0 selects for E envs of N drones */
 int mds_rollout_plan(int E, int N);

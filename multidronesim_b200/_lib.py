@@ -111,7 +111,7 @@ _SIGS = {
     "mds_xdot_nonlinear": [_PRM, _D, _D, _D, _P, _P, _I, _P],
     "mds_linear_rollout": [_PRM, _P, _D, _P, _I, _I, _P],
     "mds_rollout": [_PRM, C.POINTER(RolloutCfg), C.POINTER(GeoGains), C.POINTER(LqrGains), C.POINTER(CbfParams),
-                    State, PidState, C.POINTER(DslPidGains), DslPidState, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _P],
+                    State, PidState, C.POINTER(DslPidGains), DslPidState, _P, _P, _P, _P, _P, _P, _P, _D, _I, _I, _I, _P],
 }
 _PLAIN = {
     "mds_abi_version": ([], _I),

@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB 
                                                                 DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
                                                                 const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                 const typename TrajSpecT<Real>::seg* __restrict__ segs,
-                                                                Real* __restrict__ action, Real* __restrict__ obs_out,
+                                                                Real* __restrict__ action, const Real* __restrict__ fext, Real* __restrict__ obs_out,
                                                                 double* __restrict__ stats, double t, int E, int N_rt, int NP_rt) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
   __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB 
       prefetch_l1(reinterpret_cast<const char*>(specs + g.d) + 32);
       if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
     }
-    const Obs<Real> o = physics_body(P, st, action, (const Real*)nullptr, obs_out, sm_pos, g, N);
+    const Obs<Real> o = physics_body(P, st, action, fext, obs_out, sm_pos, g, N);
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
     typename TrajSpecT<Real>::spec spec;
     spec.kind = MDS_TRAJ_WAIT;
@@ -776,8 +776,9 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
                                                                   DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
                                                                   const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                   const typename TrajSpecT<Real>::seg* __restrict__ segs,
-                                                                  Real* __restrict__ action, Real* __restrict__ obs, Real* __restrict__ obs_log,
-                                                                  double* __restrict__ stats, double t0, double dt_ctrl, int K, int E, int N_rt, int NP_rt) {
+                                                                  Real* __restrict__ action, const Real* __restrict__ fext, Real* __restrict__ obs,
+                                                                  Real* __restrict__ obs_log, double* __restrict__ stats, double t0, double dt_ctrl, int K, int E,
+                                                                  int N_rt, int NP_rt) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
   __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
@@ -791,10 +792,12 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
     V3<Real> wb = {Real(0), Real(0), Real(0)};  // body rates: the one part of the state the observation does not carry
     typename TrajSpecT<Real>::spec spec;
     spec.kind = MDS_TRAJ_WAIT;
+    V3<Real> fx = {Real(0), Real(0), Real(0)};  // constant world-frame force on this drone (wind), if any
     if (g.valid) {
       o = load_obs(obs, g.d);
       spec = specs[g.d];
       wb = {st.pos_wx[g.d].w, st.vel_wy[g.d].w, st.wz[g.d]};
+      if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
     }
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
     const size_t obs_elems = (size_t)E * N * MDS_OBS_DIM;
@@ -809,7 +812,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
       s.p = o.p; s.qx = o.qx; s.qy = o.qy; s.qz = o.qz; s.qw = o.qw; s.v = o.v; s.w = wb;
 #pragma unroll
       for (int i = 0; i < 4; ++i) s.rpm[i] = o.rpm[i];
-      o = physics_core(P, s, rpm, v3(Real(0), Real(0), Real(0)), sm_pos, g, N);
+      o = physics_core(P, s, rpm, fx, sm_pos, g, N);
       wb = s.w;
       if (Rc.write_obs_every > 0 && --log_countdown == 0) {
         if (g.valid) store_obs(log_slot, g.d, o);
@@ -960,7 +963,7 @@ template <typename Real>
 static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr, const MdsCbfParams* cbf,
                         MdsState st, MdsPidState pid, const MdsDslPidGains* dsl, MdsDslPidState dsl_state,
                         const typename TrajSpecT<Real>::spec* specs, const typename TrajSpecT<Real>::seg* segs,
-                        Real* obs, Real* action, Real* obs_log, double* stats, double t0, int K, int E, int N, void* stream) {
+                        Real* obs, Real* action, const Real* fext, Real* obs_log, double* stats, double t0, int K, int E, int N, void* stream) {
   MDS_REQUIRE(prm && cfg && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && specs && obs && action, "rollout: null pointer");
   MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV && K > 0, "rollout: bad E, N or K");
   MDS_REQUIRE(cfg->ctrl >= MDS_CTRL_GEOMETRIC && cfg->ctrl <= MDS_CTRL_DSLPID, "rollout: unknown controller");
@@ -1028,7 +1031,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     if (FUSED) {                                                                                                                    \
       auto kern = (N == 8) ? step_fused_kernel<Real, CT, CB, 8> : step_fused_kernel<Real, CT, CB, 0>;                               \
       if (first_fused) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-      kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, OBS_PTR, stats, T, E, N, NP);              \
+      kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, fext, OBS_PTR, stats, T, E, N, NP);              \
     } else {                                                                                                                        \
       auto kern = (N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>;                                 \
       if (first_ctrl) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
@@ -1039,7 +1042,8 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   do {                                                                                                                              \
     auto kern = (N == 8) ? rollout_loop_kernel<Real, CT, CB, 8> : rollout_loop_kernel<Real, CT, CB, 0>;                             \
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
-    kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, obs, obs_log, stats, t0, prm->dt_ctrl, K, E, N, NP); \
+    kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, fext, obs, obs_log, stats, t0, prm->dt_ctrl, K, E, N, \
+                                        NP);                                                                                      \
   } while (0)
   auto launch_loop = [&]() {
     switch (R.ctrl) {
@@ -1074,8 +1078,8 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     if (fused) first_fused = false; else first_ctrl = false;
   };
   auto launch_phys = [&](Real* obs_out) {
-    if (N == 8) physics_step_kernel<Real, 8><<<blocks, threads, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
-    else physics_step_kernel<Real, 0><<<blocks, threads, 0, cs>>>(Pd, Sd, action, (const Real*)nullptr, obs_out, E, N, NP);
+    if (N == 8) physics_step_kernel<Real, 8><<<blocks, threads, 0, cs>>>(Pd, Sd, action, fext, obs_out, E, N, NP);
+    else physics_step_kernel<Real, 0><<<blocks, threads, 0, cs>>>(Pd, Sd, action, fext, obs_out, E, N, NP);
   };
   const double dt = prm->dt_ctrl;
   Real* obs_last = obs;  // buffer holding the newest observation
@@ -1225,9 +1229,10 @@ int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 *
   }                                                                                                                                                \
   int mds_rollout_##SUF(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr,                       \
                         const MdsCbfParams* cbf, MdsState st, MdsPidState pid, const MdsDslPidGains* dsl, MdsDslPidState dsl_state,                \
-                        const SPEC* specs, const SEG* segs, REAL* obs, REAL* action, REAL* obs_log, double* stats, double t0, int K, int E,        \
-                        int N, void* stream) {                                                                                                     \
-    return rollout_impl<REAL>(prm, cfg, geo, lqr, cbf, st, pid, dsl, dsl_state, specs, segs, obs, action, obs_log, stats, t0, K, E, N, stream);    \
+                        const SPEC* specs, const SEG* segs, REAL* obs, REAL* action, const REAL* fext, REAL* obs_log, double* stats, double t0,    \
+                        int K, int E, int N, void* stream) {                                                                                       \
+    return rollout_impl<REAL>(prm, cfg, geo, lqr, cbf, st, pid, dsl, dsl_state, specs, segs, obs, action, fext, obs_log, stats, t0, K, E, N,      \
+                              stream);                                                                                                             \
   }
 
 MDS_DEFINE(f32, float, MdsTrajSpecF32, MdsTrajSegF32)

@@ -89,7 +89,7 @@ class FusedRollout:
         dsl_state = self.controller.state_struct() if self.cfg.ctrl == _lib.CTRL_DSLPID else _lib.DslPidState(None, None, None)
         cbf = self.qp.cbf.c_params() if self.qp is not None else None
         _lib.call("mds_rollout", env.dtype, env._prm, self.cfg, geo, lqr, cbf, env._state_struct(), pid, dsl, dsl_state,
-                  _lib.ptr(self.trajs.specs), _lib.ptr(self.trajs.segs), _lib.ptr(env._obs), _lib.ptr(env._action), _lib.ptr(obs_log),
+                  _lib.ptr(self.trajs.specs), _lib.ptr(self.trajs.segs), _lib.ptr(env._obs), _lib.ptr(env._action), _lib.ptr(env._ext_force), _lib.ptr(obs_log),
                   _lib.ptr(self.stats), float(t_call), int(K), env.NUM_ENVS, env.NUM_DRONES, _lib.stream_ptr(env.device))
         if stages != 1:
             env.step_counter += K * env.PYB_STEPS_PER_CTRL

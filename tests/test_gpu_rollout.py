@@ -221,3 +221,23 @@ def test_full_size_env_independence(lib_built):
         assert np.array_equal(small["init"][0], big["init"][e0])
         small["rollout"].run(K)
         assert torch.equal(small["env"].obs[0], obs_big[e0]), e0
+
+
+def test_rollout_with_wind(lib_built):
+    """A constant per-drone world-frame force (the reference's wind, EnvGeometric.py:463-467; set_external_force) acts in
+    every launch plan of the rollout exactly as in the per-call loop, and changes the flight."""
+    import multidronesim_b200.trajectories as T
+    E, N, K, dtype = 4, 2, 30, torch.float64
+    specs = [dict(a=0.8, center=np.array([0, 0, 0.8]), omega=0.7, yaw_rate=0.0, phase_shift=float(k)) for k in range(N)]
+    init = np.array([[otj.Lemniscate(**sp)(0.0)[0] for sp in specs]] * E)
+    wind = np.zeros((E, N, 3)); wind[..., 0] = 0.00025 * (1 + np.arange(E))[:, None]
+    outs = {}
+    for plan in ("percall", 6, 4, 3, "calm"):
+        mds, env, c, trk, ts, ro = build(E, N, dtype, "dyn_gnd_drag_dw", [T.Lemniscate(**sp) for sp in specs] * E, "geometric", init=init)
+        if plan != "calm":
+            env.set_external_force(wind)
+        obs = percall_loop(mds, env, c, trk, ts, K, None) if plan == "percall" else ro.run(K, stages=6 if plan == "calm" else plan)
+        outs[plan] = obs.cpu().numpy().copy()
+    for plan in (6, 4, 3):
+        assert np.max(np.abs(outs[plan] - outs["percall"])) < 1e-9 * (1 + np.max(np.abs(outs["percall"]))), plan
+    assert np.max(np.abs(outs["calm"][..., 0:3] - outs[6][..., 0:3])) > 1e-5   # the wind moved the drones
