@@ -113,6 +113,7 @@ class OracleCtrlAviary:
 
     # ---- housekeeping -------------------------------------------------
     def reset(self):
+        """Upstream ``BaseAviary.reset`` / ``_housekeeping``: state back to INIT_XYZS / INIT_RPYS, zero velocities and last RPM; returns (obs, info)."""
         N = self.NUM_DRONES
         self.pos = self.INIT_XYZS.copy()
         self.quat = np.array([rpy_to_quat(self.INIT_RPYS[i]) for i in range(N)])
@@ -125,6 +126,7 @@ class OracleCtrlAviary:
         return self._compute_obs(), {"answer": 42}
 
     def set_state(self, pos, quat, vel, rpy_rates, last_rpm=None):
+        """Test hook (no upstream counterpart): overwrite pos / quat / vel / body rates / last clipped RPM of every drone."""
         N = self.NUM_DRONES
         self.pos = np.array(pos, dtype=float).reshape(N, 3)
         self.quat = np.array(quat, dtype=float).reshape(N, 4)
@@ -192,6 +194,7 @@ class OracleCtrlAviary:
 
     # ---- step ----------------------------------------------------------
     def step(self, action):
+        """Upstream ``BaseAviary.step`` under Physics.DYN as the reference calls it (simulations/EnvGeometric.py:431,469, CBFTest.py:299,350, MultiDroneExample.py:106,121): clip RPM to [0, MAX_RPM], PYB_STEPS_PER_CTRL explicit updates from a Jacobi snapshot of the positions, then obs (N,20), reward -1, False, False, {"answer": 42}."""
         N = self.NUM_DRONES
         clipped = np.clip(np.array(action, dtype=float).reshape(N, 4), 0, self.MAX_RPM)
         dt = self.PYB_TIMESTEP
@@ -207,7 +210,9 @@ class OracleCtrlAviary:
 
     # no-ops kept so reference-style loops run unchanged
     def close(self):
+        """Upstream ``BaseAviary.close`` (PyBullet disconnect): nothing to release here."""
         pass
 
     def render(self):
+        """Upstream ``BaseAviary.render`` (MultiDroneExample.py:123): no-op."""
         pass

@@ -192,6 +192,7 @@ class Lqr:
         self.ref = (np.asarray(desired_pos, float), np.asarray(desired_vel, float), float(desired_yaw), float(desired_omega))
 
     def error_state(self, obs):
+        """Error state of the LQR variants (control/lqr/lqr_controller.py:90-106, lqr_omega_controller.py:97-106, lqr_YO_controller.py:106-116): Euler error via scipy from_euler/as_euler("xyz") of R_eq^T R, position / velocity errors rotated by R_eq^T (yaw only); quirk B8."""
         p_d, v_d, yaw_d, om_d = self.ref
         dim = self.DIM[self.kind]
         x = cv.obs_to_lin_model(obs, dim, self.env)
@@ -212,9 +213,11 @@ class Lqr:
         return u
 
     def body_rates(self, obs):
+        """World -> body angular velocity with scipy's normalised R (lqr_omega_controller.py:80-84)."""
         return cv.quat_to_rot(obs[3:7]).T @ np.asarray(obs[13:16], float)
 
     def compute_low_level(self, u, obs, idx=0):
+        """``compute_low_level`` (lqr_omega_controller.py:78-88, lqr_YO_controller.py:87-98): body rates + the inner PID -> RPM."""
         dt = self.env.CTRL_TIMESTEP
         if self.kind == "omega9":
             return self.low.compute(u, dt, self.body_rates(obs))
@@ -268,6 +271,7 @@ class DslPid:
 
     def compute_from_state(self, dt, state, target_pos, target_rpy=np.zeros(3),
                            target_vel=np.zeros(3), target_rpy_rates=np.zeros(3)):
+        """Upstream ``DSLPIDControl.computeControlFromState`` -> ``_dslPIDPositionControl`` + ``_dslPIDAttitudeControl`` (call site MultiDroneExample.py:111-114).  Returns (rpm, pos_e)."""
         self.control_counter += 1
         pos, quat, vel = state[0:3], state[3:7], state[10:13]
         Rm = cv.quat_to_rot(quat)

@@ -20,6 +20,7 @@ from oracle.aviary import OracleCtrlAviary
 
 
 def make_controllers(env, kind):
+    """One controller object per drone, as the reference constructs them (simulations/EnvGeometric.py:420-426, CBFTest.py:291-292, CBFTestOrd3.py:294-295)."""
     N = env.NUM_DRONES
     if kind == "geometric":
         return [octl.Geometric(env) for _ in range(N)]
