@@ -47,11 +47,13 @@ if ROOT not in sys.path:
 N_DRONES = 8
 SWARM_OBSTACLES = [[0.2, 0.0, 0.5, 0.1]]  # == multidronesim_b200.scenarios.SWARM_OBSTACLES (checked in run_gpu_arm)
 CBF_ORDER = 3
-# Algorithmic work per drone-step of the C5 path (DESIGN.md "Roofline"): FP32 operations of the closed-form
-# math (add/mul = 1, fma = 2, transcendental/div/sqrt = 1), hand-counted per stage and cross-checked against
-# ncu's smsp__sass_thread_inst_executed_op_f{add,mul,fma} for the QP-inactive path.
-ALGO_FLOP_PER_DRONE_STEP = {"traj": 70, "lqr_yank": 130, "cbf_rows": 680, "cbf_check": 110, "qp_iteration": 90, "lowlevel": 110,
-                            "physics_gnd_drag_dw_n8": 640, "obs": 60}
+# Algorithmic work per drone-step of the C5 path (DESIGN.md "Roofline"): FP32 operations of the closed-form math
+# (add / mul / compare / min-max = 1, fma = 2, transcendental / div / sqrt = 1), hand-counted per stage at the lap-average
+# 1.5 QP iterations per solve.  Cross-check (profiles/r1_ncu_kernels.txt): ncu's executed fadd + fmul + 2 ffma per
+# drone-step in a 1.0-iteration phase is 1423 for the rollout kernel (1016 controller stack + 419 physics); the
+# table adds the compares / min-max / MUFU ops those counters leave out and the extra half iteration.
+ALGO_FLOP_PER_DRONE_STEP = {"traj": 70, "lqr_yank": 120, "cbf_rows_and_first_scan": 620, "qp_iterations_and_rescans": 230, "lowlevel": 150,
+                            "physics_gnd_drag_dw_n8": 480, "obs": 60}
 # Algorithmic HBM bytes per drone-step (fp32), per kernel of the rollout (DESIGN.md "Roofline"):
 ALGO_BYTES_CTRL_F32 = {"read_obs": 80, "read_traj_spec": 48, "read_pid": 24, "write_pid": 24, "write_action": 16}
 ALGO_BYTES_PHYS_F32 = {"read_state": 68, "read_action": 16, "write_state": 68, "write_obs": 80}  # 232 B
@@ -338,7 +340,7 @@ def run_gpu_arm(args):
     # ---- roofline of the dominant kernel: the K-steps-in-one-launch rollout kernel (this rank) ----------------
     # Every bench step is ONE launch of rollout_loop_kernel (F control steps with the state in registers), so its
     # mean launch duration is the timed region / K, on the launching stream.  It moves ~15 B per drone-step through
-    # HBM for ~1.9 kflop: FP32-pipe-bound (SURVEY.md 8d "fused K-step rollout"), peak = FMA-chain microbenchmark.
+    # HBM for ~1.73 kflop: FP32-pipe-bound (SURVEY.md 8d "fused K-step rollout"), peak = FMA-chain microbenchmark.
     if ro.plan() != 6:
         raise SystemExit("bench.py assumes the K-steps-in-one-launch plan")
     n_steps = K * F
