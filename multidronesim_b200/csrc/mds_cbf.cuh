@@ -118,6 +118,10 @@ MDS_DEV int row_partner(const RowMap& M, int N, int n, int s) {
 #define MDS_QP_BOX0 4096
 #define MDS_QP_WS_WORDS (4 * MDS_QP_QMAX + MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2 + 4)  // act, lam, d, r, chol, header
 
+// umax[comp] for a run-time comp in 0..2 by selects: a dynamically indexed member would make nvcc copy the whole
+// (kernel-parameter) CbfP block to local memory and turn every C.* read of the kernel into an LDL.
+template <typename Real> MDS_DEV Real cbf_umax(const CbfP<Real>& C, int comp) { return comp == 0 ? C.umax[0] : (comp == 1 ? C.umax[1] : C.umax[2]); }
+
 template <typename Real> struct QpCon {
   int i, j;      // drone blocks (j < 0: single block)
   Real gi[3];    // coefficients on block i; block j carries -gi (pair rows)
@@ -142,7 +146,7 @@ MDS_DEV QpCon<Real> qp_get(const typename Vec4T<Real>::type* rows, const CbfP<Re
     int comp = rem >= 3 ? rem - 3 : rem;
     Real s = rem < 3 ? Real(1) : Real(-1);
     c.gi[0] = comp == 0 ? s : Real(0); c.gi[1] = comp == 1 ? s : Real(0); c.gi[2] = comp == 2 ? s : Real(0);
-    c.rhs = C.umax[comp]; c.g2 = Real(1);
+    c.rhs = cbf_umax(C, comp); c.g2 = Real(1);
   }
   return c;
 }

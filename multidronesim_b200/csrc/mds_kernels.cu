@@ -781,6 +781,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
                                                                   int N_rt, int NP_rt) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
   __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
+  __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[MDS_BLOCK];
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
   const GroupMap g = group_map(N, NP, E);
@@ -790,7 +791,10 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
   if (g.env_valid) {
     Obs<Real> o;
     V3<Real> wb = {Real(0), Real(0), Real(0)};  // body rates: the one part of the state the observation does not carry
-    typename TrajSpecT<Real>::spec spec;
+    // The trajectory descriptor is read every step; its address escapes into the out-of-line table walk, so as an
+    // automatic it would live in local memory (LDL, L1-missing under this kernel's local footprint): stage it in
+    // shared memory instead (12-word lane stride: 128-bit reads are conflict-free per quarter warp).
+    typename TrajSpecT<Real>::spec& spec = sm_spec[threadIdx.x];
     spec.kind = MDS_TRAJ_WAIT;
     V3<Real> fx = {Real(0), Real(0), Real(0)};  // constant world-frame force on this drone (wind), if any
     if (g.valid) {
