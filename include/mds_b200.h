@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MDS_ABI_VERSION 4
+#define MDS_ABI_VERSION 5
 #define MDS_MAX_DRONES_PER_ENV 32
 #define MDS_MAX_OBSTACLES 8
 #define MDS_OBS_DIM 20
@@ -287,6 +287,45 @@ int mds_rollout_f64(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const M
                     const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
                     const MdsDslPidGains* dsl, MdsDslPidState dsl_state, const MdsTrajSpecF64* specs_dev, const MdsTrajSegF64* segs_dev, double* obs_dev, double* action_dev,
                     const double* ext_force_dev, double* obs_log_dev, double* stats_dev, double t0, int K, int E, int N, void* stream);
+
+/* ---- decentralised LQR with per-drone learned models: control/dlqr/ ------------------------- */
+/* regression target of one recursive-least-squares step */
+enum {
+  MDS_RLS_TARGET_PREDICT = 0, /* x_{t+1} - forward_predict(...)   (theta_update / theta_update2, decentralized_lqr_omega.py:110-139) */
+  MDS_RLS_TARGET_XDOT = 1     /* est_x_dot(x_{t+1}, phi) - theta' phi (approx_theta_update, decentralized_lqr.py:185-228)             */
+};
+/* project_theta (decentralized_lqr.py:230-240): never / once after the update (12-dim theta_update :183) / inside the
+ * per-robot loop (approx_theta_update :216: robots after the first of an env are also projected BEFORE their update) */
+enum { MDS_RLS_PROJECT_NONE = 0, MDS_RLS_PROJECT_AFTER = 1, MDS_RLS_PROJECT_LOOP = 2 };
+typedef struct MdsRlsCfg {
+  int m;                  /* model state dimension: 9 (omega), 10 (yank-omega), 12 (torque); inputs n = 4            */
+  int target;             /* MDS_RLS_TARGET_*                                                                        */
+  int predict_from_xtp1;  /* PREDICT: start the prediction at x_{t+1} (omega / yank-omega variants, :134) not phi[:m] */
+  int normalize_gain;     /* 1: L = P phi / (1 + phi' P phi); 0: L = P phi with P = V^-1 (theta_update2, :119-122)    */
+  int project;            /* MDS_RLS_PROJECT_*                                                                       */
+  int drones_per_env;     /* N (only read by MDS_RLS_PROJECT_LOOP)                                                   */
+  double dt;              /* env.CTRL_TIMESTEP                                                                       */
+  unsigned char theta_code[16 * 12]; /* project_theta per entry of theta [(m+4)][m] row-major: 0 zero, 1 keep, 2 one */
+} MdsRlsCfg;
+/* One RLS step for every drone.  phi_dev [D][m+4] = [e_t, u_t], xtp1_dev [D][m] = e_{t+1} (row-major per drone);
+ * theta_dev [(m+4)*m][D] and P_dev [(m+4)*(m+4)][D] are PLANES (entry k of drone d at [k*D + d]), updated in place;
+ * resid_dev optional [D][m] receives the regression residual. */
+int mds_rls_update_f32(const MdsRlsCfg* cfg, const float* phi_dev, const float* xtp1_dev, float* theta_dev, float* P_dev,
+                       float* resid_dev, int D, void* stream);
+int mds_rls_update_f64(const MdsRlsCfg* cfg, const double* phi_dev, const double* xtp1_dev, double* theta_dev, double* P_dev,
+                       double* resid_dev, int D, void* stream);
+/* error_state of the LQR family (decentralized_lqr_omega.py:174-183, lqr_omega_controller.py:97-110): obs + reference
+ * sample -> e_dev [D][dim], dim = 12 / 9 / 10 for variant MDS_CTRL_LQR_TORQUE / _OMEGA / _YANK */
+int mds_error_state_f32(const MdsDroneParams* prm, int variant, const float* obs_dev, const float* ref_dev, float* e_dev, int D, void* stream);
+int mds_error_state_f64(const MdsDroneParams* prm, int variant, const double* obs_dev, const double* ref_dev, double* e_dev, int D, void* stream);
+/* mds_lqr_ctrl with a gain per drone (DecentralizedLQR*.compute).  coupled = 0: u_d = -K_d e_d, K_dev [4*dim][D] planes.
+ * coupled = 1: u_d = -sum_j K_{d,j} e_j over the N drones j of d's environment, K_dev [N][4*dim][D] (source-major):
+ * the 12-dim reference couples robots 0 and 1 through off-diagonal blocks of Q (decentralized_lqr.py:44-53), so its K
+ * is a full 4N x 12N matrix.  Same outputs and inner loop as mds_lqr_ctrl. */
+int mds_dlqr_ctrl_f32(const MdsDroneParams* prm, int variant, const float* K_dev, int coupled, const float* obs_dev, const float* ref_dev,
+                      float* u_dev, float* action_dev, MdsPidState pid, int E, int N, void* stream);
+int mds_dlqr_ctrl_f64(const MdsDroneParams* prm, int variant, const double* K_dev, int coupled, const double* obs_dev, const double* ref_dev,
+                      double* u_dev, double* action_dev, MdsPidState pid, int E, int N, void* stream);
 
 /* launch plan (a MdsRolloutCfg.stages value) that stages == 0 selects for E envs of N drones */
 int mds_rollout_plan(int E, int N);

@@ -72,6 +72,11 @@ class CbfParams(C.Structure):
                 ("fmax", C.c_double), ("max_iter", C.c_int)]
 
 
+class RlsCfg(C.Structure):
+    _fields_ = [("m", C.c_int), ("target", C.c_int), ("predict_from_xtp1", C.c_int), ("normalize_gain", C.c_int),
+                ("project", C.c_int), ("drones_per_env", C.c_int), ("dt", C.c_double), ("theta_code", C.c_ubyte * (16 * 12))]
+
+
 class RolloutCfg(C.Structure):
     _fields_ = [("ctrl", C.c_int), ("use_cbf", C.c_int), ("num_obstacles", C.c_int),
                 ("write_obs_every", C.c_int), ("stages", C.c_int), ("obstacles", C.c_double * (MAX_OBSTACLES * 4))]
@@ -104,6 +109,9 @@ _SIGS = {
     "mds_dslpid_ctrl": [_PRM, C.POINTER(DslPidGains), _P, _P, DslPidState, _P, _P, _I, _P],
     "mds_lqr_ctrl": [_PRM, C.POINTER(LqrGains), _I, _P, _P, _P, _P, PidState, _I, _P],
     "mds_lowlevel": [_PRM, _I, _P, _P, PidState, _P, _I, _P],
+    "mds_rls_update": [C.POINTER(RlsCfg), _P, _P, _P, _P, _P, _I, _P],
+    "mds_error_state": [_PRM, _I, _P, _P, _P, _I, _P],
+    "mds_dlqr_ctrl": [_PRM, _I, _P, _I, _P, _P, _P, _P, PidState, _I, _I, _P],
     "mds_cbf_qp": [_PRM, C.POINTER(CbfParams), _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P],
     "mds_cbf_rows": [_PRM, C.POINTER(CbfParams), _P, _P, _P, _I, _P, _P, _I, _I, _P],
     "mds_cbf_prepare": [_PRM, _I, _D, _P, _P, _P, _I, _P],

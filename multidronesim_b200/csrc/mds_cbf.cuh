@@ -255,6 +255,56 @@ MDS_DEV int qp_scan(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows,
   return qp_worst_of_group(w, NP, gmask);
 }
 
+// fp32 polish, lane-0 part (rare: solves that end with >= 3 active constraints): solve (A A') lam = A u_nom - b for the
+// final active set in double and leave lam in the workspace.  Out of line: its fp64 arrays and code stay out of the
+// step loop's registers and instruction stream.
+template <typename Real>
+__device__ __noinline__ bool qp_polish_lane0(Real umax0, Real umax1, Real umax2, const typename Vec4T<Real>::type* rows,
+                                             const typename Vec4T<Real>::type* xnom, Real* ws, Real* lam, int q) {
+  auto iref = [](Real* slot) -> int& { return *reinterpret_cast<int*>(slot); };
+  CbfP<Real> C;  // only the box bounds are read (qp_get); taking the caller's block by reference would force it into local memory
+  C.umax[0] = umax0; C.umax[1] = umax1; C.umax[2] = umax2;
+  double Lm[MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2], y[MDS_QP_QMAX];
+  bool ok = true;
+  for (int a = 0; a < q && ok; ++a) {
+    QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
+    for (int b2 = 0; b2 <= a; ++b2) {
+      QpCon<Real> cb = qp_get(rows, C, iref(ws + b2));
+      double ab = (double)ca.gi[0] * cb.gi[0] + (double)ca.gi[1] * cb.gi[1] + (double)ca.gi[2] * cb.gi[2], sacc = 0.0;
+      if (ca.i == cb.i) sacc += ab;
+      if (ca.j >= 0 && ca.j == cb.j) sacc += ab;
+      if (ca.j >= 0 && ca.j == cb.i) sacc -= ab;
+      if (cb.j >= 0 && cb.j == ca.i) sacc -= ab;
+      for (int k = 0; k < b2; ++k) sacc -= Lm[a * (a + 1) / 2 + k] * Lm[b2 * (b2 + 1) / 2 + k];
+      if (a == b2) {
+        if (sacc <= 0.0) { ok = false; break; }
+        Lm[a * (a + 1) / 2 + a] = sqrt(sacc);
+      } else {
+        Lm[a * (a + 1) / 2 + b2] = sacc / Lm[b2 * (b2 + 1) / 2 + b2];
+      }
+    }
+    // right-hand side A u_nom - b from the nominal inputs kept in the 4th ... see below: unom is passed in xnom
+    auto ui = xnom[ca.i];
+    double r = (double)ca.gi[0] * ui.x + (double)ca.gi[1] * ui.y + (double)ca.gi[2] * ui.z;
+    if (ca.j >= 0) { auto uj = xnom[ca.j]; r -= (double)ca.gi[0] * uj.x + (double)ca.gi[1] * uj.y + (double)ca.gi[2] * uj.z; }
+    y[a] = r - (double)ca.rhs;
+  }
+  if (ok) {
+    for (int a = 0; a < q; ++a) {  // forward, then backward substitution
+      double sacc = y[a];
+      for (int k = 0; k < a; ++k) sacc -= Lm[a * (a + 1) / 2 + k] * y[k];
+      y[a] = sacc / Lm[a * (a + 1) / 2 + a];
+    }
+    for (int a = q - 1; a >= 0; --a) {
+      double sacc = y[a];
+      for (int k = a + 1; k < q; ++k) sacc -= Lm[k * (k + 1) / 2 + a] * y[k];
+      y[a] = sacc / Lm[a * (a + 1) / 2 + a];
+    }
+    for (int a = 0; a < q; ++a) lam[a] = (Real)y[a];
+  }
+  return ok;
+}
+
 // Goldfarb-Idnani dual active set, P = I, executed by the env's lane group.
 //   rows : smem barrier rows;  x : smem iterate, one Vec4 per drone (u_nom on entry, minimiser on exit);
 //   xnom : smem copy of u_nom that stays untouched (fp32 polish);
@@ -448,44 +498,7 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
     // loses ~1e-4 on long solves.  With the final active set A the minimiser is u_nom - A' lam, (A A') lam = A u_nom - b;
     // lane 0 solves this small system once in double and every lane rebuilds its own block from u_nom.
     if (n == 0) {
-      double Lm[MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2], y[MDS_QP_QMAX];
-      bool ok = true;
-      for (int a = 0; a < q && ok; ++a) {
-        QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
-        for (int b2 = 0; b2 <= a; ++b2) {
-          QpCon<Real> cb = qp_get(rows, C, iref(ws + b2));
-          double ab = (double)ca.gi[0] * cb.gi[0] + (double)ca.gi[1] * cb.gi[1] + (double)ca.gi[2] * cb.gi[2], sacc = 0.0;
-          if (ca.i == cb.i) sacc += ab;
-          if (ca.j >= 0 && ca.j == cb.j) sacc += ab;
-          if (ca.j >= 0 && ca.j == cb.i) sacc -= ab;
-          if (cb.j >= 0 && cb.j == ca.i) sacc -= ab;
-          for (int k = 0; k < b2; ++k) sacc -= Lm[a * (a + 1) / 2 + k] * Lm[b2 * (b2 + 1) / 2 + k];
-          if (a == b2) {
-            if (sacc <= 0.0) { ok = false; break; }
-            Lm[a * (a + 1) / 2 + a] = sqrt(sacc);
-          } else {
-            Lm[a * (a + 1) / 2 + b2] = sacc / Lm[b2 * (b2 + 1) / 2 + b2];
-          }
-        }
-        // right-hand side A u_nom - b from the nominal inputs kept in the 4th ... see below: unom is passed in xnom
-        auto ui = xnom[ca.i];
-        double r = (double)ca.gi[0] * ui.x + (double)ca.gi[1] * ui.y + (double)ca.gi[2] * ui.z;
-        if (ca.j >= 0) { auto uj = xnom[ca.j]; r -= (double)ca.gi[0] * uj.x + (double)ca.gi[1] * uj.y + (double)ca.gi[2] * uj.z; }
-        y[a] = r - (double)ca.rhs;
-      }
-      if (ok) {
-        for (int a = 0; a < q; ++a) {  // forward, then backward substitution
-          double sacc = y[a];
-          for (int k = 0; k < a; ++k) sacc -= Lm[a * (a + 1) / 2 + k] * y[k];
-          y[a] = sacc / Lm[a * (a + 1) / 2 + a];
-        }
-        for (int a = q - 1; a >= 0; --a) {
-          double sacc = y[a];
-          for (int k = a + 1; k < q; ++k) sacc -= Lm[k * (k + 1) / 2 + a] * y[k];
-          y[a] = sacc / Lm[a * (a + 1) / 2 + a];
-        }
-        for (int a = 0; a < q; ++a) lam[a] = (Real)y[a];
-      }
+      const bool ok = qp_polish_lane0<Real>(C.umax[0], C.umax[1], C.umax[2], rows, xnom, ws, lam, q);
       iref(hdr + 1) = ok ? 1 : 0;
     }
     __syncwarp(gmask);

@@ -116,14 +116,13 @@ MDS_DEV void geometric_input(const DroneP<Real>& P, const GeoP<Real>& G, const O
 // LQR error state + u = -K e (+ hover) for the three parametrisations (B8-B10).
 // variant: MDS_CTRL_LQR_TORQUE (dim 12), _OMEGA (9), _YANK (10).  Returns the UN-capped u.
 template <typename Real>
-MDS_DEV void lqr_input(const DroneP<Real>& P, const LqrP<Real>& L, int variant, const Obs<Real>& o, const Ref<Real>& r, Real u[4]) {
+MDS_DEV int lqr_error_state(const DroneP<Real>& P, int variant, const Obs<Real>& o, const Ref<Real>& r, Real e[12]) {
   Real sy, cy;
   sincos_(r.yaw, &sy, &cy);
   // Error attitude (lqr_omega_controller.py:97-104): as_euler('xyz') of R_eq^T R with R = from_euler('xyz', rpy)
   // = Rz(yaw) Ry(pitch) Rx(roll) and R_eq = Rz(yaw_d).  Rz(yaw_d)^T Rz(yaw) = Rz(yaw - yaw_d), and the obs pitch is
   // an asin() in [-pi/2, pi/2], so the Euler angles of the product are (roll, pitch, wrap(yaw - yaw_d)) in closed
   // form -- no rotation matrix, sincos or atan2 round trip (it was ~10 % of the controller kernel's instructions).
-  Real e[12];
   e[0] = o.rpy.x;
   e[1] = o.rpy.y;
   {
@@ -148,10 +147,31 @@ MDS_DEV void lqr_input(const DroneP<Real>& P, const LqrP<Real>& L, int variant, 
     e[3] = z_thrust(P, o.rpm) - P.m * P.g;
     e[4] = ev.x; e[5] = ev.y; e[6] = ev.z; e[7] = ep.x; e[8] = ep.y; e[9] = ep.z;
   }
+  return dim;
+}
+template <typename Real>
+MDS_DEV void lqr_input(const DroneP<Real>& P, const LqrP<Real>& L, int variant, const Obs<Real>& o, const Ref<Real>& r, Real u[4]) {
+  Real e[12];
+  const int dim = lqr_error_state(P, variant, o, r, e);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     Real acc = Real(0);
     for (int k = 0; k < dim; ++k) acc += L.K[i * dim + k] * e[k];
+    u[i] = -acc;
+  }
+  if (variant != MDS_CTRL_LQR_YANK) u[0] += P.m * P.g;
+}
+// The same law with a gain of the drone's own (decentralised LQR: every drone carries the K of its learned model;
+// decentralized_lqr_omega.py:185-204, decentralized_lqr.py:326-342).  K planes: element (i, k) of drone d at [(i*dim+k)*D + d].
+template <typename Real>
+MDS_DEV void dlqr_input(const DroneP<Real>& P, const Real* __restrict__ K, size_t D, size_t d, int variant, const Obs<Real>& o, const Ref<Real>& r,
+                        Real u[4]) {
+  Real e[12];
+  const int dim = lqr_error_state(P, variant, o, r, e);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    Real acc = Real(0);
+    for (int k = 0; k < dim; ++k) acc += K[(size_t)(i * dim + k) * D + d] * e[k];
     u[i] = -acc;
   }
   if (variant != MDS_CTRL_LQR_YANK) u[0] += P.m * P.g;

@@ -10,6 +10,7 @@
 #include "mds_common.cuh"
 #include "mds_ctrl.cuh"
 #include "mds_physics.cuh"
+#include "mds_sysid.cuh"
 #include "mds_traj.cuh"
 
 using namespace mds;
@@ -356,6 +357,71 @@ __global__ void lqr_ctrl_kernel(DroneP<Real> P, LqrP<Real> L, int variant, const
   }
   store4(u_out, d, u);
 }
+// DecentralizedLQR*.compute: lqr_ctrl_kernel with a gain per drone (K planes).  coupled = 0: u_d = -K_d e_d, K [4*dim][D].
+// coupled = 1: u_d = -sum_j K_{d,j} e_j over the N drones j of d's environment, K [N][4*dim][D] (source-major) -- the
+// 12-dim reference couples robots 0 and 1 through off-diagonal blocks of Q (decentralized_lqr.py:44-53), so its K is
+// a full 4N x 12N matrix.  blockDim is a multiple of N: an environment never straddles two blocks.
+template <typename Real>
+__global__ void dlqr_ctrl_kernel(DroneP<Real> P, int variant, const Real* __restrict__ K, int coupled, const Real* __restrict__ obs,
+                                 const Real* __restrict__ ref, Real* __restrict__ u_out, Real* __restrict__ action, PidP<Real> pid, int D, int N) {
+  extern __shared__ __align__(16) unsigned char dlqr_smem[];
+  Real* e_sh = reinterpret_cast<Real*>(dlqr_smem);  // [blockDim][12]
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = d < D;
+  Obs<Real> o;
+  Real e[12], u[4], rpm[4];
+  int dim = 0;
+  if (valid) {
+    o = load_obs(obs, d);
+    dim = lqr_error_state(P, variant, o, load_ref(ref, d), e);
+  }
+  if (coupled) {
+    if (valid)
+      for (int k = 0; k < dim; ++k) e_sh[threadIdx.x * 12 + k] = e[k];
+    __syncthreads();
+  }
+  if (!valid) return;
+  const size_t Ds = (size_t)D;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) u[i] = Real(0);
+  if (coupled) {
+    const int n = d % N;
+    for (int j = 0; j < N; ++j) {
+      const Real* ej = e_sh + (threadIdx.x - n + j) * 12;
+      const Real* Kj = K + (size_t)j * 4 * dim * Ds;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < dim; ++k) u[i] -= Kj[(size_t)(i * dim + k) * Ds + d] * ej[k];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      for (int k = 0; k < dim; ++k) u[i] -= K[(size_t)(i * dim + k) * Ds + d] * e[k];
+  }
+  if (variant != MDS_CTRL_LQR_YANK) u[0] += P.m * P.g;
+  if (variant == MDS_CTRL_LQR_TORQUE) {
+    input_to_action(P, u, rpm);
+    if (action) store4(action, d, rpm);
+  } else {
+    if (action) {
+      Pid<Real> ps = load_pid(pid, d);
+      low_level(P, variant, ps, u, o, rpm);
+      store_pid(pid, d, ps);
+      store4(action, d, rpm);
+      if (variant == MDS_CTRL_LQR_OMEGA) u[0] = max_(u[0], Real(0));
+    }
+    if (variant == MDS_CTRL_LQR_OMEGA) u[0] = cap_thrust(P, u[0]);
+  }
+  store4(u_out, d, u);
+}
+template <typename Real>
+__global__ void error_state_kernel(DroneP<Real> P, int variant, const Real* __restrict__ obs, const Real* __restrict__ ref, Real* __restrict__ e_out, int D) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  Real e[12];
+  const int dim = lqr_error_state(P, variant, load_obs(obs, d), load_ref(ref, d), e);
+  for (int k = 0; k < dim; ++k) e_out[(size_t)d * dim + k] = e[k];
+}
 template <typename Real>
 __global__ void dslpid_ctrl_kernel(DroneP<Real> P, DslP<Real> G, const Real* __restrict__ obs, const Real* __restrict__ target,
                                    DslStateP<Real> st, Real* __restrict__ action, Real* __restrict__ pos_e, int D) {
@@ -602,7 +668,7 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
                        const DslP<Real>& Dg, const DslStateP<Real>& dst, const CbfSmem<Real>& S, const PidP<Real>& pid,
                        const typename TrajSpecT<Real>::spec& spec,
                        const typename TrajSpecT<Real>::seg* __restrict__ segs, const Obs<Real>& o, const GroupMap& g, int N, int NP,
-                       double t, Real rpm[4], StepStats& ss) {
+                       double t, Real rpm[4], StepStats& ss, int pid_idx) {
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
   Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
   Ref<Real> ref;
@@ -651,9 +717,9 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
       }
     }
     if (g.valid) {
-      Pid<Real> ps = load_pid(pid, g.d);
+      Pid<Real> ps = load_pid(pid, pid_idx);  // pid_idx: g.d for HBM-resident state, the thread index when the caller staged it
       low_level(P, CTRL, ps, u, o, rpm);
-      store_pid(pid, g.d, ps);
+      store_pid(pid, pid_idx, ps);
     }
   }
 }
@@ -727,7 +793,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_CTRL_MINB :
       spec = specs[g.d];
       if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
     }
-    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
+    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss, g.d);
     if (g.valid) store4(action, g.d, rpm);
   }
   if (stats) stats_block_reduce<USE_CBF>(stats, g.valid ? 1 : 0, ss, ss.err);
@@ -761,7 +827,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB 
     typename TrajSpecT<Real>::spec spec;
     spec.kind = MDS_TRAJ_WAIT;
     if (g.valid) spec = specs[g.d];
-    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss);
+    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss, g.d);
     if (g.valid) store4(action, g.d, rpm);
   }
   if (stats) stats_block_reduce<USE_CBF>(stats, g.valid ? 1 : 0, ss, ss.err);
@@ -782,6 +848,11 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
   extern __shared__ __align__(32) unsigned char smem_raw[];
   __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
   __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[MDS_BLOCK];
+  // rate-PID state of the inner loop: read and rewritten every step -> staged in shared memory for the launch
+  constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
+  __shared__ typename Vec4T<Real>::type sm_pid_a[HAS_PID ? MDS_BLOCK : 1];
+  __shared__ typename Vec2T<Real>::type sm_pid_b[HAS_PID ? MDS_BLOCK : 1];
+  const PidP<Real> pid_s = {sm_pid_a, sm_pid_b};
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
   const GroupMap g = group_map(N, NP, E);
@@ -802,6 +873,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
       spec = specs[g.d];
       wb = {st.pos_wx[g.d].w, st.vel_wy[g.d].w, st.wz[g.d]};
       if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
+      if (HAS_PID) { sm_pid_a[threadIdx.x] = pid.a[g.d]; sm_pid_b[threadIdx.x] = pid.b[g.d]; }
     }
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
     const size_t obs_elems = (size_t)E * N * MDS_OBS_DIM;
@@ -809,7 +881,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
     Real* log_slot = obs_log;
     for (int k = 0; k < K; ++k) {
       StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
-      ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss);  // the host plans form t exactly like this
+      ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss, (int)threadIdx.x);  // the host plans form t exactly like this
       acc.err += ss.err; max_err = fmaxf(max_err, ss.err); acc.min_h = fminf(acc.min_h, ss.min_h);
       acc.qp_solves += ss.qp_solves; acc.qp_iters += ss.qp_iters; acc.qp_infeas += ss.qp_infeas; acc.qp_cap += ss.qp_cap;
       Drone<Real> s;
@@ -832,6 +904,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
       store_drone(st, g.d, s);
       store_obs(obs, g.d, o);
       store4(action, g.d, rpm);
+      if (HAS_PID) { pid.a[g.d] = sm_pid_a[threadIdx.x]; pid.b[g.d] = sm_pid_b[threadIdx.x]; }
       steps_done = K;
     }
   }
@@ -899,6 +972,50 @@ static int lqr_impl(const MdsDroneParams* prm, const MdsLqrGains* g, int variant
   lqr_ctrl_kernel<Real><<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*g), variant, obs, ref, u, action,
                                                                              to_dev<Real>(pid), D);
   return check_launch("lqr_ctrl");
+}
+template <typename Real>
+static int rls_impl(const MdsRlsCfg* cfg, const Real* phi, const Real* xtp1, Real* theta, Real* Pm, Real* resid, int D, void* stream) {
+  MDS_REQUIRE(cfg && phi && xtp1 && theta && Pm && D > 0, "rls_update: bad argument");
+  MDS_REQUIRE(cfg->m == 9 || cfg->m == 10 || cfg->m == 12, "rls_update: m must be 9, 10 or 12");
+  MDS_REQUIRE(cfg->target == MDS_RLS_TARGET_PREDICT || cfg->target == MDS_RLS_TARGET_XDOT, "rls_update: unknown target");
+  MDS_REQUIRE(!(cfg->target == MDS_RLS_TARGET_XDOT && cfg->m == 9), "rls_update: the reference defines est_x_dot for m = 10 and 12 only");
+  MDS_REQUIRE(cfg->project >= MDS_RLS_PROJECT_NONE && cfg->project <= MDS_RLS_PROJECT_LOOP, "rls_update: unknown projection mode");
+  MDS_REQUIRE(cfg->dt > 0.0 && cfg->drones_per_env >= 1, "rls_update: dt and drones_per_env must be positive");
+  RlsP c;
+  c.target = cfg->target; c.predict_from_xtp1 = cfg->predict_from_xtp1; c.normalize_gain = cfg->normalize_gain;
+  c.project = cfg->project; c.drones_per_env = cfg->drones_per_env; c.dt = cfg->dt;
+  for (int w = 0; w < 3; ++w) c.zero_mask[w] = c.one_mask[w] = 0ull;
+  for (int k = 0; k < (cfg->m + 4) * cfg->m; ++k) {
+    MDS_REQUIRE(cfg->theta_code[k] <= 2, "rls_update: theta_code entries must be 0, 1 or 2");
+    if (cfg->theta_code[k] == 0) c.zero_mask[k >> 6] |= 1ull << (k & 63);
+    if (cfg->theta_code[k] == 2) c.one_mask[k >> 6] |= 1ull << (k & 63);
+  }
+  const int threads = MDS_RLS_THREADS, blocks = (D + threads - 1) / threads;
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (cfg->m == 9) rls_update_kernel<Real, 9><<<blocks, threads, 0, cs>>>(c, phi, xtp1, theta, Pm, resid, D);
+  else if (cfg->m == 10) rls_update_kernel<Real, 10><<<blocks, threads, 0, cs>>>(c, phi, xtp1, theta, Pm, resid, D);
+  else rls_update_kernel<Real, 12><<<blocks, threads, 0, cs>>>(c, phi, xtp1, theta, Pm, resid, D);
+  return check_launch("rls_update");
+}
+static bool lqr_variant_ok(int v) { return v == MDS_CTRL_LQR_TORQUE || v == MDS_CTRL_LQR_OMEGA || v == MDS_CTRL_LQR_YANK; }
+template <typename Real>
+static int error_state_impl(const MdsDroneParams* prm, int variant, const Real* obs, const Real* ref, Real* e, int D, void* stream) {
+  MDS_REQUIRE(prm && obs && ref && e && D > 0, "error_state: bad argument");
+  MDS_REQUIRE(lqr_variant_ok(variant), "error_state: unknown variant");
+  error_state_kernel<Real><<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), variant, obs, ref, e, D);
+  return check_launch("error_state");
+}
+template <typename Real>
+static int dlqr_impl(const MdsDroneParams* prm, int variant, const Real* K, int coupled, const Real* obs, const Real* ref, Real* u, Real* action,
+                     MdsPidState pid, int E, int N, void* stream) {
+  MDS_REQUIRE(prm && K && obs && ref && u && E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV, "dlqr_ctrl: bad argument");
+  MDS_REQUIRE(lqr_variant_ok(variant), "dlqr_ctrl: unknown variant");
+  MDS_REQUIRE(!(action && variant != MDS_CTRL_LQR_TORQUE) || (pid.a && pid.b), "dlqr_ctrl: inner loop needs PID state");
+  const int D = E * N, threads = (128 / N) * N, blocks = (D + threads - 1) / threads;
+  const size_t smem = coupled ? (size_t)threads * 12 * sizeof(Real) : 0;
+  dlqr_ctrl_kernel<Real><<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), variant, K, coupled ? 1 : 0, obs, ref, u, action,
+                                                                          to_dev<Real>(pid), D, N);
+  return check_launch("dlqr_ctrl");
 }
 template <typename Real>
 static int lowlevel_impl(const MdsDroneParams* prm, int variant, const Real* u, const Real* obs, MdsPidState pid, Real* action, int D, void* stream) {
@@ -1206,6 +1323,16 @@ int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 *
   int mds_lqr_ctrl_##SUF(const MdsDroneParams* prm, const MdsLqrGains* g, int variant, const REAL* obs, const REAL* ref, REAL* u, REAL* action,    \
                          MdsPidState pid, int D, void* stream) {                                                                                   \
     return lqr_impl<REAL>(prm, g, variant, obs, ref, u, action, pid, D, stream);                                                                   \
+  }                                                                                                                                                \
+  int mds_rls_update_##SUF(const MdsRlsCfg* cfg, const REAL* phi, const REAL* xtp1, REAL* theta, REAL* Pm, REAL* resid, int D, void* stream) {          \
+    return rls_impl<REAL>(cfg, phi, xtp1, theta, Pm, resid, D, stream);                                                                            \
+  }                                                                                                                                                \
+  int mds_error_state_##SUF(const MdsDroneParams* prm, int variant, const REAL* obs, const REAL* ref, REAL* e, int D, void* stream) {              \
+    return error_state_impl<REAL>(prm, variant, obs, ref, e, D, stream);                                                                           \
+  }                                                                                                                                                \
+  int mds_dlqr_ctrl_##SUF(const MdsDroneParams* prm, int variant, const REAL* K, int coupled, const REAL* obs, const REAL* ref, REAL* u,           \
+                          REAL* action, MdsPidState pid, int E, int N, void* stream) {                                                             \
+    return dlqr_impl<REAL>(prm, variant, K, coupled, obs, ref, u, action, pid, E, N, stream);                                                      \
   }                                                                                                                                                \
   int mds_lowlevel_##SUF(const MdsDroneParams* prm, int variant, const REAL* u, const REAL* obs, MdsPidState pid, REAL* action, int D,             \
                          void* stream) {                                                                                                           \

@@ -196,6 +196,75 @@ def golden_cbf(ref):
     np.savez_compressed(os.path.join(OUT, "cbf_rows.npz"), **out)
 
 
+def golden_dlqr(ref):
+    """Decentralised-LQR model learning and control (control/dlqr/*.py), run by the reference classes themselves."""
+    import importlib
+    rng = np.random.default_rng(17)
+    env = drone_params("cf2p", 240, 240)
+    out = {"dt": env.CTRL_TIMESTEP}
+    with contextlib.redirect_stdout(io.StringIO()):
+        m_om = importlib.import_module("control.dlqr.decentralized_lqr_omega")
+        m_yo = importlib.import_module("control.dlqr.decentralized_lqr_yank_omega")
+        m_12 = importlib.import_module("control.dlqr.decentralized_lqr")
+        m_cf = importlib.import_module("control.dlqr.decentralized_yolqr_crazyflie")
+    N, T = 3, 4
+
+    def thetas(d):
+        return np.array([d.get_thetai(i) for i in range(N)])
+
+    def draws(m, u_scale):
+        phis = np.concatenate([rng.normal(0, 0.1, (T, N, m)), rng.normal(0, 1.0, (T, N, 4)) * u_scale], axis=2)
+        x1 = phis[:, :, :m] + rng.normal(0, 0.01, (T, N, m))
+        return phis, x1
+
+    def run(tag, make, method, m, u_scale, **kw):
+        with contextlib.redirect_stdout(io.StringIO()):
+            d = make()
+        phis, x1 = draws(m, u_scale)
+        out[f"{tag}_phi"], out[f"{tag}_x1"] = phis, x1
+        out[f"{tag}_theta0"], out[f"{tag}_P0"] = thetas(d), np.array(d.P, float).copy()
+        th, Ps = [], []
+        for t in range(T):
+            with contextlib.redirect_stdout(io.StringIO()):
+                getattr(d, method)([p.copy() for p in phis[t]], [x.copy() for x in x1[t]], **kw)
+            th.append(thetas(d))
+            Ps.append(np.array(d.P, float).copy())
+        out[f"{tag}_theta"], out[f"{tag}_P"] = np.array(th), np.array(Ps)
+        return d
+
+    u9 = np.array([0.05, 0.1, 0.1, 0.1])
+    u12 = np.array([0.05, 1e-4, 1e-4, 1e-4])
+    u10 = np.array([2.0, 0.1, 0.1, 0.1])
+    om = lambda: m_om.DecentralizedLQROmega(env, [ref.model.LinearizedOmegaModel(env) for _ in range(N)])
+    yo = lambda: m_yo.DecentralizedLQRYankOmega(env, [ref.model.LinearizedYankOmegaModel(env) for _ in range(N)])
+    t12 = lambda: m_12.DecentralizedLQR(env, [ref.model.LinearizedModel(env) for _ in range(N)])
+    cf = lambda: m_cf.DecentralizedYOLQRCrazyflie(env, [ref.model.LinearizedYankOmegaModel(env) for _ in range(N)], np.eye(10), np.eye(4))
+    d_om = run("omega9_update", om, "theta_update", 9, u9)
+    run("omega9_update2", om, "theta_update2", 9, u9)            # P holds V (information form)
+    run("yank10_update", yo, "theta_update", 10, u10)
+    d_12 = run("torque12_update", t12, "theta_update", 12, u12)  # project_theta once after the loop
+    run("torque12_approx", t12, "approx_theta_update", 12, u12)  # project_theta inside the loop
+    run("cf10_approx", cf, "approx_theta_update", 10, u10, project=True)
+    run("cf10_approx_noproj", cf, "approx_theta_update", 10, u10, project=False)
+    # control law with the learned models: compute_controller (CARE on the learned theta) then compute(obs)
+    obs = random_obs(rng, env, N, pos_scale=0.5)
+    lem = ref.traj.Lemniscate(center=np.array([0, 0, .5]), omega=1.5, yaw_rate=.1)
+    refs = pack_ref([lem(float(t)) for t in rng.uniform(0, 6, N)])
+    out["ctrl_obs"], out["ctrl_ref"] = obs, refs
+    for tag, d in (("omega9", d_om), ("torque12", d_12)):
+        d.theta = np.hstack([d.Astar, d.Bstar]).T.copy()  # a stabilisable model: the noisy prior, perturbed per robot
+        for i in range(N):
+            th = d.get_thetai(i)
+            d.overwrite_theta(th * (1.0 + 0.02 * (i + 1)), i)
+        d.compute_controller()
+        for i in range(N):
+            d.set_desired_trajectory(i, refs[i, 0:3], refs[i, 3:6], refs[i, 6:9], refs[i, 9], refs[i, 10])
+        action, u = d.compute(obs.copy())
+        out[f"ctrl_{tag}_theta"], out[f"ctrl_{tag}_K"] = thetas(d), d.K
+        out[f"ctrl_{tag}_action"], out[f"ctrl_{tag}_u"] = np.array(action), np.array(u, float)
+    np.savez_compressed(os.path.join(OUT, "dlqr.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load()
@@ -203,6 +272,7 @@ def main():
     golden_controllers(ref)
     golden_models(ref)
     golden_cbf(ref)
+    golden_dlqr(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1,0 +1,157 @@
+"""GPU parity of the decentralised-LQR path: mds_rls_update / mds_error_state / mds_dlqr_ctrl through the
+host mirror multidronesim_b200.control.dlqr against (a) theta, P, K, action, u produced by the REFERENCE's own classes
+(tests/golden/dlqr.npz) and (b) oracle/sysid.py on a larger random batch.  fp64 1e-9, fp32 2e-4 of the matrix scale."""
+import numpy as np
+import pytest
+import torch
+
+from dlqr_cases import CASES
+from helpers import rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+DTYPES = [torch.float64, torch.float32]
+TOL = {torch.float64: 1e-9, torch.float32: 2e-4}
+
+
+def make_env(E, N, dtype):
+    import multidronesim_b200 as mds
+    return mds.BatchedCtrlAviary(drone_model=mds.DroneModel("cf2p"), num_drones=N, num_envs=E, dtype=dtype)
+
+
+def make_ctrl(env, cls_name):
+    import multidronesim_b200 as mds
+    from multidronesim_b200.control import dlqr
+    model = {"DecentralizedLQROmega": mds.model.LinearizedOmegaModel, "DecentralizedLQR": mds.model.LinearizedModel}.get(cls_name, mds.model.LinearizedYankOmegaModel)
+    models = [model(env) for _ in range(env.NUM_DRONES)]
+    if cls_name == "DecentralizedYOLQRCrazyflie":
+        return dlqr.DecentralizedYOLQRCrazyflie(env, models, np.eye(10), np.eye(4))
+    return getattr(dlqr, cls_name)(env, models)
+
+
+def dev(a, dtype):
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda", dtype=dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("tag", list(CASES))
+def test_rls_vs_reference_golden(golden, tag, dtype, lib_built):
+    g = golden["dlqr"]
+    m, _target, _fx, normalize, _proj, cls_name, method, kw = CASES[tag]
+    T, N = g[tag + "_phi"].shape[:2]
+    E = 5  # the same three robots replicated in five environments: every environment must reproduce the reference
+    env = make_env(E, N, dtype)
+    c = make_ctrl(env, cls_name)
+    th0, P0 = g[tag + "_theta0"], g[tag + "_P0"]
+    assert np.abs(c.theta.cpu().numpy()[:N] - th0).max() <= 1e-6 * np.abs(th0).max()  # the constructor builds the same prior
+    if normalize:
+        assert np.abs(c.P.cpu().numpy()[:N] - P0).max() <= 1e-6 * np.abs(P0).max()
+    c.set_theta(dev(np.tile(th0, (E, 1, 1)), dtype))
+    c.set_P(dev(np.tile(P0 if normalize else np.array([np.linalg.inv(p) for p in P0]), (E, 1, 1)), dtype))
+    for t in range(T):
+        getattr(c, method)(dev(np.tile(g[tag + "_phi"][t], (E, 1)), dtype), dev(np.tile(g[tag + "_x1"][t], (E, 1)), dtype), **kw)
+        th = c.theta.cpu().numpy().astype(np.float64).reshape(E, N, m + 4, m)
+        P = c.P.cpu().numpy().astype(np.float64).reshape(E, N, m + 4, m + 4)
+        if not normalize:
+            P = np.linalg.inv(P)
+        want_th, want_P = g[tag + "_theta"][t], g[tag + "_P"][t]
+        for e in range(E):
+            assert np.abs(th[e] - want_th).max() <= TOL[dtype] * max(1.0, np.abs(want_th).max()), (tag, t, e)
+            assert np.abs(P[e] - want_P).max() <= TOL[dtype] * np.abs(want_P).max(), (tag, t, e)
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_rls_random_batch_vs_oracle(tag, lib_built):
+    """1 021 drones (not a multiple of the block), random well-conditioned P and perturbed theta, two successive updates."""
+    from oracle import sysid
+    m, target, from_x1, normalize, project, cls_name, method, kw = CASES[tag]
+    E, N = 1021 // 3 + 1, 3
+    env = make_env(E, N, torch.float64)
+    D = E * N
+    c = make_ctrl(env, cls_name)
+    rng = np.random.default_rng(5)
+    th = c.theta.cpu().numpy().copy() * (1.0 + 0.05 * rng.normal(size=(D, m + 4, m)))
+    Lr = rng.normal(0, 0.3, (D, m + 4, m + 4))
+    P = np.eye(m + 4) + Lr @ Lr.transpose(0, 2, 1)
+    c.set_theta(dev(th, torch.float64))
+    c.set_P(dev(P, torch.float64))
+    codes = sysid.project_codes(m) if project else None
+    for step in range(2):
+        phi = np.concatenate([rng.normal(0, 0.1, (D, m)), rng.normal(0, 0.05, (D, 4))], axis=1)
+        x1 = phi[:, :m] + rng.normal(0, 0.01, (D, m))
+        resid = getattr(c, method)(dev(phi, torch.float64), dev(x1, torch.float64), **kw).cpu().numpy()
+        for d in range(D):
+            th[d], P[d], r = sysid.rls_update(th[d], P[d], phi[d], x1[d], env.CTRL_TIMESTEP, target, from_x1, normalize, project, codes,
+                                              first_of_env=(d % N == 0))
+            assert np.abs(resid[d] - r).max() <= 1e-9 * max(1.0, np.abs(r).max()), (tag, step, d)
+        assert np.abs(c.theta.cpu().numpy() - th).max() <= 1e-9 * np.abs(th).max(), (tag, step)
+        assert np.abs(c.P.cpu().numpy() - P).max() <= 1e-9 * np.abs(P).max(), (tag, step)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("tag", ["omega9", "torque12"])
+def test_dlqr_compute_vs_reference_golden(golden, tag, dtype, lib_built):
+    """compute_controller (CARE on the learned models; the 12-dim variant couples robots 0 and 1 through Q) and compute(obs)."""
+    g = golden["dlqr"]
+    N = g["ctrl_obs"].shape[0]
+    E = 4
+    env = make_env(E, N, dtype)
+    c = make_ctrl(env, "DecentralizedLQROmega" if tag == "omega9" else "DecentralizedLQR")
+    m = c.m
+    c.set_theta(dev(np.tile(g[f"ctrl_{tag}_theta"], (E, 1, 1)), dtype))
+    K = c.compute_controller()
+    Kg = g[f"ctrl_{tag}_K"]
+    if tag == "omega9":
+        for i in range(N):  # block-diagonal reference K: drone i keeps block (i, i); the other blocks are zero there
+            assert np.allclose(K[i], Kg[4 * i:4 * i + 4, m * i:m * i + m], rtol=1e-7, atol=1e-9 * np.abs(Kg).max())
+        off = Kg.copy()
+        for i in range(N):
+            off[4 * i:4 * i + 4, m * i:m * i + m] = 0
+        assert np.abs(off).max() <= 1e-9 * np.abs(Kg).max()
+    else:
+        assert np.allclose(K[0], Kg, rtol=1e-6, atol=1e-8 * np.abs(Kg).max())
+        assert np.abs(Kg[0:4, m:2 * m]).max() > 1e-5 * np.abs(Kg).max()  # the coupling really is there (2e-4 of the largest gain)
+    ref = dev(np.tile(g["ctrl_ref"], (E, 1)), dtype)
+    obs = dev(np.tile(g["ctrl_obs"], (E, 1)).reshape(E, N, 20), dtype)
+    c.set_reference(ref)
+    a, u = c.compute(obs)
+    tol = 10 * (1e-9 if dtype == torch.float64 else 1e-5)
+    a, u = a.cpu().numpy().astype(np.float64), u.cpu().numpy().astype(np.float64)
+    ug = g[f"ctrl_{tag}_u"].reshape(N, 4).copy()
+    if tag == "torque12":
+        ug[:, 0] += env.M * env.G  # the 12-dim reference returns the flat u without the hover offset (decentralized_lqr.py:336-342)
+    for e in range(E):
+        assert rel_err(a[e], g[f"ctrl_{tag}_action"]) < tol, (tag, e)
+        for col in range(4):  # thrust O(0.3), rates O(1), torques O(1e-3): compare column-wise against the column scale
+            scale = max(np.abs(ug[:, col]).max(), 1e-3)
+            assert np.abs(u[e][:, col] - ug[:, col]).max() <= tol * scale, (tag, e, col)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_error_state_vs_oracle(golden, dtype, lib_built):
+    """mds_error_state for the three parametrisations against oracle.controllers.Lqr.error_state on the reference-pinned inputs."""
+    from oracle import controllers as oc
+    from oracle.constants import drone_params
+    g = golden["controllers"]
+    obs, refs = g["cf2p_obs"], g["cf2p_ref"]
+    n = obs.shape[0]
+    env = make_env(n, 1, dtype)
+    oenv = drone_params("cf2p", 240, 240)
+    for cls_name, kind in (("DecentralizedLQR", "torque12"), ("DecentralizedLQROmega", "omega9"), ("DecentralizedLQRYankOmega", "yank10")):
+        c = make_ctrl(env, cls_name)
+        c.set_reference(dev(refs, dtype))
+        got = c.error_state(dev(obs.reshape(n, 1, 20), dtype)).cpu().numpy().reshape(n, -1)
+        o = oc.Lqr(oenv, kind, K=np.zeros((4, c.m)))
+        for k in range(n):
+            o.set_desired_trajectory(0, refs[k, 0:3], refs[k, 3:6], refs[k, 6:9], refs[k, 9], refs[k, 10])
+            want = o.error_state(obs[k])
+            assert np.abs(got[k] - want).max() <= (1e-9 if dtype == torch.float64 else 2e-5) * max(1.0, np.abs(want).max()), (kind, k)
+
+
+def test_dlqr_argument_errors(lib_built):
+    from multidronesim_b200 import _lib
+    env = make_env(2, 2, torch.float64)
+    c = make_ctrl(env, "DecentralizedLQROmega")
+    with pytest.raises(_lib.MdsError):
+        c.compute(torch.zeros(2, 2, 20, device="cuda", dtype=torch.float64))  # no gains yet
+    with pytest.raises(_lib.MdsError):
+        c.project_theta()  # the reference defines no projection for the 9-dim model

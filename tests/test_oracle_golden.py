@@ -232,3 +232,26 @@ def test_linear_roll_out_matches_reference_style_integration():
     assert np.max(np.abs(y - ref_default)) < 2e-2 * (1 + np.max(np.abs(y)))   # the reference's own rtol = 1e-3 across input jumps
     tight = solve_ivp(f, [0, ts[-1]], cv.obs_to_lin_model(obs[0], 12), t_eval=ts, rtol=1e-10, atol=1e-12, max_step=dt).y.T
     assert np.max(np.abs(y - tight)) < 1e-7 * (1 + np.max(np.abs(y)))
+
+
+def test_sysid_oracle_vs_reference_classes(golden):
+    """oracle/sysid.py against theta / P produced by the reference's own Decentralized* classes over four successive
+    updates of three robots (exact matrix exponential vs the reference's RK45 forward_predict included)."""
+    from dlqr_cases import CASES
+    from oracle import sysid
+    g = golden["dlqr"]
+    dt = float(g["dt"])
+    for tag, (m, target, from_x1, normalize, project, _cls, _method, _kw) in CASES.items():
+        info = not normalize
+        codes = sysid.project_codes(m) if project else None
+        th, P = g[tag + "_theta0"].copy(), g[tag + "_P0"].copy()
+        if info:
+            P = np.array([np.linalg.inv(p) for p in P])
+        T, N = g[tag + "_phi"].shape[:2]
+        for t in range(T):
+            for i in range(N):
+                th[i], P[i], _ = sysid.rls_update(th[i], P[i], g[tag + "_phi"][t, i], g[tag + "_x1"][t, i], dt, target, from_x1, normalize,
+                                                  project, codes, first_of_env=(i == 0))
+            Pc = np.array([np.linalg.inv(p) for p in P]) if info else P
+            assert np.abs(th - g[tag + "_theta"][t]).max() <= 1e-10 * max(1.0, np.abs(g[tag + "_theta"][t]).max()), (tag, t)
+            assert np.abs(Pc - g[tag + "_P"][t]).max() <= 1e-10 * np.abs(g[tag + "_P"][t]).max(), (tag, t)
