@@ -75,8 +75,11 @@ class CBF:
 
 class DroneCBF(CBF):
     def __init__(self, env, lin_models, zscale=2.0, safety_radius=1, cbf_poles=np.array([-2.2, -2.4]), room_bounds=None,
-                 omega_max=np.array([10, 10, 10]), order=2):
+                 omega_max=np.array([10, 10, 10]), order=2, allow_extra_obstacles=False):
         self.num_agents = len(lin_models)
+        # The reference fails with more obstacles than drones (cbf.py:388 indexes agent blocks by obstacle id, quirk B14);
+        # True lifts that: up to MAX_OBSTACLES for any N (builder extension).
+        self.allow_extra_obstacles = bool(allow_extra_obstacles)
         if self.num_agents != env.NUM_DRONES:
             raise ValueError("one linear model per drone of an environment is required")
         self.xdim = lin_models[0].A.shape[0]
@@ -95,6 +98,11 @@ class DroneCBF(CBF):
                          A=A, B=B, num_agents=N)
         self.lin_models, self.env = lin_models, env
 
+    def check_obstacle_count(self, n_obs):
+        if n_obs > self.num_agents and not getattr(self, "allow_extra_obstacles", False):
+            raise IndexError("more obstacles than drones: the reference's builder fails here (cbf/cbf.py:388); "
+                             "pass DroneCBF(..., allow_extra_obstacles=True) for the extension")
+
     def num_rows(self, n_obs=0):
         return _lib.load_library().mds_cbf_num_rows(self.order, self.num_agents, n_obs)
 
@@ -104,6 +112,7 @@ class DroneCBF(CBF):
         env = self.env
         E, N = env.NUM_ENVS, env.NUM_DRONES
         n_obs = 0 if obstacles is None else obstacles.shape[0]
+        self.check_obstacle_count(n_obs)
         m = self.num_rows(n_obs)
         G = torch.empty(E, m, 4 * N, device=env.device, dtype=env.dtype)
         h = torch.empty(E, m, device=env.device, dtype=env.dtype)

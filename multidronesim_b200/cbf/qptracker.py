@@ -56,6 +56,7 @@ class DroneQPTracker(object):
                 self._obst_key, self._obst = key, pack_obstacles(x_obs, obs_r_list, env.device, env.dtype)
             obst = self._obst
         n_obs = 0 if obst is None else int(obst.shape[0])
+        self.cbf.check_obstacle_count(n_obs)
         _lib.call("mds_cbf_qp", env.dtype, env._prm, self.cbf.c_params(),
                   _lib.ptr(_lib.require_cuda(obs, "obs", env.dtype, (E, N, _lib.OBS_DIM))),
                   _lib.ptr(_lib.require_cuda(xdes, "xdes", env.dtype, (E, N, self.xdim))),

@@ -1028,7 +1028,10 @@ static int cbf_args_ok(const MdsCbfParams* c, int N, int n_obs) {
   if (!c) return fail(MDS_ERR_ARG, "%s", "cbf: null params");
   if (c->order != 2 && c->order != 3) return fail(MDS_ERR_ARG, "%s", "cbf: order must be 2 or 3");
   if (N < 1 || N > MDS_MAX_DRONES_PER_ENV) return fail(MDS_ERR_ARG, "%s", "cbf: bad N");
-  if (n_obs < 0 || n_obs > MDS_MAX_OBSTACLES || n_obs > N) return fail(MDS_ERR_ARG, "%s", "cbf: n_obs must be <= min(N, MDS_MAX_OBSTACLES) (reference quirk B14)");
+  // The reference fails for n_obs > N (it indexes agent blocks by obstacle id, cbf.py:388, quirk B14) although nothing in
+  // the barrier needs it: every obstacle row uses only drone i's own model.  The library takes up to MDS_MAX_OBSTACLES for
+  // any N; the host mirror keeps the reference's refusal unless asked (DroneCBF(allow_extra_obstacles=True)).
+  if (n_obs < 0 || n_obs > MDS_MAX_OBSTACLES) return fail(MDS_ERR_ARG, "%s", "cbf: n_obs must be in [0, MDS_MAX_OBSTACLES]");
   return MDS_OK;
 }
 template <typename Real>

@@ -42,6 +42,8 @@ class FusedRollout:
         if len(rows) > _lib.MAX_OBSTACLES:
             raise ValueError("too many obstacles")
         cfg.num_obstacles = len(rows) if qp_tracker is not None else 0
+        if qp_tracker is not None:
+            qp_tracker.cbf.check_obstacle_count(cfg.num_obstacles)
         for i, r in enumerate(rows):
             for k in range(4):
                 cfg.obstacles[4 * i + k] = float(r[k])

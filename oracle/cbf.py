@@ -91,7 +91,7 @@ def pair_row(prm, xi, xj, xi_des, xj_des, Ds, cylinder=False):
     return a, prm.K[0] * h0 + prm.K[1] * h1 + prm.K[2] * h2 + Lf
 
 
-def build_ineq(prm, x, xdes, x_obs=None, obs_r=None):
+def build_ineq(prm, x, xdes, x_obs=None, obs_r=None, allow_extra_obstacles=False):
     """Dense (G, h) exactly as ``CBF._build_ineq_const`` (cbf/cbf.py:308-367)."""
     x, xdes = np.asarray(x, float), np.asarray(xdes, float)
     N = x.shape[0]
@@ -116,7 +116,8 @@ def build_ineq(prm, x, xdes, x_obs=None, obs_r=None):
     if x_obs is not None and obs_r is not None:
         if len(x_obs) != len(obs_r):
             raise AssertionError("The lists for Obstacle positions and radii must have the same length")
-        if len(x_obs) > N:
+        if len(x_obs) > N and not allow_extra_obstacles:
+            # builder extension when allowed: the row itself only ever uses drone i's own model
             raise IndexError("reference indexes agent blocks by obstacle id: N_obs <= N (quirk B14)")
         for i in range(N):
             for j in range(len(x_obs)):

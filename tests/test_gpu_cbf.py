@@ -156,7 +156,8 @@ def test_cylinder_obstacles_vs_oracle(golden, order, dtype, tol, lib_built):
     assert os.path.isfile(path) and 'cylinder radius="0.15" length="3.0"' in open(path).read()
 
 
-@pytest.mark.parametrize("N,n_obs,order", [(5, 2, 3), (16, 1, 3), (32, 2, 3), (3, 0, 2), (1, 1, 3), (6, 3, 2)])
+@pytest.mark.parametrize("N,n_obs,order", [(5, 2, 3), (16, 1, 3), (32, 2, 3), (3, 0, 2), (1, 1, 3), (6, 3, 2),
+                                           (2, 5, 3), (1, 3, 2), (4, 8, 3)])  # the last three: more obstacles than drones (SURVEY 8f-4 extension)
 def test_qp_other_group_sizes_vs_oracle(N, n_obs, order, lib_built):
     """Lane-group sizes other than the swarm's 8 (NP = 1, 4, 8 with idle lanes, 16, 32; odd N has no 'diameter' slot):
     dense rows and QP answers in fp64 against oracle/cbf.py + oracle/qp.py on random states."""
@@ -172,8 +173,13 @@ def test_qp_other_group_sizes_vs_oracle(N, n_obs, order, lib_built):
     Mdl = mds.model.LinearizedOmegaModel if order == 2 else mds.model.LinearizedYankOmegaModel
     poles = np.array([-2.2, -2.4]) if order == 2 else np.array([-3.0, -3.6, -5.6])
     rs, zs = (0.1, 1.0) if order == 2 else (0.125, 2.0)
-    cbf = mds.cbf.DroneCBF(env, [Mdl(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=order, cbf_poles=poles)
+    extra = n_obs > N
+    cbf = mds.cbf.DroneCBF(env, [Mdl(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=order, cbf_poles=poles, allow_extra_obstacles=extra)
     trk = mds.cbf.DroneQPTracker(cbf, order=order, num_robots=N, xdim=cbf.xdim, env=env)
+    if extra:  # without the opt-in the host mirror refuses like the reference's builder does (cbf/cbf.py:388)
+        strict = mds.cbf.DroneCBF(env, [Mdl(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=order, cbf_poles=poles)
+        with pytest.raises(IndexError):
+            strict.check_obstacle_count(n_obs)
     oenv = OracleCtrlAviary(ODM.CF2P, N, physics=OPH.DYN)
     prm = ocbf.CbfParams(oenv, order, zs, rs, tuple(poles))
     spread = 0.6 * N ** (1 / 3) * (2.5 if N >= 16 else 1.0)   # big groups: sparse enough that active sets stay under the cap of 12
@@ -192,7 +198,8 @@ def test_qp_other_group_sizes_vs_oracle(N, n_obs, order, lib_built):
     st, solved = trk.status.cpu().numpy(), 0
     for e in range(E):
         x = np.array([cv.obs_to_lin_model(obs[e, i], prm.xdim, oenv) for i in range(N)])
-        Gr, hr = ocbf.build_ineq(prm, x, xdes[e], None if obst is None else [o[:3] for o in obst], None if obst is None else [o[3] for o in obst])
+        Gr, hr = ocbf.build_ineq(prm, x, xdes[e], None if obst is None else [o[:3] for o in obst], None if obst is None else [o[3] for o in obst],
+                                 allow_extra_obstacles=extra)
         assert scaled_err(Gd[e].cpu().numpy(), Gr) < 1e-9 and scaled_err(hd[e].cpu().numpy(), hr) < 1e-9
         uo, _, so, _ = solve_qp(np.eye(4 * N), -unom[e].reshape(-1), Gr, hr)
         if so == 0 and st[e] == 0:

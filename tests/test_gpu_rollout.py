@@ -30,7 +30,8 @@ def build(E, N, dtype, physics, trajs_dev, ctrl, cbf_order=None, obstacles=None,
         Mdl = M.LinearizedOmegaModel if cbf_order == 2 else M.LinearizedYankOmegaModel
         poles = np.array([-2.2, -2.4]) if cbf_order == 2 else np.array([-3.0, -3.6, -5.6])
         rs, zs = (0.1, 1.0) if cbf_order == 2 else (0.125, 2.0)
-        cbf = mds.cbf.DroneCBF(env, [Mdl(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=cbf_order, cbf_poles=poles)
+        cbf = mds.cbf.DroneCBF(env, [Mdl(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=cbf_order, cbf_poles=poles,
+                               allow_extra_obstacles=obstacles is not None and len(obstacles) > N)
         trk = mds.cbf.DroneQPTracker(cbf, order=cbf_order, num_robots=N, xdim=cbf.xdim, env=env)
     ts = mds.trajectories.TrajectorySet(trajs_dev, dtype=dtype)
     return mds, env, c, trk, ts, mds.FusedRollout(env, ts, c, trk, obstacles)
@@ -160,8 +161,9 @@ def test_cbf_closed_loop_vs_oracle(order, N, dtype, tol, lib_built):
     assert st["qp_solves"] > 0 and n_active > 0
 
 
-@pytest.mark.parametrize("ctrl,cbf_order,N", [("yank10", 3, 8), ("omega9", 2, 3), ("geometric", None, 1)])
-def test_launch_plans_agree(ctrl, cbf_order, N, lib_built):
+@pytest.mark.parametrize("ctrl,cbf_order,N,n_obs", [("yank10", 3, 8, 1), ("omega9", 2, 3, 1), ("geometric", None, 1, 0),
+                                                    ("yank10", 3, 2, 4)])  # last: more obstacles than drones
+def test_launch_plans_agree(ctrl, cbf_order, N, n_obs, lib_built):
     """MdsRolloutCfg.stages: the fused plan (one launch per step), the two-launch plan and a launch-by-launch
     replay (1, then 5 x (K-1), then 2) are the same computation: bit-identical observations and statistics,
     including the observation log."""
@@ -173,7 +175,7 @@ def test_launch_plans_agree(ctrl, cbf_order, N, lib_built):
     for e in range(E):
         for j, sp in enumerate(specs):
             init[e, j] = otj.Lemniscate(**sp)(0.0)[0] + rng.normal(0, 0.02, 3) + np.array([0, 0, 0.04 * j])
-    obstacles = [[0.2, 0.0, 0.5, 0.1]] if cbf_order is not None else None
+    obstacles = [[0.2, 0.0, 0.5, 0.1], [-0.3, 0.1, 0.6, 0.08], [0.9, 0.4, 0.45, 0.12], [-0.8, -0.3, 0.5, -0.1]][:n_obs] if cbf_order is not None else None
     outs = []
     for plan in ("fused", "two", "replay", "loop"):
         mds, env, c, trk, ts, ro = build(E, N, dtype, "dyn_gnd_drag_dw", [T.Lemniscate(**sp) for sp in specs] * E, ctrl, cbf_order, obstacles, init)
