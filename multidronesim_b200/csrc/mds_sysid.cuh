@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(MDS_RLS_THREADS) rls_update_kernel(RlsP c, con
   } else {
     // forward_predict: e' = Ahat e + Bhat u over dt from e0, Ahat = theta[:m]^T, Bhat = theta[m:]^T.  The reference runs
     // scipy RK45 (its error over one 1/240 s step is far below its 1e-3 tolerance); here the exact solution
-    // e(dt) = e0 + sum_{k>=1} dt^k / k! A^(k-1) (A e0 + B u), 12 terms.
+    // e(dt) = e0 + sum_{k>=1} dt^k / k! A^(k-1) (A e0 + B u), summed until the terms vanish in Real.
     Real acc[M], nt[M];
 #pragma unroll
     for (int j = 0; j < M; ++j) {
@@ -120,10 +120,18 @@ __global__ void __launch_bounds__(MDS_RLS_THREADS) rls_update_kernel(RlsP c, con
       for (int j = 0; j < M; ++j) nt[j] += theta[(size_t)(i * M + j) * D + d] * zi;
     }
     Real coef = Real(c.dt);
+    const Real eps = sizeof(Real) == 4 ? Real(1e-9) : Real(1e-18);
 #pragma unroll 1
-    for (int k = 1; k <= 12; ++k) {
+    for (int k = 1; k <= 16; ++k) {
+      Real big = Real(0), mag = Real(0);
 #pragma unroll
-      for (int j = 0; j < M; ++j) { acc[j] += coef * nt[j]; s_term[j][tid] = nt[j]; nt[j] = Real(0); }
+      for (int j = 0; j < M; ++j) {
+        const Real inc = coef * nt[j];
+        acc[j] += inc;
+        big = max_(big, abs_(inc)); mag = max_(mag, abs_(acc[j]));
+        s_term[j][tid] = nt[j]; nt[j] = Real(0);
+      }
+      if (big <= eps * mag) break;  // the series has converged in Real (|A| dt ~ 0.05: 5-7 terms)
       coef *= Real(c.dt) / Real(k + 1);
 #pragma unroll 1
       for (int i = 0; i < M; ++i) {
