@@ -2,15 +2,17 @@
 decentralized_lqr_omega.py, decentralized_lqr_yank_omega.py, decentralized_yolqr_crazyflie.py), batched on device.
 
 Every drone d carries its own model estimate ``theta_d = [Ahat_d, Bhat_d]^T`` [(m+4), m], its RLS matrix ``P_d``
-[(m+4), (m+4)] and its own LQR gain ``K_d`` [4, m].  The reference stores one block-diagonal theta / K for the N robots of
-its single environment; the blocks never couple (Q and R are block diagonal, so the CARE solution is too), hence one small
-problem per drone here.  Device layout: PLANES -- entry k of drone d at ``[k, d]`` -- so that one thread per drone reads and
-writes coalesced lines (``mds_rls_update``, ``mds_dlqr_ctrl``).
+[(m+4), (m+4)] and its own LQR gain.  The reference stores one block-diagonal theta for the N robots of its single
+environment; the blocks never mix in the learning step, hence one small problem per drone here.  The gain is K_d [4, m]
+where Q and R are block diagonal (9- and 10-dim variants) and the drone's four rows of the environment's full
+[4N, mN] gain where Q couples robots (12-dim variant, decentralized_lqr.py:44-53).  Device layout: PLANES -- entry k of
+drone d at ``[k, d]`` -- so that one thread per drone reads and writes coalesced lines (``mds_rls_update``, ``mds_dlqr_ctrl``).
 
   theta_update / theta_update2 / approx_theta_update : one launch of ``mds_rls_update`` for all E*N drones
   compute                                            : one launch of ``mds_dlqr_ctrl``
-  compute_controller                                 : the CARE per drone with scipy on the HOST, exactly as the reference
-                                                       does (it is called once per learning phase, not per step)
+  compute_controller                                 : the CARE with scipy on the HOST, exactly as the reference does (called
+                                                       once per learning phase, not per step; one solve per DISTINCT model:
+                                                       ~1 ms each, so a swarm of distinct learned models is a host-bound call)
 """
 from __future__ import annotations
 

@@ -984,17 +984,28 @@ static int rls_impl(const MdsRlsCfg* cfg, const Real* phi, const Real* xtp1, Rea
   RlsP c;
   c.target = cfg->target; c.predict_from_xtp1 = cfg->predict_from_xtp1; c.normalize_gain = cfg->normalize_gain;
   c.project = cfg->project; c.drones_per_env = cfg->drones_per_env; c.dt = cfg->dt;
-  for (int w = 0; w < 3; ++w) c.zero_mask[w] = c.one_mask[w] = 0ull;
-  for (int k = 0; k < (cfg->m + 4) * cfg->m; ++k) {
-    MDS_REQUIRE(cfg->theta_code[k] <= 2, "rls_update: theta_code entries must be 0, 1 or 2");
-    if (cfg->theta_code[k] == 0) c.zero_mask[k >> 6] |= 1ull << (k & 63);
-    if (cfg->theta_code[k] == 2) c.one_mask[k >> 6] |= 1ull << (k & 63);
-  }
-  const int threads = MDS_RLS_THREADS, blocks = (D + threads - 1) / threads;
+  for (int i = 0; i < 16; ++i) c.row_code[i] = 0x55555555u;
+  for (int i = 0; i < cfg->m + 4; ++i)
+    for (int j = 0; j < cfg->m; ++j) {
+      const unsigned code = cfg->theta_code[i * cfg->m + j];
+      MDS_REQUIRE(code <= 2, "rls_update: theta_code entries must be 0, 1 or 2");
+      c.row_code[i] = (c.row_code[i] & ~(3u << (2 * j))) | (code << (2 * j));
+    }
   cudaStream_t cs = (cudaStream_t)stream;
-  if (cfg->m == 9) rls_update_kernel<Real, 9><<<blocks, threads, 0, cs>>>(c, phi, xtp1, theta, Pm, resid, D);
-  else if (cfg->m == 10) rls_update_kernel<Real, 10><<<blocks, threads, 0, cs>>>(c, phi, xtp1, theta, Pm, resid, D);
-  else rls_update_kernel<Real, 12><<<blocks, threads, 0, cs>>>(c, phi, xtp1, theta, Pm, resid, D);
+  cudaError_t ae = cudaSuccess;
+#define MDS_LAUNCH_RLS(MM)                                                                                                    \
+  do {                                                                                                                        \
+    const int threads = rls_threads<Real, MM>(), blocks = (D + threads - 1) / threads;                                        \
+    const size_t smem = (size_t)rls_words_per_thread<Real, MM>() * threads * sizeof(Real);                                    \
+    auto kern = cfg->project != MDS_RLS_PROJECT_NONE ? rls_update_kernel<Real, MM, true> : rls_update_kernel<Real, MM, false>; \
+    ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
+    if (ae == cudaSuccess) kern<<<blocks, threads, smem, cs>>>(c, phi, xtp1, theta, Pm, resid, D);                            \
+  } while (0)
+  if (cfg->m == 9) MDS_LAUNCH_RLS(9);
+  else if (cfg->m == 10) MDS_LAUNCH_RLS(10);
+  else MDS_LAUNCH_RLS(12);
+#undef MDS_LAUNCH_RLS
+  if (ae != cudaSuccess) return cuda_fail("rls_update: shared-memory opt-in", ae);
   return check_launch("rls_update");
 }
 static bool lqr_variant_ok(int v) { return v == MDS_CTRL_LQR_TORQUE || v == MDS_CTRL_LQR_OMEGA || v == MDS_CTRL_LQR_YANK; }

@@ -5,9 +5,8 @@
 //   control/dlqr/decentralized_lqr.py:132-183 (theta_update2 / theta_update), :185-240 (est_x_dot, approx_theta_update,
 //   project_theta), control/dlqr/decentralized_yolqr_crazyflie.py:228-290 (same for the 10-dim yank model)
 // One thread per drone.  theta [(m+4) x m] and P [(m+4) x (m+4)] live in HBM as planes of D Reals (element k of drone d at
-// [k * D + d]): every access of a warp is one coalesced 128-byte line.  Both matrices are swept twice (gain / prediction
-// first, rank-1 update second); the second sweep re-reads lines the same SM touched microseconds earlier (L1 / L2 hits),
-// so HBM sees each matrix once in and once out.
+// [k * D + d]): every access of a warp is one coalesced line.  Each thread stages its own columns in shared memory
+// (cp.async), so HBM sees each matrix once in and once out although the algorithm sweeps them twice.
 #pragma once
 #include "mds_common.cuh"
 
@@ -20,57 +19,91 @@ struct RlsP {
   int project;            // MDS_RLS_PROJECT_*
   int drones_per_env;
   double dt;
-  unsigned long long zero_mask[3], one_mask[3];  // project_theta: bit k of entry k = i * m + j of theta [(m+4)][m]: force 0 / force 1
+  unsigned row_code[16];  // project_theta: 2 bits per entry of theta row i (bits 2j, 2j+1 for column j): 0 -> zero, 1 -> keep, 2 -> one
 };
 
-// project_theta (decentralized_lqr.py:230-240, decentralized_yolqr_crazyflie.py:245-257) on one drone's theta planes.
-// A run-time loop over bit masks: unrolled, the ~190 predicated stores keep as many addresses live (255 registers).
-template <typename Real, int M> MDS_DEV void rls_project(const RlsP& c, Real* __restrict__ theta, size_t D, size_t d) {
-#pragma unroll 1
-  for (int k = 0; k < (M + 4) * M; ++k) {
-    const unsigned long long z = k < 64 ? c.zero_mask[0] : (k < 128 ? c.zero_mask[1] : c.zero_mask[2]);
-    const unsigned long long o = k < 64 ? c.one_mask[0] : (k < 128 ? c.one_mask[1] : c.one_mask[2]);
-    if ((z >> (k & 63)) & 1ull) theta[(size_t)k * D + d] = Real(0);
-    else if ((o >> (k & 63)) & 1ull) theta[(size_t)k * D + d] = Real(1);
-  }
+// 4- / 8-byte asynchronous global -> shared copy (LDGSTS): the whole theta / P column of a thread is in flight at once
+// without passing through registers.
+template <typename Real> MDS_DEV void cp_async_real(Real* smem_dst, const Real* gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (sizeof(Real) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
+MDS_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+template <typename Real, int M> constexpr int rls_words_per_thread() { return (M + 4) * (M + 4) + (M + 4) * M + 2 * (M + 4) + M; }
+// Threads per block: ONE warp (f32) / half a warp (f64).  A staged block is 40-63 KB, so 3-5 blocks share an SM and their
+// load / compute / store phases overlap; measured at 1 M drones, m = 9 f32: 0.61 ms at 32 threads, 0.80 ms at 64 or 128.
+#ifndef MDS_RLS_T32
+#define MDS_RLS_T32 32
+#endif
+template <typename Real, int M> constexpr int rls_threads() { return sizeof(Real) == 4 ? MDS_RLS_T32 : MDS_RLS_T32 / 2; }
 
 // One RLS step for drone d.  phi = [e_t (m), u_t (4)], x1 = e_{t+1} (m).
-// Loops over matrix ROWS are run-time loops (a fully unrolled sweep lets the scheduler hoist all (m+4)^2 loads at once:
-// 255 registers and spills); the vectors a row loop indexes (phi, w = P phi, the Taylor term) therefore sit in shared
-// memory as [index][thread] columns, and everything indexed by the unrolled column loop stays in registers.
-#define MDS_RLS_THREADS 128
-template <typename Real, int M>
-__global__ void __launch_bounds__(MDS_RLS_THREADS) rls_update_kernel(RlsP c, const Real* __restrict__ phi_in, const Real* __restrict__ x1_in,
-                                                                     Real* __restrict__ theta, Real* __restrict__ Pm, Real* __restrict__ resid_out, int D_) {
-  constexpr int MN = M + 4;
-  __shared__ Real s_phi[MN][MDS_RLS_THREADS], s_w[MN][MDS_RLS_THREADS], s_term[M][MDS_RLS_THREADS];
+// Both matrices are needed twice (gain / prediction over the WHOLE matrix first, rank-one update second), and a swarm's
+// in-flight footprint (1.1 KB per drone) exceeds L2, so a second sweep over HBM planes would double the traffic.  Each
+// thread therefore stages its own columns of P and theta in shared memory ([entry][thread]: conflict-free) with cp.async,
+// works there (run-time row loops, register-resident column vectors) and writes the updated entries straight back:
+// HBM sees every entry once in and once out.  A thread only ever touches its own shared column.
+// PROJECT: whether project_theta is applied at all (compile-time: the unprojected variants carry none of its code)
+template <typename Real, int M, bool PROJECT>
+__global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP c, const Real* __restrict__ phi_in, const Real* __restrict__ x1_in,
+                                                                         Real* __restrict__ theta, Real* __restrict__ Pm, Real* __restrict__ resid_out,
+                                                                         int D_) {
+  constexpr int MN = M + 4, T = rls_threads<Real, M>();
+  extern __shared__ __align__(16) unsigned char rls_smem[];
   const int tid = threadIdx.x;
-  const size_t d = (size_t)blockIdx.x * blockDim.x + tid, D = (size_t)D_;
-  if (d >= D) return;  // no block-level synchronisation below: every thread only touches its own shared column
-  Real x1[M];
+  Real* sP = reinterpret_cast<Real*>(rls_smem) + tid;  // entry k at sP[k * T]
+  Real* sT = sP + MN * MN * T;
+  Real* s_phi = sT + MN * M * T;
+  Real* s_w = s_phi + MN * T;
+  Real* s_term = s_w + MN * T;
+  // project_theta codes per theta row, block-shared (a parameter array indexed by the run-time row would be copied to
+  // local memory); the only block barrier of the kernel, before any thread leaves
+  __shared__ unsigned s_code[16];
+  if (PROJECT && tid == 0) {
 #pragma unroll
-  for (int i = 0; i < MN; ++i) s_phi[i][tid] = phi_in[d * MN + i];
+    for (int i = 0; i < MN; ++i) s_code[i] = c.row_code[i];
+  }
+  if (PROJECT) __syncthreads();
+  const size_t d = (size_t)blockIdx.x * T + tid, D = (size_t)D_;
+  if (d >= D) return;
+#pragma unroll 1
+  for (int k = 0; k < MN * MN; ++k) cp_async_real(sP + k * T, Pm + (size_t)k * D + d);
+#pragma unroll 1
+  for (int k = 0; k < MN * M; ++k) cp_async_real(sT + k * T, theta + (size_t)k * D + d);
+  Real x1[M], phi[MN], v[MN];
+#pragma unroll
+  for (int i = 0; i < MN; ++i) { phi[i] = phi_in[d * MN + i]; s_phi[i * T] = phi[i]; v[i] = Real(0); }
 #pragma unroll
   for (int i = 0; i < M; ++i) x1[i] = x1_in[d * M + i];
+  cp_async_wait_all();
   // robots after the first of an env see the projection of the earlier robots' loop iterations before their own update
-  if (c.project == MDS_RLS_PROJECT_LOOP && (d % (size_t)c.drones_per_env) != 0) rls_project<Real, M>(c, theta, D, d);
-  // ---- gain: w = P phi, v = phi' P, s = 1 + phi' P phi
-  Real v[MN], phi[MN];
+  const bool pre_project = PROJECT && c.project == MDS_RLS_PROJECT_LOOP && (d % (size_t)c.drones_per_env) != 0;
+  if (pre_project) {
+#pragma unroll 1
+    for (int i = 0; i < MN; ++i) {
+      const unsigned word = s_code[i];
 #pragma unroll
-  for (int j = 0; j < MN; ++j) { v[j] = Real(0); phi[j] = s_phi[j][tid]; }
+      for (int j = 0; j < M; ++j) {
+        const unsigned code = (word >> (2 * j)) & 3u;
+        if (code != 1u) sT[(i * M + j) * T] = code == 0u ? Real(0) : Real(1);
+      }
+    }
+  }
+  // ---- gain: w = P phi, v = phi' P, s = 1 + phi' P phi
   Real s = Real(1);
 #pragma unroll 1
   for (int i = 0; i < MN; ++i) {
-    const Real phi_i = s_phi[i][tid];
+    const Real phi_i = s_phi[i * T];
     Real wi = Real(0);
 #pragma unroll
     for (int j = 0; j < MN; ++j) {
-      const Real p = Pm[(size_t)(i * MN + j) * D + d];
+      const Real p = sP[(i * MN + j) * T];
       wi += p * phi[j];
       v[j] += phi_i * p;
     }
-    s_w[i][tid] = wi;
+    s_w[i * T] = wi;
     s += phi_i * wi;
   }
   const Real inv_s = Real(1) / s;
@@ -98,9 +131,9 @@ __global__ void __launch_bounds__(MDS_RLS_THREADS) rls_update_kernel(RlsP c, con
     }
 #pragma unroll 1
     for (int i = 0; i < MN; ++i) {
-      const Real phi_i = s_phi[i][tid];
+      const Real phi_i = s_phi[i * T];
 #pragma unroll
-      for (int j = 0; j < M; ++j) r[j] -= theta[(size_t)(i * M + j) * D + d] * phi_i;
+      for (int j = 0; j < M; ++j) r[j] -= sT[(i * M + j) * T] * phi_i;
     }
   } else {
     // forward_predict: e' = Ahat e + Bhat u over dt from e0, Ahat = theta[:m]^T, Bhat = theta[m:]^T.  The reference runs
@@ -110,14 +143,14 @@ __global__ void __launch_bounds__(MDS_RLS_THREADS) rls_update_kernel(RlsP c, con
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       acc[j] = c.predict_from_xtp1 ? x1[j] : phi[j];
-      s_term[j][tid] = acc[j];
+      s_term[j * T] = acc[j];
       nt[j] = Real(0);
     }
 #pragma unroll 1
     for (int i = 0; i < MN; ++i) {  // A e0 + B u = theta' [e0; u]
-      const Real zi = i < M ? s_term[i][tid] : s_phi[i][tid];
+      const Real zi = i < M ? s_term[i * T] : s_phi[i * T];
 #pragma unroll
-      for (int j = 0; j < M; ++j) nt[j] += theta[(size_t)(i * M + j) * D + d] * zi;
+      for (int j = 0; j < M; ++j) nt[j] += sT[(i * M + j) * T] * zi;
     }
     Real coef = Real(c.dt);
     const Real eps = sizeof(Real) == 4 ? Real(1e-9) : Real(1e-18);
@@ -129,15 +162,15 @@ __global__ void __launch_bounds__(MDS_RLS_THREADS) rls_update_kernel(RlsP c, con
         const Real inc = coef * nt[j];
         acc[j] += inc;
         big = max_(big, abs_(inc)); mag = max_(mag, abs_(acc[j]));
-        s_term[j][tid] = nt[j]; nt[j] = Real(0);
+        s_term[j * T] = nt[j]; nt[j] = Real(0);
       }
       if (big <= eps * mag) break;  // the series has converged in Real (|A| dt ~ 0.05: 5-7 terms)
       coef *= Real(c.dt) / Real(k + 1);
 #pragma unroll 1
       for (int i = 0; i < M; ++i) {
-        const Real ti = s_term[i][tid];
+        const Real ti = s_term[i * T];
 #pragma unroll
-        for (int j = 0; j < M; ++j) nt[j] += theta[(size_t)(i * M + j) * D + d] * ti;
+        for (int j = 0; j < M; ++j) nt[j] += sT[(i * M + j) * T] * ti;
       }
     }
 #pragma unroll
@@ -147,20 +180,29 @@ __global__ void __launch_bounds__(MDS_RLS_THREADS) rls_update_kernel(RlsP c, con
 #pragma unroll
     for (int j = 0; j < M; ++j) resid_out[d * M + j] = r[j];
   }
-  // ---- theta += L r',  P -= (w / s) v
+  // ---- theta += L r' (then project_theta), P -= (w / s) v: straight from the staged columns back to the HBM planes
 #pragma unroll 1
   for (int i = 0; i < MN; ++i) {
-    const Real wi = s_w[i][tid];
+    const Real wi = s_w[i * T];
     const Real Li = c.normalize_gain ? wi * inv_s : wi;
+    if (!PROJECT) {
 #pragma unroll
-    for (int j = 0; j < M; ++j) theta[(size_t)(i * M + j) * D + d] += Li * r[j];
+      for (int j = 0; j < M; ++j) theta[(size_t)(i * M + j) * D + d] = sT[(i * M + j) * T] + Li * r[j];
+    } else {
+      const unsigned word = s_code[i];
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        const unsigned code = (word >> (2 * j)) & 3u;
+        const Real val = sT[(i * M + j) * T] + Li * r[j];
+        theta[(size_t)(i * M + j) * D + d] = code == 1u ? val : (code == 0u ? Real(0) : Real(1));
+      }
+    }
   }
-  if (c.project != MDS_RLS_PROJECT_NONE) rls_project<Real, M>(c, theta, D, d);
 #pragma unroll 1
   for (int i = 0; i < MN; ++i) {
-    const Real Li = s_w[i][tid] * inv_s;
+    const Real Li = s_w[i * T] * inv_s;
 #pragma unroll
-    for (int j = 0; j < MN; ++j) Pm[(size_t)(i * MN + j) * D + d] -= Li * v[j];
+    for (int j = 0; j < MN; ++j) Pm[(size_t)(i * MN + j) * D + d] = sP[(i * MN + j) * T] - Li * v[j];
   }
 }
 
