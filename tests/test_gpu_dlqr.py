@@ -155,3 +155,58 @@ def test_dlqr_argument_errors(lib_built):
         c.compute(torch.zeros(2, 2, 20, device="cuda", dtype=torch.float64))  # no gains yet
     with pytest.raises(_lib.MdsError):
         c.project_theta()  # the reference defines no projection for the 9-dim model
+
+
+def test_learning_loop_vs_oracle(lib_built):
+    """The warm-up learning loop of simulations/CBFTestOrd3.py:153-198 (random_warmup): random inputs -> inner loop -> env.step
+    -> error states -> theta_update, 40 control steps, every stage on device (mds_error_state, mds_lowlevel,
+    mds_physics_step, mds_rls_update) against the same loop over the oracle (aviary + controllers + sysid), fp64."""
+    import multidronesim_b200 as mds
+    from oracle import controllers as oc
+    from oracle import conversions as cv
+    from oracle import sysid
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel as ODM, Physics as OPH
+    E, N, steps, dtype = 3, 2, 40, torch.float64
+    rng = np.random.default_rng(21)
+    init = rng.uniform(-0.5, 0.5, (E, N, 3)) + np.array([0, 0, 1.0])
+    env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=N, num_envs=E, dtype=dtype, initial_xyzs=init, physics=mds.Physics.DYN)
+    dl = mds.control.DecentralizedLQROmega(env, [mds.model.LinearizedOmegaModel(env) for _ in range(N)])
+    dl.set_desired_trajectory(None, dev(init.reshape(-1, 3), dtype), np.zeros(3), np.zeros(3), 0.0, 0.0)
+    mg = env.M * env.G
+    us = np.concatenate([rng.uniform(0.7 * mg, 1.5 * mg, (steps, E, N, 1)), rng.uniform(-0.2, 0.2, (steps, E, N, 3))], axis=-1)  # sigma1-like draws
+    # oracle side, one reference-style loop per environment
+    oenvs = [OracleCtrlAviary(ODM.CF2P, N, initial_xyzs=init[e], physics=OPH.DYN) for e in range(E)]
+    octl = [[oc.Lqr(oenvs[e], "omega9", low_level=oc.ThrustOmegaPid(oenvs[e]), K=np.zeros((4, 9))) for _ in range(N)] for e in range(E)]
+    th = dl.theta.cpu().numpy().copy().reshape(E, N, 13, 9)
+    P = dl.P.cpu().numpy().copy().reshape(E, N, 13, 13)
+    oobs = [o.reset()[0] for o in oenvs]
+    obs = env.reset()[0]
+    for i in range(steps):
+        u = dev(us[i], dtype)
+        e_t = dl.error_state(obs).clone()
+        phis = torch.cat([e_t, u], dim=-1)
+        action = dl.compute_low_level(u, obs)
+        obs = env.step(action)[0]
+        e_tp1 = dl.error_state(obs).clone()
+        if i != 0:
+            dl.theta_update(phis, e_tp1)
+        for e in range(E):
+            ophis, act = [], np.zeros((N, 4))
+            for j in range(N):
+                c = octl[e][j]
+                c.set_desired_trajectory(j, init[e, j], np.zeros(3), np.zeros(3), 0.0, 0.0)
+                ophis.append(np.hstack([c.error_state(oobs[e][j]), us[i, e, j]]))
+                act[j] = c.compute_low_level(us[i, e, j].copy(), oobs[e][j])
+            oobs[e] = oenvs[e].step(act)[0]
+            if i != 0:
+                for j in range(N):
+                    th[e, j], P[e, j], _ = sysid.rls_update(th[e, j], P[e, j], ophis[j], octl[e][j].error_state(oobs[e][j]), env.CTRL_TIMESTEP,
+                                                            sysid.TARGET_PREDICT, True, True)
+    got_th = dl.theta.cpu().numpy().reshape(E, N, 13, 9)
+    got_P = dl.P.cpu().numpy().reshape(E, N, 13, 13)
+    assert np.abs(obs.cpu().numpy() - np.array(oobs))[..., :16].max() < 1e-8
+    assert np.abs(got_th - th).max() <= 1e-8 * np.abs(th).max(), np.abs(got_th - th).max()
+    assert np.abs(got_P - P).max() <= 1e-8 * np.abs(P).max()
+    prior = np.hstack([mds.model.LinearizedOmegaModel(env).Ahat, mds.model.LinearizedOmegaModel(env).Bhat]).T
+    assert np.abs(th - prior).max() > 1e-3  # the models really moved
