@@ -161,7 +161,10 @@ MDS_DEV Ref<Real> eval_traj(const typename TrajSpecT<Real>::spec& sp, const type
     case MDS_TRAJ_WAIT: return eval_wait<Real>(sp.p);
     default: break;
   }
-  return eval_traj_table<Real>(sp, segs, t);
+  // the out-of-line walk gets its OWN copy: passing `sp` itself would let its address escape and pin the caller's
+  // descriptor (read by every closed-form generator above) in local memory
+  const typename TrajSpecT<Real>::spec table_spec = sp;
+  return eval_traj_table<Real>(table_spec, segs, t);
 }
 
 }  // namespace mds
