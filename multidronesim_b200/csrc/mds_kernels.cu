@@ -78,6 +78,13 @@ MDS_DEV GroupMap group_map(int N, int NP, int E) {
   return g;
 }
 
+// Compile-time drone count that fills its lane group (N == NP, e.g. the swarm's 8): every lane of a valid environment
+// maps to a drone, so `valid` is a compile-time `true` inside the env_valid region and the per-stage `if (g.valid)`
+// guards fold away (uniform branches: fewer instructions, no measurable change in time).
+template <int NT> MDS_DEV void full_group_hint(GroupMap& g) {
+  if (NT > 0 && (NT & (NT - 1)) == 0) g.valid = true;
+}
+
 // Downwash sum for this lane's drone over its env mates; positions staged in shared memory.
 // Called by every lane of the group (two group syncs).
 template <typename Real>
@@ -292,8 +299,9 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_PHYS_MINB :
                                                                   const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N_rt, int NP_rt) {
   __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
-  const GroupMap g = group_map(N, NP, E);
+  GroupMap g = group_map(N, NP, E);
   if (!g.env_valid) return;  // whole groups leave together
+  full_group_hint<NT>(g);
   physics_body(P, st, action, fext, obs, sm_pos, g, N);
 }
 
@@ -781,9 +789,10 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_CTRL_MINB :
   extern __shared__ __align__(32) unsigned char smem_raw[];
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
-  const GroupMap g = group_map(N, NP, E);
+  GroupMap g = group_map(N, NP, E);
   StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
   if (g.env_valid) {
+    full_group_hint<NT>(g);
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
     Obs<Real> o;
     typename TrajSpecT<Real>::spec spec;
@@ -814,9 +823,10 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB 
   __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
-  const GroupMap g = group_map(N, NP, E);
+  GroupMap g = group_map(N, NP, E);
   StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
   if (g.env_valid) {
+    full_group_hint<NT>(g);
     if (g.valid) {
       prefetch_l1(specs + g.d);
       prefetch_l1(reinterpret_cast<const char*>(specs + g.d) + 32);
@@ -857,11 +867,12 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
   const PidP<Real> pid_s = STAGE ? PidP<Real>{sm_pid_a, sm_pid_b} : pid;
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
-  const GroupMap g = group_map(N, NP, E);
+  GroupMap g = group_map(N, NP, E);
   StepStats acc = {0.f, 1e30f, 0, 0, 0, 0};
   float max_err = 0.f;
   int steps_done = 0;
   if (g.env_valid) {
+    full_group_hint<NT>(g);
     Obs<Real> o;
     V3<Real> wb = {Real(0), Real(0), Real(0)};  // body rates: the one part of the state the observation does not carry
     // The trajectory descriptor is read every step; its address escapes into the out-of-line table walk, so as an

@@ -37,7 +37,7 @@ def test_struct_sizes_match_c():
 #include <stdio.h>
 #include "mds_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(MdsDslPidState), sizeof(MdsDslPidGains), sizeof(MdsDroneParams), sizeof(MdsState), sizeof(MdsPidState),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(MdsRlsCfg), sizeof(MdsDslPidState), sizeof(MdsDslPidGains), sizeof(MdsDroneParams), sizeof(MdsState), sizeof(MdsPidState),
          sizeof(MdsGeoGains), sizeof(MdsLqrGains), sizeof(MdsCbfParams), sizeof(MdsRolloutCfg), sizeof(MdsTrajSpecF32),
          sizeof(MdsTrajSpecF64), sizeof(MdsTrajSegF32), sizeof(MdsTrajSegF64));
   return 0;
@@ -48,7 +48,7 @@ int main(void) {
         exe = os.path.join(d, "s")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)  # header is plain C
         sizes = [int(x) for x in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
-    py = [ctypes.sizeof(t) for t in (_lib.DslPidState, _lib.DslPidGains, _lib.DroneParams, _lib.State, _lib.PidState, _lib.GeoGains, _lib.LqrGains, _lib.CbfParams, _lib.RolloutCfg)]
+    py = [ctypes.sizeof(t) for t in (_lib.RlsCfg, _lib.DslPidState, _lib.DslPidGains, _lib.DroneParams, _lib.State, _lib.PidState, _lib.GeoGains, _lib.LqrGains, _lib.CbfParams, _lib.RolloutCfg)]
     py += [_lib.traj_spec_dtype("f4").itemsize, _lib.traj_spec_dtype("f8").itemsize, _lib.traj_seg_dtype("f4").itemsize, _lib.traj_seg_dtype("f8").itemsize]
     assert py == sizes
 
