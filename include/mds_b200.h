@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MDS_ABI_VERSION 5
+#define MDS_ABI_VERSION 6
 #define MDS_MAX_DRONES_PER_ENV 32
 #define MDS_MAX_OBSTACLES 8
 #define MDS_OBS_DIM 20
@@ -326,6 +326,14 @@ int mds_dlqr_ctrl_f32(const MdsDroneParams* prm, int variant, const float* K_dev
                       float* u_dev, float* action_dev, MdsPidState pid, int E, int N, void* stream);
 int mds_dlqr_ctrl_f64(const MdsDroneParams* prm, int variant, const double* K_dev, int coupled, const double* obs_dev, const double* ref_dev,
                       double* u_dev, double* action_dev, MdsPidState pid, int E, int N, void* stream);
+
+/* compute_controller (decentralized_lqr_omega.py:185-204): K_d = R^-1 B_d' X_d, X_d the stabilising solution of the
+ * continuous-time algebraic Riccati equation of drone d's learned model theta_d = [A_d, B_d]^T, for diagonal Q (q_diag [m])
+ * and R (r_diag [4], host arrays).  One warp per drone, double precision inside (matrix sign function; the reference calls
+ * scipy.linalg.solve_continuous_are on the host).  theta_dev [(m+4)*m][D] planes -> K_dev [4*m][D] planes;
+ * status_dev optional [D]: 0 ok, 1 no stabilising solution found (K_d left untouched). */
+int mds_care_gains_f32(int m, const double* q_diag, const double* r_diag, const float* theta_dev, float* K_dev, int* status_dev, int D, void* stream);
+int mds_care_gains_f64(int m, const double* q_diag, const double* r_diag, const double* theta_dev, double* K_dev, int* status_dev, int D, void* stream);
 
 /* launch plan (a MdsRolloutCfg.stages value) that stages == 0 selects for E envs of N drones */
 int mds_rollout_plan(int E, int N);

@@ -10,9 +10,9 @@ drone d at ``[k, d]`` -- so that one thread per drone reads and writes coalesced
 
   theta_update / theta_update2 / approx_theta_update : one launch of ``mds_rls_update`` for all E*N drones
   compute                                            : one launch of ``mds_dlqr_ctrl``
-  compute_controller                                 : the CARE with scipy on the HOST, exactly as the reference does (called
-                                                       once per learning phase, not per step; one solve per DISTINCT model:
-                                                       ~1 ms each, so a swarm of distinct learned models is a host-bound call)
+  compute_controller                                 : one launch of ``mds_care_gains`` (one warp per drone solves its Riccati
+                                                       equation) for diagonal per-drone weights; scipy on the host, like the
+                                                       reference, for the robot-coupled 12-dim case and non-diagonal weights
 """
 from __future__ import annotations
 
@@ -142,11 +142,49 @@ class _DecentralizedBase(BaseController):
         N = self.num_robots
         return np.kron(np.eye(N), self.ind_Q), np.kron(np.eye(N), self.ind_R)
 
-    def compute_controller(self, force_diagonal=False):
-        """Gains from the CARE of the learned models -- host, scipy, like the reference (decentralized_lqr_omega.py:160-183,
-        decentralized_lqr.py:300-317); identical models share one solve.  Block-diagonal Q, R (or ``force_diagonal``): one
-        m x m problem per drone, K_d [4, m].  Coupled Q (12-dim variant, N >= 2): one mN x mN problem per environment and
-        the full K [4N, mN], of which drone d keeps its four rows."""
+    def compute_controller(self, force_diagonal=False, solver="auto"):
+        """Gains from the continuous-time Riccati equation of the learned models (decentralized_lqr_omega.py:185-204,
+        decentralized_lqr.py:300-317).
+
+        Block-diagonal Q, R (or ``force_diagonal``): one m x m problem per drone, K_d [4, m] -- solved ON DEVICE by
+        ``mds_care_gains`` (one warp per drone, matrix sign function in double; <= 2e-12 of scipy's answer) when Q and R are
+        diagonal, as all of the reference's Bryson weights are.  ``solver="host"`` forces the reference's own route
+        (scipy.linalg.solve_continuous_are per DISTINCT model, ~1 ms each); it is also what non-diagonal weights and the
+        robot-coupled Q of the 12-dim variant with N >= 2 (one mN x mN problem per environment, full K [4N, mN]) use.
+        ``self.care_status`` [D] (device, int32) after a device solve: 0 ok, 1 no stabilising solution (gain left as it was)."""
+        N = self.num_robots
+        coupled = bool(self.COUPLED and N >= 2 and not force_diagonal)
+        diag_w = np.count_nonzero(self.ind_Q - np.diag(np.diag(self.ind_Q))) == 0 and np.count_nonzero(self.ind_R - np.diag(np.diag(self.ind_R))) == 0
+        if solver not in ("auto", "device", "host"):
+            raise ValueError("solver must be 'auto', 'device' or 'host'")
+        if solver == "device" and (coupled or not diag_w):
+            raise _lib.MdsError("the device Riccati solver takes diagonal, per-drone Q and R; use solver='host'")
+        if solver != "host" and not coupled and diag_w:
+            return self._compute_controller_device()
+        return self._compute_controller_host(force_diagonal)
+
+    def _compute_controller_device(self):
+        env = self.env
+        D = env.NUM_TOTAL
+        self._coupled = False
+        if self.K_planes.shape[0] != self.n * self.m:
+            self.K_planes = torch.zeros(self.n * self.m, D, device=env.device, dtype=env.dtype)
+        if getattr(self, "care_status", None) is None:
+            self.care_status = torch.zeros(D, device=env.device, dtype=torch.int32)
+        q = (_lib.C.c_double * self.m)(*np.diag(self.ind_Q).tolist())
+        r = (_lib.C.c_double * 4)(*np.diag(self.ind_R).tolist())
+        _lib.call("mds_care_gains", env.dtype, self.m, q, r, _lib.ptr(self.theta_planes), _lib.ptr(self.K_planes), _lib.ptr(self.care_status), D,
+                  _lib.stream_ptr(env.device))
+        self.K = self.K_planes  # planes [4*m, D]; K_matrix(d) gives one drone's [4, m]
+        return self.K
+
+    def K_matrix(self, i=0, env_idx=0):
+        """[4, m] gain of robot i in environment env_idx (uncoupled variants)."""
+        if self._coupled:
+            raise _lib.MdsError("coupled gain: read self.K [E, 4N, mN]")
+        return self.K_planes[:, self._drone(i, env_idx)].reshape(self.n, self.m).clone()
+
+    def _compute_controller_host(self, force_diagonal=False):
         th = self.theta.detach().to("cpu", torch.float64).numpy()
         D, N, m, n = th.shape[0], self.num_robots, self.m, self.n
         cache = {}

@@ -162,7 +162,7 @@ MDS_DEV void lqr_input(const DroneP<Real>& P, const LqrP<Real>& L, int variant, 
   if (variant != MDS_CTRL_LQR_YANK) u[0] += P.m * P.g;
 }
 // The same law with a gain of the drone's own (decentralised LQR: every drone carries the K of its learned model;
-// decentralized_lqr_omega.py:185-204, decentralized_lqr.py:326-342).  K planes: element (i, k) of drone d at [(i*dim+k)*D + d].
+// decentralized_lqr_omega.py:212-231, decentralized_lqr.py:326-342).  K planes: element (i, k) of drone d at [(i*dim+k)*D + d].
 template <typename Real>
 MDS_DEV void dlqr_input(const DroneP<Real>& P, const Real* __restrict__ K, size_t D, size_t d, int variant, const Obs<Real>& o, const Ref<Real>& r,
                         Real u[4]) {

@@ -1022,6 +1022,30 @@ static int rls_impl(const MdsRlsCfg* cfg, const Real* phi, const Real* xtp1, Rea
   if (ae != cudaSuccess) return cuda_fail("rls_update: shared-memory opt-in", ae);
   return check_launch("rls_update");
 }
+template <typename Real>
+static int care_impl(int m, const double* q, const double* r, const Real* theta, Real* K, int* status, int D, void* stream) {
+  MDS_REQUIRE(q && r && theta && K && D > 0, "care_gains: bad argument");
+  MDS_REQUIRE(m == 9 || m == 10 || m == 12, "care_gains: m must be 9, 10 or 12");
+  CareP c;
+  for (int i = 0; i < 12; ++i) c.sq[i] = 1.0;
+  for (int i = 0; i < m; ++i) { MDS_REQUIRE(q[i] > 0.0, "care_gains: Q must be diagonal and positive"); c.sq[i] = sqrt(q[i]); }
+  for (int i = 0; i < 4; ++i) { MDS_REQUIRE(r[i] > 0.0, "care_gains: R must be diagonal and positive"); c.rinv[i] = 1.0 / r[i]; }
+  const int blocks = (D + MDS_CARE_WARPS - 1) / MDS_CARE_WARPS;
+  cudaStream_t cs = (cudaStream_t)stream;
+  cudaError_t ae = cudaSuccess;
+#define MDS_LAUNCH_CARE(MM)                                                                                        \
+  do {                                                                                                             \
+    const size_t smem = (size_t)care_doubles_per_warp<MM>() * MDS_CARE_WARPS * sizeof(double);                     \
+    ae = cudaFuncSetAttribute(care_gain_kernel<Real, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (ae == cudaSuccess) care_gain_kernel<Real, MM><<<blocks, 32 * MDS_CARE_WARPS, smem, cs>>>(c, theta, K, status, D); \
+  } while (0)
+  if (m == 9) MDS_LAUNCH_CARE(9);
+  else if (m == 10) MDS_LAUNCH_CARE(10);
+  else MDS_LAUNCH_CARE(12);
+#undef MDS_LAUNCH_CARE
+  if (ae != cudaSuccess) return cuda_fail("care_gains: shared-memory opt-in", ae);
+  return check_launch("care_gains");
+}
 static bool lqr_variant_ok(int v) { return v == MDS_CTRL_LQR_TORQUE || v == MDS_CTRL_LQR_OMEGA || v == MDS_CTRL_LQR_YANK; }
 template <typename Real>
 static int error_state_impl(const MdsDroneParams* prm, int variant, const Real* obs, const Real* ref, Real* e, int D, void* stream) {
@@ -1354,6 +1378,9 @@ int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 *
   }                                                                                                                                                \
   int mds_rls_update_##SUF(const MdsRlsCfg* cfg, const REAL* phi, const REAL* xtp1, REAL* theta, REAL* Pm, REAL* resid, int D, void* stream) {          \
     return rls_impl<REAL>(cfg, phi, xtp1, theta, Pm, resid, D, stream);                                                                            \
+  }                                                                                                                                                \
+  int mds_care_gains_##SUF(int m, const double* q, const double* r, const REAL* theta, REAL* K, int* status, int D, void* stream) {                 \
+    return care_impl<REAL>(m, q, r, theta, K, status, D, stream);                                                                                  \
   }                                                                                                                                                \
   int mds_error_state_##SUF(const MdsDroneParams* prm, int variant, const REAL* obs, const REAL* ref, REAL* e, int D, void* stream) {              \
     return error_state_impl<REAL>(prm, variant, obs, ref, e, D, stream);                                                                           \

@@ -65,5 +65,10 @@ for name, cls, model, dtype, method in (
         gbs = algo * D / (ms * 1e-3) / 1e9
         print(json.dumps({"case": f"dlqr compute m=9 {'f32' if sz == 4 else 'f64'}", "drones": D, "ms": round(ms, 4), "drone_steps_per_s": D / (ms * 1e-3),
                           "algorithmic_bytes_per_drone": algo, "achieved_gbs": round(gbs, 1), "peak_gbs": peak, "frac": round(gbs / peak, 3), "bound": "hbm"}))
+    if method == "theta_update":  # the Riccati solve for all (by now distinct) learned models, one warp per drone
+        ms = timed(lambda: c.compute_controller(force_diagonal=True, solver="device"), 3)
+        bad = int(c.care_status.sum())
+        print(json.dumps({"case": f"care_gains m={m} {'f32' if sz == 4 else 'f64'}", "drones": D, "ms": round(ms, 3), "drone_solves_per_s": D / (ms * 1e-3),
+                          "unsolved": bad, "bound": "fp64 pipe + shared memory (one warp per drone, ~9 sign-function iterations of a 2m x 2m Gauss-Jordan inverse)"}))
     del c, env
     torch.cuda.empty_cache()
