@@ -318,6 +318,12 @@ int mds_rls_update_f64(const MdsRlsCfg* cfg, const double* phi_dev, const double
  * sample -> e_dev [D][dim], dim = 12 / 9 / 10 for variant MDS_CTRL_LQR_TORQUE / _OMEGA / _YANK */
 int mds_error_state_f32(const MdsDroneParams* prm, int variant, const float* obs_dev, const float* ref_dev, float* e_dev, int D, void* stream);
 int mds_error_state_f64(const MdsDroneParams* prm, int variant, const double* obs_dev, const double* ref_dev, double* e_dev, int D, void* stream);
+/* The same error state on model STATE vectors x_dev, xdes_dev [D][dim] (decentralized_lqr_omega.py:174-183 as called with
+ * states, YOState.error_state decentralized_yolqr_crazyflie.py:88-102; attitude error in closed form, |pitch| <= pi/2) ->
+ * e_dev [D][dim] (optional) and, with K_dev [4*dim][D] planes, u_dev [D*4] = -K_d e_d (optional; no hover offset:
+ * DecentralizedYOLQRCrazyflie.compute :350-362, the FedCE wrapper's lqr_control). */
+int mds_state_feedback_f32(int variant, const float* K_dev, const float* x_dev, const float* xdes_dev, float* e_dev, float* u_dev, int D, void* stream);
+int mds_state_feedback_f64(int variant, const double* K_dev, const double* x_dev, const double* xdes_dev, double* e_dev, double* u_dev, int D, void* stream);
 /* mds_lqr_ctrl with a gain per drone (DecentralizedLQR*.compute).  coupled = 0: u_d = -K_d e_d, K_dev [4*dim][D] planes.
  * coupled = 1: u_d = -sum_j K_{d,j} e_j over the N drones j of d's environment, K_dev [N][4*dim][D] (source-major):
  * the 12-dim reference couples robots 0 and 1 through off-diagonal blocks of Q (decentralized_lqr.py:44-53), so its K

@@ -7,7 +7,7 @@ from .enums import DroneModel, Physics
 from .constants import DroneConstants
 from .envs import BatchedCtrlAviary, CtrlAviary
 from .rollout import FusedRollout, HostPipeline, PerCallPipeline
-from . import control, model, cbf, trajectories, obstacles, utils, dist, scenarios
+from . import control, model, cbf, trajectories, obstacles, utils, dist, scenarios, fedce
 
 __all__ = ["DroneModel", "Physics", "DroneConstants", "BatchedCtrlAviary", "CtrlAviary", "FusedRollout", "HostPipeline", "PerCallPipeline",
            "control", "model", "cbf", "trajectories", "obstacles", "utils", "dist", "scenarios", "_lib"]

@@ -422,6 +422,39 @@ __global__ void dlqr_ctrl_kernel(DroneP<Real> P, int variant, const Real* __rest
   }
   store4(u_out, d, u);
 }
+// error_state on model STATE vectors (not observations) and, optionally, the feedback u = -K_d e_d:
+// decentralized_lqr_omega.py:174-183, decentralized_lqr.py:288-298, YOState.error_state decentralized_yolqr_crazyflie.py:88-102
+// and DecentralizedYOLQRCrazyflie.compute (:350-362), whose states come from outside the simulator (FedCE).
+// x, x_des [D][dim]; attitude error in closed form (roll, pitch, wrap(yaw - yaw_des)), valid for |pitch| <= pi/2.
+template <typename Real>
+__global__ void state_feedback_kernel(int variant, const Real* __restrict__ K, const Real* __restrict__ x, const Real* __restrict__ xdes,
+                                      Real* __restrict__ e_out, Real* __restrict__ u_out, int D) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const int dim = variant == MDS_CTRL_LQR_TORQUE ? 12 : (variant == MDS_CTRL_LQR_OMEGA ? 9 : 10);
+  Real xs[12], xd[12], e[12];
+  for (int k = 0; k < dim; ++k) { xs[k] = x[(size_t)d * dim + k]; xd[k] = xdes[(size_t)d * dim + k]; }
+  Real sy, cy;
+  sincos_(xd[2], &sy, &cy);
+  const Real two_pi = Real(6.283185307179586476925286766559), inv_two_pi = Real(0.15915494309189533576888376337251);
+  e[0] = xs[0]; e[1] = xs[1];
+  const Real dy = xs[2] - xd[2];
+  e[2] = dy - two_pi * rint_(dy * inv_two_pi);
+  int first = 3;
+  if (variant == MDS_CTRL_LQR_YANK) { e[3] = xs[3] - xd[3]; first = 4; }
+  for (int b = first; b < dim; b += 3) {  // every remaining 3-vector (rates, velocity, position) rotated by R_eq^T (yaw only)
+    const Real ax = xs[b] - xd[b], ay = xs[b + 1] - xd[b + 1];
+    e[b] = cy * ax + sy * ay; e[b + 1] = -sy * ax + cy * ay; e[b + 2] = xs[b + 2] - xd[b + 2];
+  }
+  if (e_out)
+    for (int k = 0; k < dim; ++k) e_out[(size_t)d * dim + k] = e[k];
+  if (u_out) {
+    Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
+    for (int i = 0; i < 4; ++i)
+      for (int k = 0; k < dim; ++k) u[i] -= K[(size_t)(i * dim + k) * (size_t)D + d] * e[k];
+    store4(u_out, d, u);
+  }
+}
 template <typename Real>
 __global__ void error_state_kernel(DroneP<Real> P, int variant, const Real* __restrict__ obs, const Real* __restrict__ ref, Real* __restrict__ e_out, int D) {
   int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1055,6 +1088,14 @@ static int error_state_impl(const MdsDroneParams* prm, int variant, const Real* 
   return check_launch("error_state");
 }
 template <typename Real>
+static int state_feedback_impl(int variant, const Real* K, const Real* x, const Real* xdes, Real* e, Real* u, int D, void* stream) {
+  MDS_REQUIRE(x && xdes && (e || u) && D > 0, "state_feedback: bad argument");
+  MDS_REQUIRE(lqr_variant_ok(variant), "state_feedback: unknown variant");
+  MDS_REQUIRE(!u || K, "state_feedback: u requested without gains");
+  state_feedback_kernel<Real><<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(variant, K, x, xdes, e, u, D);
+  return check_launch("state_feedback");
+}
+template <typename Real>
 static int dlqr_impl(const MdsDroneParams* prm, int variant, const Real* K, int coupled, const Real* obs, const Real* ref, Real* u, Real* action,
                      MdsPidState pid, int E, int N, void* stream) {
   MDS_REQUIRE(prm && K && obs && ref && u && E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV, "dlqr_ctrl: bad argument");
@@ -1381,6 +1422,9 @@ int mds_cbf_num_rows(int order, int N, int n_obs) { return N * (N - 1) / 2 + 8 *
   }                                                                                                                                                \
   int mds_care_gains_##SUF(int m, const double* q, const double* r, const REAL* theta, REAL* K, int* status, int D, void* stream) {                 \
     return care_impl<REAL>(m, q, r, theta, K, status, D, stream);                                                                                  \
+  }                                                                                                                                                \
+  int mds_state_feedback_##SUF(int variant, const REAL* K, const REAL* x, const REAL* xdes, REAL* e, REAL* u, int D, void* stream) {                \
+    return state_feedback_impl<REAL>(variant, K, x, xdes, e, u, D, stream);                                                                        \
   }                                                                                                                                                \
   int mds_error_state_##SUF(const MdsDroneParams* prm, int variant, const REAL* obs, const REAL* ref, REAL* e, int D, void* stream) {              \
     return error_state_impl<REAL>(prm, variant, obs, ref, e, D, stream);                                                                           \

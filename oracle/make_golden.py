@@ -262,6 +262,32 @@ def golden_dlqr(ref):
         action, u = d.compute(obs.copy())
         out[f"ctrl_{tag}_theta"], out[f"ctrl_{tag}_K"] = thetas(d), d.K
         out[f"ctrl_{tag}_action"], out[f"ctrl_{tag}_u"] = np.array(action), np.array(u, float)
+    # FedCE wrapper (FedCE/FederatedLearning.py): YOState lists in, approx_theta_update(project=True) + u = -K e out
+    fed_mod = importlib.import_module("FedCE.FederatedLearning")
+    Nf, Tf = 2, 5
+    with contextlib.redirect_stdout(io.StringIO()):
+        fl = fed_mod.FederatedLearning(env, [ref.model.LinearizedYankOmegaModel(env) for _ in range(Nf)], np.eye(10), np.eye(4), num_drones=Nf)
+    mg = env.M * env.G
+    xs = np.concatenate([rng.uniform(-0.2, 0.2, (Tf, Nf, 3)), mg + rng.normal(0, 0.02, (Tf, Nf, 1)), rng.normal(0, 0.3, (Tf, Nf, 3)),
+                         rng.uniform(-1, 1, (Tf, Nf, 3))], axis=2)
+    xdes = np.zeros((Tf, Nf, 10))
+    xdes[:, :, 2] = rng.uniform(-0.5, 0.5, (Tf, Nf))
+    xdes[:, :, 3] = mg
+    xdes[:, :, 4:7] = rng.normal(0, 0.1, (Tf, Nf, 3))
+    xdes[:, :, 7:10] = rng.uniform(-1, 1, (Tf, Nf, 3))
+    us = np.concatenate([rng.normal(0, 2.0, (Tf, Nf, 1)), rng.normal(0, 0.1, (Tf, Nf, 3))], axis=2)
+    yo = lambda v: m_cf.YOState(*[float(a) for a in v])
+    fed_th, fed_P = [], []
+    for t in range(Tf):
+        with contextlib.redirect_stdout(io.StringIO()):
+            fl.update([yo(v) for v in xs[t]], [yo(v) for v in xdes[t]], [u.copy() for u in us[t]])
+        fed_th.append(np.array([fl.dLQR.get_thetai(i) for i in range(Nf)]))
+        fed_P.append(np.array(fl.dLQR.P, float).copy())
+    with contextlib.redirect_stdout(io.StringIO()):
+        fl.calc_controller()
+        fed_u = fl.lqr_control([yo(v) for v in xs[-1]], [yo(v) for v in xdes[-1]])
+    out["fed_x"], out["fed_xdes"], out["fed_u"] = xs, xdes, us
+    out["fed_theta"], out["fed_P"], out["fed_K"], out["fed_ctrl_u"] = np.array(fed_th), np.array(fed_P), fl.dLQR.K, np.array(fed_u)
     np.savez_compressed(os.path.join(OUT, "dlqr.npz"), **out)
 
 

@@ -246,3 +246,36 @@ def test_care_device_vs_scipy(cls_name, dtype, lib_built):
     st = c.care_status.cpu().numpy()
     assert st[0] == 1 and st[1:].sum() == 0
     assert float(c.K_planes[:, 0].min()) == 7.0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_fedce_wrapper_vs_reference_golden(golden, dtype, lib_built):
+    """multidronesim_b200.fedce.FederatedLearning against the reference's own FedCE/FederatedLearning.py driven with YOState
+    lists: five update() calls (the first only stores), then calc_controller() and lqr_control()."""
+    import multidronesim_b200 as mds
+    from multidronesim_b200.fedce import FederatedLearning
+    g = golden["dlqr"]
+    T, N = g["fed_x"].shape[:2]
+    E = 3
+    env = make_env(E, N, dtype)
+    fl = FederatedLearning(env, [mds.model.LinearizedYankOmegaModel(env) for _ in range(N)], np.eye(10), np.eye(4), num_drones=N)
+    tol = TOL[dtype]
+    for t in range(T):
+        rep = lambda a: dev(np.tile(a[None], (E, 1, 1)), dtype)
+        out = fl.update(rep(g["fed_x"][t]), rep(g["fed_xdes"][t]), rep(g["fed_u"][t]))
+        assert (out[0] is None) == (t == 0)
+        th = fl.dLQR.theta.double().cpu().numpy().reshape(E, N, 14, 10)
+        P = fl.dLQR.P.double().cpu().numpy().reshape(E, N, 14, 14)
+        for e in range(E):
+            assert np.abs(th[e] - g["fed_theta"][t]).max() <= tol * max(1.0, np.abs(g["fed_theta"][t]).max()), (t, e)
+            assert np.abs(P[e] - g["fed_P"][t]).max() <= tol * np.abs(g["fed_P"][t]).max(), (t, e)
+    fl.calc_controller()
+    Kg = g["fed_K"]
+    ktol = 1e-9 if dtype == torch.float64 else 1e-3  # fp32: the CARE of an fp32-rounded learned model
+    for i in range(N):
+        assert np.abs(fl.dLQR.K_matrix(i).double().cpu().numpy() - Kg[4 * i:4 * i + 4, 10 * i:10 * i + 10]).max() <= ktol * np.abs(Kg).max()
+    u = fl.lqr_control(rep(g["fed_x"][-1]), rep(g["fed_xdes"][-1])).double().cpu().numpy()
+    for e in range(E):
+        assert np.abs(u[e] - g["fed_ctrl_u"]).max() <= (1e-8 if dtype == torch.float64 else 2e-3) * max(1.0, np.abs(g["fed_ctrl_u"]).max())
+    sd = fl.make_desired_state(pos=[0.0, 0.0, 1.0])
+    assert sd.shape == (E, N, 10) and abs(float(sd[0, 0, 3]) - env.M * env.G) < 1e-6 and float(sd[0, 0, 9]) == 1.0
