@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MDS_ABI_VERSION 6
+#define MDS_ABI_VERSION 7
 #define MDS_MAX_DRONES_PER_ENV 32
 #define MDS_MAX_OBSTACLES 8
 #define MDS_OBS_DIM 20
@@ -90,6 +90,8 @@ typedef struct MdsDroneParams {
   int cf2x_torque_sign;        /* sign applied to the CF2X roll torque (SURVEY A.2 switch) */
   int renormalize_quat;        /* 0 = upstream (no renormalisation) */
   int ground_clamp;            /* 1 = clamp z at z_floor (composite mode default) */
+  int x_frame_mixer;           /* 0 = the reference's PLUS-frame mixer for every model (utils/model_conversions.py:74-77,90-93);
+                                  1 = for CF2X use the X-frame allocation the CF2X dynamics apply (SURVEY 8f-4 extension) */
 } MdsDroneParams;
 
 typedef struct MdsState {

@@ -39,7 +39,7 @@ class DroneParams(C.Structure):
         ("prop_x", C.c_double * 4), ("prop_y", C.c_double * 4),
         ("z_floor", C.c_double), ("dt_phys", C.c_double), ("dt_ctrl", C.c_double),
         ("substeps", C.c_int), ("drone_model", C.c_int), ("physics", C.c_int),
-        ("cf2x_torque_sign", C.c_int), ("renormalize_quat", C.c_int), ("ground_clamp", C.c_int)]
+        ("cf2x_torque_sign", C.c_int), ("renormalize_quat", C.c_int), ("ground_clamp", C.c_int), ("x_frame_mixer", C.c_int)]
 
 
 class State(C.Structure):

@@ -32,7 +32,7 @@ class DroneConstants:
     """Attributes named as the reference reads them from ``env``."""
 
     def __init__(self, drone_model=DroneModel.CF2P, physics=Physics.DYN, pyb_freq=240, ctrl_freq=240,
-                 cf2x_torque_sign=-1, renormalize_quat=False, ground_clamp=None, dw_dz_clip=None):
+                 cf2x_torque_sign=-1, renormalize_quat=False, ground_clamp=None, dw_dz_clip=None, x_frame_mixer=False):
         self.DRONE_MODEL = DroneModel(drone_model)
         self.PHYSICS = Physics(physics)
         u = URDF[self.DRONE_MODEL]
@@ -68,6 +68,9 @@ class DroneConstants:
         self.Z_FLOOR = self.COLLISION_H / 2 - self.COLLISION_Z_OFFSET
         self.cf2x_torque_sign = int(cf2x_torque_sign)
         self.renormalize_quat = bool(renormalize_quat)
+        # False: the reference's PLUS-frame mixer whatever the model (utils/model_conversions.py:74-77); True: a CF2X gets the
+        # X-frame allocation its dynamics apply, so that torque-level controllers (geometric, 12-dim LQR) fly it
+        self.x_frame_mixer = bool(x_frame_mixer)
         self.ground_clamp = (self.PHYSICS == Physics.DYN_GND_DRAG_DW) if ground_clamp is None else bool(ground_clamp)
         # Downwash magnitude alpha = DW1 (PROP_RADIUS / (4 dz))^2 is singular as dz -> 0+ (upstream only ever flies one
         # drone well above another).  The composite mode clips dz from below where alpha would exceed the drone's
@@ -92,4 +95,5 @@ class DroneConstants:
         p.cf2x_torque_sign = self.cf2x_torque_sign
         p.renormalize_quat = int(self.renormalize_quat)
         p.ground_clamp = int(self.ground_clamp)
+        p.x_frame_mixer = int(self.x_frame_mixer)
         return p

@@ -41,9 +41,15 @@ template <typename Real> MDS_DEV void action_to_input(const DroneP<Real>& P, con
   }
   Real kr = P.km / P.kf;
   u[0] = T[0] + T[1] + T[2] + T[3];
+  u[3] = kr * (-T[0] + T[1] - T[2] + T[3]);
+  if (P.x_frame_mixer && P.drone_model == MDS_DRONE_CF2X) {  // the allocation physics_substep applies to a CF2X
+    const Real l2 = P.arm_l * Real(0.70710678118654752);
+    u[1] = Real(P.cf2x_torque_sign) * l2 * (T[0] + T[1] - T[2] - T[3]);
+    u[2] = l2 * (-T[0] + T[1] + T[2] - T[3]);
+    return;
+  }
   u[1] = P.arm_l * (T[1] - T[3]);
   u[2] = P.arm_l * (T[2] - T[0]);
-  u[3] = kr * (-T[0] + T[1] - T[2] + T[3]);
 }
 
 // input_to_action: [f, tx, ty, tz] -> RPM (model_conversions.py:85-103); clamps u[0] >= 0 in
@@ -53,6 +59,12 @@ template <typename Real> MDS_DEV void input_to_action(const DroneP<Real>& P, Rea
   Real kr = P.km / P.kf;
   Real q = Real(0.25) * u[0], a = u[1] / (Real(2) * P.arm_l), b = u[2] / (Real(2) * P.arm_l), c = u[3] / (Real(4) * kr);
   Real T[4] = {q - b - c, q + a + c, q + b - c, q - a + c};
+  if (P.x_frame_mixer && P.drone_model == MDS_DRONE_CF2X) {  // inverse of the X-frame allocation (extension; the reference is PLUS-only)
+    const Real l2 = P.arm_l * Real(0.70710678118654752);
+    a = Real(P.cf2x_torque_sign) * u[1] / (Real(4) * l2);
+    b = u[2] / (Real(4) * l2);
+    T[0] = q + a - b - c; T[1] = q + a + b + c; T[2] = q - a + b - c; T[3] = q - a - b + c;
+  }
   const Real tmin = Real(MDS_MIN_RPM * MDS_MIN_RPM) * P.kf;
 #pragma unroll
   for (int i = 0; i < 4; ++i) rpm[i] = sqrt_(clamp_(T[i], tmin, P.max_thrust) / P.kf);

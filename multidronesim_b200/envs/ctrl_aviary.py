@@ -38,8 +38,8 @@ class BatchedCtrlAviary(DroneConstants):
                  initial_xyzs=None, initial_rpys=None, physics=Physics.DYN, pyb_freq=240, ctrl_freq=240,
                  gui=False, record=False, obstacles=False, user_debug_gui=True, output_folder="results",
                  num_envs=1, device="cuda", dtype=torch.float32,
-                 cf2x_torque_sign=-1, renormalize_quat=False, ground_clamp=None, dw_dz_clip=None):
-        super().__init__(drone_model, physics, pyb_freq, ctrl_freq, cf2x_torque_sign, renormalize_quat, ground_clamp, dw_dz_clip)
+                 cf2x_torque_sign=-1, renormalize_quat=False, ground_clamp=None, dw_dz_clip=None, x_frame_mixer=False):
+        super().__init__(drone_model, physics, pyb_freq, ctrl_freq, cf2x_torque_sign, renormalize_quat, ground_clamp, dw_dz_clip, x_frame_mixer)
         _lib.load_library()  # fail loudly if the CUDA extension is not built
         if not torch.cuda.is_available():
             raise _lib.MdsError("BatchedCtrlAviary needs a CUDA device: there is no CPU fallback")

@@ -86,7 +86,7 @@ class OracleCtrlAviary:
     def __init__(self, drone_model=DroneModel.CF2P, num_drones=1, initial_xyzs=None,
                  initial_rpys=None, physics=Physics.DYN, pyb_freq=240, ctrl_freq=240,
                  gui=False, record=False, user_debug_gui=False, output_folder="results",
-                 cf2x_torque_sign=-1.0, renormalize_quat=False, ground_clamp=None, dw_dz_clip=None):
+                 cf2x_torque_sign=-1.0, renormalize_quat=False, ground_clamp=None, dw_dz_clip=None, x_frame_mixer=False):
         prm = drone_params(drone_model, pyb_freq, ctrl_freq)
         self.__dict__.update(prm.__dict__)
         self.NUM_DRONES = int(num_drones)
@@ -95,6 +95,7 @@ class OracleCtrlAviary:
             raise ValueError("oracle supports Physics.DYN and Physics.DYN_GND_DRAG_DW only")
         self.cf2x_torque_sign = float(cf2x_torque_sign)
         self.renormalize_quat = bool(renormalize_quat)
+        self.x_frame_mixer = bool(x_frame_mixer)
         if dw_dz_clip is not None:
             self.DW_DZ_CLIP = float(dw_dz_clip)
         # ground-plane clamp belongs to the composite mode only (DYN stays upstream-exact)

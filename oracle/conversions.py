@@ -42,6 +42,10 @@ def mixer_matrix(env):
     """PLUS-frame [f, tx, ty, tz] = C @ motor_thrusts (utils/model_conversions.py:74-77,90-93)."""
     r = env.KM / env.KF
     L = env.L
+    if getattr(env, "x_frame_mixer", False) and getattr(getattr(env, "DRONE_MODEL", None), "value", None) == "cf2x":
+        # builder extension (SURVEY 8f-4): the X-frame allocation of the CF2X dynamics (oracle/aviary.py _substep_drone)
+        l2, s = L / np.sqrt(2.0), float(getattr(env, "cf2x_torque_sign", -1.0))
+        return np.array([[1.0, 1.0, 1.0, 1.0], [s * l2, s * l2, -s * l2, -s * l2], [-l2, l2, l2, -l2], [-r, r, -r, r]])
     return np.array([[1.0, 1.0, 1.0, 1.0],
                      [0.0, L, 0.0, -L],
                      [-L, 0.0, L, 0.0],

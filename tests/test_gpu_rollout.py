@@ -243,3 +243,35 @@ def test_rollout_with_wind(lib_built):
     for plan in (6, 4, 3):
         assert np.max(np.abs(outs[plan] - outs["percall"])) < 1e-9 * (1 + np.max(np.abs(outs["percall"]))), plan
     assert np.max(np.abs(outs["calm"][..., 0:3] - outs[6][..., 0:3])) > 1e-5   # the wind moved the drones
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-7), (torch.float32, 1e-3)])
+def test_cf2x_x_frame_mixer_tracking(dtype, tol, lib_built):
+    """SURVEY 8f-4 extension: a CF2X under the torque-level geometric controller with the X-frame mixer
+    (``x_frame_mixer=True``; the reference's mixer is PLUS-frame whatever the model).  2 s of circle tracking in
+    DYN_GND_DRAG_DW: against the oracle loop with the same switch, and the drone really tracks (it does not with
+    the PLUS-frame mixer, whose roll / pitch torques land 45 degrees off a CF2X's axes)."""
+    import multidronesim_b200 as mds
+    import multidronesim_b200.trajectories as T
+    E, N, steps = 3, 1, 480
+    kw = dict(r=1.0, v=0.5, center=np.array([0, 0, 1.0]), yaw_rate=0.0)
+    init = np.zeros((E, N, 3))
+    for e in range(E):
+        init[e, 0] = np.float32(otj.Circle(**kw)(0.0)[0] + np.array([0.03 * e, -0.02 * e, 0.01 * e]))
+    env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2X, num_drones=N, physics=mds.Physics.DYN_GND_DRAG_DW, num_envs=E, dtype=dtype,
+                                initial_xyzs=init, x_frame_mixer=True)
+    c = mds.control.GeometricControl(env)
+    ts = mds.trajectories.TrajectorySet([T.CircleTrajectory(**kw)] * E, dtype=dtype)
+    ro = mds.FusedRollout(env, ts, c, None, None)
+    log = torch.zeros(steps, E, N, 20, device="cuda", dtype=dtype)
+    ro.run(steps, obs_log=log, log_every=1)
+    got = log.double().cpu().numpy()
+    worst = 0.0
+    for e in range(E):
+        o = OracleCtrlAviary(ODM.CF2X, N, initial_xyzs=init[e], physics=OPH.DYN_GND_DRAG_DW, x_frame_mixer=True)
+        want, _ = opl.run_tracking(o, [otj.Circle(**kw)], "geometric", steps)
+        worst = max(worst, float(np.max(np.abs(got[:, e, :, 0:3] - want[:, :, 0:3]))))
+    assert worst < tol, worst
+    ref_end = otj.Circle(**kw)((steps - 1) * env.CTRL_TIMESTEP)[0]
+    assert np.abs(got[-1, :, 0, 0:3] - ref_end).max() < 0.1           # converging from a standing start: 7-8 cm behind after 2 s
+    assert ro.stats_dict()["max_pos_err"] < 0.2                       # (the PLUS-frame mixer loses a CF2X: tests/test_oracle_env.py)

@@ -85,3 +85,28 @@ def test_dslpid_hover_config1():
         act = np.array([ctrls[j].compute_from_state(env.CTRL_TIMESTEP, obs[j], target[j])[0] for j in range(2)])
         obs = env.step(act)[0]
     assert np.max(np.abs(obs[:, 0:3] - target)) < 0.05
+
+
+def test_cf2x_needs_the_x_frame_mixer():
+    """the reference's input_to_action is PLUS-frame whatever the model (utils/model_conversions.py:74-77).  On a
+    CF2X under the DYN dynamics its roll / pitch torques land 45 degrees off the body axes and the geometric controller
+    loses the drone; with ``x_frame_mixer=True`` (builder extension) the mixer inverts the allocation the dynamics apply."""
+    from oracle import conversions as cv
+    from oracle import pipeline as opl
+    from oracle import trajectories as otj
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel as ODM, Physics as OPH
+    kw = dict(r=1.0, v=0.5, center=np.array([0, 0, 1.0]), yaw_rate=0.0)
+    end = {}
+    for xf in (True, False):
+        o = OracleCtrlAviary(ODM.CF2X, 1, initial_xyzs=otj.Circle(**kw)(0.0)[0][None], physics=OPH.DYN_GND_DRAG_DW, x_frame_mixer=xf)
+        if xf:  # the mixer is the exact inverse of the CF2X allocation of the dynamics
+            u = np.array([o.M * o.G * 1.1, 2e-4, -1.5e-4, 3e-5])
+            rpm = cv.input_to_action(o, u.copy())
+            f, l2 = o.KF * rpm ** 2, o.L / np.sqrt(2.0)
+            tau = [o.cf2x_torque_sign * (f[0] + f[1] - f[2] - f[3]) * l2, (-f[0] + f[1] + f[2] - f[3]) * l2, o.KM * (-rpm[0] ** 2 + rpm[1] ** 2 - rpm[2] ** 2 + rpm[3] ** 2)]
+            assert abs(f.sum() - u[0]) < 1e-15 and np.abs(np.array(tau) - u[1:]).max() < 1e-15
+            assert np.abs(cv.action_to_input(o, rpm) - u).max() < 1e-15
+        log, _ = opl.run_tracking(o, [otj.Circle(**kw)], "geometric", 480)
+        end[xf] = float(np.abs(log[-1, 0, 0:3] - otj.Circle(**kw)(479 / 240)[0]).max())
+    assert end[True] < 0.1 and end[False] > 1.0, end
