@@ -34,6 +34,12 @@ MDS_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.asyn
 template <typename Real, int M> constexpr int rls_words_per_thread() { return (M + 4) * (M + 4) + (M + 4) * M + 2 * (M + 4) + M; }
 // Threads per block: ONE warp (f32) / half a warp (f64).  A staged block is 40-63 KB, so 3-5 blocks share an SM and their
 // load / compute / store phases overlap; measured at 1 M drones, m = 9 f32: 0.61 ms at 32 threads, 0.80 ms at 64 or 128.
+// Row loops over the staged columns: unrolled by 4 so that several rows' shared-memory loads are in flight (registers are
+// free here: occupancy is set by the staging footprint, not by registers).
+#ifndef MDS_RLS_ROW_UNROLL
+#define MDS_RLS_ROW_UNROLL 4
+#endif
+constexpr int kRlsRowUnroll = MDS_RLS_ROW_UNROLL;  // (#pragma unroll takes a constant expression, not a macro)
 #ifndef MDS_RLS_T32
 #define MDS_RLS_T32 32
 #endif
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
   }
   // ---- gain: w = P phi, v = phi' P, s = 1 + phi' P phi
   Real s = Real(1);
-#pragma unroll 1
+#pragma unroll kRlsRowUnroll
   for (int i = 0; i < MN; ++i) {
     const Real phi_i = s_phi[i * T];
     Real wi = Real(0);
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
       }
       r[3] = phi[M];
     }
-#pragma unroll 1
+#pragma unroll kRlsRowUnroll
     for (int i = 0; i < MN; ++i) {
       const Real phi_i = s_phi[i * T];
 #pragma unroll
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
       s_term[j * T] = acc[j];
       nt[j] = Real(0);
     }
-#pragma unroll 1
+#pragma unroll kRlsRowUnroll
     for (int i = 0; i < MN; ++i) {  // A e0 + B u = theta' [e0; u]
       const Real zi = i < M ? s_term[i * T] : s_phi[i * T];
 #pragma unroll
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
       }
       if (big <= eps * mag) break;  // the series has converged in Real (|A| dt ~ 0.05: 5-7 terms)
       coef *= Real(c.dt) / Real(k + 1);
-#pragma unroll 1
+#pragma unroll kRlsRowUnroll
       for (int i = 0; i < M; ++i) {
         const Real ti = s_term[i * T];
 #pragma unroll
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
     for (int j = 0; j < M; ++j) resid_out[d * M + j] = r[j];
   }
   // ---- theta += L r' (then project_theta), P -= (w / s) v: straight from the staged columns back to the HBM planes
-#pragma unroll 1
+#pragma unroll kRlsRowUnroll
   for (int i = 0; i < MN; ++i) {
     const Real wi = s_w[i * T];
     const Real Li = c.normalize_gain ? wi * inv_s : wi;
@@ -198,7 +204,7 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
       }
     }
   }
-#pragma unroll 1
+#pragma unroll kRlsRowUnroll
   for (int i = 0; i < MN; ++i) {
     const Real Li = s_w[i * T] * inv_s;
 #pragma unroll
