@@ -279,3 +279,31 @@ def test_fedce_wrapper_vs_reference_golden(golden, dtype, lib_built):
         assert np.abs(u[e] - g["fed_ctrl_u"]).max() <= (1e-8 if dtype == torch.float64 else 2e-3) * max(1.0, np.abs(g["fed_ctrl_u"]).max())
     sd = fl.make_desired_state(pos=[0.0, 0.0, 1.0])
     assert sd.shape == (E, N, 10) and abs(float(sd[0, 0, 3]) - env.M * env.G) < 1e-6 and float(sd[0, 0, 9]) == 1.0
+
+
+@pytest.mark.parametrize("E,N", [(7, 5), (1, 1), (3, 32)])
+def test_coupled_gain_law_odd_sizes(E, N, lib_built):
+    """mds_dlqr_ctrl with robot-coupled gains at group sizes that do not fill a warp (N = 5: 125-thread blocks), a single drone
+    and the largest group (N = 32): u_d = -sum_j K_dj e_j + [m g, 0, 0, 0] against numpy on the device's own error states."""
+    dtype = torch.float64
+    env = make_env(E, N, dtype)
+    c = make_ctrl(env, "DecentralizedLQR")
+    m, D = c.m, E * N
+    rng = np.random.default_rng(3)
+    Kfull = rng.normal(0, 1e-3, (E, 4 * N, m * N))                      # any gain will do: this tests the law, not the CARE
+    c._coupled = True
+    planes = Kfull.reshape(E, N, 4, N, m).transpose(3, 2, 4, 0, 1).reshape(N * 4 * m, D)
+    c.K_planes = dev(planes, dtype)
+    c.K = Kfull
+    rpy = rng.uniform(-0.3, 0.3, (D, 3))
+    from scipy.spatial.transform import Rotation
+    obs = np.concatenate([rng.uniform(-1, 1, (D, 3)), Rotation.from_euler("xyz", rpy).as_quat(), rpy, rng.normal(0, 0.5, (D, 3)),
+                          rng.normal(0, 0.5, (D, 3)), rng.uniform(12000, 17000, (D, 4))], axis=1).reshape(E, N, 20)
+    ref = np.concatenate([rng.uniform(-1, 1, (D, 3)), rng.normal(0, 0.2, (D, 3)), np.zeros((D, 3)), rng.uniform(-1, 1, (D, 1)), rng.normal(0, 0.1, (D, 1))], axis=1)
+    c.set_reference(dev(ref, dtype))
+    e = c.error_state(dev(obs, dtype)).cpu().numpy().reshape(E, N * m)
+    _, u = c.compute(dev(obs, dtype))
+    want = -(Kfull @ e[:, :, None])[:, :, 0].reshape(E, N, 4)
+    want[..., 0] += env.M * env.G
+    want[..., 0] = np.maximum(want[..., 0], 0.0)                        # input_to_action clamps the thrust in place
+    assert np.abs(u.cpu().numpy() - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
