@@ -307,3 +307,46 @@ def test_coupled_gain_law_odd_sizes(E, N, lib_built):
     want[..., 0] += env.M * env.G
     want[..., 0] = np.maximum(want[..., 0], 0.0)                        # input_to_action clamps the thrust in place
     assert np.abs(u.cpu().numpy() - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+
+def test_dlqr_as_cbf_nominal_controller_vs_oracle(lib_built):
+    """The reference's ``--controller dlqr`` loop (simulations/CBFTest.py:302-358): DecentralizedLQROmega.compute(obs,
+    skip_low_level=True) as the nominal controller of the order-2 CBF-QP, each drone with its own learned model and gain
+    (device Riccati solve), through PerCallPipeline; 80 steps, fp64, against the oracle loop with the same per-drone gains."""
+    import multidronesim_b200 as mds
+    import multidronesim_b200.trajectories as T
+    from oracle import controllers as oc
+    from oracle import pipeline as opl
+    from oracle import trajectories as otj
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel as ODM, Physics as OPH
+    E, N, steps, dtype = 2, 3, 80, torch.float64
+    rng = np.random.default_rng(4)
+    ph = np.pi / 2 - 0.3 + (2 * np.pi / (N + 0.25)) * np.arange(N)
+    specs = [dict(a=1.0, center=np.array([0, 0, 0.5]), omega=0.5, yaw_rate=0.0, phase_shift=float(p)) for p in ph]
+    obstacles = [[0.0, 0.0, 0.5, 0.1]]
+    init = np.zeros((E, N, 3))
+    for e in range(E):
+        for j, sp in enumerate(specs):
+            init[e, j] = otj.Lemniscate(**sp)(0.0)[0] + rng.normal(0, 0.02, 3) + np.array([0, 0, 0.04 * j])
+    env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=N, physics=mds.Physics.DYN_GND_DRAG_DW, num_envs=E, dtype=dtype,
+                                initial_xyzs=init)
+    models = [mds.model.LinearizedOmegaModel(env) for _ in range(N)]
+    dl = mds.control.DecentralizedLQROmega(env, models)
+    th = dl.theta.cpu().numpy() * (1.0 + 0.03 * rng.normal(size=(E * N, 13, 9)))   # every drone its own "learned" model
+    dl.set_theta(dev(th, dtype))
+    dl.compute_controller()
+    assert int(dl.care_status.sum()) == 0
+    cbf = mds.cbf.DroneCBF(env, models, safety_radius=0.1, zscale=1.0, order=2, cbf_poles=np.array([-2.2, -2.4]))
+    trk = mds.cbf.DroneQPTracker(cbf, order=2, num_robots=N, xdim=9, env=env)
+    ts = mds.trajectories.TrajectorySet([T.Lemniscate(**sp) for sp in specs] * E, dtype=dtype)
+    pipe = mds.PerCallPipeline(env, dl, trk, obstacles)
+    obs = None
+    for k in range(steps):
+        obs = pipe.step(ts.eval(k * env.CTRL_TIMESTEP))
+    got = obs.cpu().numpy()
+    for e in range(E):
+        o = OracleCtrlAviary(ODM.CF2P, N, initial_xyzs=init[e], physics=OPH.DYN_GND_DRAG_DW)
+        ctrls = [oc.Lqr(o, "omega9", oc.ThrustOmegaPid(o), K=dl.K_matrix(j, env_idx=e).cpu().numpy()) for j in range(N)]
+        _, want, info = opl.run_cbf(o, [otj.Lemniscate(**sp) for sp in specs], 2, steps, obstacles=obstacles, ctrls=ctrls)
+        assert np.abs(got[e, :, 0:3] - want[:, 0:3]).max() < 1e-6, (e, info)
