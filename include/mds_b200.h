@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MDS_ABI_VERSION 7
+#define MDS_ABI_VERSION 8
 #define MDS_MAX_DRONES_PER_ENV 32
 #define MDS_MAX_OBSTACLES 8
 #define MDS_OBS_DIM 20
@@ -171,6 +171,8 @@ typedef struct MdsRolloutCfg {
                                  t0 + k dt_ctrl on the new observation (t0 = time AFTER the first physics step)
                           1, 2 and 5 let a caller replay a rollout launch by launch with its own CUDA events. */
   double obstacles[MDS_MAX_OBSTACLES * 4]; /* cx, cy, cz, r (r < 0: vertical cylinder of radius |r|) */
+  const void* lqr_gain_planes_dev; /* optional, LQR controllers: a gain per drone, [4*dim][D] planes of Real (DecentralizedLQR*.K,
+                                      simulations/CBFTest.py:319-321 `--controller dlqr`); NULL = MdsLqrGains.K for every drone */
 } MdsRolloutCfg;
 
 /* ---- library ------------------------------------------------------------------ */

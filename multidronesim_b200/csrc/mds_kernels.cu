@@ -669,6 +669,8 @@ template <typename Real> struct RolloutP {
   int ctrl, use_cbf, n_obs, write_obs_every;
   Real u0_pre, u0_post;
   Real obstacles[MDS_MAX_OBSTACLES * 4];
+  const Real* lqr_planes;  // per-drone LQR gains [4*dim][D] (decentralised LQR), or null: the shared gain of LqrP
+  int lqr_D;
 };
 
 MDS_DEV void atomic_min_double(double* addr, double v) {
@@ -704,7 +706,7 @@ struct StepStats {
 // reference -> tracking controller -> (CBF-QP) -> inner loop -> RPM action.  CTRL / USE_CBF are compile-time so
 // that each instantiation carries only its own stage code (one kernel with run-time switches overflowed the
 // instruction cache: 55 % of the stall samples were "no instruction").
-template <typename Real, int CTRL, bool USE_CBF>
+template <typename Real, int CTRL, bool USE_CBF, bool PDK = false>  // PDK: a gain per drone (Rc.lqr_planes) instead of LqrP's
 MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const GeoP<Real>& G, const LqrP<Real>& L, const CbfP<Real>& C,
                        const DslP<Real>& Dg, const DslStateP<Real>& dst, const CbfSmem<Real>& S, const PidP<Real>& pid,
                        const typename TrajSpecT<Real>::spec& spec,
@@ -725,7 +727,8 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
       dslpid_control(P, Dg, ds, o, ref.p, v3(Real(0), Real(0), ref.yaw), ref.v, v3(Real(0), Real(0), ref.yaw_rate), rpm, &pe);
       store_dsl(dst, g.d, ds);
     } else {
-      lqr_input(P, L, CTRL, o, ref, u);
+      if (PDK) dlqr_input(P, Rc.lqr_planes, (size_t)Rc.lqr_D, (size_t)g.d, CTRL, o, ref, u);
+      else lqr_input(P, L, CTRL, o, ref, u);
       if (CTRL == MDS_CTRL_LQR_TORQUE) input_to_action(P, u, rpm);
     }
   }
@@ -835,7 +838,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_CTRL_MINB :
       spec = specs[g.d];
       if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
     }
-    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss, g.d);
+    ctrl_body<Real, CTRL, USE_CBF, (NT < 0)>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss, g.d);
     if (g.valid) store4(action, g.d, rpm);
   }
   if (stats) stats_block_reduce<USE_CBF>(stats, g.valid ? 1 : 0, ss, ss.err);
@@ -928,7 +931,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
     Real* log_slot = obs_log;
     for (int k = 0; k < K; ++k) {
       StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
-      ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss, STAGE ? (int)threadIdx.x : g.d);  // the host plans form t exactly like this
+      ctrl_body<Real, CTRL, USE_CBF, (NT < 0)>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss, STAGE ? (int)threadIdx.x : g.d);  // the host plans form t exactly like this
       acc.err += ss.err; max_err = fmaxf(max_err, ss.err); acc.min_h = fminf(acc.min_h, ss.min_h);
       acc.qp_solves += ss.qp_solves; acc.qp_iters += ss.qp_iters; acc.qp_infeas += ss.qp_infeas; acc.qp_cap += ss.qp_cap;
       Drone<Real> s;
@@ -1185,6 +1188,9 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   RolloutP<Real> R;
   memset(&R, 0, sizeof(R));
   R.ctrl = cfg->ctrl; R.use_cbf = cfg->use_cbf; R.n_obs = cfg->num_obstacles; R.write_obs_every = cfg->write_obs_every;
+  R.lqr_planes = (const Real*)cfg->lqr_gain_planes_dev; R.lqr_D = E * N;
+  MDS_REQUIRE(!R.lqr_planes || lqr_variant_ok(cfg->ctrl), "rollout: per-drone gains need an LQR controller");
+  MDS_REQUIRE(!R.lqr_planes || (cfg->stages != 3 && cfg->stages != 5), "rollout: per-drone gains run in launch plans 6 (default), 4, 1 and 2");
   GeoP<Real> G;
   memset(&G, 0, sizeof(G));
   LqrP<Real> L;
@@ -1240,53 +1246,56 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     return obs;
   };
   cudaError_t attr_err = cudaSuccess;
-#define MDS_LAUNCH_CTRL(CT, CB, FUSED, T, OBS_PTR)                                                                                  \
+  const bool PDKV = R.lqr_planes != nullptr;  // per-drone gains: the run-time-N instantiations compiled with PDK (NT = -1)
+#define MDS_LAUNCH_CTRL(CT, CB, FUSED, T, OBS_PTR, PDKC)                                                                                 \
   do {                                                                                                                              \
     if (FUSED) {                                                                                                                    \
       auto kern = (N == 8) ? step_fused_kernel<Real, CT, CB, 8> : step_fused_kernel<Real, CT, CB, 0>;                               \
       if (first_fused) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
       kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, fext, OBS_PTR, stats, T, E, N, NP);              \
     } else {                                                                                                                        \
-      auto kern = (N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>;                                 \
+      auto kern = PDKV ? ctrl_step_kernel<Real, CT, CB, (PDKC ? -1 : 0)>                                                           \
+                       : ((N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>);                       \
       if (first_ctrl) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
       kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Pi, specs, segs, (const Real*)(OBS_PTR), action, stats, T, E, N, NP);   \
     }                                                                                                                               \
   } while (0)
-#define MDS_LAUNCH_LOOP(CT, CB)                                                                                                      \
+#define MDS_LAUNCH_LOOP(CT, CB, PDKC)                                                                                                    \
   do {                                                                                                                              \
-    auto kern = (N == 8) ? rollout_loop_kernel<Real, CT, CB, 8> : rollout_loop_kernel<Real, CT, CB, 0>;                             \
+    auto kern = PDKV ? rollout_loop_kernel<Real, CT, CB, (PDKC ? -1 : 0)>                                                          \
+                     : ((N == 8) ? rollout_loop_kernel<Real, CT, CB, 8> : rollout_loop_kernel<Real, CT, CB, 0>);                   \
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
     kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, fext, obs, obs_log, stats, t0, prm->dt_ctrl, K, E, N, \
                                         NP);                                                                                      \
   } while (0)
   auto launch_loop = [&]() {
     switch (R.ctrl) {
-      case MDS_CTRL_GEOMETRIC: MDS_LAUNCH_LOOP(MDS_CTRL_GEOMETRIC, false); break;
-      case MDS_CTRL_LQR_TORQUE: MDS_LAUNCH_LOOP(MDS_CTRL_LQR_TORQUE, false); break;
-      case MDS_CTRL_DSLPID: MDS_LAUNCH_LOOP(MDS_CTRL_DSLPID, false); break;
+      case MDS_CTRL_GEOMETRIC: MDS_LAUNCH_LOOP(MDS_CTRL_GEOMETRIC, false, false); break;
+      case MDS_CTRL_LQR_TORQUE: MDS_LAUNCH_LOOP(MDS_CTRL_LQR_TORQUE, false, true); break;
+      case MDS_CTRL_DSLPID: MDS_LAUNCH_LOOP(MDS_CTRL_DSLPID, false, false); break;
       case MDS_CTRL_LQR_OMEGA:
-        if (R.use_cbf) MDS_LAUNCH_LOOP(MDS_CTRL_LQR_OMEGA, true);
-        else MDS_LAUNCH_LOOP(MDS_CTRL_LQR_OMEGA, false);
+        if (R.use_cbf) MDS_LAUNCH_LOOP(MDS_CTRL_LQR_OMEGA, true, true);
+        else MDS_LAUNCH_LOOP(MDS_CTRL_LQR_OMEGA, false, true);
         break;
       default:
-        if (R.use_cbf) MDS_LAUNCH_LOOP(MDS_CTRL_LQR_YANK, true);
-        else MDS_LAUNCH_LOOP(MDS_CTRL_LQR_YANK, false);
+        if (R.use_cbf) MDS_LAUNCH_LOOP(MDS_CTRL_LQR_YANK, true, true);
+        else MDS_LAUNCH_LOOP(MDS_CTRL_LQR_YANK, false, true);
         break;
     }
   };
   bool first_ctrl = true, first_fused = true;
   auto launch_ctrl = [&](bool fused, double t, Real* obs_ptr) {
     switch (R.ctrl) {
-      case MDS_CTRL_GEOMETRIC: MDS_LAUNCH_CTRL(MDS_CTRL_GEOMETRIC, false, fused, t, obs_ptr); break;
-      case MDS_CTRL_LQR_TORQUE: MDS_LAUNCH_CTRL(MDS_CTRL_LQR_TORQUE, false, fused, t, obs_ptr); break;
-      case MDS_CTRL_DSLPID: MDS_LAUNCH_CTRL(MDS_CTRL_DSLPID, false, fused, t, obs_ptr); break;
+      case MDS_CTRL_GEOMETRIC: MDS_LAUNCH_CTRL(MDS_CTRL_GEOMETRIC, false, fused, t, obs_ptr, false); break;
+      case MDS_CTRL_LQR_TORQUE: MDS_LAUNCH_CTRL(MDS_CTRL_LQR_TORQUE, false, fused, t, obs_ptr, true); break;
+      case MDS_CTRL_DSLPID: MDS_LAUNCH_CTRL(MDS_CTRL_DSLPID, false, fused, t, obs_ptr, false); break;
       case MDS_CTRL_LQR_OMEGA:
-        if (R.use_cbf) MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, true, fused, t, obs_ptr);
-        else MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, false, fused, t, obs_ptr);
+        if (R.use_cbf) MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, true, fused, t, obs_ptr, true);
+        else MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, false, fused, t, obs_ptr, true);
         break;
       default:
-        if (R.use_cbf) MDS_LAUNCH_CTRL(MDS_CTRL_LQR_YANK, true, fused, t, obs_ptr);
-        else MDS_LAUNCH_CTRL(MDS_CTRL_LQR_YANK, false, fused, t, obs_ptr);
+        if (R.use_cbf) MDS_LAUNCH_CTRL(MDS_CTRL_LQR_YANK, true, fused, t, obs_ptr, true);
+        else MDS_LAUNCH_CTRL(MDS_CTRL_LQR_YANK, false, fused, t, obs_ptr, true);
         break;
     }
     if (fused) first_fused = false; else first_ctrl = false;

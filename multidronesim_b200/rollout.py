@@ -14,6 +14,7 @@ from . import _lib
 from .control.dslpid import DSLPIDControl
 from .control.geometric import GeometricControl
 from .control.lqr import LQRController, LQROmegaController, LQRYankOmegaController
+from .control.dlqr import _DecentralizedBase
 
 
 class FusedRollout:
@@ -29,6 +30,12 @@ class FusedRollout:
             cfg.ctrl = _lib.CTRL_GEOMETRIC
         elif isinstance(controller, DSLPIDControl):
             cfg.ctrl = _lib.CTRL_DSLPID
+        elif isinstance(controller, _DecentralizedBase):
+            # the reference's `--controller dlqr` (simulations/CBFTest.py:319-321): every drone under its own learned gain
+            if controller.K is None or controller._coupled:
+                raise _lib.MdsError("FusedRollout takes a decentralised LQR with per-drone gains: call compute_controller() first "
+                                    "(the robot-coupled 12-dim gain runs through PerCallPipeline)")
+            cfg.ctrl = controller.VARIANT
         elif isinstance(controller, LQROmegaController):
             cfg.ctrl = _lib.CTRL_LQR_OMEGA
         elif isinstance(controller, LQRYankOmegaController):
@@ -85,8 +92,18 @@ class FusedRollout:
                 raise ValueError("obs_log too small")
         is_lqr = self.cfg.ctrl in (_lib.CTRL_LQR_TORQUE, _lib.CTRL_LQR_OMEGA, _lib.CTRL_LQR_YANK)
         geo = self.controller.c_gains() if self.cfg.ctrl == _lib.CTRL_GEOMETRIC else None
-        lqr = self.controller.c_gains() if is_lqr else None
-        pid = self.controller._pid() if is_lqr else _lib.PidState(None, None)
+        per_drone = isinstance(self.controller, _DecentralizedBase)
+        if per_drone:  # gains: the controller's K planes (re-read every call: compute_controller() may have run since)
+            if self.controller._coupled:
+                raise _lib.MdsError("robot-coupled gains cannot run in the fused rollout")
+            self.cfg.lqr_gain_planes_dev = self.controller.K_planes.data_ptr()
+            lqr = _lib.LqrGains()
+            lqr.dim = self.controller.m
+            pid = self.controller.low_level.pid_struct() if self.controller.low_level is not None else _lib.PidState(None, None)
+        else:
+            self.cfg.lqr_gain_planes_dev = None
+            lqr = self.controller.c_gains() if is_lqr else None
+            pid = self.controller._pid() if is_lqr else _lib.PidState(None, None)
         dsl = self.controller.c_gains() if self.cfg.ctrl == _lib.CTRL_DSLPID else None
         dsl_state = self.controller.state_struct() if self.cfg.ctrl == _lib.CTRL_DSLPID else _lib.DslPidState(None, None, None)
         cbf = self.qp.cbf.c_params() if self.qp is not None else None

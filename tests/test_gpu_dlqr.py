@@ -350,3 +350,45 @@ def test_dlqr_as_cbf_nominal_controller_vs_oracle(lib_built):
         ctrls = [oc.Lqr(o, "omega9", oc.ThrustOmegaPid(o), K=dl.K_matrix(j, env_idx=e).cpu().numpy()) for j in range(N)]
         _, want, info = opl.run_cbf(o, [otj.Lemniscate(**sp) for sp in specs], 2, steps, obstacles=obstacles, ctrls=ctrls)
         assert np.abs(got[e, :, 0:3] - want[:, 0:3]).max() < 1e-6, (e, info)
+
+
+@pytest.mark.parametrize("cls_name,order", [("DecentralizedLQROmega", 2), ("DecentralizedLQROmega", None), ("DecentralizedLQR", None)])
+def test_fused_rollout_with_per_drone_gains(cls_name, order, lib_built):
+    """MdsRolloutCfg.lqr_gain_planes_dev: the K-steps-in-one-launch rollout (and the two-launch plan) with a gain per drone
+    reproduce the per-call pipeline driven by the same decentralised controller (fp64; 12-dim: force_diagonal gains)."""
+    import multidronesim_b200 as mds
+    import multidronesim_b200.trajectories as T
+    from oracle import trajectories as otj
+    E, N, steps, dtype = 4, 3, 30, torch.float64
+    rng = np.random.default_rng(8)
+    ph = (2 * np.pi / (N + 0.25)) * np.arange(N)
+    specs = [dict(a=1.0, center=np.array([0, 0, 0.5]), omega=0.5, yaw_rate=0.0, phase_shift=float(p)) for p in ph]
+    obstacles = [[0.0, 0.0, 0.5, 0.1]] if order else None
+    init = np.zeros((E, N, 3))
+    for e in range(E):
+        for j, sp in enumerate(specs):
+            init[e, j] = otj.Lemniscate(**sp)(0.0)[0] + rng.normal(0, 0.02, 3) + np.array([0, 0, 0.04 * j])
+    outs = []
+    for mode in ("percall", "loop", "two"):
+        env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=N, physics=mds.Physics.DYN_GND_DRAG_DW, num_envs=E, dtype=dtype,
+                                    initial_xyzs=init)
+        dl = make_ctrl(env, cls_name)
+        th = dl.theta.cpu().numpy() * (1.0 + 0.03 * np.random.default_rng(1).normal(size=(E * N, dl.m + 4, dl.m)))
+        dl.set_theta(dev(th, dtype))
+        dl.compute_controller(force_diagonal=True)
+        trk = None
+        if order:
+            cbf = mds.cbf.DroneCBF(env, [mds.model.LinearizedOmegaModel(env) for _ in range(N)], safety_radius=0.1, zscale=1.0, order=2,
+                                   cbf_poles=np.array([-2.2, -2.4]))
+            trk = mds.cbf.DroneQPTracker(cbf, order=2, num_robots=N, xdim=9, env=env)
+        ts = mds.trajectories.TrajectorySet([T.Lemniscate(**sp) for sp in specs] * E, dtype=dtype)
+        if mode == "percall":
+            pipe = mds.PerCallPipeline(env, dl, trk, obstacles)
+            for k in range(steps):
+                obs = pipe.step(ts.eval(k * env.CTRL_TIMESTEP))
+        else:
+            ro = mds.FusedRollout(env, ts, dl, trk, obstacles)
+            obs = ro.run(steps, stages=6 if mode == "loop" else 4)
+        outs.append(obs.cpu().numpy().copy())
+    assert np.abs(outs[0][..., 0:3]).max() > 0.1
+    assert np.abs(outs[1] - outs[0])[..., :16].max() < 1e-9 and np.abs(outs[2] - outs[0])[..., :16].max() < 1e-9
