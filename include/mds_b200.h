@@ -157,7 +157,7 @@ enum {
 typedef struct MdsRolloutCfg {
   int ctrl;            /* MDS_CTRL_*                                       */
   int use_cbf;         /* 0/1; requires ctrl LQR_OMEGA (order 2) or LQR_YANK (order 3) */
-  int num_obstacles;   /* spheres shared by all envs (<= N, reference quirk B14)        */
+  int num_obstacles;   /* obstacles shared by all envs, <= MDS_MAX_OBSTACLES (the reference itself fails beyond N, quirk B14) */
   int write_obs_every; /* 0 = only after the last step; k>0 = log obs every k steps     */
   int stages;          /* launch plan for the K control steps:
                           0      whole steps, plan chosen by mds_rollout_plan(E, N) (currently always 6)
