@@ -255,3 +255,36 @@ def test_sysid_oracle_vs_reference_classes(golden):
             Pc = np.array([np.linalg.inv(p) for p in P]) if info else P
             assert np.abs(th - g[tag + "_theta"][t]).max() <= 1e-10 * max(1.0, np.abs(g[tag + "_theta"][t]).max()), (tag, t)
             assert np.abs(Pc - g[tag + "_P"][t]).max() <= 1e-10 * np.abs(g[tag + "_P"][t]).max(), (tag, t)
+
+
+def test_golden_fixtures_reproduce_from_the_reference(golden, tmp_path):
+    """Where the reference tree is present (the build container; never the GPU box), regenerate every fixture from the
+    reference's own modules (oracle/make_golden.py) and compare with the committed files: tests/golden/ is what the
+    reference computes today, not a stale copy."""
+    import os
+    from oracle import make_golden, ref_import
+    if not ref_import.reference_available():
+        pytest.skip("reference tree not present")
+    saved = make_golden.OUT
+    make_golden.OUT = str(tmp_path)
+    import warnings
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # the reference's own numpy deprecations (cbf/cbf.py:395)
+            ref = ref_import.load()
+            for fn in (make_golden.golden_trajectories, make_golden.golden_controllers, make_golden.golden_models, make_golden.golden_cbf,
+                       make_golden.golden_dlqr):
+                fn(ref)
+    finally:
+        make_golden.OUT = saved
+    fresh = {n[:-4]: np.load(os.path.join(str(tmp_path), n)) for n in os.listdir(str(tmp_path)) if n.endswith(".npz")}
+    assert sorted(fresh) == sorted(golden)
+    for name, g in golden.items():
+        assert sorted(g.files) == sorted(fresh[name].files), name
+        for k in g.files:
+            a, b = fresh[name][k], g[k]
+            assert a.shape == b.shape, (name, k)
+            if a.size and a.dtype.kind == "f":
+                assert np.abs(a - b).max() <= 1e-12 * max(1.0, float(np.abs(b).max())), (name, k)
+            else:
+                assert np.array_equal(a, b), (name, k)
