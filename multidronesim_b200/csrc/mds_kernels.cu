@@ -38,272 +38,8 @@ static int cuda_fail(const char* what, cudaError_t e) {
 #define MDS_REQUIRE(cond, msg) \
   if (!(cond)) return fail(MDS_ERR_ARG, "%s", msg)
 
-// ------------------------------------------------------------------ thread mapping
-// An environment's drones occupy NP = next_pow2(N) consecutive lanes of ONE warp ("lane group"; lanes
-// n >= N idle), so every cross-drone exchange (downwash neighbours, CBF rows, the QP) needs only
-// group-level synchronisation: shared memory + __syncwarp(gmask) / shuffles.  No block barriers.
-#ifndef MDS_BLOCK
-#define MDS_BLOCK 256
-#endif
-#ifndef MDS_CTRL_MINB
-#define MDS_CTRL_MINB 4  // resident blocks per SM the controller kernel is compiled for (64 registers)
-#endif
-#ifndef MDS_LOOP_MINB
-#define MDS_LOOP_MINB 2  // the K-step loop kernel serves small swarms: registers before occupancy
-#endif
-#ifndef MDS_FUSED_MINB
-#define MDS_FUSED_MINB 4
-#endif
-#ifndef MDS_PHYS_MINB
-#define MDS_PHYS_MINB 5
-#endif
-static inline int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
-struct GroupMap {
-  int el, n, e, d;   // env slot in block, drone in env, global env, global drone
-  bool valid;        // lane maps to a real drone
-  bool env_valid;    // group maps to a real env
-  unsigned gmask;    // lanes of this group within the warp
-};
-MDS_DEV GroupMap group_map(int N, int NP, int E) {
-  GroupMap g;
-  const int tid = threadIdx.x, lg = __ffs(NP) - 1;  // NP is a power of two
-  g.el = tid >> lg;
-  g.n = tid & (NP - 1);
-  g.e = blockIdx.x * (blockDim.x >> lg) + g.el;  // blockDim.x <= MDS_BLOCK (launch_geometry)
-  g.env_valid = g.e < E;
-  g.valid = g.env_valid && g.n < N;
-  g.d = g.e * N + g.n;
-  const int lane0 = (tid & 31) & ~(NP - 1);
-  g.gmask = NP >= 32 ? 0xffffffffu : (((1u << NP) - 1u) << lane0);
-  return g;
-}
-
-// Compile-time drone count that fills its lane group (N == NP, e.g. the swarm's 8): every lane of a valid environment
-// maps to a drone, so `valid` is a compile-time `true` inside the env_valid region and the per-stage `if (g.valid)`
-// guards fold away (uniform branches: fewer instructions, no measurable change in time).
-template <int NT> MDS_DEV void full_group_hint(GroupMap& g) {
-  if (NT > 0 && (NT & (NT - 1)) == 0) g.valid = true;
-}
-
-// Downwash sum for this lane's drone over its env mates; positions staged in shared memory.
-// Called by every lane of the group (two group syncs).
-template <typename Real>
-MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* sm_pos, V3<Real> p, const GroupMap& g, int N) {
-  typename Vec4T<Real>::type me;
-  me.x = p.x; me.y = p.y; me.z = p.z; me.w = Real(0);
-  sm_pos[threadIdx.x] = me;
-  __syncwarp(g.gmask);
-  Real dw = Real(0);
-  if (g.valid) {
-    const int base = threadIdx.x - g.n;
-#pragma unroll
-    for (int k = 1; k < N; ++k) {  // partners in circular order: no self test, unrolls when N is a compile-time constant
-      int j = g.n + k;
-      j = j >= N ? j - N : j;
-      auto q = sm_pos[base + j];
-      dw += downwash_term(P, p, v3(q.x, q.y, q.z));
-    }
-  }
-  __syncwarp(g.gmask);
-  return dw;
-}
-
-// per-env shared-memory block of the CBF stage (in Reals; every part is a multiple of 4 so that the Vec4
-// accesses stay aligned):
-//   head  max(12 NP, WS)  agents (p, dv, da per drone; 3 Vec4 each) -- overlaid by the QP workspace once the rows exist
-//   rows  4 NP RPL        one Vec4 (a0, a1, a2, rhs) per row, owner-major (mds_cbf.cuh "Row ownership")
-//   x     4 NP            the QP iterate, one Vec4 per drone
-//   xnom  4 NP            u_nom, kept for the fp32 polish of long solves
-template <typename Real> struct CbfSmem {
-  Real* env0;
-  int stride, off_rows, off_x;
-};
-static inline int cbf_env_stride(int NP, int N, int n_obs) {
-  int rpl = (N - 1) / 2 + ((N & 1) ? 0 : 1) + n_obs;
-  int head = 12 * NP > MDS_QP_WS_WORDS ? 12 * NP : ((MDS_QP_WS_WORDS + 3) & ~3);
-  return head + 4 * NP * rpl + 8 * NP;
-}
-template <typename Real> static size_t cbf_smem_bytes(int threads, int NP, int N, int n_obs) {
-  return (size_t)(threads / NP) * cbf_env_stride(NP, N, n_obs) * sizeof(Real) + 32;
-}
-// Threads per block (a power of two in [NP or 32, MDS_BLOCK]) such that the CBF stage's shared memory stays under
-// ~100 KB per block (two blocks per SM): only small lane groups in fp64 (many envs per block, each with its own QP
-// workspace) and 32-drone groups with many obstacles ever need fewer than MDS_BLOCK threads.
-template <typename Real> static int cbf_block_threads(int NP, int N, int n_obs) {
-  int threads = MDS_BLOCK;
-  const int floor_threads = NP > 32 ? NP : 32;
-  while (threads > floor_threads && cbf_smem_bytes<Real>(threads, NP, N, n_obs) > 100 * 1024) threads >>= 1;
-  return threads;
-}
-template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw, int NP, int N, int n_obs) {
-  CbfSmem<Real> s;
-  s.env0 = reinterpret_cast<Real*>(raw);
-  const RowMap M = row_map(N, n_obs);
-  int head = 12 * NP > MDS_QP_WS_WORDS ? 12 * NP : ((MDS_QP_WS_WORDS + 3) & ~3);
-  s.off_rows = head; s.off_x = head + 4 * NP * M.RPL;
-  s.stride = s.off_x + 8 * NP;  // x, then the untouched copy of u_nom
-  return s;
-}
-
-// CBF safety filter for one env by its lane group: u_nom -> u_safe for this lane's drone.
-// Every lane of a valid group calls it; returns the env's QP status, *iters_out its iteration count.
-template <typename Real>
-MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const CbfSmem<Real>& S, const Real* obstacles, int n_obs,
-                             const GroupMap& g, int N, int NP, const CbfAgent<Real>& ag, Real F, const Real unom[4], Real usafe[4],
-                             Real* min_h, int* iters_out) {
-  using R4 = typename Vec4T<Real>::type;
-  const int n = g.n;
-  const RowMap M = row_map(N, n_obs);
-  Real* env = S.env0 + (size_t)g.el * S.stride;
-  R4* agents = reinterpret_cast<R4*>(env);
-  R4* rows = reinterpret_cast<R4*>(env + S.off_rows);
-  R4* x = reinterpret_cast<R4*>(env + S.off_x);
-  R4* xnom = x + NP;
-  if (g.valid) {
-    R4 a0, a1, a2, xv;
-    a0.x = ag.p.x; a0.y = ag.p.y; a0.z = ag.p.z; a0.w = ag.dv.x;
-    a1.x = ag.dv.y; a1.y = ag.dv.z; a1.z = ag.da.x; a1.w = ag.da.y;
-    a2.x = ag.da.z; a2.y = Real(0); a2.z = Real(0); a2.w = Real(0);
-    agents[3 * n] = a0; agents[3 * n + 1] = a1; agents[3 * n + 2] = a2;
-    xv.x = unom[0]; xv.y = unom[1]; xv.z = unom[2]; xv.w = unom[3];
-    x[n] = xv;
-    xnom[n] = xv;
-  }
-  __syncwarp(g.gmask);
-  int fl = 0;
-  Real lo = Real(0), hi = Real(0);
-  QpWorst<Real> worst = {Real(0), 0x7fffffff};
-  if (g.valid) {
-    // this lane's own rows, each tested against u_nom as it is built: pair slots (compile-time count when N is),
-    // then obstacle slots
-#pragma unroll
-    for (int s = 0; s < M.S0; ++s) {
-      const int m = row_partner(M, N, n, s);
-      R4 row;
-      row.x = Real(0); row.y = Real(0); row.z = Real(0); row.w = Real(1e30);
-      if (m >= 0) {
-        CbfAgent<Real> other;
-        R4 b0 = agents[3 * m], b1 = agents[3 * m + 1], b2 = agents[3 * m + 2];
-        other.p = {b0.x, b0.y, b0.z}; other.dv = {b0.w, b1.x, b1.y}; other.da = {b1.z, b1.w, b2.x};
-        Real a3[3], rhs, h0;
-        cbf_row(P, C, ag, other, Real(2) * C.rs, C.c4inv, a3, &rhs, &h0);  // owner - partner (mds_cbf.cuh "Row ownership")
-        *min_h = min_(*min_h, h0);
-        row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
-        qp_test_row(worst, row, unom, x, n, m, n * M.RPL + s);
-      }
-      rows[n * M.RPL + s] = row;
-    }
-    for (int o = 0; o < n_obs; ++o) {
-      CbfAgent<Real> other;
-      other.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
-      other.dv = {Real(0), Real(0), Real(0)}; other.da = other.dv;
-      Real a3[3], rhs, h0, Ds, c4inv;
-      obstacle_shape(C, obstacles[4 * o + 3], &Ds, &c4inv);
-      cbf_row(P, C, ag, other, Ds, c4inv, a3, &rhs, &h0);
-      *min_h = min_(*min_h, h0);
-      R4 row;
-      row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
-      qp_test_row(worst, row, unom, x, n, -1, n * M.RPL + M.S0 + o);
-      rows[n * M.RPL + M.S0 + o] = row;
-    }
-    qp_test_box(worst, C, unom, n, 0u);
-    if (!cbf_wz_bounds(C, F, &lo, &hi)) fl = 1;
-  }
-  for (int off = NP >> 1; off > 0; off >>= 1) fl |= __shfl_xor_sync(g.gmask, fl, off);
-  const int p0 = qp_worst_of_group(worst, NP, g.gmask);
-  __syncwarp(g.gmask);  // rows complete; agents no longer needed (their storage becomes the QP workspace)
-  int status = MDS_QP_OPTIMAL, iters = 0;
-  if (fl || p0 == -2) status = MDS_QP_INFEASIBLE;
-  else if (p0 >= 0) status = qp_solve_group(C, rows, x, xnom, env, M, N, NP, n, g.valid, g.gmask, p0, &iters);
-  if (g.valid) {
-    if (status == MDS_QP_OPTIMAL) {
-      R4 xv = x[n];
-      usafe[0] = xv.x; usafe[1] = xv.y; usafe[2] = xv.z;
-      usafe[3] = clamp_(unom[3], lo, hi);
-    } else {  // reference falls back to the nominal input (cbf/qptracker.py:30-34)
-      usafe[0] = unom[0]; usafe[1] = unom[1]; usafe[2] = unom[2]; usafe[3] = unom[3];
-    }
-  }
-  __syncwarp(g.gmask);  // the env block may be reused by the next step
-  *iters_out = iters;
-  return status;
-}
-
-// ------------------------------------------------------------------ kernels: env step
-// NT > 0: drones per env as a compile-time constant (the rollout's specialisation for the 8-drone swarms: partner
-// loops unroll, lane maps fold to shifts); NT == 0: run-time N.
-template <int NT> MDS_DEV int ct_n(int n_rt) { return NT > 0 ? NT : n_rt; }
-template <int NT> MDS_DEV int ct_np(int np_rt) {
-  if (NT <= 0) return np_rt;
-  int p = 1;
-  while (p < NT) p <<= 1;
-  return p;
-}
-template <typename Real> MDS_DEV void store4(Real* p, int d, const Real v[4]) {
-  typename Vec4T<Real>::type o;
-  o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3];
-  reinterpret_cast<typename Vec4T<Real>::type*>(p)[d] = o;
-}
-template <typename Real> MDS_DEV void load4(const Real* p, int d, Real v[4]) {
-  auto o = reinterpret_cast<const typename Vec4T<Real>::type*>(p)[d];
-  v[0] = o.x; v[1] = o.y; v[2] = o.z; v[3] = o.w;
-}
-// One control period of the env for this lane's drone with the state in registers (every lane of a valid group
-// calls it): clips the action, runs the sub-steps, returns the new observation.
-template <typename Real>
-MDS_DEV Obs<Real> physics_core(const DroneP<Real>& P, Drone<Real>& s, const Real action[4], V3<Real> fx, typename Vec4T<Real>::type* sm_pos,
-                               const GroupMap& g, int N) {
-  Real rpm[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) rpm[i] = clamp_(action[i], Real(0), P.max_rpm);
-  V3<Real> av = {Real(0), Real(0), Real(0)};
-  const bool dwash = (P.physics == MDS_PHYSICS_DYN_GND_DRAG_DW) && (N > 1);
-  for (int k = 0; k < P.substeps; ++k) {
-    Real dw = Real(0);
-    if (dwash) dw = downwash_group(P, sm_pos, s.p, g, N);
-    if (g.valid) {
-      av = physics_substep(P, s, rpm, dw, fx);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) s.rpm[i] = rpm[i];
-    }
-  }
-  Obs<Real> o;
-  if (g.valid) o = make_obs(s, av);
-  return o;
-}
-
-// The same through HBM: loads the state and the action, stores the state and (if obs != nullptr) the observation,
-// and returns the observation in registers.
-template <typename Real>
-MDS_DEV Obs<Real> physics_body(const DroneP<Real>& P, const StateP<Real>& st, const Real* __restrict__ action, const Real* __restrict__ fext,
-                               Real* __restrict__ obs, typename Vec4T<Real>::type* sm_pos, const GroupMap& g, int N) {
-  Drone<Real> s;
-  s.p = {Real(0), Real(0), Real(0)};
-  Real act[4] = {Real(0), Real(0), Real(0), Real(0)};
-  V3<Real> fx = {Real(0), Real(0), Real(0)};
-  if (g.valid) {
-    s = load_drone(st, g.d);
-    load4(action, g.d, act);
-    if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
-  }
-  Obs<Real> o = physics_core(P, s, act, fx, sm_pos, g, N);
-  if (g.valid) {
-    store_drone(st, g.d, s);
-    if (obs) store_obs(obs, g.d, o);
-  }
-  return o;
-}
-
-template <typename Real, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_PHYS_MINB : 2) physics_step_kernel(DroneP<Real> P, StateP<Real> st, const Real* __restrict__ action,
-                                                                  const Real* __restrict__ fext, Real* __restrict__ obs, int E, int N_rt, int NP_rt) {
-  __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
-  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
-  GroupMap g = group_map(N, NP, E);
-  if (!g.env_valid) return;  // whole groups leave together
-  full_group_hint<NT>(g);
-  physics_body(P, st, action, fext, obs, sm_pos, g, N);
-}
+#include "mds_rollout.cuh"
+#include "mds_rollout_launch.cuh"
 
 template <typename Real>
 __global__ void obs_from_state_kernel(DroneP<Real> P, StateP<Real> st, Real* __restrict__ obs, int D) {
@@ -664,303 +400,6 @@ __global__ void linear_rollout_kernel(DroneP<Real> P, const Real* __restrict__ o
   }
 }
 
-// ------------------------------------------------------------------ kernel: fused K-step rollout
-template <typename Real> struct RolloutP {
-  int ctrl, use_cbf, n_obs, write_obs_every;
-  Real u0_pre, u0_post;
-  Real obstacles[MDS_MAX_OBSTACLES * 4];
-  const Real* lqr_planes;  // per-drone LQR gains [4*dim][D] (decentralised LQR), or null: the shared gain of LqrP
-  int lqr_D;
-};
-
-MDS_DEV void atomic_min_double(double* addr, double v) {
-  unsigned long long* a = (unsigned long long*)addr;
-  unsigned long long old = *a, assumed;
-  do {
-    assumed = old;
-    if (__longlong_as_double(assumed) <= v) break;
-    old = atomicCAS(a, assumed, __double_as_longlong(v));
-  } while (assumed != old);
-}
-MDS_DEV void atomic_max_double(double* addr, double v) {
-  unsigned long long* a = (unsigned long long*)addr;
-  unsigned long long old = *a, assumed;
-  do {
-    assumed = old;
-    if (__longlong_as_double(assumed) >= v) break;
-    old = atomicCAS(a, assumed, __double_as_longlong(v));
-  } while (assumed != old);
-}
-
-// L1 prefetch of the lines a thread will load much later (PID state after the QP, trajectory spec after the
-// physics step): the three global-load latencies of a thread then overlap instead of adding up.
-MDS_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// per-lane contributions to the rollout statistics
-struct StepStats {
-  float err, min_h;
-  int qp_solves, qp_iters, qp_infeas, qp_cap;
-};
-
-// One control step of the controller stack for this lane's drone (every lane of a valid group calls it):
-// reference -> tracking controller -> (CBF-QP) -> inner loop -> RPM action.  CTRL / USE_CBF are compile-time so
-// that each instantiation carries only its own stage code (one kernel with run-time switches overflowed the
-// instruction cache: 55 % of the stall samples were "no instruction").
-template <typename Real, int CTRL, bool USE_CBF, bool PDK = false>  // PDK: a gain per drone (Rc.lqr_planes) instead of LqrP's
-MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const GeoP<Real>& G, const LqrP<Real>& L, const CbfP<Real>& C,
-                       const DslP<Real>& Dg, const DslStateP<Real>& dst, const CbfSmem<Real>& S, const PidP<Real>& pid,
-                       const typename TrajSpecT<Real>::spec& spec,
-                       const typename TrajSpecT<Real>::seg* __restrict__ segs, const Obs<Real>& o, const GroupMap& g, int N, int NP,
-                       double t, Real rpm[4], StepStats& ss, int pid_idx) {
-  constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
-  Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
-  Ref<Real> ref;
-  if (g.valid) {
-    ref = eval_traj<Real>(spec, segs, t);
-    ss.err = (float)norm(o.p - ref.p);
-    if (CTRL == MDS_CTRL_GEOMETRIC) {
-      geometric_input(P, G, o, ref, u);
-      input_to_action(P, u, rpm);
-    } else if (CTRL == MDS_CTRL_DSLPID) {
-      DslState<Real> ds = load_dsl(dst, g.d);
-      V3<Real> pe;
-      dslpid_control(P, Dg, ds, o, ref.p, v3(Real(0), Real(0), ref.yaw), ref.v, v3(Real(0), Real(0), ref.yaw_rate), rpm, &pe);
-      store_dsl(dst, g.d, ds);
-    } else {
-      if (PDK) dlqr_input(P, Rc.lqr_planes, (size_t)Rc.lqr_D, (size_t)g.d, CTRL, o, ref, u);
-      else lqr_input(P, L, CTRL, o, ref, u);
-      if (CTRL == MDS_CTRL_LQR_TORQUE) input_to_action(P, u, rpm);
-    }
-  }
-  if (HAS_PID) {
-    if (USE_CBF) {
-      CbfAgent<Real> ag;
-      ag.p = {Real(0), Real(0), Real(0)}; ag.dv = ag.p; ag.da = ag.p;
-      Real F = Real(0), unom[4] = {Real(0), Real(0), Real(0), Real(0)}, usafe[4] = {Real(0), Real(0), Real(0), Real(0)};
-      if (g.valid) {
-        if (CTRL == MDS_CTRL_LQR_OMEGA) u[0] = cap_thrust(P, u[0]);  // skip_low_level=True returns cap_u(u)
-        Real xd[10];
-        xd[0] = Real(0); xd[1] = Real(0); xd[2] = ref.yaw;
-        if (CTRL == MDS_CTRL_LQR_OMEGA) { xd[3] = ref.v.x; xd[4] = ref.v.y; xd[5] = ref.v.z; }
-        else { xd[3] = P.g * P.m; xd[4] = ref.v.x; xd[5] = ref.v.y; xd[6] = ref.v.z; }
-        ag = cbf_agent(P, C, o, xd, &F);
-        unom[0] = u[0] - Rc.u0_pre; unom[1] = u[1]; unom[2] = u[2]; unom[3] = u[3];
-      }
-      Real mh = Real(1e30);
-      int it = 0;
-      int stt = cbf_filter_group(P, C, S, Rc.obstacles, Rc.n_obs, g, N, NP, ag, F, unom, usafe, &mh, &it);
-      if (g.valid) {
-        ss.min_h = (float)mh;
-        if (g.n == 0) {
-          ss.qp_solves = (it > 0 || stt != MDS_QP_OPTIMAL);
-          ss.qp_iters = it;
-          ss.qp_infeas = (stt == MDS_QP_INFEASIBLE);
-          ss.qp_cap = (stt == MDS_QP_ITER_CAP);
-        }
-        u[0] = usafe[0] + Rc.u0_post; u[1] = usafe[1]; u[2] = usafe[2]; u[3] = usafe[3];
-      }
-    }
-    if (g.valid) {
-      Pid<Real> ps = load_pid(pid, pid_idx);  // pid_idx: g.d for HBM-resident state, the thread index when the caller staged it
-      low_level(P, CTRL, ps, u, o, rpm);
-      store_pid(pid, pid_idx, ps);
-    }
-  }
-}
-
-// Block-wide accumulation of the statistics (called by EVERY thread of the block).
-// Per-warp reduction with redux.sync on integer images (counters; non-negative float bits order like unsigned
-// ints; the barrier minimum goes through an order-preserving float -> int map) and five float shuffles for the
-// error sum, then shared memory and ONE set of atomics per block: same-address atomics from every warp cost
-// more than the whole step (1.6 ms vs 0.4 ms per step at 1M drones).
-template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ stats, int drone_steps, const StepStats& ss, float max_err) {
-  __shared__ float sm_f[MDS_BLOCK / 32][2];
-  __shared__ int sm_i[MDS_BLOCK / 32][6];
-  const int n_warps = blockDim.x >> 5;
-  const unsigned full = 0xffffffffu;
-  int mh_i = __float_as_int(ss.min_h);
-  mh_i = mh_i >= 0 ? mh_i : (mh_i ^ 0x7fffffff);
-  const int w_steps = __reduce_add_sync(full, drone_steps), w_solves = __reduce_add_sync(full, ss.qp_solves);
-  const int w_iters = __reduce_add_sync(full, ss.qp_iters), w_inf = __reduce_add_sync(full, ss.qp_infeas), w_cap = __reduce_add_sync(full, ss.qp_cap);
-  const unsigned w_maxe = __reduce_max_sync(full, __float_as_uint(max_err));
-  const int w_minh = __reduce_min_sync(full, mh_i);
-  float w_sum = ss.err;
-  for (int off = 16; off > 0; off >>= 1) w_sum += __shfl_xor_sync(full, w_sum, off);
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) {
-    sm_f[w][0] = w_sum; sm_f[w][1] = __uint_as_float(w_maxe);
-    sm_i[w][0] = w_steps; sm_i[w][1] = w_solves; sm_i[w][2] = w_iters; sm_i[w][3] = w_inf; sm_i[w][4] = w_cap; sm_i[w][5] = w_minh;
-  }
-  __syncthreads();
-  if (threadIdx.x < MDS_STAT_COUNT) {
-    const int k = threadIdx.x;
-    double acc = 0.0;
-    if (k == MDS_STAT_SUM_POS_ERR) {
-      for (int i = 0; i < n_warps; ++i) acc += (double)sm_f[i][0];
-    } else if (k == MDS_STAT_MAX_POS_ERR) {
-      for (int i = 0; i < n_warps; ++i) acc = fmax(acc, (double)sm_f[i][1]);
-    } else if (k == MDS_STAT_MIN_BARRIER) {
-      int m = sm_i[0][5];
-      for (int i = 1; i < n_warps; ++i) m = min(m, sm_i[i][5]);
-      acc = (double)__int_as_float(m >= 0 ? m : (m ^ 0x7fffffff));
-    } else {
-      const int col = k == MDS_STAT_DRONE_STEPS ? 0 : (k == MDS_STAT_QP_SOLVES ? 1 : (k == MDS_STAT_QP_ITERS ? 2 : (k == MDS_STAT_QP_INFEASIBLE ? 3 : 4)));
-      long long t = 0;
-      for (int i = 0; i < n_warps; ++i) t += sm_i[i][col];
-      acc = (double)t;
-    }
-    if (k == MDS_STAT_MAX_POS_ERR) atomic_max_double(&stats[k], acc);
-    else if (k == MDS_STAT_MIN_BARRIER) { if (USE_CBF) atomic_min_double(&stats[k], acc); }
-    else if (acc != 0.0) atomicAdd(&stats[k], acc);
-  }
-}
-
-// controller stack alone: obs (HBM) -> action (HBM)
-template <typename Real, int CTRL, bool USE_CBF, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_CTRL_MINB : 2) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
-                                                               DslP<Real> Dg, DslStateP<Real> dst, PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
-                                                               const typename TrajSpecT<Real>::seg* __restrict__ segs,
-                                                               const Real* __restrict__ obs, Real* __restrict__ action,
-                                                               double* __restrict__ stats, double t, int E, int N_rt, int NP_rt) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
-  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
-  GroupMap g = group_map(N, NP, E);
-  StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
-  if (g.env_valid) {
-    full_group_hint<NT>(g);
-    Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
-    Obs<Real> o;
-    typename TrajSpecT<Real>::spec spec;
-    spec.kind = MDS_TRAJ_WAIT;
-    if (g.valid) {  // every global load of this thread is issued here, before the first dependent instruction
-      o = load_obs(obs, g.d);
-      spec = specs[g.d];
-      if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
-    }
-    ctrl_body<Real, CTRL, USE_CBF, (NT < 0)>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss, g.d);
-    if (g.valid) store4(action, g.d, rpm);
-  }
-  if (stats) stats_block_reduce<USE_CBF>(stats, g.valid ? 1 : 0, ss, ss.err);
-}
-
-// One launch per control step inside a rollout: the env advances under the PREVIOUS step's action, and the
-// controller stack runs on the new observation while it is still in registers (the observation is written for the
-// caller / the log but never read back; the action buffer is read and rewritten by the same thread).  Blocks of
-// one grid are in different phases (HBM-heavy physics, issue-heavy controller), which overlap on an SM.
-template <typename Real, int CTRL, bool USE_CBF, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB : 2) step_fused_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
-                                                                DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
-                                                                const typename TrajSpecT<Real>::spec* __restrict__ specs,
-                                                                const typename TrajSpecT<Real>::seg* __restrict__ segs,
-                                                                Real* __restrict__ action, const Real* __restrict__ fext, Real* __restrict__ obs_out,
-                                                                double* __restrict__ stats, double t, int E, int N_rt, int NP_rt) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
-  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
-  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
-  GroupMap g = group_map(N, NP, E);
-  StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
-  if (g.env_valid) {
-    full_group_hint<NT>(g);
-    if (g.valid) {
-      prefetch_l1(specs + g.d);
-      prefetch_l1(reinterpret_cast<const char*>(specs + g.d) + 32);
-      if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
-    }
-    const Obs<Real> o = physics_body(P, st, action, fext, obs_out, sm_pos, g, N);
-    Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
-    typename TrajSpecT<Real>::spec spec;
-    spec.kind = MDS_TRAJ_WAIT;
-    if (g.valid) spec = specs[g.d];
-    ctrl_body<Real, CTRL, USE_CBF>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss, g.d);
-    if (g.valid) store4(action, g.d, rpm);
-  }
-  if (stats) stats_block_reduce<USE_CBF>(stats, g.valid ? 1 : 0, ss, ss.err);
-}
-
-// K control steps in ONE launch.  Environments never interact, and everything that couples the drones of an
-// environment (downwash, CBF rows, QP) is exchanged inside its lane group, so a group can run its env forward on its
-// own: the observation and the body rates stay in registers from step to step, HBM sees the initial load, the PID
-// state (L1-resident), the log slots that are due and the final store.  No launch per step, no grid-wide barrier.
-template <typename Real, int CTRL, bool USE_CBF, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
-                                                                  DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
-                                                                  const typename TrajSpecT<Real>::spec* __restrict__ specs,
-                                                                  const typename TrajSpecT<Real>::seg* __restrict__ segs,
-                                                                  Real* __restrict__ action, const Real* __restrict__ fext, Real* __restrict__ obs,
-                                                                  Real* __restrict__ obs_log, double* __restrict__ stats, double t0, double dt_ctrl, int K, int E,
-                                                                  int N_rt, int NP_rt) {
-  extern __shared__ __align__(32) unsigned char smem_raw[];
-  __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
-  // fp32 stages the per-step read-mostly data (trajectory descriptor, rate-PID state) in shared memory for the launch;
-  // fp64 does not: with the CBF stage's 91 KB that would leave one resident block per SM instead of two (0.41 vs 0.31 ms)
-  constexpr bool STAGE = sizeof(Real) == 4;
-  __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[STAGE ? MDS_BLOCK : 1];
-  constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
-  __shared__ typename Vec4T<Real>::type sm_pid_a[(STAGE && HAS_PID) ? MDS_BLOCK : 1];
-  __shared__ typename Vec2T<Real>::type sm_pid_b[(STAGE && HAS_PID) ? MDS_BLOCK : 1];
-  const PidP<Real> pid_s = STAGE ? PidP<Real>{sm_pid_a, sm_pid_b} : pid;
-  const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
-  CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
-  GroupMap g = group_map(N, NP, E);
-  StepStats acc = {0.f, 1e30f, 0, 0, 0, 0};
-  float max_err = 0.f;
-  int steps_done = 0;
-  if (g.env_valid) {
-    full_group_hint<NT>(g);
-    Obs<Real> o;
-    V3<Real> wb = {Real(0), Real(0), Real(0)};  // body rates: the one part of the state the observation does not carry
-    // The trajectory descriptor is read every step; its address escapes into the out-of-line table walk, so as an
-    // automatic it would live in local memory (LDL, L1-missing under this kernel's local footprint): stage it in
-    // shared memory instead (12-word lane stride: 128-bit reads are conflict-free per quarter warp).
-    typename TrajSpecT<Real>::spec spec_reg;
-    typename TrajSpecT<Real>::spec& spec = STAGE ? sm_spec[threadIdx.x] : spec_reg;
-    spec.kind = MDS_TRAJ_WAIT;
-    V3<Real> fx = {Real(0), Real(0), Real(0)};  // constant world-frame force on this drone (wind), if any
-    if (g.valid) {
-      o = load_obs(obs, g.d);
-      spec = specs[g.d];
-      wb = {st.pos_wx[g.d].w, st.vel_wy[g.d].w, st.wz[g.d]};
-      if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
-      if (STAGE && HAS_PID) { sm_pid_a[threadIdx.x] = pid.a[g.d]; sm_pid_b[threadIdx.x] = pid.b[g.d]; }
-    }
-    Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
-    const size_t obs_elems = (size_t)E * N * MDS_OBS_DIM;
-    int log_countdown = Rc.write_obs_every;  // steps until the next log slot is due (no division in the loop)
-    Real* log_slot = obs_log;
-    for (int k = 0; k < K; ++k) {
-      StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
-      ctrl_body<Real, CTRL, USE_CBF, (NT < 0)>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss, STAGE ? (int)threadIdx.x : g.d);  // the host plans form t exactly like this
-      acc.err += ss.err; max_err = fmaxf(max_err, ss.err); acc.min_h = fminf(acc.min_h, ss.min_h);
-      acc.qp_solves += ss.qp_solves; acc.qp_iters += ss.qp_iters; acc.qp_infeas += ss.qp_infeas; acc.qp_cap += ss.qp_cap;
-      Drone<Real> s;
-      s.p = o.p; s.qx = o.qx; s.qy = o.qy; s.qz = o.qz; s.qw = o.qw; s.v = o.v; s.w = wb;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) s.rpm[i] = o.rpm[i];
-      o = physics_core(P, s, rpm, fx, sm_pos, g, N);
-      wb = s.w;
-      if (Rc.write_obs_every > 0 && --log_countdown == 0) {
-        if (g.valid) store_obs(log_slot, g.d, o);
-        log_slot += obs_elems;
-        log_countdown = Rc.write_obs_every;
-      }
-    }
-    if (g.valid) {
-      Drone<Real> s;
-      s.p = o.p; s.qx = o.qx; s.qy = o.qy; s.qz = o.qz; s.qw = o.qw; s.v = o.v; s.w = wb;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) s.rpm[i] = o.rpm[i];
-      store_drone(st, g.d, s);
-      store_obs(obs, g.d, o);
-      store4(action, g.d, rpm);
-      if (STAGE && HAS_PID) { pid.a[g.d] = sm_pid_a[threadIdx.x]; pid.b[g.d] = sm_pid_b[threadIdx.x]; }
-      steps_done = K;
-    }
-  }
-  if (stats) stats_block_reduce<USE_CBF>(stats, steps_done, acc, max_err);
-}
-
 // ------------------------------------------------------------------ FMA-chain peak microbenchmark
 template <typename Real> __global__ void fma_peak_kernel(Real* out, int iters) {
   Real a0 = Real(threadIdx.x) * Real(1e-3), a1 = a0 + Real(1), a2 = a0 + Real(2), a3 = a0 + Real(3);
@@ -1252,59 +691,13 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     return obs;
   };
   cudaError_t attr_err = cudaSuccess;
-  const bool PDKV = R.lqr_planes != nullptr;  // per-drone gains: the run-time-N instantiations compiled with PDK (NT = -1)
-#define MDS_LAUNCH_CTRL(CT, CB, FUSED, T, OBS_PTR, PDKC)                                                                                 \
-  do {                                                                                                                              \
-    if (FUSED) {                                                                                                                    \
-      auto kern = (N == 8) ? step_fused_kernel<Real, CT, CB, 8> : step_fused_kernel<Real, CT, CB, 0>;                               \
-      if (first_fused) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-      kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, fext, OBS_PTR, stats, T, E, N, NP);              \
-    } else {                                                                                                                        \
-      auto kern = PDKV ? ctrl_step_kernel<Real, CT, CB, (PDKC ? -1 : 0)>                                                           \
-                       : ((N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>);                       \
-      if (first_ctrl) attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
-      kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Pi, specs, segs, (const Real*)(OBS_PTR), action, stats, T, E, N, NP);   \
-    }                                                                                                                               \
-  } while (0)
-#define MDS_LAUNCH_LOOP(CT, CB, PDKC)                                                                                                    \
-  do {                                                                                                                              \
-    auto kern = PDKV ? rollout_loop_kernel<Real, CT, CB, (PDKC ? -1 : 0)>                                                          \
-                     : ((N == 8) ? rollout_loop_kernel<Real, CT, CB, 8> : rollout_loop_kernel<Real, CT, CB, 0>);                   \
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
-    kern<<<blocks, threads, smem, cs>>>(Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, fext, obs, obs_log, stats, t0, prm->dt_ctrl, K, E, N, \
-                                        NP);                                                                                      \
-  } while (0)
-  auto launch_loop = [&]() {
-    switch (R.ctrl) {
-      case MDS_CTRL_GEOMETRIC: MDS_LAUNCH_LOOP(MDS_CTRL_GEOMETRIC, false, false); break;
-      case MDS_CTRL_LQR_TORQUE: MDS_LAUNCH_LOOP(MDS_CTRL_LQR_TORQUE, false, true); break;
-      case MDS_CTRL_DSLPID: MDS_LAUNCH_LOOP(MDS_CTRL_DSLPID, false, false); break;
-      case MDS_CTRL_LQR_OMEGA:
-        if (R.use_cbf) MDS_LAUNCH_LOOP(MDS_CTRL_LQR_OMEGA, true, true);
-        else MDS_LAUNCH_LOOP(MDS_CTRL_LQR_OMEGA, false, true);
-        break;
-      default:
-        if (R.use_cbf) MDS_LAUNCH_LOOP(MDS_CTRL_LQR_YANK, true, true);
-        else MDS_LAUNCH_LOOP(MDS_CTRL_LQR_YANK, false, true);
-        break;
-    }
-  };
+  RolloutLaunch<Real> RL{Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, fext, obs, obs_log, stats, E, N, NP, blocks, threads, smem, cs};
+  auto keep = [&](cudaError_t e) { if (e != cudaSuccess) attr_err = e; };
+  auto launch_loop = [&]() { keep(launch_loop_kernel<Real>(RL, t0, prm->dt_ctrl, K)); };
   bool first_ctrl = true, first_fused = true;
   auto launch_ctrl = [&](bool fused, double t, Real* obs_ptr) {
-    switch (R.ctrl) {
-      case MDS_CTRL_GEOMETRIC: MDS_LAUNCH_CTRL(MDS_CTRL_GEOMETRIC, false, fused, t, obs_ptr, false); break;
-      case MDS_CTRL_LQR_TORQUE: MDS_LAUNCH_CTRL(MDS_CTRL_LQR_TORQUE, false, fused, t, obs_ptr, true); break;
-      case MDS_CTRL_DSLPID: MDS_LAUNCH_CTRL(MDS_CTRL_DSLPID, false, fused, t, obs_ptr, false); break;
-      case MDS_CTRL_LQR_OMEGA:
-        if (R.use_cbf) MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, true, fused, t, obs_ptr, true);
-        else MDS_LAUNCH_CTRL(MDS_CTRL_LQR_OMEGA, false, fused, t, obs_ptr, true);
-        break;
-      default:
-        if (R.use_cbf) MDS_LAUNCH_CTRL(MDS_CTRL_LQR_YANK, true, fused, t, obs_ptr, true);
-        else MDS_LAUNCH_CTRL(MDS_CTRL_LQR_YANK, false, fused, t, obs_ptr, true);
-        break;
-    }
-    if (fused) first_fused = false; else first_ctrl = false;
+    if (fused) { keep(launch_fused_kernel<Real>(RL, t, obs_ptr, first_fused)); first_fused = false; }
+    else { keep(launch_ctrl_kernel<Real>(RL, t, obs_ptr, first_ctrl)); first_ctrl = false; }
   };
   auto launch_phys = [&](Real* obs_out) {
     if (N == 8) physics_step_kernel<Real, 8><<<blocks, threads, 0, cs>>>(Pd, Sd, action, fext, obs_out, E, N, NP);
@@ -1332,8 +725,6 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     obs_last = obs_slot(K);
     launch_phys(obs_last);
   }
-#undef MDS_LAUNCH_CTRL
-#undef MDS_LAUNCH_LOOP
   if (attr_err != cudaSuccess) return cuda_fail("rollout: shared memory opt-in failed", attr_err);
   if (obs_last != obs) {
     cudaError_t e = cudaMemcpyAsync(obs, obs_last, obs_elems * sizeof(Real), cudaMemcpyDeviceToDevice, cs);
