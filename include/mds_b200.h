@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MDS_ABI_VERSION 8
+#define MDS_ABI_VERSION 9
 #define MDS_MAX_DRONES_PER_ENV 32
 #define MDS_MAX_OBSTACLES 8
 #define MDS_OBS_DIM 20
@@ -135,7 +135,10 @@ typedef struct MdsCbfParams {
   double kcbf[3];        /* place_poles gain, order entries */
   double umax[4];
   double fmin, fmax;     /* order-3 force-bound rows (cbf.py:446-464) */
-  int max_iter;          /* active-set iteration cap (0 = default 64) */
+  int max_iter;          /* iteration cap of the in-shared-memory active-set solver (0 = default 64); a solve that exceeds it, or
+                          * whose active set outgrows its 12 slots, is repeated by the scratch solver (no cap on the active set) */
+  int no_state_bounds;   /* 0 = CBF(do_state_bounds=True), the reference's default: order-3 force-bound rows on column 4i+3
+                          * (cbf.py:446-476); 1 = do_state_bounds=False: those rows are not emitted */
 } MdsCbfParams;
 
 /* per-drone trajectory descriptor, 48 B (f32) / 80 B (f64).  MDS_TRAJ_TABLE: segments

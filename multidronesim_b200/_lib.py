@@ -69,7 +69,7 @@ class LqrGains(C.Structure):
 class CbfParams(C.Structure):
     _fields_ = [("order", C.c_int), ("zscale", C.c_double), ("safety_radius", C.c_double),
                 ("kcbf", C.c_double * 3), ("umax", C.c_double * 4), ("fmin", C.c_double),
-                ("fmax", C.c_double), ("max_iter", C.c_int)]
+                ("fmax", C.c_double), ("max_iter", C.c_int), ("no_state_bounds", C.c_int)]
 
 
 class RlsCfg(C.Structure):

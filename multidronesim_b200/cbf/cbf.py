@@ -51,6 +51,7 @@ class CBF:
         for i in range(4):
             c.umax[i] = float(um[i])
         c.fmin, c.fmax, c.max_iter = float(self.Fmin), float(self.Fmax), int(self.max_iter)
+        c.no_state_bounds = 0 if self.do_state_bounds else 1
         return c
 
     def update_cbf_gain(self, cbf_poles):
@@ -104,7 +105,10 @@ class DroneCBF(CBF):
                              "pass DroneCBF(..., allow_extra_obstacles=True) for the extension")
 
     def num_rows(self, n_obs=0):
-        return _lib.load_library().mds_cbf_num_rows(self.order, self.num_agents, n_obs)
+        m = _lib.load_library().mds_cbf_num_rows(self.order, self.num_agents, n_obs)
+        if self.order == 3 and not self.do_state_bounds:   # no force-bound rows (cbf/cbf.py:473-476)
+            m -= 2 * self.num_agents
+        return m
 
     def build_ineq_const(self, obs, xdes, obstacles=None):
         """Dense (G [E,m,4N], h [E,m]) in the reference's row order (cbf/cbf.py:308-367) for inspection /

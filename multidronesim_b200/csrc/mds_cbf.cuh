@@ -18,65 +18,73 @@
 
 namespace mds {
 
-#define MDS_QP_QMAX 12  // max simultaneously active constraints handled (else status ITER_CAP)
+#define MDS_QP_QMAX 12  // active constraints the in-shared-memory solver holds; larger sets go to the scratch solver (qp_solve_group<.., true>)
 
 // what a barrier row needs from one agent: position, velocity error, linearised acceleration error
 template <typename Real> struct CbfAgent {
   V3<Real> p, dv, da;
 };
 
+// ORD: relative degree as a compile-time constant (2 or 3), or 0 = read C.order at run time
+template <int ORD, typename Real> MDS_DEV int cbf_order(const CbfP<Real>& C) { return ORD ? ORD : C.order; }
+
 // obs + xdes (linear-model layout) -> CbfAgent.  order 2: xdes = [0,0,yaw,vel,pos];
 // order 3: xdes = [0,0,yaw,F_des,vel,pos].  Also returns the current thrust F (order 3 force rows).
-template <typename Real>
+template <int ORD, typename Real>
 MDS_DEV CbfAgent<Real> cbf_agent(const DroneP<Real>& P, const CbfP<Real>& C, const Obs<Real>& o, const Real* xd, Real* F_out) {
   CbfAgent<Real> a;
   a.p = o.p;
   Real roll = o.rpy.x - xd[0], pitch = o.rpy.y - xd[1];
-  if (C.order == 2) {
+  if (cbf_order<ORD>(C) == 2) {
     a.dv = {o.v.x - xd[3], o.v.y - xd[4], o.v.z - xd[5]};
     a.da = {P.g * pitch, -P.g * roll, Real(0)};
     *F_out = Real(0);
   } else {
     Real F = z_thrust(P, o.rpm);
     a.dv = {o.v.x - xd[4], o.v.y - xd[5], o.v.z - xd[6]};
-    a.da = {P.g * pitch, -P.g * roll, (F - xd[3]) / P.m};
+    a.da = {P.g * pitch, -P.g * roll, (F - xd[3]) * P.inv_m};
     *F_out = F;
   }
   return a;
 }
 
 // One ECBF row between agent i and agent/obstacle j (obstacle: dv = da = 0).  a3 = LgLf^{r-1}h on
-// i's block (columns u0, wx, wy); rhs = Kcbf.[h, hdot, (hddot)] + Lf^r h; h0 = barrier value.
+// i's block (columns u0, wx, wy); rhs = Kcbf.[h, hdot, (hddot)] + Lf^r h; h0 = barrier value.  Ds4 = Ds^4;
 // c4inv = 1 / zscale^4 for agents and sphere obstacles; 0 for a vertical-cylinder obstacle (the z terms vanish).
-template <typename Real>
+// The closed forms of the header are grouped around  rho = ex^2 + ey^2,  s = e_xy . dv_xy,  w = |dv_xy|^2:
+//   H dv = (4 rho dvx + 8 ex s, 4 rho dvy + 8 ey s, Hzz dvz),  dv'H dv = 4 rho w + 8 s^2 + Hzz dvz^2,
+//   q(dv).dv = 24 (s w + ez dvz^3 / c^4)
+// so that a row is ~60 instructions, most of them FMAs (products-then-sums cost 95).
+template <int ORD, typename Real>
 MDS_DEV void cbf_row(const DroneP<Real>& P, const CbfP<Real>& C, const CbfAgent<Real>& ai, const CbfAgent<Real>& aj,
-                     Real Ds, Real c4inv, Real a3[3], Real* rhs, Real* h0_out) {
-  V3<Real> e = ai.p - aj.p, dv = ai.dv - aj.dv, da = ai.da - aj.da;
-  Real ex2 = e.x * e.x, ey2 = e.y * e.y, ez2 = e.z * e.z;
-  Real rho = ex2 + ey2;
-  V3<Real> d = {Real(4) * e.x * rho, Real(4) * e.y * rho, Real(4) * e.z * ez2 * c4inv};
-  Real Hxx = Real(12) * ex2 + Real(4) * ey2, Hxy = Real(8) * e.x * e.y, Hyy = Real(4) * ex2 + Real(12) * ey2;
-  Real Hzz = Real(12) * ez2 * c4inv;
-  V3<Real> Hdv = {Hxx * dv.x + Hxy * dv.y, Hxy * dv.x + Hyy * dv.y, Hzz * dv.z};
-  Real Ds2 = Ds * Ds;
-  Real h0 = rho * rho + ez2 * ez2 * c4inv - Ds2 * Ds2;
-  Real h1 = dot(d, dv);
-  Real inv_m = Real(1) / P.m;
+                     Real Ds4, Real c4inv, Real a3[3], Real* rhs, Real* h0_out) {
+  const Real ex = ai.p.x - aj.p.x, ey = ai.p.y - aj.p.y, ez = ai.p.z - aj.p.z;
+  const Real dvx = ai.dv.x - aj.dv.x, dvy = ai.dv.y - aj.dv.y, dvz = ai.dv.z - aj.dv.z;
+  const Real dax = ai.da.x - aj.da.x, day = ai.da.y - aj.da.y;
+  const Real rho = fma_(ey, ey, ex * ex), ez2 = ez * ez, ez2c = ez2 * c4inv, rho4 = Real(4) * rho;
+  const Real s = fma_(ey, dvy, ex * dvx);
+  const Real dvx2 = dvx * dvx, dvy2 = dvy * dvy;
+  const Real dz = Real(4) * (ez * ez2c), dx = rho4 * ex, dy = rho4 * ey;  // d = dh/de
+  const Real h0 = fma_(rho, rho, fma_(ez2, ez2c, -Ds4));
+  const Real h1 = fma_(rho4, s, dz * dvz);
+  const Real Hzz = Real(12) * ez2c;
   *h0_out = h0;
-  if (C.order == 2) {
-    Real Lf = dot(d, da) + dot(dv, Hdv);
-    a3[0] = d.z * inv_m; a3[1] = Real(0); a3[2] = Real(0);
-    *rhs = C.k0 * h0 + C.k1 * h1 + Lf;
+  if (cbf_order<ORD>(C) == 2) {
+    const Real Lf = fma_(dx, dax, dy * day) + fma_(rho4, dvx2 + dvy2, fma_(Real(8) * s, s, Hzz * dvz * dvz));
+    a3[0] = dz * P.inv_m; a3[1] = Real(0); a3[2] = Real(0);
+    *rhs = fma_(C.k0, h0, fma_(C.k1, h1, Lf));
     return;
   }
+  const Real daz = ai.da.z - aj.da.z;
+  const Real ex8 = Real(8) * ex;
+  const Real Hxx = fma_(ex8, ex, rho4), Hyy = fma_(Real(8) * ey, ey, rho4), Hxy = ex8 * ey;
   // hdots[2] with the reference's hard-coded indices 6,7,8 of the 10-dim state (quirk B12)
-  Real h2 = d.y * da.x + d.z * da.y + Hxx * da.z * da.z + Real(2) * Hxy * da.z * dv.x + Hyy * dv.x * dv.x + Hzz * dv.y * dv.y;
-  V3<Real> q = {Real(24) * e.x * dv.x * dv.x + Real(16) * e.y * dv.x * dv.y + Real(8) * e.x * dv.y * dv.y,
-                Real(8) * e.y * dv.x * dv.x + Real(16) * e.x * dv.x * dv.y + Real(24) * e.y * dv.y * dv.y,
-                Real(24) * e.z * c4inv * dv.z * dv.z};
-  Real Lf = Real(3) * dot(da, Hdv) + dot(q, dv);
-  a3[0] = d.z * inv_m; a3[1] = -P.g * d.y; a3[2] = P.g * d.x;
-  *rhs = C.k0 * h0 + C.k1 * h1 + C.k2 * h2 + Lf;
+  const Real h2 = fma_(dy, dax, fma_(dz, day, fma_(daz, fma_(Hxx, daz, Real(2) * Hxy * dvx), fma_(Hyy, dvx2, Hzz * dvy2))));
+  const Real daHdv = fma_(rho4, fma_(dax, dvx, day * dvy), fma_(Real(8) * s, fma_(ex, dax, ey * day), Hzz * dvz * daz));
+  const Real qdv = Real(24) * fma_(s, dvx2 + dvy2, (c4inv * ez) * (dvz * dvz * dvz));
+  const Real Lf = fma_(Real(3), daHdv, qdv);
+  a3[0] = dz * P.inv_m; a3[1] = -P.g * dy; a3[2] = P.g * dx;
+  *rhs = fma_(C.k0, h0, fma_(C.k1, h1, fma_(C.k2, h2, Lf)));
 }
 
 // ----------------------------------------------------------------------------------------
@@ -163,9 +171,10 @@ template <typename Real> MDS_DEV Real qp_dot_x(const QpCon<Real>& c, const typen
   *mag = m;
   return s;
 }
-template <typename Real> MDS_DEV Real qp_dot_g(const QpCon<Real>& a, const QpCon<Real>& b) {
-  Real ab = a.gi[0] * b.gi[0] + a.gi[1] * b.gi[1] + a.gi[2] * b.gi[2];
-  Real s = Real(0);
+// g_a . g_b accumulated in W (the scratch solver and the polish work in double whatever the row precision)
+template <typename W, typename Real> MDS_DEV W qp_dot_g(const QpCon<Real>& a, const QpCon<Real>& b) {
+  W ab = (W)a.gi[0] * (W)b.gi[0] + (W)a.gi[1] * (W)b.gi[1] + (W)a.gi[2] * (W)b.gi[2];
+  W s = W(0);
   if (a.i == b.i) s += ab;
   if (a.j >= 0 && a.j == b.j) s += ab;
   if (a.j >= 0 && a.j == b.i) s -= ab;
@@ -255,26 +264,24 @@ MDS_DEV int qp_scan(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows,
   return qp_worst_of_group(w, NP, gmask);
 }
 
-// fp32 polish, lane-0 part (rare: solves that end with >= 3 active constraints): solve (A A') lam = A u_nom - b for the
-// final active set in double and leave lam in the workspace.  Out of line: its fp64 arrays and code stay out of the
-// step loop's registers and instruction stream.
-template <typename Real>
-__device__ __noinline__ bool qp_polish_lane0(Real umax0, Real umax1, Real umax2, const typename Vec4T<Real>::type* rows,
-                                             const typename Vec4T<Real>::type* xnom, Real* ws, Real* lam, int q) {
-  auto iref = [](Real* slot) -> int& { return *reinterpret_cast<int*>(slot); };
+// int stored in a workspace slot of either width (the active list shares the Real / double workspace)
+template <typename W> MDS_DEV int& ws_int(W* slot) { return *reinterpret_cast<int*>(slot); }
+template <typename W> MDS_DEV int ws_int(const W* slot) { return *reinterpret_cast<const int*>(slot); }
+
+// fp32 polish, lane-0 part (solves that end with >= 3 active constraints): solve (A A') lam = A u_nom - b for the final
+// active set in double and leave lam in the workspace.  act = packed active list (one int per W slot); Lm, y = double
+// scratch of q (q + 1) / 2 and q entries.
+template <typename Real, typename W>
+MDS_DEV bool qp_polish_core(Real umax0, Real umax1, Real umax2, const typename Vec4T<Real>::type* rows, const typename Vec4T<Real>::type* xnom,
+                            const W* act, double* Lm, double* y, W* lam, int q) {
   CbfP<Real> C;  // only the box bounds are read (qp_get); taking the caller's block by reference would force it into local memory
   C.umax[0] = umax0; C.umax[1] = umax1; C.umax[2] = umax2;
-  double Lm[MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2], y[MDS_QP_QMAX];
   bool ok = true;
   for (int a = 0; a < q && ok; ++a) {
-    QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
+    QpCon<Real> ca = qp_get(rows, C, ws_int(act + a));
     for (int b2 = 0; b2 <= a; ++b2) {
-      QpCon<Real> cb = qp_get(rows, C, iref(ws + b2));
-      double ab = (double)ca.gi[0] * cb.gi[0] + (double)ca.gi[1] * cb.gi[1] + (double)ca.gi[2] * cb.gi[2], sacc = 0.0;
-      if (ca.i == cb.i) sacc += ab;
-      if (ca.j >= 0 && ca.j == cb.j) sacc += ab;
-      if (ca.j >= 0 && ca.j == cb.i) sacc -= ab;
-      if (cb.j >= 0 && cb.j == ca.i) sacc -= ab;
+      QpCon<Real> cb = qp_get(rows, C, ws_int(act + b2));
+      double sacc = qp_dot_g<double>(ca, cb);
       for (int k = 0; k < b2; ++k) sacc -= Lm[a * (a + 1) / 2 + k] * Lm[b2 * (b2 + 1) / 2 + k];
       if (a == b2) {
         if (sacc <= 0.0) { ok = false; break; }
@@ -283,7 +290,6 @@ __device__ __noinline__ bool qp_polish_lane0(Real umax0, Real umax1, Real umax2,
         Lm[a * (a + 1) / 2 + b2] = sacc / Lm[b2 * (b2 + 1) / 2 + b2];
       }
     }
-    // right-hand side A u_nom - b from the nominal inputs kept in the 4th ... see below: unom is passed in xnom
     auto ui = xnom[ca.i];
     double r = (double)ca.gi[0] * ui.x + (double)ca.gi[1] * ui.y + (double)ca.gi[2] * ui.z;
     if (ca.j >= 0) { auto uj = xnom[ca.j]; r -= (double)ca.gi[0] * uj.x + (double)ca.gi[1] * uj.y + (double)ca.gi[2] * uj.z; }
@@ -300,39 +306,51 @@ __device__ __noinline__ bool qp_polish_lane0(Real umax0, Real umax1, Real umax2,
       for (int k = a + 1; k < q; ++k) sacc -= Lm[k * (k + 1) / 2 + a] * y[k];
       y[a] = sacc / Lm[a * (a + 1) / 2 + a];
     }
-    for (int a = 0; a < q; ++a) lam[a] = (Real)y[a];
+    for (int a = 0; a < q; ++a) lam[a] = (W)y[a];
   }
   return ok;
+}
+// in-shared-memory solver: the double arrays live in this function's own frame (out of line, off the step loop's registers)
+template <typename Real>
+__device__ __noinline__ bool qp_polish_small(Real umax0, Real umax1, Real umax2, const typename Vec4T<Real>::type* rows,
+                                             const typename Vec4T<Real>::type* xnom, Real* ws, Real* lam, int q) {
+  double Lm[MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2], y[MDS_QP_QMAX];
+  return qp_polish_core<Real, Real>(umax0, umax1, umax2, rows, xnom, ws, Lm, y, lam, q);
 }
 
 // Goldfarb-Idnani dual active set, P = I, executed by the env's lane group.
 //   rows : smem barrier rows;  x : smem iterate, one Vec4 per drone (u_nom on entry, minimiser on exit);
 //   xnom : smem copy of u_nom that stays untouched (fp32 polish);
-//   ws   : smem workspace of MDS_QP_WS_WORDS Reals;  p0 : the most violated constraint at u_nom (packed),
-//   found by the row builder's own scan.
+//   ws   : workspace -- BIG = false: MDS_QP_WS_WORDS Reals of shared memory, at most MDS_QP_QMAX active constraints;
+//          BIG = true: a slot of the global scratch in double (QpScratch), at most qmax = 3 N active constraints (the number of
+//          coupled variables, i.e. no cap at all);
+//   p0   : the most violated constraint at u_nom (packed).
 // Work split: scans and the primal update are spread over the lanes (lane n owns drone n's inputs, rows and
-// box bounds).  The first iteration (empty active set: z = g_p, t = -s_p / |g_p|^2) is computed redundantly by
-// every lane with no workspace traffic -- in the C5 workload it is the only one for most environments.  From
-// the second iteration on, the O(q^2) scalar part (triangular solves with the Cholesky factor of the active
-// Gram matrix, step lengths, multiplier and factor updates) is done by the group's lane 0 and published
-// through shared memory between __syncwarp(gmask) points.
+// box bounds).  BIG = false computes the first iteration (empty active set: z = g_p, t = -s_p / |g_p|^2) redundantly on
+// every lane with no workspace traffic.  From then on the O(q^2) scalar part (triangular solves with the Cholesky factor
+// of the active Gram matrix, step lengths, multiplier and factor updates) is done by the group's lane 0 and published
+// through the workspace between __syncwarp(gmask) points.
+// Returns MDS_QP_ITER_CAP when the workspace / iteration budget is exhausted or the factor breaks down; the caller then
+// repeats the solve with BIG = true, whose own ITER_CAP is final.
 enum { MDS_QP_ACT_FULL = 0, MDS_QP_ACT_DROP = 1, MDS_QP_ACT_STOP = 2 };
 
-template <typename Real>
+template <typename Real, typename W, bool BIG>
 MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows, typename Vec4T<Real>::type* x,
-                           const typename Vec4T<Real>::type* xnom, Real* ws, const RowMap& M, int N, int NP, int n, bool valid,
+                           const typename Vec4T<Real>::type* xnom, W* ws, int qmax_rt, const RowMap& M, int N, int NP, int n, bool valid,
                            unsigned gmask, int p0, int* iters_out) {
   using R4 = typename Vec4T<Real>::type;
-  const Real tol = qp_tol<Real>();
-  const Real zn_eps = sizeof(Real) == 4 ? Real(1e-5) : Real(1e-10);
-  const Real INF = Real(1e30);
-  // workspace: one int per Real slot for act / header ints
-  Real* lam = ws + MDS_QP_QMAX;
-  Real* dv = ws + 2 * MDS_QP_QMAX;
-  Real* rv = ws + 3 * MDS_QP_QMAX;
-  Real* Lc = ws + 4 * MDS_QP_QMAX;  // packed lower-triangular Cholesky factor of the active Gram matrix
-  Real* hdr = Lc + MDS_QP_QMAX * (MDS_QP_QMAX + 1) / 2;  // [0] t, [1] action, [2] dropped index, [3] status
-  auto iref = [](Real* slot) -> int& { return *reinterpret_cast<int*>(slot); };
+  const int qmax = BIG ? qmax_rt : MDS_QP_QMAX;
+  const int max_iter = BIG ? 16 * qmax + 64 : C.max_iter;
+  const W tol = (W)qp_tol<Real>();
+  const W zn_eps = sizeof(Real) == 4 ? W(1e-5) : W(1e-10);
+  const W INF = W(1e30);
+  // workspace: act | lam | d | r (qmax each) | Lc (packed lower-triangular Cholesky factor of the active Gram matrix) | hdr
+  // (| Lm | y : double scratch of the polish, BIG only)
+  W* lam = ws + qmax;
+  W* dv = ws + 2 * qmax;
+  W* rv = ws + 3 * qmax;
+  W* Lc = ws + 4 * qmax;
+  W* hdr = Lc + qmax * (qmax + 1) / 2;  // [0] t, [1] action, [2] dropped index, [3] status
   unsigned rowmask = 0, boxmask = 0;  // this lane's own active rows (slots) / box bounds (6 bits)
   auto set_active = [&](int con, bool on) {
     const int id = con & 0xffff;
@@ -350,24 +368,24 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
   auto publish_x = [&]() {
     if (valid) { R4 v; v.x = xn[0]; v.y = xn[1]; v.z = xn[2]; v.w = x3; x[n] = v; }
   };
-  int q = 0, iters = 1, status = MDS_QP_OPTIMAL;
+  int q = 0, iters = 0, status = MDS_QP_OPTIMAL;
   int p = p0;
   QpCon<Real> cp = qp_get(rows, C, p);
-  Real lam_p = Real(0);  // meaningful on lane 0 only
-  // ---- first iteration, empty active set
-  {
+  W lam_p = W(0);  // meaningful on lane 0 only
+  bool need_scan = false;
+  if (!BIG) {  // ---- first iteration, empty active set
     Real mag, gx = qp_dot_x(cp, x, &mag);
     Real t = -(cp.rhs - gx) / cp.g2;  // g2 > 0: zero rows are reported by the scan as infeasible
     __syncwarp(gmask);                // every lane has read x before anyone overwrites it
 #pragma unroll
     for (int k = 0; k < 3; ++k) xn[k] -= t * qp_coef(cp, n, k);
     publish_x();
-    if (n == 0) { iref(ws) = p; lam[0] = t; Lc[0] = sqrt_(cp.g2); }
+    if (n == 0) { ws_int(ws) = p; lam[0] = (W)t; Lc[0] = (W)sqrt_(cp.g2); }
     set_active(p, true);
-    q = 1;
+    q = 1; iters = 1;
+    need_scan = true;
     __syncwarp(gmask);
   }
-  bool need_scan = true;
   // ONE flat loop (scan-if-needed -> scalar part -> primal step -> add or drop) instead of nested
   // outer/inner loops: the lane groups of a warp then stay converged on the same instructions even when
   // one group takes a full step and another a partial step (nested loops serialised the groups, ~4x).
@@ -377,51 +395,51 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
       if (p == -1) break;  // optimal
       if (p == -2) { status = MDS_QP_INFEASIBLE; break; }
       cp = qp_get(rows, C, p);
-      lam_p = Real(0);
+      lam_p = W(0);
     }
     ++iters;
     // ---- scalar part (lane 0): d = L^-1 Na g_p, zn = |g_p|^2 - |d|^2, r = L^-T d, step lengths, multipliers
     if (n == 0) {
       int action = MDS_QP_ACT_FULL, st = MDS_QP_OPTIMAL, kdrop = -1;
-      Real t = Real(0), zn = cp.g2;
-      if (iters > C.max_iter) {
+      W t = W(0), zn = (W)cp.g2;
+      if (iters > max_iter) {
         action = MDS_QP_ACT_STOP; st = MDS_QP_ITER_CAP;
       } else {
-        Real dd = Real(0);
+        W dd = W(0);
         for (int a = 0; a < q; ++a) {
-          QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
-          Real sacc = qp_dot_g(ca, cp);
+          QpCon<Real> ca = qp_get(rows, C, ws_int(ws + a));
+          W sacc = qp_dot_g<W>(ca, cp);
           for (int k = 0; k < a; ++k) sacc -= Lc[a * (a + 1) / 2 + k] * dv[k];
           sacc /= Lc[a * (a + 1) / 2 + a];
           dv[a] = sacc;
           dd += sacc * sacc;
         }
-        zn = cp.g2 - dd;
+        zn = (W)cp.g2 - dd;
         for (int a = q - 1; a >= 0; --a) {
-          Real sacc = dv[a];
+          W sacc = dv[a];
           for (int k = a + 1; k < q; ++k) sacc -= Lc[k * (k + 1) / 2 + a] * rv[k];
           rv[a] = sacc / Lc[a * (a + 1) / 2 + a];
         }
-        Real t1 = INF;
+        W t1 = INF;
         for (int a = 0; a < q; ++a) {
-          Real ra = rv[a];
+          W ra = rv[a];
           if (ra > tol) {
-            Real cnd = lam[a] / ra;
+            W cnd = lam[a] / ra;
             if (cnd < t1) { t1 = cnd; kdrop = a; }
           }
         }
         Real mag, gx = qp_dot_x(cp, x, &mag);
-        Real s_p = cp.rhs - gx;
-        Real t2 = (zn > zn_eps * cp.g2) ? -s_p / zn : INF;
-        t = min_(t1, t2);
+        W s_p = (W)(cp.rhs - gx);
+        W t2 = (zn > zn_eps * (W)cp.g2) ? -s_p / zn : INF;
+        t = t1 < t2 ? t1 : t2;
         if (t >= INF) {
           action = MDS_QP_ACT_STOP; st = MDS_QP_INFEASIBLE;
         } else {
           for (int a = 0; a < q; ++a) lam[a] -= t * rv[a];
           lam_p += t;
           if (t2 <= t1) {
-            action = (q == MDS_QP_QMAX) ? MDS_QP_ACT_STOP : MDS_QP_ACT_FULL;
-            if (q == MDS_QP_QMAX) st = MDS_QP_ITER_CAP;
+            action = (q == qmax) ? MDS_QP_ACT_STOP : MDS_QP_ACT_FULL;
+            if (q == qmax) st = MDS_QP_ITER_CAP;
           } else {
             action = MDS_QP_ACT_DROP;
           }
@@ -429,22 +447,22 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
         }
       }
       hdr[0] = t;
-      iref(hdr + 1) = action;
-      iref(hdr + 2) = kdrop;
-      iref(hdr + 3) = st;
+      ws_int(hdr + 1) = action;
+      ws_int(hdr + 2) = kdrop;
+      ws_int(hdr + 3) = st;
     }
     __syncwarp(gmask);
-    const int action = iref(hdr + 1), kdrop = iref(hdr + 2);
-    if (action == MDS_QP_ACT_STOP) { status = iref(hdr + 3); break; }
-    const Real t = hdr[0];
+    const int action = ws_int(hdr + 1), kdrop = ws_int(hdr + 2);
+    if (action == MDS_QP_ACT_STOP) { status = ws_int(hdr + 3); break; }
+    const Real t = (Real)hdr[0];
     // ---- own block of z = g_p - Na' r and the primal step (skipped for a pure dual step)
     if (!(t < Real(0)) && valid) {
       Real zk[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) zk[k] = qp_coef(cp, n, k);
       for (int a = 0; a < q; ++a) {
-        QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
-        Real ra = rv[a];
+        QpCon<Real> ca = qp_get(rows, C, ws_int(ws + a));
+        Real ra = (Real)rv[a];
 #pragma unroll
         for (int k = 0; k < 3; ++k) zk[k] -= ra * qp_coef(ca, n, k);
       }
@@ -452,14 +470,14 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
       for (int k = 0; k < 3; ++k) xn[k] -= t * zk[k];
       publish_x();
     }
-    const int pd = (action == MDS_QP_ACT_DROP) ? iref(ws + kdrop) : -1;
+    const int pd = (action == MDS_QP_ACT_DROP) ? ws_int(ws + kdrop) : -1;
     __syncwarp(gmask);  // x updated; every lane has consumed act / r of this iteration
     if (action == MDS_QP_ACT_FULL) {  // constraint p becomes active: append its row to the Cholesky factor
       if (n == 0) {
-        Real dd = Real(0);
-        for (int k = 0; k < q; ++k) { Real v = dv[k]; Lc[q * (q + 1) / 2 + k] = v; dd += v * v; }
-        Lc[q * (q + 1) / 2 + q] = sqrt_(cp.g2 - dd);
-        iref(ws + q) = p;
+        W dd = W(0);
+        for (int k = 0; k < q; ++k) { W v = dv[k]; Lc[q * (q + 1) / 2 + k] = v; dd += v * v; }
+        Lc[q * (q + 1) / 2 + q] = sqrt_((W)cp.g2 - dd);
+        ws_int(ws + q) = p;
         lam[q] = lam_p;
       }
       set_active(p, true);
@@ -470,27 +488,27 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
       --q;
       need_scan = false;
       if (n == 0) {
-        for (int a = kdrop; a < q; ++a) { iref(ws + a) = iref(ws + a + 1); lam[a] = lam[a + 1]; }
+        for (int a = kdrop; a < q; ++a) { ws_int(ws + a) = ws_int(ws + a + 1); lam[a] = lam[a + 1]; }
         int st = MDS_QP_OPTIMAL;
         for (int a = 0; a < q; ++a) {
-          QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
+          QpCon<Real> ca = qp_get(rows, C, ws_int(ws + a));
           for (int b2 = 0; b2 <= a; ++b2) {
-            QpCon<Real> cb = qp_get(rows, C, iref(ws + b2));
-            Real sacc = qp_dot_g(ca, cb);
+            QpCon<Real> cb = qp_get(rows, C, ws_int(ws + b2));
+            W sacc = qp_dot_g<W>(ca, cb);
             for (int k = 0; k < b2; ++k) sacc -= Lc[a * (a + 1) / 2 + k] * Lc[b2 * (b2 + 1) / 2 + k];
             if (a == b2) {
-              if (sacc <= Real(0)) { st = MDS_QP_ITER_CAP; sacc = Real(1); }
+              if (sacc <= W(0)) { st = MDS_QP_ITER_CAP; sacc = W(1); }
               Lc[a * (a + 1) / 2 + a] = sqrt_(sacc);
             } else {
               Lc[a * (a + 1) / 2 + b2] = sacc / Lc[b2 * (b2 + 1) / 2 + b2];
             }
           }
         }
-        iref(hdr + 3) = st;
+        ws_int(hdr + 3) = st;
       }
     }
     __syncwarp(gmask);
-    if (action == MDS_QP_ACT_DROP && iref(hdr + 3) != MDS_QP_OPTIMAL) { status = iref(hdr + 3); break; }
+    if (action == MDS_QP_ACT_DROP && ws_int(hdr + 3) != MDS_QP_OPTIMAL) { status = ws_int(hdr + 3); break; }
   }
   __syncwarp(gmask);
   if (sizeof(Real) == 4 && status == MDS_QP_OPTIMAL && q >= 3) {
@@ -498,15 +516,21 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
     // loses ~1e-4 on long solves.  With the final active set A the minimiser is u_nom - A' lam, (A A') lam = A u_nom - b;
     // lane 0 solves this small system once in double and every lane rebuilds its own block from u_nom.
     if (n == 0) {
-      const bool ok = qp_polish_lane0<Real>(C.umax[0], C.umax[1], C.umax[2], rows, xnom, ws, lam, q);
-      iref(hdr + 1) = ok ? 1 : 0;
+      bool ok;
+      if (BIG) {
+        double* Lm = reinterpret_cast<double*>(hdr + 4);
+        ok = qp_polish_core<Real, W>(C.umax[0], C.umax[1], C.umax[2], rows, xnom, ws, Lm, Lm + qmax * (qmax + 1) / 2, lam, q);
+      } else {
+        ok = qp_polish_small<Real>(C.umax[0], C.umax[1], C.umax[2], rows, xnom, reinterpret_cast<Real*>(ws), reinterpret_cast<Real*>(lam), q);
+      }
+      ws_int(hdr + 1) = ok ? 1 : 0;
     }
     __syncwarp(gmask);
-    if (iref(hdr + 1) && valid) {
+    if (ws_int(hdr + 1) && valid) {
       auto un = xnom[n];
       double z0 = un.x, z1 = un.y, z2 = un.z;
       for (int a = 0; a < q; ++a) {
-        QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
+        QpCon<Real> ca = qp_get(rows, C, ws_int(ws + a));
         const double la = (double)lam[a];
         z0 -= la * (double)qp_coef(ca, n, 0); z1 -= la * (double)qp_coef(ca, n, 1); z2 -= la * (double)qp_coef(ca, n, 2);
       }
@@ -519,13 +543,45 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
     // certify: rows held active must still be satisfied (guards breakdown on nearly dependent active sets)
     const Real ctol = sizeof(Real) == 4 ? Real(1e-3) : Real(1e-7);
     for (int a = 0; a < q; ++a) {
-      QpCon<Real> ca = qp_get(rows, C, iref(ws + a));
+      QpCon<Real> ca = qp_get(rows, C, ws_int(ws + a));
       Real mag, gx = qp_dot_x(ca, x, &mag);
       if (ca.rhs - gx < -ctol * (abs_(ca.rhs) + mag + Real(1e-12))) status = MDS_QP_ITER_CAP;
     }
   }
   *iters_out = iters;
   return status;
+}
+
+// The scratch solver, out of line: rare (active sets beyond MDS_QP_QMAX, factor breakdown), so its code stays off the step loop.
+// Lane 0 of the group claims a slot of the global scratch (flags: 0 free / 1 taken; a busy pool is waited for -- holders
+// never wait for anything, so the wait ends), the group repeats the solve from u_nom with the scalar part in double, and
+// lane 0 releases the slot.
+template <typename Real>
+__device__ __noinline__ int qp_solve_group_big(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows, typename Vec4T<Real>::type* x,
+                                               const typename Vec4T<Real>::type* xnom, const RowMap& M, int N, int NP, int n, bool valid,
+                                               unsigned gmask, int p0, int* iters_out) {
+  const QpScratch& S = C.scr;
+  if (S.base == nullptr || S.slots <= 0) { *iters_out = 0; return MDS_QP_ITER_CAP; }
+  const int lane0 = __ffs(gmask) - 1;
+  int slot = -1;
+  if (n == 0) {
+    unsigned h = (blockIdx.x * 2654435761u) ^ (threadIdx.x * 40503u);
+    for (;;) {
+      slot = (int)(h % (unsigned)S.slots);
+      if (atomicCAS(S.flags + slot, 0, 1) == 0) break;
+      h = h * 1664525u + 1013904223u;
+    }
+    __threadfence();
+  }
+  slot = __shfl_sync(gmask, slot, lane0);
+  double* ws = S.base + (size_t)slot * (size_t)S.slot_doubles;
+  const int st = qp_solve_group<Real, double, true>(C, rows, x, xnom, ws, S.qmax, M, N, NP, n, valid, gmask, p0, iters_out);
+  __syncwarp(gmask);
+  if (n == 0) {
+    __threadfence();
+    atomicExch(S.flags + slot, 0);
+  }
+  return st;
 }
 
 // Obstacle record (cx, cy, cz, r): r > 0 is the reference's sphere (super-ellipsoid barrier with the agents' zscale,
@@ -539,9 +595,9 @@ template <typename Real> MDS_DEV void obstacle_shape(const CbfP<Real>& C, Real r
 
 // decoupled 4th input (wz): box +-umax[3] merged with the order-3 force-bound rows, which the
 // reference places on column 4i+3 (cbf.py:456-460).  Returns false when the interval is empty.
-template <typename Real> MDS_DEV bool cbf_wz_bounds(const CbfP<Real>& C, Real F, Real* lo, Real* hi) {
+template <int ORD, typename Real> MDS_DEV bool cbf_wz_bounds(const CbfP<Real>& C, Real F, Real* lo, Real* hi) {
   *lo = -C.umax[3]; *hi = C.umax[3];
-  if (C.order == 3) {
+  if (cbf_order<ORD>(C) == 3 && C.state_bounds) {  // custom_force_bound_const, emitted only with do_state_bounds (cbf.py:473-476)
     *hi = min_(*hi, C.k2 * (C.fmax - F));
     *lo = max_(*lo, -(C.k2 * (F - C.fmin)));
   }

@@ -94,6 +94,8 @@ MDS_DEV float exp_(float x) { return expf(x); }
 MDS_DEV double exp_(double x) { return exp(x); }
 MDS_DEV float tan_(float x) { return tanf(x); }
 MDS_DEV double tan_(double x) { return tan(x); }
+MDS_DEV float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+MDS_DEV double fma_(double a, double b, double c) { return fma(a, b, c); }
 MDS_DEV float rint_(float x) { return rintf(x); }
 MDS_DEV double rint_(double x) { return rint(x); }
 MDS_DEV float abs_(float x) { return fabsf(x); }
@@ -112,6 +114,7 @@ template <typename Real> struct DroneP {
   Real gnd_eff_coeff, prop_radius, gnd_eff_h_clip, drag_xy, drag_z, dw1, dw2, dw3, dw_dz_clip;
   Real prop_x[4], prop_y[4];
   Real z_floor, dt_phys, dt_ctrl;
+  Real inv_m, inv_ixx, inv_iyy, inv_izz;  // derived on the host (to_dev): no divisions by constants in the kernels
   int substeps, drone_model, physics, cf2x_torque_sign, renormalize_quat, ground_clamp, x_frame_mixer;
 };
 template <typename Real> inline DroneP<Real> to_dev(const MdsDroneParams& p) {
@@ -124,6 +127,7 @@ template <typename Real> inline DroneP<Real> to_dev(const MdsDroneParams& p) {
   d.dw1 = Real(p.dw1); d.dw2 = Real(p.dw2); d.dw3 = Real(p.dw3); d.dw_dz_clip = Real(p.dw_dz_clip);
   for (int i = 0; i < 4; ++i) { d.prop_x[i] = Real(p.prop_x[i]); d.prop_y[i] = Real(p.prop_y[i]); }
   d.z_floor = Real(p.z_floor); d.dt_phys = Real(p.dt_phys); d.dt_ctrl = Real(p.dt_ctrl);
+  d.inv_m = Real(1.0 / p.m); d.inv_ixx = Real(1.0 / p.ixx); d.inv_iyy = Real(1.0 / p.iyy); d.inv_izz = Real(1.0 / p.izz);
   d.substeps = p.substeps; d.drone_model = p.drone_model; d.physics = p.physics;
   d.cf2x_torque_sign = p.cf2x_torque_sign; d.renormalize_quat = p.renormalize_quat; d.ground_clamp = p.ground_clamp; d.x_frame_mixer = p.x_frame_mixer;
   return d;
@@ -139,15 +143,27 @@ template <typename Real> inline LqrP<Real> to_dev(const MdsLqrGains& g) {
   d.dim = g.dim;
   return d;
 }
+// Scratch of the large-active-set QP solver (mds_cbf.cuh qp_solve_group_big): `slots` slots of `slot_doubles` doubles in
+// global memory + one claim flag each; owned by the library (mds_kernels.cu qp_scratch_for), sized for qmax = 3 N.
+struct QpScratch {
+  double* base;
+  int* flags;
+  int slots, qmax;
+  long long slot_doubles;
+};
 template <typename Real> struct CbfP {
-  int order, max_iter;
-  Real c4inv, inv_c, rs, k0, k1, k2, umax[4], fmin, fmax;
+  int order, max_iter, state_bounds;
+  Real c4inv, inv_c, rs, ds4_pair, k0, k1, k2, umax[4], fmin, fmax;
+  QpScratch scr;
 };
 template <typename Real> inline CbfP<Real> to_dev(const MdsCbfParams& c) {
   CbfP<Real> d;
   d.order = c.order; d.max_iter = c.max_iter > 0 ? c.max_iter : 64;
   double c4 = c.zscale * c.zscale * c.zscale * c.zscale;
   d.c4inv = Real(1.0 / c4); d.inv_c = Real(1.0 / c.zscale); d.rs = Real(c.safety_radius);
+  d.ds4_pair = Real(16.0 * c.safety_radius * c.safety_radius * c.safety_radius * c.safety_radius);  // (2 r_safe)^4
+  d.state_bounds = c.no_state_bounds ? 0 : 1;
+  d.scr = QpScratch{nullptr, nullptr, 0, 0, 0};
   d.k0 = Real(c.kcbf[0]); d.k1 = Real(c.kcbf[1]); d.k2 = Real(c.order == 3 ? c.kcbf[2] : 0.0);
   for (int i = 0; i < 4; ++i) d.umax[i] = Real(c.umax[i]);
   d.fmin = Real(c.fmin); d.fmax = Real(c.fmax);

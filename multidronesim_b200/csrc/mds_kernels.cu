@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "mds_cbf.cuh"
 #include "mds_common.cuh"
 #include "mds_ctrl.cuh"
@@ -227,7 +229,7 @@ __global__ void lowlevel_kernel(DroneP<Real> P, int variant, const Real* __restr
 }
 
 // ------------------------------------------------------------------ kernels: CBF
-template <typename Real>
+template <typename Real, int ORD>
 __global__ void __launch_bounds__(MDS_BLOCK) cbf_qp_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __restrict__ obs, const Real* __restrict__ xdes,
                                                             const Real* __restrict__ unom_g, const Real* __restrict__ obstacles, int n_obs,
                                                             Real* __restrict__ usafe_g, int* __restrict__ status, int* __restrict__ iters,
@@ -244,12 +246,12 @@ __global__ void __launch_bounds__(MDS_BLOCK) cbf_qp_kernel(DroneP<Real> P, CbfP<
     Obs<Real> o = load_obs(obs, g.d);
     Real xd[10];
     for (int k = 0; k < xdim; ++k) xd[k] = xdes[(size_t)g.d * xdim + k];
-    ag = cbf_agent(P, C, o, xd, &F);
+    ag = cbf_agent<ORD>(P, C, o, xd, &F);
     load4(unom_g, g.d, unom);
   }
   Real min_h = Real(1e30);
   int it = 0;
-  int st = cbf_filter_group(P, C, S, obstacles, n_obs, g, N, NP, ag, F, unom, usafe, &min_h, &it);
+  int st = cbf_filter_group<ORD>(P, C, S, obstacles, n_obs, g, N, NP, ag, F, unom, usafe, &min_h, &it);
   if (g.valid) {
     store4(usafe_g, g.d, usafe);
     if (g.n == 0) {
@@ -282,7 +284,8 @@ __global__ void cbf_rows_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __rest
   if (e >= E) return;
   const int xdim = C.order == 2 ? 9 : 10;
   const int n_pairs = N * (N - 1) / 2, W = 4 * N;
-  const int m = n_pairs + 8 * N + (C.order == 3 ? 2 * N : 0) + N * n_obs;
+  const bool force_rows = C.order == 3 && C.state_bounds;
+  const int m = n_pairs + 8 * N + (force_rows ? 2 * N : 0) + N * n_obs;
   Real* G = Gm + (size_t)e * m * W;
   Real* h = hv + (size_t)e * m;
   for (size_t k = 0; k < (size_t)m * W; ++k) G[k] = Real(0);
@@ -290,20 +293,20 @@ __global__ void cbf_rows_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __rest
     Obs<Real> o = load_obs(obs, e * N + i);
     Real xd[10];
     for (int k = 0; k < xdim; ++k) xd[k] = xdes[(size_t)(e * N + i) * xdim + k];
-    return cbf_agent(P, C, o, xd, F);
+    return cbf_agent<0>(P, C, o, xd, F);
   };
   int row = 0;
   Real F, a3[3], rhs, h0;
   for (int i = 0; i < N - 1; ++i)
     for (int j = i + 1; j < N; ++j) {
       CbfAgent<Real> ai = agent(i, &F), aj = agent(j, &F);
-      cbf_row(P, C, ai, aj, Real(2) * C.rs, C.c4inv, a3, &rhs, &h0);
+      cbf_row<0>(P, C, ai, aj, C.ds4_pair, C.c4inv, a3, &rhs, &h0);
       for (int c = 0; c < 3; ++c) { G[(size_t)row * W + 4 * i + c] = -a3[c]; G[(size_t)row * W + 4 * j + c] = a3[c]; }
       h[row++] = rhs;
     }
   for (int k = 0; k < W; ++k) { G[(size_t)row * W + k] = Real(1); h[row++] = C.umax[k & 3]; }
   for (int k = 0; k < W; ++k) { G[(size_t)row * W + k] = Real(-1); h[row++] = C.umax[k & 3]; }
-  if (C.order == 3)
+  if (force_rows)
     for (int i = 0; i < N; ++i) {
       agent(i, &F);
       G[(size_t)row * W + 4 * i + 3] = Real(1); h[row++] = C.k2 * (C.fmax - F);
@@ -316,7 +319,7 @@ __global__ void cbf_rows_kernel(DroneP<Real> P, CbfP<Real> C, const Real* __rest
       aj.dv = {Real(0), Real(0), Real(0)}; aj.da = aj.dv;
       Real Ds, c4inv;
       obstacle_shape(C, obstacles[4 * o + 3], &Ds, &c4inv);
-      cbf_row(P, C, ai, aj, Ds, c4inv, a3, &rhs, &h0);
+      cbf_row<0>(P, C, ai, aj, (Ds * Ds) * (Ds * Ds), c4inv, a3, &rhs, &h0);
       for (int c = 0; c < 3; ++c) G[(size_t)row * W + 4 * i + c] = -a3[c];
       h[row++] = rhs;
     }
@@ -562,6 +565,38 @@ static int lowlevel_impl(const MdsDroneParams* prm, int variant, const Real* u, 
   lowlevel_kernel<Real><<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(to_dev<Real>(*prm), variant, u, obs, to_dev<Real>(pid), action, D);
   return check_launch("lowlevel");
 }
+// Scratch of the large-active-set QP solver (mds_cbf.cuh qp_solve_group_big): one pool per device, owned by the library,
+// allocated at the first CBF launch (so that call must not sit inside a stream capture) and regrown when a larger
+// drone count shows up.  MDS_QP_SCRATCH_SLOTS solves can be in flight at once; further ones wait for a slot.
+#ifndef MDS_QP_SCRATCH_SLOTS
+#define MDS_QP_SCRATCH_SLOTS 1024
+#endif
+#define MDS_MAX_DEVICES 64
+static QpScratch g_qp_scratch[MDS_MAX_DEVICES];
+static std::mutex g_qp_scratch_mutex;
+static long long qp_slot_doubles(int qmax) {  // act | lam | d | r | y (qmax each) + Lc | Lm (qmax (qmax + 1) / 2 each) + hdr (4)
+  return 5LL * qmax + (long long)qmax * (qmax + 1) + 4;
+}
+static int qp_scratch_for(int N, QpScratch* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail("qp scratch", e);
+  if (dev < 0 || dev >= MDS_MAX_DEVICES) return fail(MDS_ERR_ARG, "%s", "qp scratch: device index out of range");
+  std::lock_guard<std::mutex> lock(g_qp_scratch_mutex);
+  QpScratch& S = g_qp_scratch[dev];
+  const int qmax = 3 * N;  // the coupled variables of an environment: an active set cannot be larger
+  if (S.base == nullptr || S.qmax < qmax) {
+    if (S.base) { cudaFree(S.base); cudaFree(S.flags); S.base = nullptr; S.flags = nullptr; }  // cudaFree waits for kernels in flight
+    const long long sd = qp_slot_doubles(qmax);
+    e = cudaMalloc((void**)&S.base, (size_t)MDS_QP_SCRATCH_SLOTS * (size_t)sd * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&S.flags, MDS_QP_SCRATCH_SLOTS * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(S.flags, 0, MDS_QP_SCRATCH_SLOTS * sizeof(int));
+    if (e != cudaSuccess) { S.base = nullptr; S.flags = nullptr; return cuda_fail("qp scratch allocation", e); }
+    S.slots = MDS_QP_SCRATCH_SLOTS; S.qmax = qmax; S.slot_doubles = sd;
+  }
+  *out = S;
+  return MDS_OK;
+}
 static int cbf_args_ok(const MdsCbfParams* c, int N, int n_obs) {
   if (!c) return fail(MDS_ERR_ARG, "%s", "cbf: null params");
   if (c->order != 2 && c->order != 3) return fail(MDS_ERR_ARG, "%s", "cbf: order must be 2 or 3");
@@ -581,10 +616,13 @@ static int cbf_qp_impl(const MdsDroneParams* prm, const MdsCbfParams* c, const R
   MDS_REQUIRE(n_obs == 0 || obstacles, "cbf_qp: obstacles pointer is null");
   const int NP = next_pow2(N), threads = cbf_block_threads<Real>(NP, N, n_obs), epb = threads / NP, blocks = (E + epb - 1) / epb;
   size_t smem = cbf_smem_bytes<Real>(threads, NP, N, n_obs);
-  cudaError_t e = cudaFuncSetAttribute(cbf_qp_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  CbfP<Real> C = to_dev<Real>(*c);
+  rc = qp_scratch_for(N, &C.scr);
+  if (rc) return rc;
+  auto kern = c->order == 2 ? cbf_qp_kernel<Real, 2> : cbf_qp_kernel<Real, 3>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail("cbf_qp: shared memory opt-in failed", e);
-  cbf_qp_kernel<Real><<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), to_dev<Real>(*c), obs, xdes, unom, obstacles, n_obs, usafe,
-                                                                          status, iters, E, N, NP);
+  kern<<<blocks, threads, smem, (cudaStream_t)stream>>>(to_dev<Real>(*prm), C, obs, xdes, unom, obstacles, n_obs, usafe, status, iters, E, N, NP);
   return check_launch("cbf_qp");
 }
 template <typename Real>
@@ -664,6 +702,8 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     MDS_REQUIRE((cfg->ctrl == MDS_CTRL_LQR_OMEGA && cbf->order == 2) || (cfg->ctrl == MDS_CTRL_LQR_YANK && cbf->order == 3),
                 "rollout: CBF order 2 needs LQR_OMEGA, order 3 needs LQR_YANK");
     C = to_dev<Real>(*cbf);
+    rc = qp_scratch_for(N, &C.scr);
+    if (rc) return rc;
     for (int i = 0; i < cfg->num_obstacles * 4; ++i) R.obstacles[i] = Real(cfg->obstacles[i]);
     // reference caller: nominal_us[:,0] -= M*G before the QP (CBFTest.py:339, CBFTestOrd3.py:344);
     // added back only for order 2 (CBFTest.py:346 vs CBFTestOrd3.py:350)

@@ -120,7 +120,16 @@ template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw
 
 // CBF safety filter for one env by its lane group: u_nom -> u_safe for this lane's drone.
 // Every lane of a valid group calls it; returns the env's QP status, *iters_out its iteration count.
-template <typename Real>
+//
+// Flow.  Constraints that touch ONE drone's inputs (its obstacle rows and its +-umax box) are orthogonal between
+// drones, so each lane first handles its own in registers: it finds its most violated one at u_nom and projects onto
+// it (one closed-form Goldfarb-Idnani step).  The lanes then publish their agents and projected inputs, build their pair
+// rows and test them -- and their other single-drone rows -- at the projected point.  If nothing is violated the point is
+// the QP's minimiser (it minimises |u - u_nom|^2 on an active set with positive multipliers and is feasible for every
+// other row), and the step is over without any group-wide argmin, workspace or second scan: in the swarm workloads that
+// is nearly every step.  Otherwise the group runs the cooperative active-set solver from u_nom (qp_solve_group), and if
+// that one runs out of workspace / iterations or its factor breaks down, the scratch solver (qp_solve_group_big).
+template <int ORD, typename Real>
 MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const CbfSmem<Real>& S, const Real* obstacles, int n_obs,
                              const GroupMap& g, int N, int NP, const CbfAgent<Real>& ag, Real F, const Real unom[4], Real usafe[4],
                              Real* min_h, int* iters_out) {
@@ -132,23 +141,84 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
   R4* rows = reinterpret_cast<R4*>(env + S.off_rows);
   R4* x = reinterpret_cast<R4*>(env + S.off_x);
   R4* xnom = x + NP;
+  int fl = 0, escalate = 0, touched = 0;
+  Real lo = Real(0), hi = Real(0);
+  Real xn[3] = {unom[0], unom[1], unom[2]};
   if (g.valid) {
+    // ---- own single-drone rows: obstacle rows (built here), box bounds; most violated one at u_nom
+    QpWorst<Real> worst = {Real(0), 0x7fffffff};
+    Real wa[3] = {Real(0), Real(0), Real(0)}, wsl = Real(0), wa2 = Real(1);  // coefficients / slack / |a|^2 of the worst obstacle row
+    const CbfAgent<Real> zero = {{Real(0), Real(0), Real(0)}, {Real(0), Real(0), Real(0)}, {Real(0), Real(0), Real(0)}};
+    for (int o = 0; o < n_obs; ++o) {
+      CbfAgent<Real> other = zero;
+      other.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
+      Real a3[3], rhs, h0, Ds, c4inv;
+      obstacle_shape(C, obstacles[4 * o + 3], &Ds, &c4inv);
+      const Real Ds2 = Ds * Ds;
+      cbf_row<ORD>(P, C, ag, other, Ds2 * Ds2, c4inv, a3, &rhs, &h0);
+      *min_h = min_(*min_h, h0);
+      R4 row;
+      row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
+      rows[n * M.RPL + M.S0 + o] = row;
+      // G u = -a . u_n <= rhs
+      const Real sl = rhs + (a3[0] * xn[0] + a3[1] * xn[1] + a3[2] * xn[2]);
+      if (sl < Real(0)) {
+        const Real mag = abs_(a3[0] * xn[0]) + abs_(a3[1] * xn[1]) + abs_(a3[2] * xn[2]);
+        if (sl < -qp_tol<Real>() * (abs_(rhs) + mag + Real(1e-12))) {
+          const Real a2 = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2];
+          if (!(a2 > Real(0))) escalate = 1;  // zero row with negative rhs: the cooperative path reports it as infeasible
+          const Real v = sl * rsqrt_(max_(a2, Real(1e-30)));
+          if (v < worst.v) { worst.v = v; worst.con = o; wa[0] = a3[0]; wa[1] = a3[1]; wa[2] = a3[2]; wsl = sl; wa2 = a2; }
+        }
+      }
+    }
+    int wbox = -1;  // component of the most violated box bound, if it beats every obstacle row
+#pragma unroll
+    for (int comp = 0; comp < 3; ++comp) {
+      const Real ax = abs_(xn[comp]);
+      const Real sl = C.umax[comp] - ax;
+      if (sl < -qp_tol<Real>() * (C.umax[comp] + ax + Real(1e-12)) && sl < worst.v) { worst.v = sl; worst.con = MDS_QP_BOX0; wbox = comp; }
+    }
+    if (worst.con != 0x7fffffff) {  // one projection: u_n <- u_n - t g,  t = -slack / |g|^2
+      touched = 1;
+      if (wbox >= 0) {
+#pragma unroll
+        for (int comp = 0; comp < 3; ++comp)
+          if (comp == wbox) xn[comp] = xn[comp] < Real(0) ? -C.umax[comp] : C.umax[comp];
+      } else {
+        const Real t = -wsl / wa2;  // g = -a
+        xn[0] += t * wa[0]; xn[1] += t * wa[1]; xn[2] += t * wa[2];
+      }
+      // the other single-drone rows at the projected point (the projected row itself holds with equality: skipped)
+      for (int o = 0; o < n_obs; ++o) {
+        if (wbox < 0 && o == worst.con) continue;
+        const R4 row = rows[n * M.RPL + M.S0 + o];
+        const Real sl = row.w + (row.x * xn[0] + row.y * xn[1] + row.z * xn[2]);
+        if (sl < Real(0)) {
+          const Real mag = abs_(row.x * xn[0]) + abs_(row.y * xn[1]) + abs_(row.z * xn[2]);
+          if (sl < -qp_tol<Real>() * (abs_(row.w) + mag + Real(1e-12))) escalate = 1;
+        }
+      }
+#pragma unroll
+      for (int comp = 0; comp < 3; ++comp) {
+        if (comp == wbox) continue;
+        const Real ax = abs_(xn[comp]);
+        if (C.umax[comp] - ax < -qp_tol<Real>() * (C.umax[comp] + ax + Real(1e-12))) escalate = 1;
+      }
+    }
+    if (!cbf_wz_bounds<ORD>(C, F, &lo, &hi)) fl = 1;
+    // ---- publish the agent and the projected inputs
     R4 a0, a1, a2, xv;
     a0.x = ag.p.x; a0.y = ag.p.y; a0.z = ag.p.z; a0.w = ag.dv.x;
     a1.x = ag.dv.y; a1.y = ag.dv.z; a1.z = ag.da.x; a1.w = ag.da.y;
     a2.x = ag.da.z; a2.y = Real(0); a2.z = Real(0); a2.w = Real(0);
     agents[3 * n] = a0; agents[3 * n + 1] = a1; agents[3 * n + 2] = a2;
-    xv.x = unom[0]; xv.y = unom[1]; xv.z = unom[2]; xv.w = unom[3];
+    xv.x = xn[0]; xv.y = xn[1]; xv.z = xn[2]; xv.w = unom[3];
     x[n] = xv;
-    xnom[n] = xv;
   }
   __syncwarp(g.gmask);
-  int fl = 0;
-  Real lo = Real(0), hi = Real(0);
-  QpWorst<Real> worst = {Real(0), 0x7fffffff};
   if (g.valid) {
-    // this lane's own rows, each tested against u_nom as it is built: pair slots (compile-time count when N is),
-    // then obstacle slots
+    // ---- own pair rows (compile-time count when N is), each tested at the projected point as it is built
 #pragma unroll
     for (int s = 0; s < M.S0; ++s) {
       const int m = row_partner(M, N, n, s);
@@ -156,42 +226,57 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
       row.x = Real(0); row.y = Real(0); row.z = Real(0); row.w = Real(1e30);
       if (m >= 0) {
         CbfAgent<Real> other;
-        R4 b0 = agents[3 * m], b1 = agents[3 * m + 1], b2 = agents[3 * m + 2];
+        R4 b0 = agents[3 * m], b1 = agents[3 * m + 1], b2 = agents[3 * m + 2], xm = x[m];
         other.p = {b0.x, b0.y, b0.z}; other.dv = {b0.w, b1.x, b1.y}; other.da = {b1.z, b1.w, b2.x};
         Real a3[3], rhs, h0;
-        cbf_row(P, C, ag, other, Real(2) * C.rs, C.c4inv, a3, &rhs, &h0);  // owner - partner (mds_cbf.cuh "Row ownership")
+        cbf_row<ORD>(P, C, ag, other, C.ds4_pair, C.c4inv, a3, &rhs, &h0);  // owner - partner (mds_cbf.cuh "Row ownership")
         *min_h = min_(*min_h, h0);
         row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
-        qp_test_row(worst, row, unom, x, n, m, n * M.RPL + s);
+        // G u = -a . u_n + a . u_m <= rhs
+        const Real d0 = xm.x - xn[0], d1 = xm.y - xn[1], d2 = xm.z - xn[2];
+        const Real sl = rhs - (a3[0] * d0 + a3[1] * d1 + a3[2] * d2);
+        if (sl < Real(0)) {
+          const Real mag = abs_(a3[0] * xn[0]) + abs_(a3[1] * xn[1]) + abs_(a3[2] * xn[2]) + abs_(a3[0] * xm.x) + abs_(a3[1] * xm.y) + abs_(a3[2] * xm.z);
+          if (sl < -qp_tol<Real>() * (abs_(rhs) + mag + Real(1e-12))) escalate = 1;
+        }
       }
       rows[n * M.RPL + s] = row;
     }
-    for (int o = 0; o < n_obs; ++o) {
-      CbfAgent<Real> other;
-      other.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
-      other.dv = {Real(0), Real(0), Real(0)}; other.da = other.dv;
-      Real a3[3], rhs, h0, Ds, c4inv;
-      obstacle_shape(C, obstacles[4 * o + 3], &Ds, &c4inv);
-      cbf_row(P, C, ag, other, Ds, c4inv, a3, &rhs, &h0);
-      *min_h = min_(*min_h, h0);
-      R4 row;
-      row.x = a3[0]; row.y = a3[1]; row.z = a3[2]; row.w = rhs;
-      qp_test_row(worst, row, unom, x, n, -1, n * M.RPL + M.S0 + o);
-      rows[n * M.RPL + M.S0 + o] = row;
-    }
-    qp_test_box(worst, C, unom, n, 0u);
-    if (!cbf_wz_bounds(C, F, &lo, &hi)) fl = 1;
   }
-  for (int off = NP >> 1; off > 0; off >>= 1) fl |= __shfl_xor_sync(g.gmask, fl, off);
-  const int p0 = qp_worst_of_group(worst, NP, g.gmask);
-  __syncwarp(g.gmask);  // rows complete; agents no longer needed (their storage becomes the QP workspace)
-  int status = MDS_QP_OPTIMAL, iters = 0;
-  if (fl || p0 == -2) status = MDS_QP_INFEASIBLE;
-  else if (p0 >= 0) status = qp_solve_group(C, rows, x, xnom, env, M, N, NP, n, g.valid, g.gmask, p0, &iters);
+  const unsigned esc_mask = __ballot_sync(g.gmask, escalate != 0) & g.gmask;
+  const unsigned fl_mask = __ballot_sync(g.gmask, fl != 0) & g.gmask;
+  const unsigned touched_mask = __ballot_sync(g.gmask, touched != 0) & g.gmask;
+  int status = MDS_QP_OPTIMAL, iters = touched_mask ? 1 : 0;
+  if (fl_mask) {
+    status = MDS_QP_INFEASIBLE;
+  } else if (esc_mask) {
+    // ---- cooperative solve from u_nom (agents are no longer needed: their storage becomes the QP workspace)
+    __syncwarp(g.gmask);  // every lane has read its partners' agents and projected inputs
+    if (g.valid) {
+      R4 xv;
+      xv.x = unom[0]; xv.y = unom[1]; xv.z = unom[2]; xv.w = unom[3];
+      x[n] = xv; xnom[n] = xv;
+    }
+    __syncwarp(g.gmask);
+    const Real un3[3] = {unom[0], unom[1], unom[2]};
+    const int p0 = qp_scan(C, rows, x, un3, M, N, NP, n, g.valid, 0u, 0u, g.gmask);
+    if (p0 == -2) status = MDS_QP_INFEASIBLE;
+    else if (p0 >= 0) {
+      status = qp_solve_group<Real, Real, false>(C, rows, x, xnom, env, 0, M, N, NP, n, g.valid, g.gmask, p0, &iters);
+      if (status == MDS_QP_ITER_CAP) {
+        __syncwarp(g.gmask);
+        if (g.valid) { R4 xv = xnom[n]; x[n] = xv; }
+        __syncwarp(g.gmask);
+        int it2 = 0;
+        status = qp_solve_group_big<Real>(C, rows, x, xnom, M, N, NP, n, g.valid, g.gmask, p0, &it2);
+        iters += it2;
+      }
+    }
+    if (g.valid) { R4 xv = x[n]; xn[0] = xv.x; xn[1] = xv.y; xn[2] = xv.z; }
+  }
   if (g.valid) {
     if (status == MDS_QP_OPTIMAL) {
-      R4 xv = x[n];
-      usafe[0] = xv.x; usafe[1] = xv.y; usafe[2] = xv.z;
+      usafe[0] = xn[0]; usafe[1] = xn[1]; usafe[2] = xn[2];
       usafe[3] = clamp_(unom[3], lo, hi);
     } else {  // reference falls back to the nominal input (cbf/qptracker.py:30-34)
       usafe[0] = unom[0]; usafe[1] = unom[1]; usafe[2] = unom[2]; usafe[3] = unom[3];
@@ -327,6 +412,7 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
                        const typename TrajSpecT<Real>::seg* __restrict__ segs, const Obs<Real>& o, const GroupMap& g, int N, int NP,
                        double t, Real rpm[4], StepStats& ss, int pid_idx) {
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
+  constexpr int ORD = CTRL == MDS_CTRL_LQR_OMEGA ? 2 : 3;  // rollout_impl pairs the order-2 filter with LQR_OMEGA, order 3 with LQR_YANK
   Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
   Ref<Real> ref;
   if (g.valid) {
@@ -357,12 +443,12 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
         xd[0] = Real(0); xd[1] = Real(0); xd[2] = ref.yaw;
         if (CTRL == MDS_CTRL_LQR_OMEGA) { xd[3] = ref.v.x; xd[4] = ref.v.y; xd[5] = ref.v.z; }
         else { xd[3] = P.g * P.m; xd[4] = ref.v.x; xd[5] = ref.v.y; xd[6] = ref.v.z; }
-        ag = cbf_agent(P, C, o, xd, &F);
+        ag = cbf_agent<ORD>(P, C, o, xd, &F);
         unom[0] = u[0] - Rc.u0_pre; unom[1] = u[1]; unom[2] = u[2]; unom[3] = u[3];
       }
       Real mh = Real(1e30);
       int it = 0;
-      int stt = cbf_filter_group(P, C, S, Rc.obstacles, Rc.n_obs, g, N, NP, ag, F, unom, usafe, &mh, &it);
+      int stt = cbf_filter_group<ORD>(P, C, S, Rc.obstacles, Rc.n_obs, g, N, NP, ag, F, unom, usafe, &mh, &it);
       if (g.valid) {
         ss.min_h = (float)mh;
         if (g.n == 0) {

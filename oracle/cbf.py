@@ -91,7 +91,7 @@ def pair_row(prm, xi, xj, xi_des, xj_des, Ds, cylinder=False):
     return a, prm.K[0] * h0 + prm.K[1] * h1 + prm.K[2] * h2 + Lf
 
 
-def build_ineq(prm, x, xdes, x_obs=None, obs_r=None, allow_extra_obstacles=False):
+def build_ineq(prm, x, xdes, x_obs=None, obs_r=None, allow_extra_obstacles=False, do_state_bounds=True):
     """Dense (G, h) exactly as ``CBF._build_ineq_const`` (cbf/cbf.py:308-367)."""
     x, xdes = np.asarray(x, float), np.asarray(xdes, float)
     N = x.shape[0]
@@ -107,7 +107,7 @@ def build_ineq(prm, x, xdes, x_obs=None, obs_r=None, allow_extra_obstacles=False
     eye = np.eye(4 * N)
     rows_G += list(eye) + list(-eye)            # cbf.py:400-412
     rows_h += list(np.tile(prm.umax, 2 * N))
-    if prm.order == 3:                          # cbf.py:446-464: acts on column 4i+3 (wz), quirk kept
+    if prm.order == 3 and do_state_bounds:      # cbf.py:446-476: acts on column 4i+3 (wz), quirk kept; only with do_state_bounds
         for i in range(N):
             gp, gm = np.zeros(4 * N), np.zeros(4 * N)
             gp[4 * i + 3], gm[4 * i + 3] = 1.0, -1.0

@@ -26,7 +26,7 @@ def test_header_symbols_exported(lib_built):
     for n in names:
         assert hasattr(lib_built, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names  # the ctypes table covers exactly the header
-    assert lib_built.mds_abi_version() == 8
+    assert lib_built.mds_abi_version() == 9
     assert lib_built.mds_cbf_num_rows(2, 8, 1) == 100 and lib_built.mds_cbf_num_rows(3, 8, 1) == 116  # SURVEY App. C row counts
     assert lib_built.mds_cbf_num_rows(2, 2, 1) == 19 and lib_built.mds_cbf_num_rows(3, 7, 0) == 91
 

@@ -53,7 +53,8 @@ def test_qp_matches_oracle_fp64(golden, name, order, N, lib_built):
     for e in range(obs.shape[0]):
         Gr, hr, un = g[f"{name}_G"][e], g[f"{name}_h"][e], g[f"{name}_unom"][e]
         uo, lam, so, _ = solve_qp(np.eye(4 * N), -un.reshape(-1), Gr, hr)
-        if so == 0 and st[e] == 0:
+        if so == 0:
+            assert st[e] == 0, (e, int(st[e]))        # the oracle solved it: the device must not fall back to the nominal input
             assert np.max(np.abs(u[e].reshape(-1) - uo)) < 1e-7 * (1 + np.max(np.abs(uo))), e
             n_solved += 1
         elif so == 1:
@@ -78,9 +79,10 @@ def test_qp_fp32_within_1e4(golden, name, order, N, lib_built):
     for e in range(obs.shape[0]):
         Gr, hr, un = g[f"{name}_G"][e], g[f"{name}_h"][e], g[f"{name}_unom"][e]
         uo, lam, so, _ = solve_qp(np.eye(4 * N), -un.reshape(-1), Gr, hr)
-        if so == 0 and st[e] == 0:
-            # per input column, relative to that column's bound (yank O(1), rates O(10))
-            err = np.abs(u[e] - uo.reshape(N, 4)) / np.maximum(1.0, np.abs(np.asarray(cbf.umax))[None, :])
+        if so == 0:
+            assert st[e] == 0, (e, int(st[e]))
+            # north_star: "CBF-filtered actions must agree to 1e-4": absolute, every column (yank O(1), rates up to 10 rad/s)
+            err = np.abs(u[e] - uo.reshape(N, 4))
             assert np.max(err) < 1e-4, (e, np.max(err))
             checked += 1
         if st[e] != 0:
@@ -144,10 +146,10 @@ def test_cylinder_obstacles_vs_oracle(golden, order, dtype, tol, lib_built):
         assert scaled_err(Gd[e].double().cpu().numpy(), Gr) < max(tol, 1e-5 if dtype == torch.float32 else 0)
         assert scaled_err(hd[e].double().cpu().numpy(), hr) < max(tol, 1e-5 if dtype == torch.float32 else 0)
         uo, _, so, _ = solve_qp(np.eye(4 * N), -unom_h[e].reshape(-1), Gr, hr)
-        if so == 0 and st[e] == 0:
-            # per input column, relative to that column's bound (as test_qp_fp32_within_1e4)
-            err = np.abs(u[e] - uo.reshape(N, 4)) / np.maximum(1.0, np.abs(np.asarray(cbf.umax))[None, :])
-            assert np.max(err) < max(tol, 1e-8), (e, np.max(err))
+        if so == 0:
+            assert st[e] == 0, (e, int(st[e]))
+            err = np.abs(u[e] - uo.reshape(N, 4))
+            assert np.max(err) < max(tol, 1e-8) * (1.0 if dtype == torch.float32 else 1 + np.max(np.abs(uo))), (e, np.max(err))
             solved += 1
     assert solved >= (1 if order == 2 else 2)   # order-2 rows vanish at ez = 0: most random order-2 cases are infeasible
     import os
@@ -182,7 +184,7 @@ def test_qp_other_group_sizes_vs_oracle(N, n_obs, order, lib_built):
             strict.check_obstacle_count(n_obs)
     oenv = OracleCtrlAviary(ODM.CF2P, N, physics=OPH.DYN)
     prm = ocbf.CbfParams(oenv, order, zs, rs, tuple(poles))
-    spread = 0.6 * N ** (1 / 3) * (2.5 if N >= 16 else 1.0)   # big groups: sparse enough that active sets stay under the cap of 12
+    spread = 0.6 * N ** (1 / 3)
     rpy = rng.uniform(-0.3, 0.3, (E, N, 3))
     obs = np.concatenate([rng.uniform(-spread, spread, (E, N, 3)), Rotation.from_euler("xyz", rpy.reshape(-1, 3)).as_quat().reshape(E, N, 4), rpy,
                           rng.normal(0, 0.5, (E, N, 3)), rng.normal(0, 0.5, (E, N, 3)), rng.uniform(12000, 17000, (E, N, 4))], axis=-1)
@@ -202,7 +204,8 @@ def test_qp_other_group_sizes_vs_oracle(N, n_obs, order, lib_built):
                                  allow_extra_obstacles=extra)
         assert scaled_err(Gd[e].cpu().numpy(), Gr) < 1e-9 and scaled_err(hd[e].cpu().numpy(), hr) < 1e-9
         uo, _, so, _ = solve_qp(np.eye(4 * N), -unom[e].reshape(-1), Gr, hr)
-        if so == 0 and st[e] == 0:
+        if so == 0:
+            assert st[e] == 0, (e, int(st[e]))
             assert np.max(np.abs(u[e].reshape(-1) - uo)) < 1e-7 * (1 + np.max(np.abs(uo))), (e, np.max(np.abs(u[e].reshape(-1) - uo)))
             solved += 1
         elif so == 1:
@@ -210,3 +213,107 @@ def test_qp_other_group_sizes_vs_oracle(N, n_obs, order, lib_built):
         if st[e] != 0:
             assert np.array_equal(u[e], unom[e])
     assert solved >= (1 if order == 2 else 3), (solved, st.tolist())
+
+
+def dense_case(N, n_obs, order, E, seed):
+    """Random dense swarm (positions in a cube of half-width 0.6 N^(1/3)): many barrier rows active at once."""
+    from oracle import cbf as ocbf
+    from oracle.aviary import OracleCtrlAviary
+    from oracle.constants import DroneModel as ODM, Physics as OPH
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    oenv = OracleCtrlAviary(ODM.CF2P, N, physics=OPH.DYN)
+    poles = (-2.2, -2.4) if order == 2 else (-3.0, -3.6, -5.6)
+    rs, zs = (0.1, 1.0) if order == 2 else (0.125, 2.0)
+    prm = ocbf.CbfParams(oenv, order, zs, rs, poles)
+    spread = 0.6 * N ** (1 / 3)
+    rpy = rng.uniform(-0.3, 0.3, (E, N, 3))
+    obs = np.concatenate([rng.uniform(-spread, spread, (E, N, 3)), Rotation.from_euler("xyz", rpy.reshape(-1, 3)).as_quat().reshape(E, N, 4), rpy,
+                          rng.normal(0, 0.5, (E, N, 3)), rng.normal(0, 0.5, (E, N, 3)), rng.uniform(12000, 17000, (E, N, 4))], axis=-1)
+    xdes = np.zeros((E, N, prm.xdim))
+    xdes[..., -3:] = obs[..., 0:3] + rng.normal(0, 0.2, (E, N, 3))
+    if order == 3:
+        xdes[..., 3] = oenv.M * oenv.G
+    unom = rng.normal(0, 1.0, (E, N, 4)) * np.array([0.5, 2.0, 2.0, 2.0])
+    obst = np.concatenate([rng.uniform(-spread, spread, (n_obs, 3)), rng.uniform(0.05, 0.2, (n_obs, 1))], axis=1) if n_obs else None
+    return oenv, prm, poles, rs, zs, obs, xdes, unom, obst
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("N,n_obs,min_active", [(8, 1, 7), (16, 1, 13), (32, 2, 25)])
+def test_dense_swarms_never_fall_back(N, n_obs, min_active, dtype, lib_built):
+    """The hole VERDICT r1 names: 'oracle solved, device gave up'.  Dense random swarms whose optimal active sets exceed the
+    12 slots of the in-shared-memory solver (up to 34 at N = 32): the device must report OPTIMAL wherever the oracle does and
+    return the same minimiser (fp64 1e-7 relative, fp32 1e-4 absolute), through the scratch solver where needed."""
+    import multidronesim_b200 as mds
+    from oracle import cbf as ocbf
+    from oracle import conversions as cv
+    E, order = 24, 3
+    oenv, prm, poles, rs, zs, obs, xdes, unom, obst = dense_case(N, n_obs, order, E, 100 + N)
+    env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=N, num_envs=E, dtype=dtype)
+    cbf = mds.cbf.DroneCBF(env, [mds.model.LinearizedYankOmegaModel(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=order,
+                           cbf_poles=np.array(poles))
+    trk = mds.cbf.DroneQPTracker(cbf, order=order, num_robots=N, xdim=cbf.xdim, env=env)
+    dev = lambda a: None if a is None else torch.as_tensor(a, device="cuda", dtype=dtype).contiguous()
+    # Solver parity: both solvers get the SAME problem data.  fp64: the oracle's own rows (the device rows equal them to 1e-9,
+    # test_qp_other_group_sizes_vs_oracle).  fp32: the rows the device built in fp32 (mds_cbf_rows, the same row code as the QP
+    # kernel) -- a row error of 1e-6 moves the minimiser by 1e-6 / |a|, which is the rows' conditioning, not the solver's.
+    Gd, hd = cbf.build_ineq_const(dev(obs), dev(xdes), dev(obst))
+    Gd, hd = Gd.double().cpu().numpy(), hd.double().cpu().numpy()
+    u = trk.compute_control(dev(obs), dev(xdes), dev(unom), x_obs=dev(obst)).double().cpu().numpy()
+    st, it = trk.status.cpu().numpy(), trk.iters.cpu().numpy()
+    unom_seen = unom if dtype == torch.float64 else unom.astype(np.float32).astype(np.float64)
+    n_opt, most_active, worst, worst_e2e = 0, 0, 0.0, 0.0
+    for e in range(E):
+        x = np.array([cv.obs_to_lin_model(obs[e, i], prm.xdim, oenv) for i in range(N)])
+        Gr, hr = ocbf.build_ineq(prm, x, xdes[e], [o[:3] for o in obst], [o[3] for o in obst])
+        if dtype == torch.float64:
+            assert scaled_err(Gd[e], Gr) < 1e-9 and scaled_err(hd[e], hr) < 1e-9
+        ue, _, se, _ = solve_qp(np.eye(4 * N), -unom[e].reshape(-1), Gr, hr)          # fp64 data end to end
+        uo, lam, so, _ = solve_qp(np.eye(4 * N), -unom_seen[e].reshape(-1), Gd[e], hd[e])  # the device's data
+        if so == 0:
+            assert st[e] == 0, (e, int(st[e]), int(it[e]), int((lam > 0).sum()))
+            err = np.max(np.abs(u[e].reshape(-1) - uo))
+            worst = max(worst, err)
+            assert err < (1e-7 * (1 + np.max(np.abs(uo))) if dtype == torch.float64 else 1e-4), (e, err, int((lam > 0).sum()))
+            n_opt += 1
+            most_active = max(most_active, int((lam > 0).sum()))
+            if se == 0:
+                worst_e2e = max(worst_e2e, float(np.max(np.abs(u[e].reshape(-1) - ue))))
+        elif so == 1:
+            assert st[e] != 0, e
+    print(f"dense N={N} {dtype}: solver parity {worst:.2e}, vs fp64 rows end to end {worst_e2e:.2e}, largest active set {most_active}")
+    assert worst_e2e < (1e-6 if dtype == torch.float64 else 5e-3)
+    assert n_opt >= E // 2 and most_active >= min_active, (n_opt, most_active)
+
+
+def test_do_state_bounds_false(lib_built):
+    """CBF(do_state_bounds=False) (cbf/cbf.py:473-476): no force-bound rows -- 2 N fewer rows, and the 4th input is
+    clamped by the +-umax box alone."""
+    import multidronesim_b200 as mds
+    from oracle import cbf as ocbf
+    from oracle import conversions as cv
+    N, E, order, dtype = 4, 6, 3, torch.float64
+    oenv, prm, poles, rs, zs, obs, xdes, unom, obst = dense_case(N, 1, order, E, 7)
+    unom[..., 3] = np.linspace(-12, 12, E * N).reshape(E, N)  # beyond both the box (10) and the force-bound interval
+    env = mds.BatchedCtrlAviary(drone_model=mds.DroneModel.CF2P, num_drones=N, num_envs=E, dtype=dtype)
+    dev = lambda a: torch.as_tensor(a, device="cuda", dtype=dtype).contiguous()
+    outs = {}
+    for flag in (True, False):
+        cbf = mds.cbf.DroneCBF(env, [mds.model.LinearizedYankOmegaModel(env) for _ in range(N)], safety_radius=rs, zscale=zs, order=order,
+                               cbf_poles=np.array(poles))
+        cbf.do_state_bounds = flag
+        trk = mds.cbf.DroneQPTracker(cbf, order=order, num_robots=N, xdim=cbf.xdim, env=env)
+        G, h = cbf.build_ineq_const(dev(obs), dev(xdes), dev(obst))
+        assert G.shape[1] == N * (N - 1) // 2 + 8 * N + (2 * N if flag else 0) + N
+        u = trk.compute_control(dev(obs), dev(xdes), dev(unom), x_obs=dev(obst)).cpu().numpy()
+        st = trk.status.cpu().numpy()
+        for e in range(E):
+            x = np.array([cv.obs_to_lin_model(obs[e, i], prm.xdim, oenv) for i in range(N)])
+            Gr, hr = ocbf.build_ineq(prm, x, xdes[e], [o[:3] for o in obst], [o[3] for o in obst], do_state_bounds=flag)
+            assert scaled_err(G[e].cpu().numpy(), Gr) < 1e-9 and scaled_err(h[e].cpu().numpy(), hr) < 1e-9
+            uo, _, so, _ = solve_qp(np.eye(4 * N), -unom[e].reshape(-1), Gr, hr)
+            if so == 0:
+                assert st[e] == 0 and np.max(np.abs(u[e].reshape(-1) - uo)) < 1e-7 * (1 + np.max(np.abs(uo))), (flag, e)
+        outs[flag] = u
+    assert np.max(np.abs(outs[True][..., 3] - outs[False][..., 3])) > 1e-3   # the force-bound rows do bind in this case

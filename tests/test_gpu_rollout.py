@@ -147,11 +147,12 @@ def test_cbf_closed_loop_vs_oracle(order, N, dtype, tol, lib_built):
     log = torch.zeros(steps, E, N, 20, device="cuda", dtype=dtype)
     ro.run(steps, obs_log=log, log_every=1)
     got = log.double().cpu().numpy()
-    worst, n_active = 0.0, 0
+    worst, n_active, ora_fail = 0.0, 0, 0
     for e in range(E):
         o = OracleCtrlAviary(ODM.CF2P, N, initial_xyzs=init[e], physics=OPH.DYN_GND_DRAG_DW)
         want, _, info = opl.run_cbf(o, [otj.Lemniscate(**sp) for sp in specs], order, steps, obstacles=obstacles)
         n_active += info["solves"]
+        ora_fail += info["status"][1] + info["status"][2]
         # fp64 follows the oracle through infeasible steps too (same nominal fallback); fp32 is compared only
         # where the oracle's QP always solved (a borderline feasibility flip would fork the trajectories)
         if dtype == torch.float64 or info["status"][1] + info["status"][2] == 0:
@@ -159,6 +160,37 @@ def test_cbf_closed_loop_vs_oracle(order, N, dtype, tol, lib_built):
     st = ro.stats_dict()
     assert worst < tol, worst
     assert st["qp_solves"] > 0 and n_active > 0
+    assert st["qp_iter_cap"] == 0                                    # the device never gives up on a QP ...
+    if dtype == torch.float64 or ora_fail == 0:
+        assert st["qp_infeasible"] == ora_fail, (st, ora_fail)       # ... and falls back to the nominal input exactly where the oracle does
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-6), (torch.float32, 5e-3)])
+def test_c5_full_lap_vs_oracle(dtype, tol, lib_built):
+    """The bench workload (scenarios.cbf_swarm: 8 drones on one lemniscate, order-3 filter, sphere beside the crossing) over a
+    whole lap (3024 control steps) against oracle/pipeline.run_cbf: same positions, and every QP the oracle solves the
+    device solves (no iteration-cap or infeasible fallbacks)."""
+    import multidronesim_b200 as mds
+    from multidronesim_b200 import scenarios
+    E, N, steps, every = 3, 8, 3024, 126
+    sw = scenarios.cbf_swarm(E, N, order=3, dtype=dtype)
+    ro = sw["rollout"]
+    log = torch.zeros(steps // every, E, N, 20, device="cuda", dtype=dtype)
+    ro.run(steps, obs_log=log, log_every=every)
+    got = log.double().cpu().numpy()
+    st = ro.stats_dict()
+    phase = (2 * np.pi / (N + 0.25)) * np.arange(N)
+    worst, fails = 0.0, 0
+    for e in range(E):
+        o = OracleCtrlAviary(ODM.CF2P, N, initial_xyzs=sw["init"][e], physics=OPH.DYN_GND_DRAG_DW)
+        trajs = [otj.Lemniscate(a=1.0, omega=0.5, center=np.array([0, 0, 0.5]), yaw_rate=0.0, phase_shift=float(p)) for p in phase]
+        want, _, info = opl.run_cbf(o, trajs, 3, steps, obstacles=scenarios.SWARM_OBSTACLES)
+        fails += info["status"][1] + info["status"][2]
+        worst = max(worst, float(np.max(np.abs(got[:, e, :, 0:3] - want[every - 1::every, :, 0:3]))))
+    assert fails == 0                                   # the bench scenario is feasible all the way in the oracle ...
+    assert st["qp_iter_cap"] == 0 and st["qp_infeasible"] == 0, st   # ... and on the device
+    assert worst < tol, worst
+    assert st["qp_solves"] > 0.5 * E * steps            # the filter is active in most steps of this workload
 
 
 @pytest.mark.parametrize("ctrl,cbf_order,N,n_obs", [("yank10", 3, 8, 1), ("omega9", 2, 3, 1), ("geometric", None, 1, 0),
