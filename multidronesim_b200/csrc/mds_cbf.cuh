@@ -555,13 +555,15 @@ MDS_DEV int qp_solve_group(const CbfP<Real>& C, const typename Vec4T<Real>::type
 // The scratch solver, out of line: rare (active sets beyond MDS_QP_QMAX, factor breakdown), so its code stays off the step loop.
 // Lane 0 of the group claims a slot of the global scratch (flags: 0 free / 1 taken; a busy pool is waited for -- holders
 // never wait for anything, so the wait ends), the group repeats the solve from u_nom with the scalar part in double, and
-// lane 0 releases the slot.
+// lane 0 releases the slot.  Everything comes BY VALUE: a reference to the caller's parameter block (or to any of its
+// locals) would pin that object in local memory for the whole kernel.  Returns status | iterations << 8.
 template <typename Real>
-__device__ __noinline__ int qp_solve_group_big(const CbfP<Real>& C, const typename Vec4T<Real>::type* rows, typename Vec4T<Real>::type* x,
-                                               const typename Vec4T<Real>::type* xnom, const RowMap& M, int N, int NP, int n, bool valid,
-                                               unsigned gmask, int p0, int* iters_out) {
-  const QpScratch& S = C.scr;
-  if (S.base == nullptr || S.slots <= 0) { *iters_out = 0; return MDS_QP_ITER_CAP; }
+__device__ __noinline__ int qp_solve_group_big(Real umax0, Real umax1, Real umax2, QpScratch S, const typename Vec4T<Real>::type* rows,
+                                               typename Vec4T<Real>::type* x, const typename Vec4T<Real>::type* xnom, RowMap M, int N, int NP, int n,
+                                               bool valid, unsigned gmask, int p0) {
+  if (S.base == nullptr || S.slots <= 0) return MDS_QP_ITER_CAP;
+  CbfP<Real> C;  // the solver reads the box bounds only
+  C.umax[0] = umax0; C.umax[1] = umax1; C.umax[2] = umax2; C.max_iter = 0;
   const int lane0 = __ffs(gmask) - 1;
   int slot = -1;
   if (n == 0) {
@@ -575,13 +577,14 @@ __device__ __noinline__ int qp_solve_group_big(const CbfP<Real>& C, const typena
   }
   slot = __shfl_sync(gmask, slot, lane0);
   double* ws = S.base + (size_t)slot * (size_t)S.slot_doubles;
-  const int st = qp_solve_group<Real, double, true>(C, rows, x, xnom, ws, S.qmax, M, N, NP, n, valid, gmask, p0, iters_out);
+  int iters = 0;
+  const int st = qp_solve_group<Real, double, true>(C, rows, x, xnom, ws, S.qmax, M, N, NP, n, valid, gmask, p0, &iters);
   __syncwarp(gmask);
   if (n == 0) {
     __threadfence();
     atomicExch(S.flags + slot, 0);
   }
-  return st;
+  return st | (iters << 8);
 }
 
 // Obstacle record (cx, cy, cz, r): r > 0 is the reference's sphere (super-ellipsoid barrier with the agents' zscale,

@@ -84,7 +84,23 @@ MDS_DEV void sincos_(float x, float* s, float* c) {
   *c = ((q + 1) & 2) ? -cc : cc;
 }
 MDS_DEV void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
-MDS_DEV float atan2_(float y, float x) { return atan2f(y, x); }
+// fp32 atan2 from ONE division: the ratio of the smaller to the larger magnitude, reduced to |t| <= tan(pi/8) by
+// atan(a) = pi/4 + atan((a - 1) / (a + 1)) with numerator and denominator selected before dividing, then cephes atanf's
+// degree-9 odd polynomial (peak relative error 2e-7) and the octant fix-ups.  libdevice's atan2f is ~42 instructions and
+// runs twice per drone-step (roll and yaw of the observation); this is ~24.
+MDS_DEV float atan2_(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const bool mid = mn > 0.41421356237f * mx;
+  const float num = mid ? mn - mx : mn, den = mid ? mn + mx : mx;
+  const float t = den > 0.f ? num / den : 0.f;  // atan2(0, 0) = 0
+  const float z = t * t;
+  float r = fmaf(fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f), z * t, t);
+  if (mid) r += 0.78539816339744831f;
+  if (ay > ax) r = 1.57079632679489662f - r;
+  if (x < 0.f) r = 3.14159265358979324f - r;
+  return copysignf(r, y);
+}
 MDS_DEV double atan2_(double y, double x) { return atan2(y, x); }
 MDS_DEV float asin_(float x) { return asinf(x); }
 MDS_DEV double asin_(double x) { return asin(x); }
@@ -132,6 +148,19 @@ template <typename Real> inline DroneP<Real> to_dev(const MdsDroneParams& p) {
   d.cf2x_torque_sign = p.cf2x_torque_sign; d.renormalize_quat = p.renormalize_quat; d.ground_clamp = p.ground_clamp; d.x_frame_mixer = p.x_frame_mixer;
   return d;
 }
+// Compile-time view of the run-time switches of the parameter block.  SPEC = 0: read them from P (any configuration).
+// SPEC = 1: the swarm configuration of the reference's CBF mains -- physics DYN_GND_DRAG_DW, CF2P, one physics sub-step
+// per control period, no quaternion renormalisation, ground clamp on, PLUS-frame mixer; the host selects it when P matches
+// exactly (mds_kernels.cu phys_spec_of), so the step loop carries none of the mode branches.
+template <int SPEC> struct PhysSpec {
+  template <typename Real> static MDS_DEV int physics(const DroneP<Real>& P) { return SPEC == 1 ? MDS_PHYSICS_DYN_GND_DRAG_DW : P.physics; }
+  template <typename Real> static MDS_DEV int drone_model(const DroneP<Real>& P) { return SPEC == 1 ? MDS_DRONE_CF2P : P.drone_model; }
+  template <typename Real> static MDS_DEV int substeps(const DroneP<Real>& P) { return SPEC == 1 ? 1 : P.substeps; }
+  template <typename Real> static MDS_DEV bool renormalize(const DroneP<Real>& P) { return SPEC == 1 ? false : P.renormalize_quat != 0; }
+  template <typename Real> static MDS_DEV bool ground_clamp(const DroneP<Real>& P) { return SPEC == 1 ? true : P.ground_clamp != 0; }
+  template <typename Real> static MDS_DEV bool x_frame_mixer(const DroneP<Real>& P) { return SPEC == 1 ? false : P.x_frame_mixer != 0; }
+};
+
 template <typename Real> struct GeoP { Real kp, kv, kr, kw, g_ctrl, max_tilt, tan_max_tilt; };
 template <typename Real> inline GeoP<Real> to_dev(const MdsGeoGains& g) {
   return GeoP<Real>{Real(g.kp), Real(g.kv), Real(g.kr), Real(g.kw), Real(g.g_ctrl), Real(g.max_tilt), Real(tan(g.max_tilt))};
@@ -154,6 +183,7 @@ struct QpScratch {
 template <typename Real> struct CbfP {
   int order, max_iter, state_bounds;
   Real c4inv, inv_c, rs, ds4_pair, k0, k1, k2, umax[4], fmin, fmax;
+  Real umax_hi[3];  // |u_c| beyond this violates the box bound by more than the solver's relative tolerance
   QpScratch scr;
 };
 template <typename Real> inline CbfP<Real> to_dev(const MdsCbfParams& c) {
@@ -166,6 +196,10 @@ template <typename Real> inline CbfP<Real> to_dev(const MdsCbfParams& c) {
   d.scr = QpScratch{nullptr, nullptr, 0, 0, 0};
   d.k0 = Real(c.kcbf[0]); d.k1 = Real(c.kcbf[1]); d.k2 = Real(c.order == 3 ? c.kcbf[2] : 0.0);
   for (int i = 0; i < 4; ++i) d.umax[i] = Real(c.umax[i]);
+  {
+    const double tol = sizeof(Real) == 4 ? 2e-6 : 1e-11;  // qp_tol<Real>() of mds_cbf.cuh
+    for (int i = 0; i < 3; ++i) d.umax_hi[i] = Real((c.umax[i] * (1.0 + tol) + tol * 1e-12) / (1.0 - tol));
+  }
   d.fmin = Real(c.fmin); d.fmax = Real(c.fmax);
   return d;
 }

@@ -28,11 +28,11 @@ template <typename Real> MDS_DEV M3<Real> quat_to_rot_scipy(Real x, Real y, Real
 
 // calc_z_thrust: model_conversions.py:137-143
 template <typename Real> MDS_DEV Real z_thrust(const DroneP<Real>& P, const Real rpm[4]) {
-  return P.kf * rpm[0] * rpm[0] + P.kf * rpm[1] * rpm[1] + P.kf * rpm[2] * rpm[2] + P.kf * rpm[3] * rpm[3];
+  return P.kf * rpm[0] * rpm[0] + P.kf * rpm[1] * rpm[1] + P.kf * rpm[2] * rpm[2] + P.kf * rpm[3] * rpm[3];  // summation order of calc_z_thrust
 }
 
 // action_to_input: RPM -> [f, tx, ty, tz], PLUS-frame mixer (model_conversions.py:69-83)
-template <typename Real> MDS_DEV void action_to_input(const DroneP<Real>& P, const Real rpm_in[4], Real u[4]) {
+template <int SPEC = 0, typename Real> MDS_DEV void action_to_input(const DroneP<Real>& P, const Real rpm_in[4], Real u[4]) {
   Real T[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -42,7 +42,7 @@ template <typename Real> MDS_DEV void action_to_input(const DroneP<Real>& P, con
   Real kr = P.km / P.kf;
   u[0] = T[0] + T[1] + T[2] + T[3];
   u[3] = kr * (-T[0] + T[1] - T[2] + T[3]);
-  if (P.x_frame_mixer && P.drone_model == MDS_DRONE_CF2X) {  // the allocation physics_substep applies to a CF2X
+  if (PhysSpec<SPEC>::x_frame_mixer(P) && PhysSpec<SPEC>::drone_model(P) == MDS_DRONE_CF2X) {  // the allocation physics_substep applies to a CF2X
     const Real l2 = P.arm_l * Real(0.70710678118654752);
     u[1] = Real(P.cf2x_torque_sign) * l2 * (T[0] + T[1] - T[2] - T[3]);
     u[2] = l2 * (-T[0] + T[1] + T[2] - T[3]);
@@ -54,12 +54,12 @@ template <typename Real> MDS_DEV void action_to_input(const DroneP<Real>& P, con
 
 // input_to_action: [f, tx, ty, tz] -> RPM (model_conversions.py:85-103); clamps u[0] >= 0 in
 // place; closed-form inverse of the mixer; per-motor clip to [MIN_RPM^2 kf, MAX_THRUST] (B6).
-template <typename Real> MDS_DEV void input_to_action(const DroneP<Real>& P, Real u[4], Real rpm[4]) {
+template <int SPEC = 0, typename Real> MDS_DEV void input_to_action(const DroneP<Real>& P, Real u[4], Real rpm[4]) {
   u[0] = max_(u[0], Real(0));
   Real kr = P.km / P.kf;
   Real q = Real(0.25) * u[0], a = u[1] / (Real(2) * P.arm_l), b = u[2] / (Real(2) * P.arm_l), c = u[3] / (Real(4) * kr);
   Real T[4] = {q - b - c, q + a + c, q + b - c, q - a + c};
-  if (P.x_frame_mixer && P.drone_model == MDS_DRONE_CF2X) {  // inverse of the X-frame allocation (extension; the reference is PLUS-only)
+  if (PhysSpec<SPEC>::x_frame_mixer(P) && PhysSpec<SPEC>::drone_model(P) == MDS_DRONE_CF2X) {  // inverse of the X-frame allocation (extension; the reference is PLUS-only)
     const Real l2 = P.arm_l * Real(0.70710678118654752);
     a = Real(P.cf2x_torque_sign) * u[1] / (Real(4) * l2);
     b = u[2] / (Real(4) * l2);
@@ -216,7 +216,7 @@ template <typename Real> MDS_DEV void store_pid(const PidP<Real>& s, int d, cons
 
 // ThrustOmegaController.computeControlFromInput + omega_PID (thrust_omega_ctrl.py:81-132, B11).
 // `thrust` already resolved (yank variant integrates before calling).  w_b = body rates.
-template <typename Real>
+template <int SPEC = 0, typename Real>
 MDS_DEV void thrust_omega_pid(const DroneP<Real>& P, Pid<Real>& s, Real thrust, V3<Real> w_target, V3<Real> w_b, Real rpm[4]) {
   const Real dt = P.dt_ctrl;
   thrust = max_(thrust, Real(0));
@@ -234,7 +234,7 @@ MDS_DEV void thrust_omega_pid(const DroneP<Real>& P, Pid<Real>& s, Real thrust, 
                  clamp_(kp * e.y + ki * s.integ.y + kd * rate_e.y, Real(-3200), Real(3200)),
                  clamp_(kp * e.z + ki * s.integ.z + kd * rate_e.z, Real(-3200), Real(3200))};
   Real pw[4];
-  if (P.drone_model == MDS_DRONE_CF2X) {
+  if (PhysSpec<SPEC>::drone_model(P) == MDS_DRONE_CF2X) {
     pw[0] = pwm_t + (Real(-0.5) * tq.x - Real(0.5) * tq.y - tq.z);
     pw[1] = pwm_t + (Real(-0.5) * tq.x + Real(0.5) * tq.y + tq.z);
     pw[2] = pwm_t + (Real(0.5) * tq.x + Real(0.5) * tq.y - tq.z);
@@ -337,14 +337,16 @@ MDS_DEV void dslpid_control(const DroneP<Real>& P, const DslP<Real>& G, DslState
 }
 
 // compute_low_level (lqr_omega_controller.py:78-88, lqr_YO_controller.py:87-98): world ->
-// body rates with scipy's normalised R, then the inner loop.
-template <typename Real>
-MDS_DEV void low_level(const DroneP<Real>& P, int variant, Pid<Real>& s, const Real u[4], const Obs<Real>& o, Real rpm[4]) {
+// body rates with scipy's normalised R, then the inner loop.  R_out (optional) receives that matrix: it is the attitude the
+// physics step starts from, so the fused rollout hands it on instead of rebuilding it from the quaternion.
+template <int SPEC = 0, typename Real>
+MDS_DEV void low_level(const DroneP<Real>& P, int variant, Pid<Real>& s, const Real u[4], const Obs<Real>& o, Real rpm[4], M3<Real>* R_out = nullptr) {
   M3<Real> R = quat_to_rot_scipy(o.qx, o.qy, o.qz, o.qw);
   V3<Real> w_b = mulT(R, o.av);
   Real thrust = u[0];
   if (variant == MDS_CTRL_LQR_YANK) thrust = z_thrust(P, o.rpm) + u[0] * P.dt_ctrl;
-  thrust_omega_pid(P, s, thrust, v3(u[1], u[2], u[3]), w_b, rpm);
+  thrust_omega_pid<SPEC>(P, s, thrust, v3(u[1], u[2], u[3]), w_b, rpm);
+  if (R_out) *R_out = R;
 }
 
 }  // namespace mds

@@ -659,6 +659,11 @@ static int xdot_nonlinear_impl(const MdsDroneParams* prm, double jx, double jy, 
   return check_launch("xdot_nonlinear");
 }
 extern "C" int mds_rollout_plan(int E, int N);
+// PhysSpec<1> (mds_common.cuh): the swarm configuration of the reference's CBF mains, compiled without its mode switches
+static int phys_spec_of(const MdsDroneParams& p) {
+  return (p.physics == MDS_PHYSICS_DYN_GND_DRAG_DW && p.drone_model == MDS_DRONE_CF2P && p.substeps == 1 && !p.renormalize_quat && p.ground_clamp &&
+          !p.x_frame_mixer) ? 1 : 0;
+}
 template <typename Real>
 static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo, const MdsLqrGains* lqr, const MdsCbfParams* cbf,
                         MdsState st, MdsPidState pid, const MdsDslPidGains* dsl, MdsDslPidState dsl_state,
@@ -713,6 +718,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     R.n_obs = 0;
   }
   MDS_REQUIRE(!(cfg->write_obs_every > 0) || obs_log, "rollout: obs_log buffer missing");
+  MDS_REQUIRE(cfg->write_obs_every <= 32767, "rollout: write_obs_every must be <= 32767");
   const int NP = next_pow2(N), threads = R.use_cbf ? cbf_block_threads<Real>(NP, N, R.n_obs) : MDS_BLOCK, epb = threads / NP;
   const int blocks = (E + epb - 1) / epb;
   size_t smem = R.use_cbf ? cbf_smem_bytes<Real>(threads, NP, N, R.n_obs) : 32;
@@ -731,9 +737,25 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     return obs;
   };
   cudaError_t attr_err = cudaSuccess;
-  RolloutLaunch<Real> RL{Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, fext, obs, obs_log, stats, E, N, NP, blocks, threads, smem, cs};
+  RolloutLaunch<Real> RL{Pd, R, G, L, C, Dg, Ds, Sd, Pi, specs, segs, action, fext, obs, obs_log, stats, E, N, NP, blocks, threads, phys_spec_of(*prm), smem, cs};
   auto keep = [&](cudaError_t e) { if (e != cudaSuccess) attr_err = e; };
-  auto launch_loop = [&]() { keep(launch_loop_kernel<Real>(RL, t0, prm->dt_ctrl, K)); };
+  // the loop kernel packs two rare-event counters into 16 bits each: longer runs go out as several launches (whole log periods each)
+  auto launch_loop = [&]() {
+    RolloutLaunch<Real> RLL = RL;  // the loop kernel has its own block size (MDS_LOOP_BLOCK)
+    RLL.threads = R.use_cbf ? cbf_block_threads<Real>(NP, N, R.n_obs, MDS_LOOP_BLOCK) : MDS_LOOP_BLOCK;
+    if (RLL.threads < NP) RLL.threads = NP;
+    const int epb_l = RLL.threads / NP;
+    RLL.blocks = (E + epb_l - 1) / epb_l;
+    RLL.smem = R.use_cbf ? cbf_smem_bytes<Real>(RLL.threads, NP, N, R.n_obs) : 32;
+    const int every = R.write_obs_every;
+    int chunk = 16384;
+    if (every > 0) chunk = every >= 16384 ? every : (16384 / every) * every;
+    for (int k0 = 0; k0 < K; k0 += chunk) {
+      RolloutLaunch<Real> part = RLL;
+      if (every > 0) part.obs_log = obs_log + (size_t)(k0 / every) * obs_elems;
+      keep(launch_loop_kernel<Real>(part, t0 + k0 * prm->dt_ctrl, prm->dt_ctrl, K - k0 < chunk ? K - k0 : chunk));
+    }
+  };
   bool first_ctrl = true, first_fused = true;
   auto launch_ctrl = [&](bool fused, double t, Real* obs_ptr) {
     if (fused) { keep(launch_fused_kernel<Real>(RL, t, obs_ptr, first_fused)); first_fused = false; }

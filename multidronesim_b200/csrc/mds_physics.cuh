@@ -7,48 +7,74 @@
 
 namespace mds {
 
-// Pairwise downwash on a drone at `pi` from one drone at `pj`: only drones
-// above (dz > 0) and within 10 m in the plane contribute alpha * exp(-(dxy/beta)^2 / 2).
-template <typename Real>
-MDS_DEV Real downwash_term(const DroneP<Real>& P, V3<Real> pi, V3<Real> pj) {
+// Downwash on the LOWER drone of a pair: dz > 0 its distance below the other, dxy2 the squared distance in
+// the plane; only pairs within 10 m in the plane interact:  alpha * exp(-(dxy / beta)^2 / 2).
+template <typename Real> MDS_DEV Real downwash_pair(const DroneP<Real>& P, Real dz, Real dxy2) {
+  Real q = P.prop_radius / (Real(4) * max_(dz, P.dw_dz_clip));  // clip: App. A.4 regularisation (0 = upstream)
+  Real alpha = P.dw1 * q * q;
+  Real beta = P.dw2 * dz + P.dw3;
+  return alpha * exp_(Real(-0.5) * dxy2 / (beta * beta));
+}
+// the same as seen from drone i: contribution of a drone at pj
+template <typename Real> MDS_DEV Real downwash_term(const DroneP<Real>& P, V3<Real> pi, V3<Real> pj) {
   Real dz = pj.z - pi.z;
   Real dx = pj.x - pi.x, dy = pj.y - pi.y;
   Real dxy2 = dx * dx + dy * dy;
-  if (dz > Real(0) && dxy2 < Real(100)) {
-    Real q = P.prop_radius / (Real(4) * max_(dz, P.dw_dz_clip));  // clip: App. A.4 regularisation (0 = upstream)
-    Real alpha = P.dw1 * q * q;
-    Real beta = P.dw2 * dz + P.dw3;
-    return alpha * exp_(Real(-0.5) * dxy2 / (beta * beta));
-  }
+  if (dz > Real(0) && dxy2 < Real(100)) return downwash_pair(P, dz, dxy2);
   return Real(0);
 }
 
-// One sub-step.  `rpm` is the clipped action; `dw` the summed downwash (0 for DYN);
-// `fext` an optional world-frame force.  Returns the world angular velocity that
-// PyBullet would be handed: R(q_old) * w_new.
-template <typename Real>
-MDS_DEV V3<Real> physics_substep(const DroneP<Real>& P, Drone<Real>& s, const Real rpm[4], Real dw, V3<Real> fext) {
+// cos(x) and sin(x) / x * h for the quaternion update, x = |w| h, h = dt / 2.  fp32: the polynomials of sincos_ on
+// x^2 (|x| < pi/4, i.e. |w| < 377 rad/s at 240 Hz -- beyond that the general path), no division by |w| and no
+// small-|w| branch; fp64: upstream's literal form.
+MDS_DEV bool quat_step_coeffs(float wn2, float h, float* cs, float* k) {
+  const float x2 = wn2 * h * h;
+  if (x2 < 0.6f) {
+    *k = h * fmaf(fmaf(fmaf(-1.9515295891e-4f, x2, 8.3321608736e-3f), x2, -1.6666654611e-1f), x2, 1.0f);
+    *cs = fmaf(fmaf(fmaf(2.443315711809948e-5f, x2, -1.388731625493765e-3f), x2, 4.166664568298827e-2f), x2 * x2, fmaf(-0.5f, x2, 1.0f));
+    return true;
+  }
+  const float wn = sqrtf(wn2);
+  float sn;
+  sincos_(wn * h, &sn, cs);
+  *k = sn / wn;
+  return true;
+}
+MDS_DEV bool quat_step_coeffs(double wn2, double h, double* cs, double* k) {
+  const double wn = sqrt(wn2);
+  if (!(wn > 1e-8)) return false;  // upstream leaves the quaternion alone
+  double sn;
+  sincos(wn * h, &sn, cs);
+  *k = sn / wn;
+  return true;
+}
+
+// One sub-step.  `rpm` is the clipped action; `dw` the summed downwash (0 for DYN); `fext` an optional world-frame
+// force; R = the rotation matrix of the CURRENT attitude (quat_to_mat(s.q), or the controller's copy of it).
+// Returns the world angular velocity that PyBullet would be handed: R(q_old) * w_new.
+template <int SPEC, typename Real>
+MDS_DEV V3<Real> physics_substep(const DroneP<Real>& P, Drone<Real>& s, const Real rpm[4], Real dw, V3<Real> fext, const M3<Real>& R) {
+  using S = PhysSpec<SPEC>;
   const Real dt = P.dt_phys;
-  M3<Real> R = quat_to_mat(s.qx, s.qy, s.qz, s.qw);
   Real f[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) f[i] = P.kf * rpm[i] * rpm[i];
   V3<Real> extra = fext;
-  if (P.physics == MDS_PHYSICS_DYN_GND_DRAG_DW) {
-    // ground effect: per-prop height above the plane, gated on |roll|, |pitch| < pi/2
-    // |roll| < pi/2 and |pitch| < pi/2 of Bullet's getEulerFromQuaternion without the atan2/asin: pitch is
-    // asin(sarg) (+-pi/2 exactly inside the +-0.99999 gimbal branches), roll = atan2(A, B) is inside (-pi/2, pi/2)
-    // iff B > 0 (or A = B = 0).
+  if (S::physics(P) == MDS_PHYSICS_DYN_GND_DRAG_DW) {
+    // ground effect: per-prop height above the plane, gated on |roll|, |pitch| < pi/2 of Bullet's getEulerFromQuaternion
+    // without the atan2/asin: pitch is asin(sarg) (+-pi/2 exactly inside the +-0.99999 gimbal branches), roll = atan2(A, B)
+    // is inside (-pi/2, pi/2) iff B > 0 (or A = B = 0).
     const Real sarg = Real(-2) * (s.qx * s.qz - s.qw * s.qy);
     const Real rollA = Real(2) * (s.qy * s.qz + s.qw * s.qx);
     const Real rollB = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz;
     if (abs_(sarg) < Real(0.99999) && (rollB > Real(0) || (rollB == Real(0) && rollA == Real(0)))) {
+      const Real pr4 = Real(0.25) * P.prop_radius;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         Real h = s.p.z + R.m[6] * P.prop_x[i] + R.m[7] * P.prop_y[i];
         h = max_(h, P.gnd_eff_h_clip);
-        Real q = P.prop_radius / (Real(4) * h);
-        f[i] = f[i] + f[i] * P.gnd_eff_coeff * q * q;
+        Real q = pr4 / h;
+        f[i] = fma_(f[i] * P.gnd_eff_coeff, q * q, f[i]);
       }
     }
     // rotor-speed-scaled linear drag from the PREVIOUS clipped RPM
@@ -58,11 +84,11 @@ MDS_DEV V3<Real> physics_substep(const DroneP<Real>& P, Drone<Real>& s, const Re
     extra.z -= P.drag_z * wsum * s.v.z;
   }
   Real thrust = (f[0] + f[1] + f[2] + f[3]) - dw;
-  V3<Real> F = {R.m[2] * thrust + extra.x, R.m[5] * thrust + extra.y, R.m[8] * thrust + extra.z - P.m * P.g};
+  V3<Real> F = {fma_(R.m[2], thrust, extra.x), fma_(R.m[5], thrust, extra.y), fma_(R.m[8], thrust, extra.z) - P.m * P.g};
   Real zt0 = P.km * rpm[0] * rpm[0], zt1 = P.km * rpm[1] * rpm[1], zt2 = P.km * rpm[2] * rpm[2], zt3 = P.km * rpm[3] * rpm[3];
   V3<Real> tau;
   tau.z = -zt0 + zt1 - zt2 + zt3;
-  if (P.drone_model == MDS_DRONE_CF2X) {
+  if (S::drone_model(P) == MDS_DRONE_CF2X) {
     const Real l2 = P.arm_l * Real(0.70710678118654752);
     tau.x = Real(P.cf2x_torque_sign) * (f[0] + f[1] - f[2] - f[3]) * l2;
     tau.y = (-f[0] + f[1] + f[2] - f[3]) * l2;
@@ -72,29 +98,25 @@ MDS_DEV V3<Real> physics_substep(const DroneP<Real>& P, Drone<Real>& s, const Re
   }
   V3<Real> Jw = {P.ixx * s.w.x, P.iyy * s.w.y, P.izz * s.w.z};
   tau = tau - cross(s.w, Jw);
-  V3<Real> wdot = {tau.x / P.ixx, tau.y / P.iyy, tau.z / P.izz};
-  Real inv_m = Real(1) / P.m;
-  s.v = s.v + dt * (inv_m * F);
-  s.w = s.w + dt * wdot;
-  s.p = s.p + dt * s.v;  // semi-implicit Euler: uses the NEW velocity
+  const Real dtm = dt * P.inv_m;
+  s.v = {fma_(dtm, F.x, s.v.x), fma_(dtm, F.y, s.v.y), fma_(dtm, F.z, s.v.z)};
+  s.w = {fma_(dt * P.inv_ixx, tau.x, s.w.x), fma_(dt * P.inv_iyy, tau.y, s.w.y), fma_(dt * P.inv_izz, tau.z, s.w.z)};
+  s.p = {fma_(dt, s.v.x, s.p.x), fma_(dt, s.v.y, s.p.y), fma_(dt, s.v.z, s.p.z)};  // semi-implicit Euler: uses the NEW velocity
   // quaternion exponential update with the NEW body rates (upstream _integrateQ)
-  Real wn = norm(s.w);
-  if (wn > Real(1e-8)) {
-    Real sn, cs;
-    sincos_(wn * dt * Real(0.5), &sn, &cs);
-    Real k = sn / wn;
+  Real cs, k;
+  if (quat_step_coeffs(dot(s.w, s.w), dt * Real(0.5), &cs, &k)) {
     Real p = s.w.x, q = s.w.y, r = s.w.z;
     Real x = s.qx, y = s.qy, z = s.qz, w = s.qw;
-    s.qx = cs * x + k * (r * y - q * z + p * w);
-    s.qy = cs * y + k * (-r * x + p * z + q * w);
-    s.qz = cs * z + k * (q * x - p * y + r * w);
-    s.qw = cs * w + k * (-p * x - q * y - r * z);
-    if (P.renormalize_quat) {
+    s.qx = fma_(cs, x, k * (r * y - q * z + p * w));
+    s.qy = fma_(cs, y, k * (-r * x + p * z + q * w));
+    s.qz = fma_(cs, z, k * (q * x - p * y + r * w));
+    s.qw = fma_(cs, w, k * (-p * x - q * y - r * z));
+    if (S::renormalize(P)) {
       Real inv = rsqrt_(s.qx * s.qx + s.qy * s.qy + s.qz * s.qz + s.qw * s.qw);
       s.qx *= inv; s.qy *= inv; s.qz *= inv; s.qw *= inv;
     }
   }
-  if (P.ground_clamp && s.p.z < P.z_floor) {
+  if (S::ground_clamp(P) && s.p.z < P.z_floor) {
     s.p.z = P.z_floor;
     s.v.z = max_(s.v.z, Real(0));
   }

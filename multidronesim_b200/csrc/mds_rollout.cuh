@@ -24,6 +24,9 @@ using namespace mds;
 #ifndef MDS_LOOP_MINB
 #define MDS_LOOP_MINB 2  // the K-step loop kernel serves small swarms: registers before occupancy
 #endif
+#ifndef MDS_LOOP_BLOCK
+#define MDS_LOOP_BLOCK 256  // threads per block of the K-step loop kernel (a multiple of 32, <= MDS_BLOCK); with MDS_LOOP_MINB it sets the register cap
+#endif
 #ifndef MDS_FUSED_MINB
 #define MDS_FUSED_MINB 4
 #endif
@@ -58,24 +61,44 @@ template <int NT> MDS_DEV void full_group_hint(GroupMap& g) {
   if (NT > 0 && (NT & (NT - 1)) == 0) g.valid = true;
 }
 
-// Downwash sum for this lane's drone over its env mates; positions staged in shared memory.
-// Called by every lane of the group (two group syncs).
+// Downwash sum for this lane's drone over its env mates; positions staged in shared memory.  Called by every lane of the
+// group (two group syncs, shuffles).  Only the LOWER drone of a pair feels the other's downwash, so each unordered pair is
+// evaluated once, by the lane that owns it under the CBF stage's ownership (mds_cbf.cuh: lane n owns (n, n+s+1 mod N) for
+// s < (N-1)/2, and the "diameter" (n, n+N/2) for n < N/2 when N is even); the owner keeps the term if it is the lower one
+// and otherwise hands it to its partner with one shuffle per slot.
 template <typename Real>
-MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* sm_pos, V3<Real> p, const GroupMap& g, int N) {
+MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* sm_pos, V3<Real> p, const GroupMap& g, int N, int NP) {
   typename Vec4T<Real>::type me;
   me.x = p.x; me.y = p.y; me.z = p.z; me.w = Real(0);
   sm_pos[threadIdx.x] = me;
   __syncwarp(g.gmask);
   Real dw = Real(0);
-  if (g.valid) {
-    const int base = threadIdx.x - g.n;
+  const int n = g.n, base = threadIdx.x - n, lane0 = (threadIdx.x & 31) - n;
+  const int K1 = (N - 1) >> 1, half = (N & 1) ? 0 : (N >> 1), S0 = K1 + (half ? 1 : 0);
 #pragma unroll
-    for (int k = 1; k < N; ++k) {  // partners in circular order: no self test, unrolls when N is a compile-time constant
-      int j = g.n + k;
-      j = j >= N ? j - N : j;
-      auto q = sm_pos[base + j];
-      dw += downwash_term(P, p, v3(q.x, q.y, q.z));
+  for (int s = 0; s < S0; ++s) {
+    int m = n, src = n;  // partner of the pair this lane owns in slot s; lane whose slot-s pair has this lane as partner
+    bool own = false, recv = false;
+    if (g.valid) {
+      if (s < K1) {
+        m = n + s + 1; m = m >= N ? m - N : m;
+        src = n - s - 1; src = src < 0 ? src + N : src;
+        own = true; recv = true;
+      } else if (n < half) { m = n + half; own = true; }
+      else { src = n - half; recv = true; }
     }
+    Real give = Real(0);
+    if (own) {
+      const auto q = sm_pos[base + m];
+      const Real dz = q.z - p.z, dx = q.x - p.x, dy = q.y - p.y;  // dz > 0: the partner is above, this drone is pushed down
+      const Real dxy2 = dx * dx + dy * dy;
+      Real v = Real(0);
+      if (dz != Real(0) && dxy2 < Real(100)) v = downwash_pair(P, abs_(dz), dxy2);
+      if (dz > Real(0)) dw += v;
+      else give = v;
+    }
+    const Real got = __shfl_sync(g.gmask, give, lane0 + src);
+    if (recv) dw += got;
   }
   __syncwarp(g.gmask);
   return dw;
@@ -102,10 +125,13 @@ template <typename Real> static size_t cbf_smem_bytes(int threads, int NP, int N
 // Threads per block (a power of two in [NP or 32, MDS_BLOCK]) such that the CBF stage's shared memory stays under
 // ~100 KB per block (two blocks per SM): only small lane groups in fp64 (many envs per block, each with its own QP
 // workspace) and 32-drone groups with many obstacles ever need fewer than MDS_BLOCK threads.
-template <typename Real> static int cbf_block_threads(int NP, int N, int n_obs) {
-  int threads = MDS_BLOCK;
+template <typename Real> static int cbf_block_threads(int NP, int N, int n_obs, int max_threads = MDS_BLOCK) {
+  int threads = max_threads;
   const int floor_threads = NP > 32 ? NP : 32;
-  while (threads > floor_threads && cbf_smem_bytes<Real>(threads, NP, N, n_obs) > 100 * 1024) threads >>= 1;
+  while (threads > floor_threads && cbf_smem_bytes<Real>(threads, NP, N, n_obs) > 100 * 1024) {
+    threads = (threads >> 1) & ~31;  // whole warps (the loop kernel may start from 224 or 192)
+    if (threads < floor_threads) threads = floor_threads;
+  }
   return threads;
 }
 template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw, int NP, int N, int n_obs) {
@@ -146,8 +172,8 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
   Real xn[3] = {unom[0], unom[1], unom[2]};
   if (g.valid) {
     // ---- own single-drone rows: obstacle rows (built here), box bounds; most violated one at u_nom
-    QpWorst<Real> worst = {Real(0), 0x7fffffff};
-    Real wa[3] = {Real(0), Real(0), Real(0)}, wsl = Real(0), wa2 = Real(1);  // coefficients / slack / |a|^2 of the worst obstacle row
+    Real wv = Real(0);  // normalised slack of the most violated row so far (negative)
+    int wcon = -1;      // its obstacle index, or MDS_QP_BOX0 + component for a box bound
     const CbfAgent<Real> zero = {{Real(0), Real(0), Real(0)}, {Real(0), Real(0), Real(0)}, {Real(0), Real(0), Real(0)}};
     for (int o = 0; o < n_obs; ++o) {
       CbfAgent<Real> other = zero;
@@ -168,30 +194,35 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
           const Real a2 = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2];
           if (!(a2 > Real(0))) escalate = 1;  // zero row with negative rhs: the cooperative path reports it as infeasible
           const Real v = sl * rsqrt_(max_(a2, Real(1e-30)));
-          if (v < worst.v) { worst.v = v; worst.con = o; wa[0] = a3[0]; wa[1] = a3[1]; wa[2] = a3[2]; wsl = sl; wa2 = a2; }
+          if (v < wv) { wv = v; wcon = o; }
         }
       }
     }
-    int wbox = -1;  // component of the most violated box bound, if it beats every obstacle row
-#pragma unroll
-    for (int comp = 0; comp < 3; ++comp) {
-      const Real ax = abs_(xn[comp]);
-      const Real sl = C.umax[comp] - ax;
-      if (sl < -qp_tol<Real>() * (C.umax[comp] + ax + Real(1e-12)) && sl < worst.v) { worst.v = sl; worst.con = MDS_QP_BOX0; wbox = comp; }
+    // box bounds: |u| > umax_hi  <=>  umax - |u| < -tol (umax + |u|).  One flag per component, tested with literal indices:
+    // a component INDEX would let nvcc turn the selects into dynamically indexed accesses, i.e. move u_n and the whole
+    // parameter block C into local memory.
+    bool wb0 = false, wb1 = false, wb2 = false;
+#define MDS_BOX_WORST(K, FLAG)                                                                   \
+    {                                                                                             \
+      const Real ax = abs_(xn[K]);                                                                \
+      if (ax > C.umax_hi[K] && C.umax[K] - ax < wv) { wv = C.umax[K] - ax; wcon = MDS_QP_BOX0; wb0 = wb1 = wb2 = false; FLAG = true; } \
     }
-    if (worst.con != 0x7fffffff) {  // one projection: u_n <- u_n - t g,  t = -slack / |g|^2
+    MDS_BOX_WORST(0, wb0) MDS_BOX_WORST(1, wb1) MDS_BOX_WORST(2, wb2)
+#undef MDS_BOX_WORST
+    if (wcon >= 0) {  // one projection: u_n <- u_n - t g,  t = -slack / |g|^2
       touched = 1;
-      if (wbox >= 0) {
-#pragma unroll
-        for (int comp = 0; comp < 3; ++comp)
-          if (comp == wbox) xn[comp] = xn[comp] < Real(0) ? -C.umax[comp] : C.umax[comp];
+      if (wcon == MDS_QP_BOX0) {
+        if (wb0) xn[0] = xn[0] < Real(0) ? -C.umax[0] : C.umax[0];
+        if (wb1) xn[1] = xn[1] < Real(0) ? -C.umax[1] : C.umax[1];
+        if (wb2) xn[2] = xn[2] < Real(0) ? -C.umax[2] : C.umax[2];
       } else {
-        const Real t = -wsl / wa2;  // g = -a
-        xn[0] += t * wa[0]; xn[1] += t * wa[1]; xn[2] += t * wa[2];
+        const R4 row = rows[n * M.RPL + M.S0 + wcon];  // g = -a
+        const Real t = -(row.w + (row.x * xn[0] + row.y * xn[1] + row.z * xn[2])) / (row.x * row.x + row.y * row.y + row.z * row.z);
+        xn[0] += t * row.x; xn[1] += t * row.y; xn[2] += t * row.z;
       }
       // the other single-drone rows at the projected point (the projected row itself holds with equality: skipped)
       for (int o = 0; o < n_obs; ++o) {
-        if (wbox < 0 && o == worst.con) continue;
+        if (o == wcon) continue;
         const R4 row = rows[n * M.RPL + M.S0 + o];
         const Real sl = row.w + (row.x * xn[0] + row.y * xn[1] + row.z * xn[2]);
         if (sl < Real(0)) {
@@ -199,12 +230,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
           if (sl < -qp_tol<Real>() * (abs_(row.w) + mag + Real(1e-12))) escalate = 1;
         }
       }
-#pragma unroll
-      for (int comp = 0; comp < 3; ++comp) {
-        if (comp == wbox) continue;
-        const Real ax = abs_(xn[comp]);
-        if (C.umax[comp] - ax < -qp_tol<Real>() * (C.umax[comp] + ax + Real(1e-12))) escalate = 1;
-      }
+      if ((!wb0 && abs_(xn[0]) > C.umax_hi[0]) || (!wb1 && abs_(xn[1]) > C.umax_hi[1]) || (!wb2 && abs_(xn[2]) > C.umax_hi[2])) escalate = 1;
     }
     if (!cbf_wz_bounds<ORD>(C, F, &lo, &hi)) fl = 1;
     // ---- publish the agent and the projected inputs
@@ -243,13 +269,12 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
       rows[n * M.RPL + s] = row;
     }
   }
-  const unsigned esc_mask = __ballot_sync(g.gmask, escalate != 0) & g.gmask;
-  const unsigned fl_mask = __ballot_sync(g.gmask, fl != 0) & g.gmask;
-  const unsigned touched_mask = __ballot_sync(g.gmask, touched != 0) & g.gmask;
-  int status = MDS_QP_OPTIMAL, iters = touched_mask ? 1 : 0;
-  if (fl_mask) {
+  // one group-wide OR of (escalate, infeasible 4th-input interval, projected) -- the step's only collective in the common case
+  const unsigned any = __reduce_or_sync(g.gmask, (unsigned)(escalate | (fl << 1) | (touched << 2)));
+  int status = MDS_QP_OPTIMAL, iters = (any & 4u) ? 1 : 0;
+  if (any & 2u) {
     status = MDS_QP_INFEASIBLE;
-  } else if (esc_mask) {
+  } else if (any & 1u) {
     // ---- cooperative solve from u_nom (agents are no longer needed: their storage becomes the QP workspace)
     __syncwarp(g.gmask);  // every lane has read its partners' agents and projected inputs
     if (g.valid) {
@@ -267,9 +292,9 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
         __syncwarp(g.gmask);
         if (g.valid) { R4 xv = xnom[n]; x[n] = xv; }
         __syncwarp(g.gmask);
-        int it2 = 0;
-        status = qp_solve_group_big<Real>(C, rows, x, xnom, M, N, NP, n, g.valid, g.gmask, p0, &it2);
-        iters += it2;
+        const int big = qp_solve_group_big<Real>(C.umax[0], C.umax[1], C.umax[2], C.scr, rows, x, xnom, M, N, NP, n, g.valid, g.gmask, p0);
+        status = big & 0xff;
+        iters += big >> 8;
       }
     }
     if (g.valid) { R4 xv = x[n]; xn[0] = xv.x; xn[1] = xv.y; xn[2] = xv.z; }
@@ -307,20 +332,24 @@ template <typename Real> MDS_DEV void load4(const Real* p, int d, Real v[4]) {
   v[0] = o.x; v[1] = o.y; v[2] = o.z; v[3] = o.w;
 }
 // One control period of the env for this lane's drone with the state in registers (every lane of a valid group
-// calls it): clips the action, runs the sub-steps, returns the new observation.
-template <typename Real>
+// calls it): clips the action, runs the sub-steps, returns the new observation.  R0 (optional): the rotation matrix of the
+// attitude the period starts from, when the caller already has it (the inner loop of the controller stack builds it).
+template <int SPEC, typename Real>
 MDS_DEV Obs<Real> physics_core(const DroneP<Real>& P, Drone<Real>& s, const Real action[4], V3<Real> fx, typename Vec4T<Real>::type* sm_pos,
-                               const GroupMap& g, int N) {
+                               const GroupMap& g, int N, int NP, const M3<Real>* R0 = nullptr) {
+  using S = PhysSpec<SPEC>;
   Real rpm[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) rpm[i] = clamp_(action[i], Real(0), P.max_rpm);
   V3<Real> av = {Real(0), Real(0), Real(0)};
-  const bool dwash = (P.physics == MDS_PHYSICS_DYN_GND_DRAG_DW) && (N > 1);
-  for (int k = 0; k < P.substeps; ++k) {
+  const bool dwash = (S::physics(P) == MDS_PHYSICS_DYN_GND_DRAG_DW) && (N > 1);
+  const int substeps = S::substeps(P);
+  for (int k = 0; k < substeps; ++k) {
     Real dw = Real(0);
-    if (dwash) dw = downwash_group(P, sm_pos, s.p, g, N);
+    if (dwash) dw = downwash_group(P, sm_pos, s.p, g, N, NP);
     if (g.valid) {
-      av = physics_substep(P, s, rpm, dw, fx);
+      const M3<Real> R = (R0 != nullptr && k == 0) ? *R0 : quat_to_mat(s.qx, s.qy, s.qz, s.qw);
+      av = physics_substep<SPEC>(P, s, rpm, dw, fx, R);
 #pragma unroll
       for (int i = 0; i < 4; ++i) s.rpm[i] = rpm[i];
     }
@@ -334,7 +363,7 @@ MDS_DEV Obs<Real> physics_core(const DroneP<Real>& P, Drone<Real>& s, const Real
 // and returns the observation in registers.
 template <typename Real>
 MDS_DEV Obs<Real> physics_body(const DroneP<Real>& P, const StateP<Real>& st, const Real* __restrict__ action, const Real* __restrict__ fext,
-                               Real* __restrict__ obs, typename Vec4T<Real>::type* sm_pos, const GroupMap& g, int N) {
+                               Real* __restrict__ obs, typename Vec4T<Real>::type* sm_pos, const GroupMap& g, int N, int NP) {
   Drone<Real> s;
   s.p = {Real(0), Real(0), Real(0)};
   Real act[4] = {Real(0), Real(0), Real(0), Real(0)};
@@ -344,7 +373,7 @@ MDS_DEV Obs<Real> physics_body(const DroneP<Real>& P, const StateP<Real>& st, co
     load4(action, g.d, act);
     if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
   }
-  Obs<Real> o = physics_core(P, s, act, fx, sm_pos, g, N);
+  Obs<Real> o = physics_core<0>(P, s, act, fx, sm_pos, g, N, NP);
   if (g.valid) {
     store_drone(st, g.d, s);
     if (obs) store_obs(obs, g.d, o);
@@ -360,7 +389,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_PHYS_MINB :
   GroupMap g = group_map(N, NP, E);
   if (!g.env_valid) return;  // whole groups leave together
   full_group_hint<NT>(g);
-  physics_body(P, st, action, fext, obs, sm_pos, g, N);
+  physics_body(P, st, action, fext, obs, sm_pos, g, N, NP);
 }
 
 // ------------------------------------------------------------------ kernel: fused K-step rollout
@@ -405,12 +434,14 @@ struct StepStats {
 // reference -> tracking controller -> (CBF-QP) -> inner loop -> RPM action.  CTRL / USE_CBF are compile-time so
 // that each instantiation carries only its own stage code (one kernel with run-time switches overflowed the
 // instruction cache: 55 % of the stall samples were "no instruction").
-template <typename Real, int CTRL, bool USE_CBF, bool PDK = false>  // PDK: a gain per drone (Rc.lqr_planes) instead of LqrP's
+// PDK: a gain per drone (Rc.lqr_planes) instead of LqrP's; SPEC: compile-time parameter switches (PhysSpec); R_out (optional)
+// receives the rotation matrix of the observation's attitude when the inner loop built it (HAS_PID controllers).
+template <typename Real, int CTRL, bool USE_CBF, bool PDK = false, int SPEC = 0>
 MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const GeoP<Real>& G, const LqrP<Real>& L, const CbfP<Real>& C,
                        const DslP<Real>& Dg, const DslStateP<Real>& dst, const CbfSmem<Real>& S, const PidP<Real>& pid,
                        const typename TrajSpecT<Real>::spec& spec,
                        const typename TrajSpecT<Real>::seg* __restrict__ segs, const Obs<Real>& o, const GroupMap& g, int N, int NP,
-                       double t, Real rpm[4], StepStats& ss, int pid_idx) {
+                       double t, Real rpm[4], StepStats& ss, int pid_idx, M3<Real>* R_out = nullptr) {
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
   constexpr int ORD = CTRL == MDS_CTRL_LQR_OMEGA ? 2 : 3;  // rollout_impl pairs the order-2 filter with LQR_OMEGA, order 3 with LQR_YANK
   Real u[4] = {Real(0), Real(0), Real(0), Real(0)};
@@ -420,7 +451,7 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
     ss.err = (float)norm(o.p - ref.p);
     if (CTRL == MDS_CTRL_GEOMETRIC) {
       geometric_input(P, G, o, ref, u);
-      input_to_action(P, u, rpm);
+      input_to_action<SPEC>(P, u, rpm);
     } else if (CTRL == MDS_CTRL_DSLPID) {
       DslState<Real> ds = load_dsl(dst, g.d);
       V3<Real> pe;
@@ -429,7 +460,7 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
     } else {
       if (PDK) dlqr_input(P, Rc.lqr_planes, (size_t)Rc.lqr_D, (size_t)g.d, CTRL, o, ref, u);
       else lqr_input(P, L, CTRL, o, ref, u);
-      if (CTRL == MDS_CTRL_LQR_TORQUE) input_to_action(P, u, rpm);
+      if (CTRL == MDS_CTRL_LQR_TORQUE) input_to_action<SPEC>(P, u, rpm);
     }
   }
   if (HAS_PID) {
@@ -462,7 +493,7 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
     }
     if (g.valid) {
       Pid<Real> ps = load_pid(pid, pid_idx);  // pid_idx: g.d for HBM-resident state, the thread index when the caller staged it
-      low_level(P, CTRL, ps, u, o, rpm);
+      low_level<SPEC>(P, CTRL, ps, u, o, rpm, R_out);
       store_pid(pid, pid_idx, ps);
     }
   }
@@ -568,7 +599,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB 
       prefetch_l1(reinterpret_cast<const char*>(specs + g.d) + 32);
       if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
     }
-    const Obs<Real> o = physics_body(P, st, action, fext, obs_out, sm_pos, g, N);
+    const Obs<Real> o = physics_body(P, st, action, fext, obs_out, sm_pos, g, N, NP);
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
     typename TrajSpecT<Real>::spec spec;
     spec.kind = MDS_TRAJ_WAIT;
@@ -581,10 +612,12 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB 
 
 // K control steps in ONE launch.  Environments never interact, and everything that couples the drones of an
 // environment (downwash, CBF rows, QP) is exchanged inside its lane group, so a group can run its env forward on its
-// own: the observation and the body rates stay in registers from step to step, HBM sees the initial load, the PID
-// state (L1-resident), the log slots that are due and the final store.  No launch per step, no grid-wide barrier.
-template <typename Real, int CTRL, bool USE_CBF, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+// own: the observation and the body rates stay in registers from step to step, HBM sees the initial load, the log slots
+// that are due and the final store.  No launch per step, no grid-wide barrier.
+// SPEC: compile-time parameter switches (PhysSpec); K <= 32767 (rollout_impl splits longer runs): the rare-event counters
+// share one register.
+template <typename Real, int CTRL, bool USE_CBF, int NT, int SPEC>
+__global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
                                                                   DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
                                                                   const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                   const typename TrajSpecT<Real>::seg* __restrict__ segs,
@@ -592,19 +625,21 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
                                                                   Real* __restrict__ obs_log, double* __restrict__ stats, double t0, double dt_ctrl, int K, int E,
                                                                   int N_rt, int NP_rt) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
-  __shared__ typename Vec4T<Real>::type sm_pos[MDS_BLOCK];
-  // fp32 stages the per-step read-mostly data (trajectory descriptor, rate-PID state) in shared memory for the launch;
+  using R4 = typename Vec4T<Real>::type;
+  __shared__ R4 sm_pos[MDS_LOOP_BLOCK];
+  // fp32 stages the per-step read-mostly data (trajectory descriptor, rate-PID state, wind) in shared memory for the launch;
   // fp64 does not: with the CBF stage's 91 KB that would leave one resident block per SM instead of two (0.41 vs 0.31 ms)
   constexpr bool STAGE = sizeof(Real) == 4;
-  __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[STAGE ? MDS_BLOCK : 1];
+  __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[STAGE ? MDS_LOOP_BLOCK : 1];
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
-  __shared__ typename Vec4T<Real>::type sm_pid_a[(STAGE && HAS_PID) ? MDS_BLOCK : 1];
-  __shared__ typename Vec2T<Real>::type sm_pid_b[(STAGE && HAS_PID) ? MDS_BLOCK : 1];
+  __shared__ R4 sm_pid_a[(STAGE && HAS_PID) ? MDS_LOOP_BLOCK : 1];
+  __shared__ typename Vec2T<Real>::type sm_pid_b[(STAGE && HAS_PID) ? MDS_LOOP_BLOCK : 1];
+  __shared__ R4 sm_fx[STAGE ? MDS_LOOP_BLOCK : 1];
   const PidP<Real> pid_s = STAGE ? PidP<Real>{sm_pid_a, sm_pid_b} : pid;
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
   GroupMap g = group_map(N, NP, E);
-  StepStats acc = {0.f, 1e30f, 0, 0, 0, 0};
+  StepStats acc = {0.f, 1e30f, 0, 0, 0, 0};  // qp_infeas holds infeasible | iteration-cap << 16
   float max_err = 0.f;
   int steps_done = 0;
   if (g.env_valid) {
@@ -617,12 +652,16 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
     typename TrajSpecT<Real>::spec spec_reg;
     typename TrajSpecT<Real>::spec& spec = STAGE ? sm_spec[threadIdx.x] : spec_reg;
     spec.kind = MDS_TRAJ_WAIT;
-    V3<Real> fx = {Real(0), Real(0), Real(0)};  // constant world-frame force on this drone (wind), if any
+    V3<Real> fx_reg = {Real(0), Real(0), Real(0)};  // constant world-frame force on this drone (wind), if any
+    const bool has_fx = fext != nullptr;
     if (g.valid) {
       o = load_obs(obs, g.d);
       spec = specs[g.d];
       wb = {st.pos_wx[g.d].w, st.vel_wy[g.d].w, st.wz[g.d]};
-      if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
+      if (has_fx) {
+        fx_reg = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
+        if (STAGE) { R4 f4; f4.x = fx_reg.x; f4.y = fx_reg.y; f4.z = fx_reg.z; f4.w = Real(0); sm_fx[threadIdx.x] = f4; }
+      }
       if (STAGE && HAS_PID) { sm_pid_a[threadIdx.x] = pid.a[g.d]; sm_pid_b[threadIdx.x] = pid.b[g.d]; }
     }
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
@@ -631,14 +670,21 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
     Real* log_slot = obs_log;
     for (int k = 0; k < K; ++k) {
       StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
-      ctrl_body<Real, CTRL, USE_CBF, (NT < 0)>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss, STAGE ? (int)threadIdx.x : g.d);  // the host plans form t exactly like this
+      M3<Real> R;
+      ctrl_body<Real, CTRL, USE_CBF, (NT < 0), SPEC>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss,
+                                                     STAGE ? (int)threadIdx.x : g.d, HAS_PID ? &R : nullptr);  // the host plans form t exactly like this
       acc.err += ss.err; max_err = fmaxf(max_err, ss.err); acc.min_h = fminf(acc.min_h, ss.min_h);
-      acc.qp_solves += ss.qp_solves; acc.qp_iters += ss.qp_iters; acc.qp_infeas += ss.qp_infeas; acc.qp_cap += ss.qp_cap;
+      acc.qp_solves += ss.qp_solves; acc.qp_iters += ss.qp_iters; acc.qp_infeas += ss.qp_infeas + (ss.qp_cap << 16);
       Drone<Real> s;
       s.p = o.p; s.qx = o.qx; s.qy = o.qy; s.qz = o.qz; s.qw = o.qw; s.v = o.v; s.w = wb;
 #pragma unroll
       for (int i = 0; i < 4; ++i) s.rpm[i] = o.rpm[i];
-      o = physics_core(P, s, rpm, fx, sm_pos, g, N);
+      V3<Real> fx = fx_reg;
+      if (STAGE) {
+        fx = {Real(0), Real(0), Real(0)};
+        if (has_fx && g.valid) { const R4 f4 = sm_fx[threadIdx.x]; fx = {f4.x, f4.y, f4.z}; }
+      }
+      o = physics_core<SPEC>(P, s, rpm, fx, sm_pos, g, N, NP, HAS_PID ? &R : nullptr);
       wb = s.w;
       if (Rc.write_obs_every > 0 && --log_countdown == 0) {
         if (g.valid) store_obs(log_slot, g.d, o);
@@ -658,5 +704,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(
       steps_done = K;
     }
   }
+  acc.qp_cap = acc.qp_infeas >> 16;
+  acc.qp_infeas &= 0xffff;
   if (stats) stats_block_reduce<USE_CBF>(stats, steps_done, acc, max_err);
 }

@@ -23,6 +23,7 @@ template <typename Real> struct RolloutLaunch {
   Real* obs_log;
   double* stats;
   int E, N, NP, blocks, threads;
+  int spec;  // PhysSpec instantiation the parameter block qualifies for (0 = none: run-time switches)
   size_t smem;
   cudaStream_t cs;
 };

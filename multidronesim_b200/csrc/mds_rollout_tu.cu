@@ -36,8 +36,9 @@ struct LoopLauncher {
   cudaError_t err;
   template <int CT, bool CB, bool PDKC> void run() {
     const bool pdk = a.R.lqr_planes != nullptr;  // per-drone gains: the run-time-N instantiation compiled with PDK (NT = -1)
-    auto kern = pdk ? rollout_loop_kernel<Real, CT, CB, (PDKC ? -1 : 0)>
-                    : ((a.N == 8) ? rollout_loop_kernel<Real, CT, CB, 8> : rollout_loop_kernel<Real, CT, CB, 0>);
+    auto kern = pdk ? rollout_loop_kernel<Real, CT, CB, (PDKC ? -1 : 0), 0>
+                    : (a.spec == 1 ? ((a.N == 8) ? rollout_loop_kernel<Real, CT, CB, 8, 1> : rollout_loop_kernel<Real, CT, CB, 0, 1>)
+                                   : ((a.N == 8) ? rollout_loop_kernel<Real, CT, CB, 8, 0> : rollout_loop_kernel<Real, CT, CB, 0, 0>));
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
     kern<<<a.blocks, a.threads, a.smem, a.cs>>>(a.Pd, a.R, a.G, a.L, a.C, a.Dg, a.Ds, a.Sd, a.Pi, a.specs, a.segs, a.action, a.fext, a.obs, a.obs_log,
                                                  a.stats, t0, dt_ctrl, K, a.E, a.N, a.NP);
