@@ -274,7 +274,14 @@ template <typename Real> MDS_DEV Obs<Real> load_obs(const Real* __restrict__ obs
   o.rpm[0] = f.x; o.rpm[1] = f.y; o.rpm[2] = f.z; o.rpm[3] = f.w;
   return o;
 }
-template <typename Real> MDS_DEV void store_obs(Real* __restrict__ obs, int d, const Obs<Real>& o) {
+MDS_DEV void store_vec4(float4* p, float4 v, bool stream) { if (stream) __stcs(p, v); else *p = v; }
+MDS_DEV void store_vec4(double4* p, double4 v, bool stream) {
+  if (stream) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(v.z, v.w)); }
+  else *p = v;
+}
+// stream = true: write-once data nobody on this SM reads back (the observation log): streaming stores, so that they
+// do not displace the L1 lines the step loop lives on
+template <typename Real> MDS_DEV void store_obs(Real* __restrict__ obs, int d, const Obs<Real>& o, bool stream = false) {
   using R4 = typename Vec4T<Real>::type;
   R4* o4 = reinterpret_cast<R4*>(obs + (size_t)d * MDS_OBS_DIM);
   R4 a, b, c, e, f;
@@ -283,7 +290,7 @@ template <typename Real> MDS_DEV void store_obs(Real* __restrict__ obs, int d, c
   c.x = o.rpy.y; c.y = o.rpy.z; c.z = o.v.x; c.w = o.v.y;
   e.x = o.v.z; e.y = o.av.x; e.z = o.av.y; e.w = o.av.z;
   f.x = o.rpm[0]; f.y = o.rpm[1]; f.z = o.rpm[2]; f.w = o.rpm[3];
-  o4[0] = a; o4[1] = b; o4[2] = c; o4[3] = e; o4[4] = f;
+  store_vec4(o4, a, stream); store_vec4(o4 + 1, b, stream); store_vec4(o4 + 2, c, stream); store_vec4(o4 + 3, e, stream); store_vec4(o4 + 4, f, stream);
 }
 template <typename Real> MDS_DEV Obs<Real> make_obs(const Drone<Real>& s, V3<Real> ang_v_world) {
   Obs<Real> o;

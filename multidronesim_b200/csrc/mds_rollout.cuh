@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_loop_ke
       o = physics_core<SPEC>(P, s, rpm, fx, sm_pos, g, N, NP, HAS_PID ? &R : nullptr);
       wb = s.w;
       if (Rc.write_obs_every > 0 && --log_countdown == 0) {
-        if (g.valid) store_obs(log_slot, g.d, o);
+        if (g.valid) store_obs(log_slot, g.d, o, true);  // streaming stores: the log is write-once
         log_slot += obs_elems;
         log_countdown = Rc.write_obs_every;
       }
