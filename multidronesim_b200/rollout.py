@@ -197,9 +197,45 @@ class HostPipeline:
             obs_host.copy_(self.obs_dev[slot].reshape(obs_host.shape), non_blocking=True)
             self.obs_free[slot].record(self.s_out)
         self.k += 1
+        self.last_ref_ready = self.ref_ready[slot]   # fires when ``ref_host`` has been read: the caller may overwrite it then
         return self.obs_free[slot]
 
     def synchronize(self):
         self.s_in.synchronize()
+        self.s_out.synchronize()
+        torch.cuda.current_stream(self.env.device).synchronize()
+
+
+class HostRollout:
+    """K-step host call: ``step`` advances every environment K control steps in ONE launch (``FusedRollout``: trajectories,
+    controllers, CBF-QP, inner loop and physics on device, every step's observation written to a device log), then moves
+    the K observations to PINNED host memory with one large D2H copy on a copy stream.  Two device log buffers: the copy of
+    call j overlaps the launch of call j + 1.  The returned event fires when ``obs_host`` [K, E, N, 20] is complete.
+    The device-resident form of the reference's ``observations.append(obs)`` + ``np.save`` (simulations/EnvGeometric.py:470-473,553-556)."""
+
+    def __init__(self, rollout, K):
+        env = rollout.env
+        self.ro, self.K, self.env = rollout, int(K), env
+        self.s_out = torch.cuda.Stream(env.device)
+        self.log = [torch.empty(self.K, env.NUM_ENVS, env.NUM_DRONES, _lib.OBS_DIM, device=env.device, dtype=env.dtype) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.j = 0
+
+    def step(self, obs_host):
+        slot = self.j & 1
+        cs = torch.cuda.current_stream(self.env.device)
+        if self.j >= 2:
+            cs.wait_event(self.free[slot])
+        self.ro.run(self.K, obs_log=self.log[slot], log_every=1)
+        self.ready[slot].record(cs)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ready[slot])
+            obs_host.copy_(self.log[slot].reshape(obs_host.shape), non_blocking=True)
+            self.free[slot].record(self.s_out)
+        self.j += 1
+        return self.free[slot]
+
+    def synchronize(self):
         self.s_out.synchronize()
         torch.cuda.current_stream(self.env.device).synchronize()

@@ -288,3 +288,25 @@ def test_golden_fixtures_reproduce_from_the_reference(golden, tmp_path):
                 assert np.abs(a - b).max() <= 1e-12 * max(1.0, float(np.abs(b).max())), (name, k)
             else:
                 assert np.array_equal(a, b), (name, k)
+
+
+def test_reference_loop_equals_port_closed_loop():
+    """oracle/ref_pipeline.ReferenceLoop (the reference's own Lemniscate / LQRYankOmegaController / YankOmegaController / DroneCBF /
+    DroneQPTracker objects in the loop of simulations/CBFTestOrd3.py:305-360) and the numpy port oracle/pipeline.run_cbf, continued
+    from the same state in steady flight, produce the same observations: the port IS the reference's closed loop (both around the
+    oracle env step and QP solver).  Runs wherever the reference packages are importable (/root/reference or oracle/_ref)."""
+    import copy
+    import bench
+    from oracle import pipeline as opl, ref_pipeline as rpl
+    if rpl.reference_root() is None:
+        pytest.skip("reference packages not available (python -m oracle.build_ref)")
+    env, trajs = bench._oracle_env(0)
+    ctrls = opl.make_controllers(env, "yank10")
+    opl.run_cbf(env, trajs, 3, 240, obstacles=bench.SWARM_OBSTACLES, ctrls=ctrls, t0=0.0, log=False)
+    loop = rpl.ReferenceLoop(copy.deepcopy(env), 3, bench._lem_specs(), bench.SWARM_OBSTACLES)
+    loop.adopt_inner_loop_state(ctrls)
+    loop.t = 240 * env.CTRL_TIMESTEP
+    o_ref = loop.run(30)
+    _, o_port, info = opl.run_cbf(env, trajs, 3, 30, obstacles=bench.SWARM_OBSTACLES, ctrls=ctrls, t0=240 * env.CTRL_TIMESTEP, log=False)
+    assert info["solves"] > 0 and loop.qp_fallbacks == 0
+    assert np.max(np.abs(o_ref - o_port)) < 1e-8

@@ -28,6 +28,18 @@ for r in rows[2:]:
     dur = float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))
     row = {"kernel": name.split("(")[0].replace("void ", ""), "envs": envs, "dtype": dtype, "dram_bytes_per_launch": tot,
            "ncu_duration_" + units[hdr.index("gpu__time_duration.sum")]: dur, "report": os.path.basename(rep)}
+    # the hardware's own FP fraction: executed (add + mul + 2 fma) thread-instructions per cycle / (2 x fma peak per cycle)
+    val = lambda m: float(r[hdr.index(m)].replace(",", "")) if m in hdr else None
+    p = "d" if dtype == "f64" else "f"
+    rates = [val(f"smsp__sass_thread_inst_executed_op_{p}{op}_pred_on.sum.per_cycle_elapsed") for op in ("add", "mul", "fma")]
+    peak = val(f"sm__sass_thread_inst_executed_op_{p}fma_pred_on.sum.peak_sustained")
+    if None not in rates and peak:
+        row.update({"fp_add_per_cycle": rates[0], "fp_mul_per_cycle": rates[1], "fp_fma_per_cycle": rates[2], "fp_fma_peak_per_cycle": peak,
+                    "fp_frac_counters": (rates[0] + rates[1] + 2 * rates[2]) / (2 * peak)})
+    for m, key in (("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
+                   ("launch__registers_per_thread", "registers_per_thread"), ("smsp__inst_executed.sum", "warp_instructions")):
+        if val(m) is not None:
+            row[key] = val(m)
     tab["kernels"] = [k for k in tab["kernels"] if not (k["kernel"] == row["kernel"] and k["envs"] == envs and k["dtype"] == dtype)] + [row]
     print(row)
 json.dump(tab, open(out_path, "w"), indent=1)
