@@ -307,3 +307,53 @@ def test_cf2x_x_frame_mixer_tracking(dtype, tol, lib_built):
     ref_end = otj.Circle(**kw)((steps - 1) * env.CTRL_TIMESTEP)[0]
     assert np.abs(got[-1, :, 0, 0:3] - ref_end).max() < 0.1           # converging from a standing start: 7-8 cm behind after 2 s
     assert ro.stats_dict()["max_pos_err"] < 0.2                       # (the PLUS-frame mixer loses a CF2X: tests/test_oracle_env.py)
+
+
+def test_host_pipelines_equal_device_paths(lib_built):
+    """HostPipeline (pinned host references in, pinned host observations out, three streams / two slots) delivers, step by step,
+    exactly what PerCallPipeline computes with device buffers; its ref-ready event fires before the host reference buffer is
+    reused.  HostRollout (K-step host call: one launch + one large D2H, double-buffered) delivers FusedRollout's observation log."""
+    import multidronesim_b200 as mds
+    import multidronesim_b200.trajectories as T
+    E, N, steps, dtype = 7, 4, 12, torch.float32
+    rng = np.random.default_rng(4)
+    specs = lem_params(N, E, rng)
+    obstacles = [[0.2, 0.0, 0.5, 0.1]]
+    init = np.zeros((E, N, 3))
+    for e in range(E):
+        for j, sp in enumerate(specs):
+            init[e, j] = otj.Lemniscate(**sp)(0.0)[0] + rng.normal(0, 0.02, 3) + np.array([0, 0, 0.04 * j])
+    trajs_dev = [T.Lemniscate(**sp) for sp in specs] * E
+    # device-buffer path
+    mds_, env, c, trk, ts, ro = build(E, N, dtype, "dyn_gnd_drag_dw", trajs_dev, "yank10", 3, obstacles, init)
+    pipe = mds.PerCallPipeline(env, c, trk, obstacles)
+    want = []
+    for k in range(steps):
+        want.append(pipe.step(ts.eval(k * env.CTRL_TIMESTEP)).clone().cpu().numpy())
+    # host-buffer path: ONE pinned reference buffer reused every step (legal once last_ref_ready has fired)
+    mds_, env2, c2, trk2, ts2, ro2 = build(E, N, dtype, "dyn_gnd_drag_dw", trajs_dev, "yank10", 3, obstacles, init)
+    hp = mds.HostPipeline(env2, c2, trk2, obstacles)
+    ref_host = torch.empty(E * N, 11, dtype=dtype).pin_memory()
+    obs_host = [torch.empty(E, N, 20, dtype=dtype).pin_memory() for _ in range(2)]
+    for k in range(steps):
+        ref_host.copy_(ts2.eval(k * env2.CTRL_TIMESTEP))
+        torch.cuda.synchronize()
+        done = hp.step(ref_host, obs_host[k & 1])
+        hp.last_ref_ready.synchronize()          # the reference buffer may be overwritten from here on
+        ref_host.fill_(float("nan"))
+        done.synchronize()
+        assert np.array_equal(obs_host[k & 1].numpy(), want[k]), k
+    hp.synchronize()
+    # K-step host call against the fused rollout's own log
+    K = 6
+    mds_, env3, c3, trk3, ts3, ro3 = build(E, N, dtype, "dyn_gnd_drag_dw", trajs_dev, "yank10", 3, obstacles, init)
+    log = torch.zeros(2 * K, E, N, 20, device="cuda", dtype=dtype)
+    ro3.run(2 * K, obs_log=log, log_every=1)
+    mds_, env4, c4, trk4, ts4, ro4 = build(E, N, dtype, "dyn_gnd_drag_dw", trajs_dev, "yank10", 3, obstacles, init)
+    hr = mds.HostRollout(ro4, K)
+    out = [torch.empty(K, E, N, 20, dtype=dtype).pin_memory() for _ in range(2)]
+    evs = [hr.step(out[j]) for j in range(2)]
+    for j in range(2):
+        evs[j].synchronize()
+        assert np.array_equal(out[j].numpy(), log[j * K:(j + 1) * K].cpu().numpy()), j
+    hr.synchronize()
