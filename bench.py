@@ -95,6 +95,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary configurations (C2, C3 order 2, C4, C5 fp64)")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="sub-swarms per GPU, each advanced on its own CUDA stream (multidronesim_b200.SwarmStreams): "
+                                                           "the tail wave of one sub-swarm's launch is filled by the next launch of another; 1 = one launch per step")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     return ap.parse_args()
 
@@ -224,7 +226,8 @@ def workload_config(args, envs, per_gpu=True):
     return {"workload": "C5 swarm sweep: envs x 8 drones, Physics.DYN_GND_DRAG_DW 240 Hz, Lemniscate refs, LQR-yank-omega nominal, "
                         "order-3 CBF-QP (r_safe 0.125, zscale 2, poles -3/-3.6/-5.6) + sphere obstacle r=0.1 at (0.2, 0, 0.5), YankOmega inner loop",
             "envs_per_gpu" if per_gpu else "envs": envs, "drones_per_env": N_DRONES, "drone_model": "cf2p", "cbf_order": CBF_ORDER,
-            "control_steps_per_step": args.fuse if per_gpu else args.ref_steps_per_step, "settle_steps": args.settle, "parallelism": f"env-sharded x{args.gpus}",
+            "control_steps_per_step": args.fuse if per_gpu else args.ref_steps_per_step, "settle_steps": args.settle,
+            "parallelism": f"env-sharded x{args.gpus}" + (f", {max(1, args.streams)} sub-swarms per GPU on their own CUDA streams" if per_gpu else ""),
             "obs": "every control step's observation is written to HBM (log ring of control_steps_per_step slots)",
             "l2": "working set (state+obs+traj specs+PID+obs log > 2 GB per GPU) exceeds the 126 MB L2; no flush needed"}
 
@@ -371,8 +374,7 @@ def run_gpu_arm(args):
     D = E * N
     sms = mds._lib.device_info()["sm_count"]
 
-    sc = scenarios.cbf_swarm(E, N, order=CBF_ORDER, dtype=dtype, device=dev, env_offset=rank * E)
-    env, ro, ctrl = sc["env"], sc["rollout"], sc["ctrl"]
+    P_STREAMS = max(1, args.streams)
 
     def barrier():
         if world > 1:
@@ -384,34 +386,59 @@ def run_gpu_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident headline -------------------------------------------------------------
-    # every control step's observation is materialised in HBM (a ring of F log slots, reused by each launch), as the
-    # reference's loop does (observations.append(obs)); a drone-step therefore includes its 80 B observation write
-    obs_ring = torch.empty(F, E, N, 20, device=dev, dtype=dtype)
-    step = lambda: ro.run(F, obs_log=obs_ring, log_every=1)
-    with ClockSampler(local_rank) as clk:  # sampling starts with the settle phase: nvidia-smi needs ~0.2 s to deliver its first line
-        for _ in range(args.settle // F):
+    def timed_swarm(n_envs, env_offset, clk=None):
+        """settle + warm up + time K bench steps of an n_envs-environment swarm cut into P_STREAMS sub-swarms; every control step's
+        observation is materialised in HBM (per sub-swarm a ring of F log slots, reused by each launch), as the reference's loop
+        does (observations.append(obs)): a drone-step includes its 80 B observation write"""
+        swarm, subs = scenarios.cbf_swarm_streams(n_envs, P_STREAMS, N, order=CBF_ORDER, dtype=dtype, device=dev, env_offset=env_offset)
+        rings = [torch.empty(F, s_["env"].NUM_ENVS, N, 20, device=dev, dtype=dtype) for s_ in subs]
+        step = lambda: swarm.run(F, obs_logs=rings, log_every=1)
+        for _ in range(args.settle // F + W):
             step()
-        for _ in range(W):
-            step()
+        swarm.synchronize()
+        swarm.reset_stats()
         torch.cuda.synchronize()
-        ro.reset_stats()
-        snap = snapshot(env, ctrl, ro)
         barrier()
-        ms, t_wall0, t_wall1 = time_launches(torch, step, K)
+        cur = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(cur)
+        swarm.fork()          # the sub-swarm streams start after e0 ...
+        for _ in range(K):
+            step()
+        swarm.join()          # ... and e1 is recorded after all of them
+        e1.record(cur)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
         barrier()
+        if not all(r.plan() == 6 for r in swarm.rollouts):
+            raise SystemExit("bench.py assumes the K-steps-in-one-launch plan")
+        return e0.elapsed_time(e1), w0, w1, swarm.stats().clone()
+
+    # ---- device-resident headline -------------------------------------------------------------
+    with ClockSampler(local_rank) as clk:  # sampling starts with the settle phase: nvidia-smi needs ~0.2 s to deliver its first line
+        ms, t_wall0, t_wall1, stats_rank = timed_swarm(E, rank * E)
         time.sleep(0.12)  # let the sample that covers the end of the region arrive
     ms_max = max_over_ranks(ms)
     value = world * D * F * K / (ms_max * 1e-3)
-    stats_all = mds.dist.gather_stats(ro.stats)  # the path's only collective (NCCL all-gather of 8 doubles per rank)
+    stats_all = mds.dist.gather_stats(stats_rank)  # the path's only collective (NCCL all-gather of 8 doubles per rank)
     stats = dict(zip(mds._lib.STAT_NAMES, mds.dist.reduce_stats(stats_all).tolist()))
     clocks = clk.summary(t_wall0, t_wall1)
+    torch.cuda.empty_cache()
+
+    # one full-size swarm for the per-call replay and the host-buffer path, settled like the headline's
+    sc = scenarios.cbf_swarm(E, N, order=CBF_ORDER, dtype=dtype, device=dev, env_offset=rank * E)
+    env, ro, ctrl = sc["env"], sc["rollout"], sc["ctrl"]
+    obs_ring = torch.empty(F, E, N, 20, device=dev, dtype=dtype)
+    for _ in range(args.settle // F + W):
+        ro.run(F, obs_log=obs_ring, log_every=1)
+    torch.cuda.synchronize()
+    ro.reset_stats()
+    snap = snapshot(env, ctrl, ro)
 
     # ---- roofline of the dominant kernel: the K-steps-in-one-launch rollout kernel (this rank) ----------------
-    # Every bench step is ONE launch of rollout_loop_kernel (F control steps with the state in registers), so its
-    # mean launch duration is the timed region / K, on the launching stream.
-    if ro.plan() != 6:
-        raise SystemExit("bench.py assumes the K-steps-in-one-launch plan")
+    # Every bench step is one launch of rollout_loop_kernel per sub-swarm (F control steps with the state in registers); the
+    # launches of the P_STREAMS sub-swarms overlap on the GPU, so the kernel's duration per bench step is the timed region / K.
     n_steps = K * F
     launch_ms = ms / K
     peaks = measured_peaks()
@@ -425,7 +452,8 @@ def run_gpu_arm(args):
     tf = flop_step * D * F / (launch_ms * 1e-3) / 1e12
     gbs = bytes_launch * D / (launch_ms * 1e-3) / 1e9
     cap = ncu_capture("rollout_loop_kernel", E, args.dtype)
-    roofline = {"bound": "fp64" if use_f64 else "fp32", "kernel": f"rollout_loop_kernel<{sfx}, MDS_CTRL_LQR_YANK, true, 8, 1>", "achieved": tf, "peak": fpk,
+    roofline = {"bound": "fp64" if use_f64 else "fp32", "kernel": f"rollout_loop_kernel<{sfx}, MDS_CTRL_LQR_YANK, true, 8, 1>",
+                "launches_per_step": P_STREAMS, "envs_per_launch": E // P_STREAMS, "achieved": tf, "peak": fpk,
                 "unit": "TFLOP/s", "frac": tf / fpk, "peak_source": fpk_src, "peak_nominal": fpk_nominal, "peak_fma_chain": fpk_chain,
                 "frac_counters": cap.get("fp_frac_counters") if cap else None,
                 "frac_counters_source": (f"profiles/{cap['report']}: executed (fadd + fmul + 2 ffma) per cycle / (2 x ffma peak_sustained), ncu --set full of one launch"
@@ -440,8 +468,6 @@ def run_gpu_arm(args):
 
     # ---- the per-call kernels against the HBM roofline: replay with one launch per kernel ----------------------
     # (MdsRolloutCfg.stages 1 = controller kernel, 2 = physics kernel; a CUDA event pair around every launch)
-    restore(env, ctrl, ro, snap)
-    torch.cuda.synchronize()
     n_rep = min(n_steps, 240)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_rep)]
     for k in range(n_rep):
@@ -476,27 +502,19 @@ def run_gpu_arm(args):
     if not args.no_strong:
         if world == 1:
             strong = {"value": value, "unit": "drone-steps/s", "total_envs": E, "envs_per_gpu": E, "ms_per_step": ms_max / K, "efficiency": 1.0,
-                      "note": "N = 1: the fixed swarm is the weak-scaling shard"}
+                      "streams_per_gpu": P_STREAMS, "note": "N = 1: the fixed swarm is the weak-scaling shard"}
         else:
             b0, b1 = mds.dist.env_shard(E, rank, world)
             Es = b1 - b0
-            sc_s = scenarios.cbf_swarm(Es, N, order=CBF_ORDER, dtype=dtype, device=dev, env_offset=b0)
-            ro_s = sc_s["rollout"]
-            ring_s = torch.empty(F, Es, N, 20, device=dev, dtype=dtype)
-            step_s = lambda: ro_s.run(F, obs_log=ring_s, log_every=1)
-            for _ in range(args.settle // F + W):
-                step_s()
-            torch.cuda.synchronize()
-            barrier()
-            ms_s, _, _ = time_launches(torch, step_s, K)
-            barrier()
+            ms_s, _, _, _ = timed_swarm(Es, b0)
             ms_s = max_over_ranks(ms_s)
             v_s = E * N * F * K / (ms_s * 1e-3)
             strong = {"value": v_s, "unit": "drone-steps/s", "total_envs": E, "envs_per_gpu": Es, "ms_per_step": ms_s / K,
-                      "efficiency": v_s / value,
-                      "note": f"{E} environments in total, contiguous shards of {Es} per GPU (dist.env_shard), same launches as `value`; efficiency = strong value / "
-                              f"weak value (= N x the rate of one GPU on the full {E}-environment shard, measured in this run)"}
-            del sc_s, ro_s, ring_s
+                      "efficiency": v_s / value, "streams_per_gpu": P_STREAMS,
+                      "note": f"{E} environments in total, contiguous shards of {Es} per GPU (dist.env_shard), each cut into {P_STREAMS} sub-swarms on their own "
+                              f"streams like `value`; efficiency = strong value / weak value (= N x the rate of one GPU on the full {E}-environment shard, "
+                              "measured in this run)"}
+            torch.cuda.empty_cache()
 
     # ---- the other BASELINE.json configurations (N = 1 only; every rank of a multi-GPU run would repeat them) ----------
     configs = None
@@ -509,7 +527,7 @@ def run_gpu_arm(args):
         line = {"metric": METRIC, "value": value, "unit": "drone-steps/s",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, E),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": K, "roofline": roofline, "roofline_ctrl": roofline_ctrl,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": K * P_STREAMS, "roofline": roofline, "roofline_ctrl": roofline_ctrl,
                 "roofline_physics": roofline_physics, "strong": strong, "configs": configs,
                 "cpu_baseline": (cpu.get("reference") or cpu.get("port")) if cpu else None,
                 "cpu_baseline_port": cpu.get("port") if cpu and "reference" in cpu else None,

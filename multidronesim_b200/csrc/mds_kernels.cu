@@ -4,6 +4,7 @@
 // downwash neighbours and CBF rows are staged through shared memory.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -668,6 +669,18 @@ static int xdot_nonlinear_impl(const MdsDroneParams* prm, double jx, double jy, 
   return check_launch("xdot_nonlinear");
 }
 extern "C" int mds_rollout_plan(int E, int N);
+extern "C" int mds_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes);
+static int cached_sm_count() {
+  static int sm_of_device[MDS_MAX_DEVICES];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MDS_MAX_DEVICES) return 0;
+  if (sm_of_device[dev] == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    sm_of_device[dev] = sms;
+  }
+  return sm_of_device[dev];
+}
 // PhysSpec<1> (mds_common.cuh): the swarm configuration of the reference's CBF mains, compiled without its mode switches
 static int phys_spec_of(const MdsDroneParams& p) {
   return (p.physics == MDS_PHYSICS_DYN_GND_DRAG_DW && p.drone_model == MDS_DRONE_CF2P && p.substeps == 1 && !p.renormalize_quat && p.ground_clamp &&
@@ -681,13 +694,13 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   MDS_REQUIRE(prm && cfg && st.pos_wx && st.quat && st.vel_wy && st.rpm && st.wz && specs && obs && action, "rollout: null pointer");
   MDS_REQUIRE(E > 0 && N > 0 && N <= MDS_MAX_DRONES_PER_ENV && K > 0, "rollout: bad E, N or K");
   MDS_REQUIRE(cfg->ctrl >= MDS_CTRL_GEOMETRIC && cfg->ctrl <= MDS_CTRL_DSLPID, "rollout: unknown controller");
-  MDS_REQUIRE(cfg->stages >= 0 && cfg->stages <= 6, "rollout: stages must be 0..6");
+  MDS_REQUIRE(cfg->stages >= 0 && cfg->stages <= 7, "rollout: stages must be 0..7");
   RolloutP<Real> R;
   memset(&R, 0, sizeof(R));
   R.ctrl = cfg->ctrl; R.use_cbf = cfg->use_cbf; R.n_obs = cfg->num_obstacles; R.write_obs_every = cfg->write_obs_every;
   R.lqr_planes = (const Real*)cfg->lqr_gain_planes_dev; R.lqr_D = E * N;
   MDS_REQUIRE(!R.lqr_planes || lqr_variant_ok(cfg->ctrl), "rollout: per-drone gains need an LQR controller");
-  MDS_REQUIRE(!R.lqr_planes || (cfg->stages != 3 && cfg->stages != 5), "rollout: per-drone gains run in launch plans 6 (default), 4, 1 and 2");
+  MDS_REQUIRE(!R.lqr_planes || (cfg->stages != 3 && cfg->stages != 5), "rollout: per-drone gains run in launch plans 6 / 7 (default), 4, 1 and 2");
   GeoP<Real> G;
   memset(&G, 0, sizeof(G));
   LqrP<Real> L;
@@ -740,7 +753,10 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   // followed by a controller step (ctrl | K-1 x [physics + ctrl] | physics); 4: two launches (ctrl, physics) per step;
   // 1: controller kernel only; 2: physics kernel only; 5: K fused launches [physics under the current action
   // buffer + controller at t0 + k dt] -- with 1 and 2 it lets a caller replay a rollout launch by launch.
-  const int mode = cfg->stages == 0 ? mds_rollout_plan(E, N) : cfg->stages;
+  int mode = cfg->stages == 0 ? mds_rollout_plan(E, N) : cfg->stages;
+  // the queue plan re-reads a tile's state after another SM wrote it; the DSL PID state goes through plain (L1-cached) loads
+  if (mode == 7 && cfg->stages == 0 && (cfg->ctrl == MDS_CTRL_DSLPID || NP > 32)) mode = 6;
+  MDS_REQUIRE(!(mode == 7 && (cfg->ctrl == MDS_CTRL_DSLPID || NP > 32)), "rollout: plan 7 does not take the DSL PID controller");
   auto obs_slot = [&](int j) -> Real* {  // where the observation after physics step j (1-based) goes
     if (R.write_obs_every > 0 && (j % R.write_obs_every) == 0) return obs_log + (size_t)(j / R.write_obs_every - 1) * obs_elems;
     return obs;
@@ -752,6 +768,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   auto launch_loop = [&]() {
     RolloutLaunch<Real> RLL = RL;  // the loop kernel has its own block size (MDS_LOOP_BLOCK)
     RLL.threads = R.use_cbf ? cbf_block_threads<Real>(NP, N, R.n_obs, MDS_LOOP_BLOCK) : MDS_LOOP_BLOCK;
+    if (const char* force = getenv("MDS_LOOP_THREADS")) { const int t = atoi(force); if (t >= 32 && t <= RLL.threads && t % 32 == 0) RLL.threads = t; }  // experiment knob
     if (RLL.threads < NP) RLL.threads = NP;
     const int epb_l = RLL.threads / NP;
     RLL.blocks = (E + epb_l - 1) / epb_l;
@@ -764,6 +781,43 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
       if (every > 0) part.obs_log = obs_log + (size_t)(k0 / every) * obs_elems;
       keep(launch_loop_kernel<Real>(part, t0 + k0 * prm->dt_ctrl, prm->dt_ctrl, K - k0 < chunk ? K - k0 : chunk));
     }
+  };
+  // plan 7: the same K steps from a device-side work queue (rollout_queue_kernel): a persistent grid whose warps pull
+  // (warp-tile of environments, chunk of steps) tasks; the queue lives in stream-ordered memory for the duration of the call
+  cudaError_t queue_err = cudaSuccess;
+  auto launch_queue = [&]() {
+    RolloutLaunch<Real> RLQ = RL;
+    RLQ.threads = R.use_cbf ? cbf_block_threads<Real>(NP, N, R.n_obs, MDS_LOOP_BLOCK) : MDS_LOOP_BLOCK;
+    if (RLQ.threads < 32) RLQ.threads = 32;
+    RLQ.smem = R.use_cbf ? cbf_smem_bytes<Real>(RLQ.threads, NP, N, R.n_obs) : 32;
+    int per_sm = 0;
+    const int sms = cached_sm_count();  // cudaGetDeviceProperties costs milliseconds: once per device
+    if (sms <= 0) { queue_err = cudaErrorUnknown; return; }
+    RolloutQueue q{nullptr, nullptr, 0, 0, 0};
+    keep(launch_queue_kernel<Real>(RLQ, t0, prm->dt_ctrl, K, q, sms, true, &per_sm));
+    if (attr_err != cudaSuccess || per_sm < 1) { if (attr_err == cudaSuccess) queue_err = cudaErrorLaunchOutOfResources; return; }
+    const int envs_per_tile = 32 / NP, warps_per_block = RLQ.threads / 32;
+    q.tiles = (E + envs_per_tile - 1) / envs_per_tile;
+    int grid = sms * per_sm;
+    if (grid > (q.tiles + warps_per_block - 1) / warps_per_block) grid = (q.tiles + warps_per_block - 1) / warps_per_block;
+    const long long slots = (long long)grid * warps_per_block;
+    // ~8 tasks per resident warp: enough slack for the queue to even out the tail, few enough that the per-chunk state
+    // round trip through HBM (~350 B per drone) stays small against the chunk's steps
+    long long chunks = (8 * slots + q.tiles - 1) / q.tiles;
+    if (const char* force = getenv("MDS_QUEUE_CHUNKS")) chunks = atoi(force);  // experiment knob (tools/exp_queue.py)
+    if (chunks < 1) chunks = 1;
+    if (chunks > K) chunks = K;
+    q.chunk_steps = (int)((K + chunks - 1) / chunks);
+    q.chunks = (K + q.chunk_steps - 1) / q.chunk_steps;
+    int* mem = nullptr;
+    queue_err = cudaMallocAsync((void**)&mem, (size_t)(q.tiles + 1) * sizeof(int), cs);
+    if (queue_err != cudaSuccess) return;
+    queue_err = cudaMemsetAsync(mem, 0, (size_t)(q.tiles + 1) * sizeof(int), cs);
+    q.head = mem; q.progress = mem + 1;
+    RLQ.blocks = grid;
+    if (queue_err == cudaSuccess) keep(launch_queue_kernel<Real>(RLQ, t0, prm->dt_ctrl, K, q, sms, false, &per_sm));
+    cudaError_t fe = cudaFreeAsync(mem, cs);
+    if (queue_err == cudaSuccess) queue_err = fe;
   };
   bool first_ctrl = true, first_fused = true;
   auto launch_ctrl = [&](bool fused, double t, Real* obs_ptr) {
@@ -790,6 +844,9 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
     for (int k = 0; k < K; ++k) { obs_last = obs_slot(k + 1); launch_ctrl(true, t0 + k * dt, obs_last); }
   } else if (mode == 6) {
     launch_loop();  // writes the final observation to `obs` itself
+  } else if (mode == 7) {
+    launch_queue();
+    if (queue_err != cudaSuccess) return cuda_fail("rollout: work queue", queue_err);
   } else {
     launch_ctrl(false, t0, obs);
     for (int k = 1; k < K; ++k) { obs_last = obs_slot(k); launch_ctrl(true, t0 + k * dt, obs_last); }

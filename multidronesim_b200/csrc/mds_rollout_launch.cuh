@@ -33,3 +33,7 @@ template <typename Real> struct RolloutLaunch {
 template <typename Real> cudaError_t launch_loop_kernel(const RolloutLaunch<Real>& a, double t0, double dt_ctrl, int K);
 template <typename Real> cudaError_t launch_ctrl_kernel(const RolloutLaunch<Real>& a, double t, const Real* obs_in, bool set_attr);
 template <typename Real> cudaError_t launch_fused_kernel(const RolloutLaunch<Real>& a, double t, Real* obs_out, bool set_attr);
+// the work-queue form of the K-step rollout (rollout_queue_kernel); q: device queue already zeroed on a.cs, tiles / chunks set by the caller.
+// *grid_blocks (in: 0 = ask) receives / provides the persistent grid size
+template <typename Real> cudaError_t launch_queue_kernel(const RolloutLaunch<Real>& a, double t0, double dt_ctrl, int K, RolloutQueue q, int sm_count, bool query_only,
+                                                         int* blocks_per_sm);

@@ -81,8 +81,8 @@ class FusedRollout:
         env = self.env
         if t0 is None:
             t0 = self.t
-        if stages not in (0, 1, 2, 3, 4, 5, 6):
-            raise ValueError("stages must be 0..6")
+        if stages not in (0, 1, 2, 3, 4, 5, 6, 7):
+            raise ValueError("stages must be 0..7")
         t_call = t0 + env.CTRL_TIMESTEP if stages == 5 else t0  # 5: the controller runs after the physics step
         self.cfg.stages = int(stages)
         self.cfg.write_obs_every = int(log_every) if obs_log is not None else 0
@@ -239,3 +239,65 @@ class HostRollout:
     def synchronize(self):
         self.s_out.synchronize()
         torch.cuda.current_stream(self.env.device).synchronize()
+
+
+class SwarmStreams:
+    """P independent sub-swarms, each a ``FusedRollout`` over its own ``BatchedCtrlAviary``, advanced on P CUDA streams.
+
+    Environments never interact, so a swarm can be cut into sub-swarms that progress independently.  One ``mds_rollout``
+    launch of E environments occupies the GPU in waves of equal blocks (148 SMs x 2 blocks x 32 environments on B200), and
+    its last wave is rarely full: 15 625 environments (BASELINE.json configs[4] on one of 8 GPUs) are 1.65 waves and cost 2.
+    With the sub-swarms on separate streams the block scheduler fills the tail of one sub-swarm's launch with the blocks of
+    the next launch of another, across calls: measured 1.18e10 -> 1.43e10 drone-steps/s at 15 625 environments, 1.42e10 ->
+    1.46e10 at 125 000 (tools/exp_streams.py).  ``run`` is asynchronous and does NOT join the streams -- that is the point;
+    call ``synchronize()`` (or ``join()`` to order the caller's stream after them) before reading any sub-swarm's tensors."""
+
+    def __init__(self, rollouts):
+        self.rollouts = list(rollouts)
+        dev = self.rollouts[0].env.device
+        self.device = dev
+        self.streams = [torch.cuda.Stream(dev) for _ in self.rollouts]
+        cur = torch.cuda.current_stream(dev)
+        for st in self.streams:   # the sub-swarms' tensors were initialised on the caller's stream
+            st.wait_stream(cur)
+
+    @property
+    def num_envs(self):
+        return sum(r.env.NUM_ENVS for r in self.rollouts)
+
+    def run(self, K, obs_logs=None, log_every=0):
+        """Advance every sub-swarm K control steps (one launch each, on its own stream).  ``obs_logs``: one log tensor per sub-swarm."""
+        for i, (ro, st) in enumerate(zip(self.rollouts, self.streams)):
+            with torch.cuda.stream(st):
+                ro.run(K, obs_log=None if obs_logs is None else obs_logs[i], log_every=log_every)
+
+    def fork(self):
+        """order the sub-swarm streams after the caller's stream (e.g. after an event recorded there)"""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+
+    def join(self):
+        """order the caller's stream after everything queued on the sub-swarm streams"""
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def synchronize(self):
+        for st in self.streams:
+            st.synchronize()
+
+    def reset_stats(self):
+        self.join()
+        for ro in self.rollouts:
+            ro.reset_stats()
+        self.fork()
+
+    def stats(self):
+        """the sub-swarms' statistics combined (layout include/mds_b200.h MDS_STAT_*)"""
+        from .dist import reduce_stats
+        self.join()
+        return reduce_stats(torch.stack([ro.stats for ro in self.rollouts], dim=0))
+
+    def stats_dict(self):
+        return dict(zip(_lib.STAT_NAMES, self.stats().tolist()))

@@ -96,6 +96,19 @@ def cbf_swarm(num_envs, num_drones=8, order=3, dtype=torch.float32, device="cuda
     return dict(env=env, ctrl=ctrl, cbf=cbf, tracker=trk, trajs=trajs, obstacles=obstacles, rollout=rollout, init=init)
 
 
+def cbf_swarm_streams(num_envs, parts, num_drones=8, order=3, dtype=torch.float32, device="cuda", seed=3, env_offset=0, **kw):
+    """The same swarm as ``cbf_swarm(num_envs, ...)`` cut into ``parts`` contiguous sub-swarms (dist.env_shard), each with its own
+    env / controller / rollout, wrapped in ``SwarmStreams``.  Env e has the same initial condition whichever way the swarm is cut
+    (counter-hash of the absolute env index).  -> (SwarmStreams, [sub-swarm dicts])"""
+    from .dist import env_shard
+    from .rollout import SwarmStreams
+    subs = []
+    for p in range(int(parts)):
+        b0, b1 = env_shard(int(num_envs), p, int(parts))
+        subs.append(cbf_swarm(b1 - b0, num_drones, order=order, dtype=dtype, device=device, seed=seed, env_offset=env_offset + b0, **kw))
+    return SwarmStreams([s["rollout"] for s in subs]), subs
+
+
 def tracking_swarm(num_envs, dtype=torch.float32, device="cuda", seed=1, env_offset=0, physics=Physics.DYN_GND_DRAG_DW):
     """C2: one drone per env, geometric SE(3) controller; even envs track CircleTrajectory(r=1, v=0.5,
     centre (0,0,1)), odd envs Lemniscate(a=1, omega=1.5, centre (0,0,0.5)) with a random phase shift;

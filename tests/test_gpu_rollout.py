@@ -357,3 +357,64 @@ def test_host_pipelines_equal_device_paths(lib_built):
         evs[j].synchronize()
         assert np.array_equal(out[j].numpy(), log[j * K:(j + 1) * K].cpu().numpy()), j
     hr.synchronize()
+
+
+@pytest.mark.parametrize("ctrl,cbf_order,N,E,K,every,dtype", [("yank10", 3, 8, 301, 24, 1, torch.float32), ("yank10", 3, 8, 45, 13, 3, torch.float64),
+                                                              ("omega9", 2, 3, 77, 10, 2, torch.float32), ("geometric", None, 1, 500, 16, 4, torch.float32),
+                                                              ("torque12", None, 5, 33, 7, 0, torch.float64)])
+def test_work_queue_plan_equals_loop_plan(ctrl, cbf_order, N, E, K, every, dtype, lib_built):
+    """Launch plan 7 (rollout_queue_kernel: a persistent grid whose warps pull (tile of environments, chunk of steps) tasks from a
+    device-side queue, the tile's state going through HBM between chunks) computes what plan 6 (one block-scheduled launch, state in
+    registers for all K steps) computes: same final observations / state / controller state, same observation log, same counters.
+    Sizes that leave the last warp-tile partly empty and chunkings that do not divide K."""
+    import multidronesim_b200.trajectories as T
+    rng = np.random.default_rng(21)
+    specs = [dict(a=1.0, center=np.array([0, 0, 0.5]), omega=0.5, yaw_rate=0.1, phase_shift=float(2 * np.pi / (N + 0.25) * k)) for k in range(N)]
+    init = np.zeros((E, N, 3))
+    for e in range(E):
+        for j, sp in enumerate(specs):
+            init[e, j] = otj.Lemniscate(**sp)(0.0)[0] + rng.normal(0, 0.02, 3) + np.array([0, 0, 0.04 * j])
+    obstacles = [[0.2, 0.0, 0.5, 0.1]] if cbf_order is not None else None
+    outs = []
+    for plan in (6, 7):
+        mds, env, c, trk, ts, ro = build(E, N, dtype, "dyn_gnd_drag_dw", [T.Lemniscate(**sp) for sp in specs] * E, ctrl, cbf_order, obstacles, init)
+        log = torch.zeros(max(1, K // max(1, every)), E, N, 20, device="cuda", dtype=dtype)
+        for _ in range(2):   # two calls: the second starts from the state the first one stored
+            ro.run(K, obs_log=log if every else None, log_every=every, stages=plan)
+        torch.cuda.synchronize()
+        pid = (c.low_level._a.cpu().numpy().copy(), c.low_level._b.cpu().numpy().copy()) if ctrl in ("yank10", "omega9") else ()
+        outs.append((env.obs.cpu().numpy().copy(), log.cpu().numpy().copy(), ro.stats.cpu().numpy().copy(), env.state_dict(), pid, env._action.cpu().numpy().copy()))
+    a, b = outs
+    # two compilations of the same step code (nvcc may contract a*b+c differently in each): equal to rounding, amplified
+    # over 2 K closed-loop steps -- not bit for bit
+    tol = dict(rtol=2e-4, atol=2e-4) if dtype == torch.float32 else dict(rtol=1e-9, atol=1e-9)
+    assert np.allclose(a[0], b[0], **tol) and np.allclose(a[1], b[1], **tol) and np.allclose(a[5], b[5], rtol=tol["rtol"], atol=tol["atol"] * 2e4)
+    assert np.abs(a[1]).max() > 0 or not every
+    for k in a[3]:
+        va, vb = a[3][k], b[3][k]
+        if isinstance(va, torch.Tensor):
+            assert np.allclose(va.double().cpu().numpy(), vb.double().cpu().numpy(), rtol=tol["rtol"], atol=tol["atol"] * (2e4 if "rpm" in k else 1)), k
+        else:
+            assert va == vb, k
+    for x, y in zip(a[4], b[4]):
+        assert np.allclose(x, y, rtol=tol["rtol"], atol=tol["atol"] * 10)
+    # counters exact; the error sum is accumulated per thread in a different grouping (float): close
+    assert np.array_equal(a[2][[0, 4, 6, 7]], b[2][[0, 4, 6, 7]]) and np.allclose(a[2], b[2], rtol=1e-4)
+
+
+def test_swarm_streams_equal_one_swarm(lib_built):
+    """scenarios.cbf_swarm_streams: the C5 swarm cut into sub-swarms advanced on their own CUDA streams (SwarmStreams) is, env for
+    env, the swarm run as one: identical observations (same kernel, same per-env inputs) and the same combined statistics."""
+    from multidronesim_b200 import scenarios
+    E, K = 90, 30
+    one = scenarios.cbf_swarm(E, 8, order=3)
+    one["rollout"].run(K); one["rollout"].run(K)
+    swarm, subs = scenarios.cbf_swarm_streams(E, 3, 8, order=3)
+    swarm.run(K); swarm.run(K)
+    swarm.synchronize()
+    got = torch.cat([s["env"].obs for s in subs], dim=0)
+    assert torch.equal(got, one["env"].obs)
+    a, b = one["rollout"].stats_dict(), swarm.stats_dict()
+    for k in ("drone_steps", "qp_solves", "qp_iters", "qp_infeasible", "qp_iter_cap", "max_pos_err", "min_barrier"):
+        assert a[k] == b[k], k
+    assert abs(a["sum_pos_err"] - b["sum_pos_err"]) < 1e-6 * a["sum_pos_err"]
