@@ -166,6 +166,10 @@ typedef struct MdsRolloutCfg {
                           0      whole steps, plan chosen by mds_rollout_plan(E, N) (currently always 6)
                           6      all K steps in ONE launch: observation and body rates stay in registers from step to
                                  step (environments are independent and a lane group owns its environment)
+                          7      the same K steps from a device-side work queue: a persistent grid whose warps pull
+                                 (warp-tile of environments, chunk of steps) tasks; a tile's state goes through HBM between
+                                 its chunks.  Same results as 6 to rounding; not for MDS_CTRL_DSLPID.  Measured equal to 6
+                                 at large E and not better at small E, so 0 never selects it.
                           3      whole steps, fused: ctrl | K-1 x [physics + ctrl in one launch] | physics
                           4      whole steps as two launches each (controller kernel, physics kernel)
                           1      controller kernel only (action_dev <- controller stack at obs_dev; env does not advance)
@@ -243,7 +247,15 @@ int mds_lowlevel_f64(const MdsDroneParams* prm, int variant, const double* u_dev
 /* ---- CBF-QP: replaces DroneQPTracker.compute_control (cbf/qptracker.py:22-34) ------ */
 /* xdes_dev [E*N*xdim]; u_nom_dev / u_safe_dev [E*N*4]; obstacles_dev [n_obs*4] = cx,cy,cz,r
  * (shared by all envs; r > 0: sphere as cbf/cbf.py:380-383; r < 0: vertical cylinder of radius |r|, unbounded
- * height, through (cx, cy) -- builder extension, the reference has spheres only) ; status_dev [E] int32 ; iters_dev [E] int32 (may be NULL). */
+ * height, through (cx, cy) -- builder extension, the reference has spheres only) ; status_dev [E] int32 ; iters_dev [E] int32 (may be NULL).
+ * status: MDS_QP_OPTIMAL -> u_safe is the QP's minimiser; MDS_QP_INFEASIBLE / MDS_QP_ITER_CAP -> u_safe = u_nom (the reference's
+ * except branch, cbf/qptracker.py:30-34,105-114).  The solve has three tiers: (1) every drone projects onto its most violated
+ * single-drone row (obstacle rows, +-umax box) in registers and the step ends there if no row is violated at the projected
+ * point; (2) otherwise the environment's lane group runs a dual active-set solve in shared memory (<= 12 active rows,
+ * MdsCbfParams.max_iter iterations); (3) a solve that outgrows (2), or whose factor breaks down, is repeated in a per-device
+ * scratch pool with room for 3 N active rows, the number of coupled variables (no cap), scalar part in double.  ITER_CAP is
+ * therefore only ever the scratch solver's own iteration limit (16 * 3N + 64).  The pool is allocated at the first CBF call
+ * on a device (make that call outside any stream capture). */
 int mds_cbf_qp_f32(const MdsDroneParams* prm, const MdsCbfParams* cbf, const float* obs_dev,
                    const float* xdes_dev, const float* u_nom_dev, const float* obstacles_dev, int n_obs,
                    float* u_safe_dev, int* status_dev, int* iters_dev, int E, int N, void* stream);
@@ -285,7 +297,9 @@ int mds_xdot_nonlinear_f64(const MdsDroneParams* prm, double jx, double jy, doub
  * Everything is enqueued on `stream` with no host synchronisation.
  * obs_dev [D*20] in/out (observation before the first / after the last step); action_dev [D*4] scratch;
  * ext_force_dev optional [D*3] constant world-frame force per drone (wind, EnvGeometric.py:463-467);
- * obs_log_dev optional [K/write_obs_every][D*20]; stats_dev optional [MDS_STAT_COUNT] doubles (accumulated). */
+ * obs_log_dev optional [K/write_obs_every][D*20]; stats_dev optional [MDS_STAT_COUNT] doubles (accumulated).
+ * With the CBF filter the library keeps a per-device scratch pool for QPs whose active set outgrows the in-kernel
+ * workspace (allocated at the first such call: make that call outside any stream capture). */
 int mds_rollout_f32(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, const MdsGeoGains* geo,
                     const MdsLqrGains* lqr, const MdsCbfParams* cbf, MdsState st, MdsPidState pid,
                     const MdsDslPidGains* dsl, MdsDslPidState dsl_state, const MdsTrajSpecF32* specs_dev, const MdsTrajSegF32* segs_dev, float* obs_dev, float* action_dev,

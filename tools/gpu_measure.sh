@@ -12,7 +12,7 @@ python bench.py --no-cpu-baseline > $out/${tag}_plain_bench.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file $out/${tag}_launches.csv \
       python bench.py --no-cpu-baseline > $out/${tag}_ncu_launches.log 2>&1
 # one launch of each: the rollout kernel (24 steps), then the per-call pair (tools/prof_rollout.py runs plan 6, then 4)
-python tools/prof_rollout.py 125000 480 24 > $out/${tag}_plain_prof.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:"rollout_loop|ctrl_step|physics_step" -s 20 -c 3 -f -o $out/${tag}_prof \
-      python tools/prof_rollout.py 125000 480 24 > $out/${tag}_ncu_prof.log 2>&1
+python tools/prof_rollout.py 125000 1512 24 > $out/${tag}_plain_prof.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"rollout_loop|ctrl_step|physics_step" -s 63 -c 3 -f -o $out/${tag}_prof \
+      python tools/prof_rollout.py 125000 1512 24 > $out/${tag}_ncu_prof.log 2>&1
 tail -2 $out/${tag}_ncu_prof.log

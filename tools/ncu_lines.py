@@ -11,11 +11,16 @@ import tempfile
 
 rep, so, pat = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-sass = []  # the library holds one cubin per translation unit: scan them all
-for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
-    sass += subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+# The library holds one cubin per translation unit and cuobjdump names them after the SOURCE file (six of them are
+# mds_rollout_tu.sm_100a.cubin), so extracting from the .so overwrites them: disassemble the objects next to it instead.
+import glob
+objs = [so] if so.endswith(".o") else sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(so)), "build", "*.o")))
+sass = []
+for obj in objs:
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        sass += subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
