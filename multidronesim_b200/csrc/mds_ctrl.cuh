@@ -129,8 +129,8 @@ MDS_DEV void geometric_input(const DroneP<Real>& P, const GeoP<Real>& G, const O
 // variant: MDS_CTRL_LQR_TORQUE (dim 12), _OMEGA (9), _YANK (10).  Returns the UN-capped u.
 template <typename Real>
 MDS_DEV int lqr_error_state(const DroneP<Real>& P, int variant, const Obs<Real>& o, const Ref<Real>& r, Real e[12]) {
-  Real sy, cy;
-  sincos_(r.yaw, &sy, &cy);
+  Real sy = Real(0), cy = Real(1);
+  if (r.yaw != Real(0)) sincos_(r.yaw, &sy, &cy);  // a zero reference yaw (the reference's mains) needs no sincos
   // Error attitude (lqr_omega_controller.py:97-104): as_euler('xyz') of R_eq^T R with R = from_euler('xyz', rpy)
   // = Rz(yaw) Ry(pitch) Rx(roll) and R_eq = Rz(yaw_d).  Rz(yaw_d)^T Rz(yaw) = Rz(yaw - yaw_d), and the obs pitch is
   // an asin() in [-pi/2, pi/2], so the Euler angles of the product are (roll, pitch, wrap(yaw - yaw_d)) in closed

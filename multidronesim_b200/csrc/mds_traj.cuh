@@ -58,6 +58,11 @@ template <typename Real> MDS_DEV Ref<Real> eval_lemniscate(const Real* p, double
   o.v = {-a * om * (s2 * s2 + s2 + (s2 - Real(1)) * c2) * inv2, -a * om * s * (s2 + Real(2) * c2 + Real(1)) * inv2, Real(0)};
   o.a = {Real(4) * a * om * om * sin2 * (Real(3) * cos2 + Real(7)) * ik3,
          a * om * om * c * (Real(44) * cos2 + cos4 - Real(21)) * ik3, Real(0)};
+  if (p[5] == Real(0)) {            // no yaw motion (the reference's mains): sin(0) = 0, cos(0) = 1 without the sincos
+    o.yaw = Real(0);
+    o.yaw_rate = Real(0);
+    return o;
+  }
   Real sy, cy;
   sincos_(Real(reduce_2pi((double)p[5] * t)), &sy, &cy);
   o.yaw = pi * sy;                  // quirk B19
