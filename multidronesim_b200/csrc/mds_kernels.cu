@@ -495,17 +495,14 @@ static int rls_impl(const MdsRlsCfg* cfg, const Real* phi, const Real* xtp1, Rea
     }
   cudaStream_t cs = (cudaStream_t)stream;
   cudaError_t ae = cudaSuccess;
-  // Lanes per drone, by measurement at 1 M drones (tools/bench_sysid.py): the two-lane kernel wins where a thread's column is
-  // long and the residual is the cheap x_dot form (m = 12 approx_theta_update: 1.26 vs 1.53 ms); the one-lane kernel wins
-  // elsewhere (m = 9: 0.60 vs 0.74 ms f32, 1.28 vs 1.56 ms f64; m = 12 theta_update: 1.41 vs 1.48 ms) -- its full 128-byte
-  // lines per warp access beat the pair kernel's two 64-byte half-lines.
+  // One thread per drone, one warp (f32) / half a warp (f64) per block; P is read from its upper triangle (mds_sysid.cuh).  Round 1's
+  // two-lanes-per-drone variant for the 12-dim x_dot form lost to this kernel once the triangle halved its staging footprint
+  // (1.14 vs 1.26 ms per 1 M drones) and is gone.
 #define MDS_LAUNCH_RLS(MM)                                                                                                    \
   do {                                                                                                                        \
-    const bool two = (MM == 12) && cfg->target == MDS_RLS_TARGET_XDOT;                                                        \
-    const int threads = rls_threads<Real, MM>(), per_block = two ? threads / 2 : threads, blocks = (D + per_block - 1) / per_block; \
-    const size_t smem = (size_t)rls_words_per_thread<Real, MM>() * per_block * sizeof(Real);                                  \
-    auto kern = two ? (cfg->project != MDS_RLS_PROJECT_NONE ? rls_update2_kernel<Real, MM, true> : rls_update2_kernel<Real, MM, false>) \
-                    : (cfg->project != MDS_RLS_PROJECT_NONE ? rls_update_kernel<Real, MM, true> : rls_update_kernel<Real, MM, false>);  \
+    const int threads = rls_threads<Real, MM>(), blocks = (D + threads - 1) / threads;                                       \
+    const size_t smem = (size_t)rls_words_per_thread<Real, MM>() * threads * sizeof(Real);                                    \
+    auto kern = cfg->project != MDS_RLS_PROJECT_NONE ? rls_update_kernel<Real, MM, true> : rls_update_kernel<Real, MM, false>; \
     ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
     if (ae == cudaSuccess) kern<<<blocks, threads, smem, cs>>>(c, phi, xtp1, theta, Pm, resid, D);                            \
   } while (0)

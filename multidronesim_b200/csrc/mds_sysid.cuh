@@ -31,7 +31,10 @@ template <typename Real> MDS_DEV void cp_async_real(Real* smem_dst, const Real* 
 }
 MDS_DEV void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-template <typename Real, int M> constexpr int rls_words_per_thread() { return (M + 4) * (M + 4) + (M + 4) * M + 2 * (M + 4) + M; }
+// P is symmetric (identity-scaled prior, rank-one updates), so only its upper triangle is read and staged
+template <typename Real, int M> constexpr int rls_words_per_thread() { return (M + 4) * (M + 5) / 2 + (M + 4) * M + 2 * (M + 4) + M; }
+// index of entry (i, j), i <= j, in the row-major packed upper triangle of an MN x MN matrix
+template <int MN> MDS_DEV constexpr int rls_tri(int i, int j) { return i * MN - i * (i - 1) / 2 + (j - i); }
 // Threads per block: ONE warp (f32) / half a warp (f64).  A staged block is 40-63 KB, so 3-5 blocks share an SM and their
 // load / compute / store phases overlap; measured at 1 M drones, m = 9 f32: 0.61 ms at 32 threads, 0.80 ms at 64 or 128.
 // Row loops over the staged columns: unrolled by 4 so that several rows' shared-memory loads are in flight (registers are
@@ -59,8 +62,9 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
   constexpr int MN = M + 4, T = rls_threads<Real, M>();
   extern __shared__ __align__(16) unsigned char rls_smem[];
   const int tid = threadIdx.x;
-  Real* sP = reinterpret_cast<Real*>(rls_smem) + tid;  // entry k at sP[k * T]
-  Real* sT = sP + MN * MN * T;
+  constexpr int TRI = MN * (MN + 1) / 2;
+  Real* sP = reinterpret_cast<Real*>(rls_smem) + tid;  // packed upper triangle of P: entry (i, j >= i) at sP[rls_tri<MN>(i, j) * T]
+  Real* sT = sP + TRI * T;
   Real* s_phi = sT + MN * M * T;
   Real* s_w = s_phi + MN * T;
   Real* s_term = s_w + MN * T;
@@ -75,10 +79,12 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
   const size_t d = (size_t)blockIdx.x * T + tid, D = (size_t)D_;
   if (d >= D) return;
 #pragma unroll 1
-  for (int k = 0; k < MN * MN; ++k) cp_async_real(sP + k * T, Pm + (size_t)k * D + d);
+  for (int i = 0; i < MN; ++i)
+#pragma unroll 1
+    for (int j = i; j < MN; ++j) cp_async_real(sP + rls_tri<MN>(i, j) * T, Pm + (size_t)(i * MN + j) * D + d);
 #pragma unroll 1
   for (int k = 0; k < MN * M; ++k) cp_async_real(sT + k * T, theta + (size_t)k * D + d);
-  Real x1[M], phi[MN], v[MN];
+  Real x1[M], phi[MN], v[MN];  // v = phi' P = (P phi)' = w' by symmetry: accumulated from both halves of the triangle
 #pragma unroll
   for (int i = 0; i < MN; ++i) { phi[i] = phi_in[d * MN + i]; s_phi[i * T] = phi[i]; v[i] = Real(0); }
 #pragma unroll
@@ -97,21 +103,43 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
       }
     }
   }
-  // ---- gain: w = P phi, v = phi' P, s = 1 + phi' P phi
+  // ---- gain: w = P phi (= v'), s = 1 + phi' P phi.  Row i of the triangle holds P(i, j >= i): it contributes P(i,j) phi_j to w_i and,
+  // for j > i, P(i,j) phi_i to w_j
   Real s = Real(1);
-#pragma unroll kRlsRowUnroll
-  for (int i = 0; i < MN; ++i) {
-    const Real phi_i = s_phi[i * T];
-    Real wi = Real(0);
+  if (sizeof(Real) == 4) {  // fully unrolled: every index is static, w lives in v[] (255 registers in fp32, no spills)
 #pragma unroll
-    for (int j = 0; j < MN; ++j) {
-      const Real p = sP[(i * MN + j) * T];
-      wi += p * phi[j];
-      v[j] += phi_i * p;
+    for (int i = 0; i < MN; ++i) {
+      Real wi = v[i];
+#pragma unroll
+      for (int j = i; j < MN; ++j) {
+        const Real p = sP[rls_tri<MN>(i, j) * T];
+        wi += p * phi[j];
+        if (j > i) v[j] += p * phi[i];
+      }
+      v[i] = wi;
     }
-    s_w[i * T] = wi;
-    s += phi_i * wi;
+  } else {  // fp64: a run-time row loop (the full unroll spills 850 B): the row's own part of w_i goes to shared memory, the
+            // transposed contributions to v[j] with static j; the two halves are joined afterwards
+#pragma unroll 2
+    for (int i = 0; i < MN; ++i) {
+      const Real phi_i = s_phi[i * T];
+      Real wi = Real(0);
+      const int row0 = i * MN - i * (i - 1) / 2 - i;  // rls_tri(i, j) = row0 + j
+#pragma unroll
+      for (int j = 0; j < MN; ++j) {
+        if (j >= i) {
+          const Real p = sP[(row0 + j) * T];
+          wi += p * phi[j];
+          if (j > i) v[j] += p * phi_i;
+        }
+      }
+      s_w[i * T] = wi;
+    }
+#pragma unroll
+    for (int i = 0; i < MN; ++i) v[i] += s_w[i * T];
   }
+#pragma unroll
+  for (int i = 0; i < MN; ++i) { s_w[i * T] = v[i]; s += phi[i] * v[i]; }
   const Real inv_s = Real(1) / s;
   // ---- regression residual r (m)
   Real r[M];
@@ -204,203 +232,32 @@ __global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update_kernel(RlsP
       }
     }
   }
-#pragma unroll kRlsRowUnroll
-  for (int i = 0; i < MN; ++i) {
-    const Real Li = s_w[i * T] * inv_s;
+  // P -= (w / s) w': both triangles are written (the planes keep the full square), exactly symmetric
+  if (sizeof(Real) == 4) {
 #pragma unroll
-    for (int j = 0; j < MN; ++j) Pm[(size_t)(i * MN + j) * D + d] = sP[(i * MN + j) * T] - Li * v[j];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Two lanes per drone: the lanes of a pair split the ROWS of P and theta (lane h owns rows i = h mod 2), so the same
-// shared-memory footprint per drone feeds twice the threads, each with half the work; column sums (v = phi' P, the prediction /
-// residual) are completed with one xor-shuffle per entry inside the pair.  A block is 32 (f32) / 16 (f64) threads = 16 / 8
-// drones; pairs never straddle a warp, all exchanges use the pair's mask.  Used where it measures faster (rls_impl): the long
-// columns of the 12-dim model with the x_dot residual; elsewhere the one-lane kernel's full-line accesses win.
-template <typename Real, int M, bool PROJECT>
-__global__ void __launch_bounds__(rls_threads<Real, M>()) rls_update2_kernel(RlsP c, const Real* __restrict__ phi_in, const Real* __restrict__ x1_in,
-                                                                          Real* __restrict__ theta, Real* __restrict__ Pm, Real* __restrict__ resid_out,
-                                                                          int D_) {
-  constexpr int MN = M + 4, T = rls_threads<Real, M>(), S = T / 2;  // S drones (shared columns) per block
-  extern __shared__ __align__(16) unsigned char rls_smem[];
-  __shared__ unsigned s_code[16];
-  const int tid = threadIdx.x, slot = tid >> 1, h = tid & 1;
-  if (PROJECT && tid == 0) {
+    for (int i = 0; i < MN; ++i) {
+      const Real Li = v[i] * inv_s;
 #pragma unroll
-    for (int i = 0; i < MN; ++i) s_code[i] = c.row_code[i];
-  }
-  if (PROJECT) __syncthreads();
-  Real* sP = reinterpret_cast<Real*>(rls_smem) + slot;  // entry k of this drone at sP[k * S]
-  Real* sT = sP + MN * MN * S;
-  Real* s_phi = sT + MN * M * S;
-  Real* s_w = s_phi + MN * S;
-  Real* s_term = s_w + MN * S;
-  const size_t d = (size_t)blockIdx.x * S + slot, D = (size_t)D_;
-  if (d >= D) return;  // both lanes of a pair leave together
-  const unsigned pair = 3u << ((tid & 31) & ~1);
-  // staging: lane h copies the entries of its own rows (the rows it will also write back)
-#pragma unroll 1
-  for (int i = h; i < MN; i += 2)
-#pragma unroll
-    for (int j = 0; j < MN; ++j) cp_async_real(sP + (i * MN + j) * S, Pm + (size_t)(i * MN + j) * D + d);
-#pragma unroll 1
-  for (int i = h; i < MN; i += 2)
-#pragma unroll
-    for (int j = 0; j < M; ++j) cp_async_real(sT + (i * M + j) * S, theta + (size_t)(i * M + j) * D + d);
-  Real x1[M], phi[MN], v[MN];
-#pragma unroll
-  for (int i = 0; i < MN; ++i) { phi[i] = phi_in[d * MN + i]; v[i] = Real(0); }
-  if (h == 0) {
-#pragma unroll
-    for (int i = 0; i < MN; ++i) s_phi[i * S] = phi[i];
-  }
-#pragma unroll
-  for (int i = 0; i < M; ++i) x1[i] = x1_in[d * M + i];
-  cp_async_wait_all();
-  __syncwarp(pair);
-  const bool pre_project = PROJECT && c.project == MDS_RLS_PROJECT_LOOP && (d % (size_t)c.drones_per_env) != 0;
-  if (pre_project) {
-#pragma unroll 1
-    for (int i = h; i < MN; i += 2) {
-      const unsigned word = s_code[i];
-#pragma unroll
-      for (int j = 0; j < M; ++j) {
-        const unsigned code = (word >> (2 * j)) & 3u;
-        if (code != 1u) sT[(i * M + j) * S] = code == 0u ? Real(0) : Real(1);
+      for (int j = i; j < MN; ++j) {
+        const Real pij = sP[rls_tri<MN>(i, j) * T] - Li * v[j];
+        Pm[(size_t)(i * MN + j) * D + d] = pij;
+        if (j > i) Pm[(size_t)(j * MN + i) * D + d] = pij;
       }
     }
-    __syncwarp(pair);
-  }
-  // ---- gain: w = P phi (own rows), v = phi' P and s = 1 + phi' P phi (partial sums, completed across the pair)
-  Real s = Real(0);
-#pragma unroll 2
-  for (int i = h; i < MN; i += 2) {
-    const Real phi_i = s_phi[i * S];
-    Real wi = Real(0);
-#pragma unroll
-    for (int j = 0; j < MN; ++j) {
-      const Real p = sP[(i * MN + j) * S];
-      wi += p * phi[j];
-      v[j] += phi_i * p;
-    }
-    s_w[i * S] = wi;
-    s += phi_i * wi;
-  }
-#pragma unroll
-  for (int j = 0; j < MN; ++j) v[j] += __shfl_xor_sync(pair, v[j], 1);
-  s += __shfl_xor_sync(pair, s, 1);
-  s += Real(1);
-  const Real inv_s = Real(1) / s;
-  // ---- regression residual r (m), identical in both lanes
-  Real r[M];
-  if (c.target == MDS_RLS_TARGET_XDOT) {
-    Real part[M];
-#pragma unroll
-    for (int j = 0; j < M; ++j) part[j] = Real(0);
-#pragma unroll 2
-    for (int i = h; i < MN; i += 2) {
-      const Real phi_i = s_phi[i * S];
-#pragma unroll
-      for (int j = 0; j < M; ++j) part[j] += sT[(i * M + j) * S] * phi_i;
-    }
-#pragma unroll
-    for (int j = 0; j < M; ++j) part[j] += __shfl_xor_sync(pair, part[j], 1);
-    const Real inv_dt = Real(1.0 / c.dt);
-    if (M == 12) {  // decentralized_lqr.py:185-198
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        r[k] = x1[3 + k];
-        r[3 + k] = (x1[3 + k] - phi[3 + k]) * inv_dt;
-        r[6 + k] = (x1[6 + k] - phi[6 + k]) * inv_dt;
-        r[9 + k] = x1[6 + k];
-      }
-    } else {  // decentralized_yolqr_crazyflie.py:228-243
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        r[k] = phi[M + 1 + k];
-        r[4 + k] = (x1[4 + k] - phi[4 + k]) * inv_dt;
-        r[7 + k] = x1[4 + k];
-      }
-      r[3] = phi[M];
-    }
-#pragma unroll
-    for (int j = 0; j < M; ++j) r[j] -= part[j];
   } else {
-    // forward_predict by the exact series (see the one-lane kernel); every product theta' z is split by rows and summed
-    // across the pair, so both lanes carry the same acc / nt and take the same exit
-    Real acc[M], nt[M];
-#pragma unroll
-    for (int j = 0; j < M; ++j) { acc[j] = c.predict_from_xtp1 ? x1[j] : phi[j]; nt[j] = Real(0); }
-    if (h == 0) {
-#pragma unroll
-      for (int j = 0; j < M; ++j) s_term[j * S] = acc[j];
-    }
-    __syncwarp(pair);
 #pragma unroll 2
-    for (int i = h; i < MN; i += 2) {  // A e0 + B u = theta' [e0; u]
-      const Real zi = i < M ? s_term[i * S] : s_phi[i * S];
+    for (int i = 0; i < MN; ++i) {
+      const Real Li = s_w[i * T] * inv_s;
+      const int row0 = i * MN - i * (i - 1) / 2 - i;
 #pragma unroll
-      for (int j = 0; j < M; ++j) nt[j] += sT[(i * M + j) * S] * zi;
-    }
-#pragma unroll
-    for (int j = 0; j < M; ++j) nt[j] += __shfl_xor_sync(pair, nt[j], 1);
-    Real coef = Real(c.dt);
-    const Real eps = sizeof(Real) == 4 ? Real(1e-9) : Real(1e-18);
-#pragma unroll 1
-    for (int k = 1; k <= 16; ++k) {
-      Real big = Real(0), mag = Real(0);
-      __syncwarp(pair);  // the partner has read the previous term
-#pragma unroll
-      for (int j = 0; j < M; ++j) {
-        const Real inc = coef * nt[j];
-        acc[j] += inc;
-        big = max_(big, abs_(inc)); mag = max_(mag, abs_(acc[j]));
-        if (h == 0) s_term[j * S] = nt[j];
-        nt[j] = Real(0);
-      }
-      if (big <= eps * mag) break;
-      coef *= Real(c.dt) / Real(k + 1);
-      __syncwarp(pair);
-#pragma unroll 2
-      for (int i = h; i < M; i += 2) {
-        const Real ti = s_term[i * S];
-#pragma unroll
-        for (int j = 0; j < M; ++j) nt[j] += sT[(i * M + j) * S] * ti;
-      }
-#pragma unroll
-      for (int j = 0; j < M; ++j) nt[j] += __shfl_xor_sync(pair, nt[j], 1);
-    }
-#pragma unroll
-    for (int j = 0; j < M; ++j) r[j] = x1[j] - acc[j];
-  }
-  if (resid_out && h == 0) {
-#pragma unroll
-    for (int j = 0; j < M; ++j) resid_out[d * M + j] = r[j];
-  }
-  // ---- own rows: theta += L r' (then project_theta), P -= (w / s) v
-#pragma unroll 2
-  for (int i = h; i < MN; i += 2) {
-    const Real wi = s_w[i * S];
-    const Real Li = c.normalize_gain ? wi * inv_s : wi;
-    if (!PROJECT) {
-#pragma unroll
-      for (int j = 0; j < M; ++j) theta[(size_t)(i * M + j) * D + d] = sT[(i * M + j) * S] + Li * r[j];
-    } else {
-      const unsigned word = s_code[i];
-#pragma unroll
-      for (int j = 0; j < M; ++j) {
-        const unsigned code = (word >> (2 * j)) & 3u;
-        const Real val = sT[(i * M + j) * S] + Li * r[j];
-        theta[(size_t)(i * M + j) * D + d] = code == 1u ? val : (code == 0u ? Real(0) : Real(1));
+      for (int j = 0; j < MN; ++j) {
+        if (j >= i) {
+          const Real pij = sP[(row0 + j) * T] - Li * v[j];
+          Pm[(size_t)(i * MN + j) * D + d] = pij;
+          if (j > i) Pm[(size_t)(j * MN + i) * D + d] = pij;
+        }
       }
     }
-  }
-#pragma unroll 2
-  for (int i = h; i < MN; i += 2) {
-    const Real Li = s_w[i * S] * inv_s;
-#pragma unroll
-    for (int j = 0; j < MN; ++j) Pm[(size_t)(i * MN + j) * D + d] = sP[(i * MN + j) * S] - Li * v[j];
   }
 }
 
