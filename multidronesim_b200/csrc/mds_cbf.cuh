@@ -55,36 +55,52 @@ MDS_DEV CbfAgent<Real> cbf_agent(const DroneP<Real>& P, const CbfP<Real>& C, con
 //   H dv = (4 rho dvx + 8 ex s, 4 rho dvy + 8 ey s, Hzz dvz),  dv'H dv = 4 rho w + 8 s^2 + Hzz dvz^2,
 //   q(dv).dv = 24 (s w + ez dvz^3 / c^4)
 // so that a row is ~60 instructions, most of them FMAs (products-then-sums cost 95).
+// The row as a function of the RELATIVE state (e, dv, da) = agent i - agent j.  T = Real evaluates one row; T = F2
+// (mds_common.cuh) evaluates two rows of the same owner at once with Blackwell's packed fp32 instructions: the parameters
+// (Ds4, c4inv, gains, 1/m, g) are scalars and broadcast inside the instruction.
+template <int ORD, typename Real, typename T>
+MDS_DEV void cbf_row_rel(const DroneP<Real>& P, const CbfP<Real>& C, T ex, T ey, T ez, T dvx, T dvy, T dvz, T dax, T day, T daz,
+                         Real Ds4, Real c4inv, T a3[3], T* rhs, T* h0_out) {
+  const T rho = fma_(ey, ey, ex * ex), ez2 = ez * ez, ez2c = ez2 * T(c4inv), rho4 = T(Real(4)) * rho;
+  const T s = fma_(ey, dvy, ex * dvx);
+  const T dvx2 = dvx * dvx, dvy2 = dvy * dvy;
+  const T dz = T(Real(4)) * (ez * ez2c), dx = rho4 * ex, dy = rho4 * ey;  // d = dh/de
+  const T h0 = fma_(rho, rho, fma_(ez2, ez2c, T(-Ds4)));
+  const T h1 = fma_(rho4, s, dz * dvz);
+  const T Hzz = T(Real(12)) * ez2c;
+  *h0_out = h0;
+  if (cbf_order<ORD>(C) == 2) {
+    const T Lf = fma_(dx, dax, dy * day) + fma_(rho4, dvx2 + dvy2, fma_(T(Real(8)) * s, s, Hzz * dvz * dvz));
+    a3[0] = dz * T(P.inv_m); a3[1] = T(Real(0)); a3[2] = T(Real(0));
+    *rhs = fma_(T(C.k0), h0, fma_(T(C.k1), h1, Lf));
+    return;
+  }
+  const T ex8 = T(Real(8)) * ex;
+  const T Hxx = fma_(ex8, ex, rho4), Hyy = fma_(T(Real(8)) * ey, ey, rho4), Hxy = ex8 * ey;
+  // hdots[2] with the reference's hard-coded indices 6,7,8 of the 10-dim state (quirk B12)
+  const T h2 = fma_(dy, dax, fma_(dz, day, fma_(daz, fma_(Hxx, daz, T(Real(2)) * Hxy * dvx), fma_(Hyy, dvx2, Hzz * dvy2))));
+  const T daHdv = fma_(rho4, fma_(dax, dvx, day * dvy), fma_(T(Real(8)) * s, fma_(ex, dax, ey * day), Hzz * dvz * daz));
+  const T qdv = T(Real(24)) * fma_(s, dvx2 + dvy2, (T(c4inv) * ez) * (dvz * dvz * dvz));
+  const T Lf = fma_(T(Real(3)), daHdv, qdv);
+  a3[0] = dz * T(P.inv_m); a3[1] = T(-P.g) * dy; a3[2] = T(P.g) * dx;
+  *rhs = fma_(T(C.k0), h0, fma_(T(C.k1), h1, fma_(T(C.k2), h2, Lf)));
+}
 template <int ORD, typename Real>
 MDS_DEV void cbf_row(const DroneP<Real>& P, const CbfP<Real>& C, const CbfAgent<Real>& ai, const CbfAgent<Real>& aj,
                      Real Ds4, Real c4inv, Real a3[3], Real* rhs, Real* h0_out) {
-  const Real ex = ai.p.x - aj.p.x, ey = ai.p.y - aj.p.y, ez = ai.p.z - aj.p.z;
-  const Real dvx = ai.dv.x - aj.dv.x, dvy = ai.dv.y - aj.dv.y, dvz = ai.dv.z - aj.dv.z;
-  const Real dax = ai.da.x - aj.da.x, day = ai.da.y - aj.da.y;
-  const Real rho = fma_(ey, ey, ex * ex), ez2 = ez * ez, ez2c = ez2 * c4inv, rho4 = Real(4) * rho;
-  const Real s = fma_(ey, dvy, ex * dvx);
-  const Real dvx2 = dvx * dvx, dvy2 = dvy * dvy;
-  const Real dz = Real(4) * (ez * ez2c), dx = rho4 * ex, dy = rho4 * ey;  // d = dh/de
-  const Real h0 = fma_(rho, rho, fma_(ez2, ez2c, -Ds4));
-  const Real h1 = fma_(rho4, s, dz * dvz);
-  const Real Hzz = Real(12) * ez2c;
-  *h0_out = h0;
-  if (cbf_order<ORD>(C) == 2) {
-    const Real Lf = fma_(dx, dax, dy * day) + fma_(rho4, dvx2 + dvy2, fma_(Real(8) * s, s, Hzz * dvz * dvz));
-    a3[0] = dz * P.inv_m; a3[1] = Real(0); a3[2] = Real(0);
-    *rhs = fma_(C.k0, h0, fma_(C.k1, h1, Lf));
-    return;
-  }
-  const Real daz = ai.da.z - aj.da.z;
-  const Real ex8 = Real(8) * ex;
-  const Real Hxx = fma_(ex8, ex, rho4), Hyy = fma_(Real(8) * ey, ey, rho4), Hxy = ex8 * ey;
-  // hdots[2] with the reference's hard-coded indices 6,7,8 of the 10-dim state (quirk B12)
-  const Real h2 = fma_(dy, dax, fma_(dz, day, fma_(daz, fma_(Hxx, daz, Real(2) * Hxy * dvx), fma_(Hyy, dvx2, Hzz * dvy2))));
-  const Real daHdv = fma_(rho4, fma_(dax, dvx, day * dvy), fma_(Real(8) * s, fma_(ex, dax, ey * day), Hzz * dvz * daz));
-  const Real qdv = Real(24) * fma_(s, dvx2 + dvy2, (c4inv * ez) * (dvz * dvz * dvz));
-  const Real Lf = fma_(Real(3), daHdv, qdv);
-  a3[0] = dz * P.inv_m; a3[1] = -P.g * dy; a3[2] = P.g * dx;
-  *rhs = fma_(C.k0, h0, fma_(C.k1, h1, fma_(C.k2, h2, Lf)));
+  cbf_row_rel<ORD, Real, Real>(P, C, ai.p.x - aj.p.x, ai.p.y - aj.p.y, ai.p.z - aj.p.z, ai.dv.x - aj.dv.x, ai.dv.y - aj.dv.y,
+                               ai.dv.z - aj.dv.z, ai.da.x - aj.da.x, ai.da.y - aj.da.y, ai.da.z - aj.da.z, Ds4, c4inv, a3, rhs, h0_out);
+}
+// Two rows of one owner at once: (ai - aj0) in the low halves, (ai - aj1) in the high halves.  The nine differences are scalar
+// subtractions written straight into the halves (no packing moves); everything after them is packed.
+template <int ORD>
+MDS_DEV void cbf_row2(const DroneP<float>& P, const CbfP<float>& C, const CbfAgent<float>& ai, const CbfAgent<float>& aj0,
+                      const CbfAgent<float>& aj1, float Ds4, float c4inv, F2 a3[3], F2* rhs, F2* h0_out) {
+  cbf_row_rel<ORD, float, F2>(P, C, F2(ai.p.x - aj0.p.x, ai.p.x - aj1.p.x), F2(ai.p.y - aj0.p.y, ai.p.y - aj1.p.y),
+                              F2(ai.p.z - aj0.p.z, ai.p.z - aj1.p.z), F2(ai.dv.x - aj0.dv.x, ai.dv.x - aj1.dv.x),
+                              F2(ai.dv.y - aj0.dv.y, ai.dv.y - aj1.dv.y), F2(ai.dv.z - aj0.dv.z, ai.dv.z - aj1.dv.z),
+                              F2(ai.da.x - aj0.da.x, ai.da.x - aj1.da.x), F2(ai.da.y - aj0.da.y, ai.da.y - aj1.da.y),
+                              F2(ai.da.z - aj0.da.z, ai.da.z - aj1.da.z), Ds4, c4inv, a3, rhs, h0_out);
 }
 
 // ----------------------------------------------------------------------------------------

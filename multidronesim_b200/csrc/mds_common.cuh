@@ -121,6 +121,30 @@ MDS_DEV double min_(double a, double b) { return fmin(a, b); }
 MDS_DEV float max_(float a, float b) { return fmaxf(a, b); }
 MDS_DEV double max_(double a, double b) { return fmax(a, b); }
 template <typename Real> MDS_DEV Real clamp_(Real x, Real lo, Real hi) { return min_(max_(x, lo), hi); }
+
+// Two independent fp32 values in one 64-bit register pair.  Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2,
+// PTX fma.rn.f32x2) do both lanes in ONE issue slot; the FMA pipe is busy for two cycles, so the flop rate is that of two
+// scalar instructions (tools/ffma2_probe.cu: 74.1 vs 72.8 TFLOP/s) but the second issue slot goes to other work -- which
+// is what an issue-bound kernel like the fused rollout is short of.  A scalar operand broadcasts for free (SASS `R7.F32`,
+// `UR6.F32`, immediates), there is no negate modifier (a - b is written fma(b, -1, a): exact), and the halves stay
+// addressable as ordinary registers.  The same expression templates run scalar (T = Real) or on two rows / rotors / angles
+// at once (T = F2); each lane of a packed result is the IEEE result of the scalar instruction.
+struct F2 {
+  float2 v;
+  F2() = default;
+  MDS_DEV F2(float s) : v(make_float2(s, s)) {}
+  MDS_DEV F2(float a, float b) : v(make_float2(a, b)) {}
+};
+MDS_DEV F2 operator+(F2 a, F2 b) { F2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
+MDS_DEV F2 operator*(F2 a, F2 b) { F2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
+MDS_DEV F2 fma_(F2 a, F2 b, F2 c) { F2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
+MDS_DEV F2 operator-(F2 a, F2 b) { return fma_(b, F2(-1.f), a); }
+// number of fp32 lanes of an arithmetic type, and lane access
+template <typename T> struct Lanes { static constexpr int n = 1; };
+template <> struct Lanes<F2> { static constexpr int n = 2; };
+MDS_DEV float lane(float x, int) { return x; }
+MDS_DEV double lane(double x, int) { return x; }
+MDS_DEV float lane(F2 x, int i) { return i ? x.v.y : x.v.x; }
 template <typename Real> MDS_DEV Real norm(V3<Real> a) { return sqrt_(dot(a, a)); }
 template <typename Real> MDS_DEV Real sign_(Real x) { return (x > Real(0)) ? Real(1) : ((x < Real(0)) ? Real(-1) : Real(0)); }
 

@@ -155,7 +155,9 @@ template <typename Real> MDS_DEV CbfSmem<Real> cbf_smem_carve(unsigned char* raw
 // other row), and the step is over without any group-wide argmin, workspace or second scan: in the swarm workloads that
 // is nearly every step.  Otherwise the group runs the cooperative active-set solver from u_nom (qp_solve_group), and if
 // that one runs out of workspace / iterations or its factor breaks down, the scratch solver (qp_solve_group_big).
-template <int ORD, typename Real>
+// NT > 0 (compile-time drone count) in fp32: the pair rows are evaluated two at a time with packed fp32 instructions
+// (cbf_row2) and stay in registers -- they are written to shared memory only if the cooperative solver is needed.
+template <int ORD, typename Real, int NT = 0>
 MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const CbfSmem<Real>& S, const Real* obstacles, int n_obs,
                              const GroupMap& g, int N, int NP, const CbfAgent<Real>& ag, Real F, const Real unom[4], Real usafe[4],
                              Real* min_h, int* iters_out) {
@@ -243,7 +245,45 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
     x[n] = xv;
   }
   __syncwarp(g.gmask);
-  if (g.valid) {
+  constexpr bool PACK = (NT > 1) && sizeof(Real) == 4;
+  constexpr int S0C = PACK ? (NT - 1) / 2 + ((NT & 1) ? 0 : 1) : 1, NPAIR = (S0C + 1) / 2;
+  F2 pa[NPAIR][3], prhs[NPAIR];  // packed path: the pair rows, slot 2q in the low halves and 2q + 1 in the high halves
+  if constexpr (PACK) {
+    if (g.valid) {
+#pragma unroll
+      for (int q = 0; q < NPAIR; ++q) {
+        const int s0 = 2 * q, s1 = 2 * q + 1;
+        // a slot below K1 always has a partner (compile-time); the "diameter" slot only for the lower half of the drones
+        const bool ok0 = s0 < M.K1 || n < M.half, ok1 = s1 < S0C && (s1 < M.K1 || n < M.half);
+        const int m0 = ok0 ? row_partner(M, N, n, s0) : n, m1 = ok1 ? row_partner(M, N, n, s1) : n;
+        CbfAgent<float> o0, o1;
+        const R4 b0 = agents[3 * m0], b1 = agents[3 * m0 + 1], b2 = agents[3 * m0 + 2], xm0 = x[m0];
+        const R4 c0 = agents[3 * m1], c1 = agents[3 * m1 + 1], c2 = agents[3 * m1 + 2], xm1 = x[m1];
+        o0.p = {b0.x, b0.y, b0.z}; o0.dv = {b0.w, b1.x, b1.y}; o0.da = {b1.z, b1.w, b2.x};
+        o1.p = {c0.x, c0.y, c0.z}; o1.dv = {c0.w, c1.x, c1.y}; o1.da = {c1.z, c1.w, c2.x};
+        F2 rhs, h0;
+        cbf_row2<ORD>(P, C, ag, o0, o1, C.ds4_pair, C.c4inv, pa[q], &rhs, &h0);  // owner - partner (mds_cbf.cuh "Row ownership")
+        if (ok0) *min_h = min_(*min_h, h0.v.x);
+        else { pa[q][0].v.x = 0.f; pa[q][1].v.x = 0.f; pa[q][2].v.x = 0.f; rhs.v.x = 1e30f; }  // unused slot: a never-violated row
+        if (ok1) *min_h = min_(*min_h, h0.v.y);
+        else { pa[q][0].v.y = 0.f; pa[q][1].v.y = 0.f; pa[q][2].v.y = 0.f; rhs.v.y = 1e30f; }
+        prhs[q] = rhs;
+        // G u = -a . u_n + a . u_m <= rhs  <=>  slack = rhs + a . (u_n - u_m) >= 0
+        const F2 sl = fma_(pa[q][2], F2(xn[2] - xm0.z, xn[2] - xm1.z),
+                           fma_(pa[q][1], F2(xn[1] - xm0.y, xn[1] - xm1.y), fma_(pa[q][0], F2(xn[0] - xm0.x, xn[0] - xm1.x), rhs)));
+        if (sl.v.x < 0.f) {
+          const float a0 = pa[q][0].v.x, a1 = pa[q][1].v.x, a2 = pa[q][2].v.x;
+          const float mag = abs_(a0 * xn[0]) + abs_(a1 * xn[1]) + abs_(a2 * xn[2]) + abs_(a0 * xm0.x) + abs_(a1 * xm0.y) + abs_(a2 * xm0.z);
+          if (sl.v.x < -qp_tol<float>() * (abs_(rhs.v.x) + mag + 1e-12f)) escalate = 1;
+        }
+        if (sl.v.y < 0.f) {
+          const float a0 = pa[q][0].v.y, a1 = pa[q][1].v.y, a2 = pa[q][2].v.y;
+          const float mag = abs_(a0 * xn[0]) + abs_(a1 * xn[1]) + abs_(a2 * xn[2]) + abs_(a0 * xm1.x) + abs_(a1 * xm1.y) + abs_(a2 * xm1.z);
+          if (sl.v.y < -qp_tol<float>() * (abs_(rhs.v.y) + mag + 1e-12f)) escalate = 1;
+        }
+      }
+    }
+  } else if (g.valid) {
     // ---- own pair rows (compile-time count when N is), each tested at the projected point as it is built
 #pragma unroll
     for (int s = 0; s < M.S0; ++s) {
@@ -276,6 +316,18 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
     status = MDS_QP_INFEASIBLE;
   } else if (any & 1u) {
     // ---- cooperative solve from u_nom (agents are no longer needed: their storage becomes the QP workspace)
+    if constexpr (PACK) {  // the solver reads the rows from shared memory
+      if (g.valid) {
+#pragma unroll
+        for (int q = 0; q < NPAIR; ++q) {
+          R4 r0, r1;
+          r0.x = pa[q][0].v.x; r0.y = pa[q][1].v.x; r0.z = pa[q][2].v.x; r0.w = prhs[q].v.x;
+          r1.x = pa[q][0].v.y; r1.y = pa[q][1].v.y; r1.z = pa[q][2].v.y; r1.w = prhs[q].v.y;
+          rows[n * M.RPL + 2 * q] = r0;
+          if (2 * q + 1 < S0C) rows[n * M.RPL + 2 * q + 1] = r1;
+        }
+      }
+    }
     __syncwarp(g.gmask);  // every lane has read its partners' agents and projected inputs
     if (g.valid) {
       R4 xv;
@@ -436,7 +488,7 @@ struct StepStats {
 // instruction cache: 55 % of the stall samples were "no instruction").
 // PDK: a gain per drone (Rc.lqr_planes) instead of LqrP's; SPEC: compile-time parameter switches (PhysSpec); R_out (optional)
 // receives the rotation matrix of the observation's attitude when the inner loop built it (HAS_PID controllers).
-template <typename Real, int CTRL, bool USE_CBF, bool PDK = false, int SPEC = 0>
+template <typename Real, int CTRL, bool USE_CBF, bool PDK = false, int SPEC = 0, int NT = 0>
 MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const GeoP<Real>& G, const LqrP<Real>& L, const CbfP<Real>& C,
                        const DslP<Real>& Dg, const DslStateP<Real>& dst, const CbfSmem<Real>& S, const PidP<Real>& pid,
                        const typename TrajSpecT<Real>::spec& spec,
@@ -479,7 +531,7 @@ MDS_DEV void ctrl_body(const DroneP<Real>& P, const RolloutP<Real>& Rc, const Ge
       }
       Real mh = Real(1e30);
       int it = 0;
-      int stt = cbf_filter_group<ORD>(P, C, S, Rc.obstacles, Rc.n_obs, g, N, NP, ag, F, unom, usafe, &mh, &it);
+      int stt = cbf_filter_group<ORD, Real, NT>(P, C, S, Rc.obstacles, Rc.n_obs, g, N, NP, ag, F, unom, usafe, &mh, &it);
       if (g.valid) {
         ss.min_h = (float)mh;
         if (g.n == 0) {
@@ -569,7 +621,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_CTRL_MINB :
       spec = specs[g.d];
       if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
     }
-    ctrl_body<Real, CTRL, USE_CBF, (NT < 0)>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss, g.d);
+    ctrl_body<Real, CTRL, USE_CBF, (NT < 0), 0, NT>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss, g.d);
     if (g.valid) store4(action, g.d, rpm);
   }
   if (stats) stats_block_reduce<USE_CBF>(stats, g.valid ? 1 : 0, ss, ss.err);
@@ -671,7 +723,7 @@ __global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_loop_ke
     for (int k = 0; k < K; ++k) {
       StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
       M3<Real> R;
-      ctrl_body<Real, CTRL, USE_CBF, (NT < 0), SPEC>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss,
+      ctrl_body<Real, CTRL, USE_CBF, (NT < 0), SPEC, NT>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss,
                                                      STAGE ? (int)threadIdx.x : g.d, HAS_PID ? &R : nullptr);  // the host plans form t exactly like this
       acc.err += ss.err; max_err = fmaxf(max_err, ss.err); acc.min_h = fminf(acc.min_h, ss.min_h);
       acc.qp_solves += ss.qp_solves; acc.qp_iters += ss.qp_iters; acc.qp_infeas += ss.qp_infeas + (ss.qp_cap << 16);
@@ -837,7 +889,7 @@ __global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_queue_k
     for (int k = k0; k < k1; ++k) {
       StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
       M3<Real> R;
-      ctrl_body<Real, CTRL, USE_CBF, (NT < 0), SPEC>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss,
+      ctrl_body<Real, CTRL, USE_CBF, (NT < 0), SPEC, NT>(P, Rc, G, L, C, Dg, dst, S, pid_s, spec, segs, o, g, N, NP, t0 + (double)k * dt_ctrl, rpm, ss,
                                                      STAGE ? (int)threadIdx.x : 0, HAS_PID ? &R : nullptr);
       if (dup) { ss.err = 0.f; ss.min_h = 1e30f; ss.qp_solves = ss.qp_iters = ss.qp_infeas = ss.qp_cap = 0; }
       tk.err += ss.err; max_err = fmaxf(max_err, ss.err); tk.min_h = fminf(tk.min_h, ss.min_h);
