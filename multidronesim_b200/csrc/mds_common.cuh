@@ -189,11 +189,15 @@ template <typename Real> struct GeoP { Real kp, kv, kr, kw, g_ctrl, max_tilt, ta
 template <typename Real> inline GeoP<Real> to_dev(const MdsGeoGains& g) {
   return GeoP<Real>{Real(g.kp), Real(g.kv), Real(g.kr), Real(g.kw), Real(g.g_ctrl), Real(g.max_tilt), Real(tan(g.max_tilt))};
 }
-template <typename Real> struct LqrP { Real K[48]; int dim; };
+// K: the reference's row-major 4 x dim gain; Kt: its transpose (Kt[4 k + i] = K[i dim + k]), so that the two gain entries a
+// packed fp32 FMA multiplies one error component with are one 64-bit kernel-parameter operand (lqr_input, fp32).
+template <typename Real> struct LqrP { Real K[48]; alignas(16) Real Kt[48]; int dim; };
 template <typename Real> inline LqrP<Real> to_dev(const MdsLqrGains& g) {
   LqrP<Real> d;
-  for (int i = 0; i < 48; ++i) d.K[i] = Real(g.K[i]);
+  for (int i = 0; i < 48; ++i) { d.K[i] = Real(g.K[i]); d.Kt[i] = Real(0); }
   d.dim = g.dim;
+  for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < g.dim && k < 12; ++k) d.Kt[4 * k + i] = Real(g.K[i * g.dim + k]);
   return d;
 }
 // Scratch of the large-active-set QP solver (mds_cbf.cuh qp_solve_group_big): `slots` slots of `slot_doubles` doubles in

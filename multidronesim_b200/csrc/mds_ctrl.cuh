@@ -173,6 +173,23 @@ MDS_DEV void lqr_input(const DroneP<Real>& P, const LqrP<Real>& L, int variant, 
   }
   if (variant != MDS_CTRL_LQR_YANK) u[0] += P.m * P.g;
 }
+// fp32: two inputs per instruction (packed FMA on the transposed gain; the error component broadcasts)
+#ifndef MDS_NO_LQR_PACK
+MDS_DEV void lqr_input(const DroneP<float>& P, const LqrP<float>& L, int variant, const Obs<float>& o, const Ref<float>& r, float u[4]) {
+  float e[12];
+  const int dim = lqr_error_state(P, variant, o, r, e);
+  const float2* Kt = reinterpret_cast<const float2*>(L.Kt);
+  F2 a01(0.f), a23(0.f);
+  for (int k = 0; k < dim; ++k) {
+    F2 k01, k23;
+    k01.v = Kt[2 * k]; k23.v = Kt[2 * k + 1];
+    a01 = fma_(k01, F2(e[k]), a01);
+    a23 = fma_(k23, F2(e[k]), a23);
+  }
+  u[0] = -a01.v.x; u[1] = -a01.v.y; u[2] = -a23.v.x; u[3] = -a23.v.y;
+  if (variant != MDS_CTRL_LQR_YANK) u[0] += P.m * P.g;
+}
+#endif
 // The same law with a gain of the drone's own (decentralised LQR: every drone carries the K of its learned model;
 // decentralized_lqr_omega.py:212-231, decentralized_lqr.py:326-342).  K planes: element (i, k) of drone d at [(i*dim+k)*D + d].
 template <typename Real>

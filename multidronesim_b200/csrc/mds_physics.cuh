@@ -15,6 +15,16 @@ template <typename Real> MDS_DEV Real downwash_pair(const DroneP<Real>& P, Real 
   Real beta = P.dw2 * dz + P.dw3;
   return alpha * exp_(Real(-0.5) * dxy2 / (beta * beta));
 }
+// two pairs at once (fp32, packed arithmetic; the reciprocals and the exponentials are per half: MUFU has no packed form)
+MDS_DEV F2 downwash_pair2(const DroneP<float>& P, F2 dz, F2 dxy2) {
+  const float pr4 = 0.25f * P.prop_radius;
+  const F2 q(pr4 / max_(dz.v.x, P.dw_dz_clip), pr4 / max_(dz.v.y, P.dw_dz_clip));
+  const F2 alpha = F2(P.dw1) * q * q;
+  const F2 beta = fma_(F2(P.dw2), dz, F2(P.dw3));
+  const F2 b2 = beta * beta;
+  const F2 arg = dxy2 * F2(-0.72134752044448170f) * F2(1.f / b2.v.x, 1.f / b2.v.y);  // -0.5 log2(e)
+  return alpha * F2(exp2f(arg.v.x), exp2f(arg.v.y));
+}
 // the same as seen from drone i: contribution of a drone at pj
 template <typename Real> MDS_DEV Real downwash_term(const DroneP<Real>& P, V3<Real> pi, V3<Real> pj) {
   Real dz = pj.z - pi.z;

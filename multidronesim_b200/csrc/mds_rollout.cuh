@@ -54,6 +54,20 @@ MDS_DEV GroupMap group_map(int N, int NP, int E) {
   return g;
 }
 
+// OR over the lane group.  __reduce_or_sync with a partial run-time mask makes the lane groups of a warp take turns
+// (WARPSYNC.EXCLUSIVE: 6 instructions per group, 24 per warp); log2(NP) butterfly shuffles serve all groups at once.
+MDS_DEV unsigned group_or(unsigned gmask, int NP, unsigned v) {
+#ifndef MDS_NO_OR_SHFL
+  if (NP < 32) {
+#pragma unroll
+    for (int w = 1; w < 32; w <<= 1)
+      if (w < NP) v |= __shfl_xor_sync(gmask, v, w);
+    return v;
+  }
+#endif
+  return __reduce_or_sync(gmask, v);
+}
+
 // Compile-time drone count that fills its lane group (N == NP, e.g. the swarm's 8): every lane of a valid environment
 // maps to a drone, so `valid` is a compile-time `true` inside the env_valid region and the per-stage `if (g.valid)`
 // guards fold away (uniform branches: fewer instructions, no measurable change in time).
@@ -103,6 +117,51 @@ MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* s
   __syncwarp(g.gmask);
   return dw;
 }
+
+// fp32: two slots per pass with packed fp32 arithmetic (mds_common.cuh F2) -- slot s in the low halves, slot s + 1 in the
+// high halves; a slot this lane does not own is evaluated against the lane's own position (dz = 0: no force).  Per pair of
+// slots ~30 instructions instead of 2 x 25, and the half-populated "diameter" slot rides along for free.
+#ifndef MDS_NO_DW_PACK
+MDS_DEV float downwash_group(const DroneP<float>& P, float4* sm_pos, V3<float> p, const GroupMap& g, int N, int NP) {
+  sm_pos[threadIdx.x] = make_float4(p.x, p.y, p.z, 0.f);
+  __syncwarp(g.gmask);
+  float dw = 0.f;
+  const int n = g.n, base = threadIdx.x - n, lane0 = (threadIdx.x & 31) - n;
+  const int K1 = (N - 1) >> 1, half = (N & 1) ? 0 : (N >> 1), S0 = K1 + (half ? 1 : 0);
+#pragma unroll
+  for (int s = 0; s < S0; s += 2) {
+    int m[2] = {n, n}, src[2] = {n, n};
+    bool recv[2] = {false, false};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int sl = s + h;
+      if (g.valid && sl < S0) {
+        if (sl < K1) {
+          m[h] = n + sl + 1; m[h] = m[h] >= N ? m[h] - N : m[h];
+          src[h] = n - sl - 1; src[h] = src[h] < 0 ? src[h] + N : src[h];
+          recv[h] = true;
+        } else if (n < half) m[h] = n + half;
+        else { src[h] = n - half; recv[h] = true; }
+      }
+    }
+    const float4 q0 = sm_pos[base + m[0]], q1 = sm_pos[base + m[1]];
+    const F2 dz(q0.z - p.z, q1.z - p.z), dx(q0.x - p.x, q1.x - p.x), dy(q0.y - p.y, q1.y - p.y);  // dz > 0: the partner is above
+    const F2 dxy2 = fma_(dy, dy, dx * dx);
+    const F2 v = downwash_pair2(P, F2(abs_(dz.v.x), abs_(dz.v.y)), dxy2);
+    const float v0 = (dz.v.x != 0.f && dxy2.v.x < 100.f) ? v.v.x : 0.f, v1 = (dz.v.y != 0.f && dxy2.v.y < 100.f) ? v.v.y : 0.f;
+    dw += dz.v.x > 0.f ? v0 : 0.f;
+    dw += dz.v.y > 0.f ? v1 : 0.f;
+    const float got0 = __shfl_sync(g.gmask, dz.v.x > 0.f ? 0.f : v0, lane0 + src[0]);
+    if (recv[0]) dw += got0;
+    if (s + 1 < S0) {
+      const float got1 = __shfl_sync(g.gmask, dz.v.y > 0.f ? 0.f : v1, lane0 + src[1]);
+      if (recv[1]) dw += got1;
+    }
+  }
+  __syncwarp(g.gmask);
+  return dw;
+}
+#endif
 
 // per-env shared-memory block of the CBF stage (in Reals; every part is a multiple of 4 so that the Vec4
 // accesses stay aligned):
@@ -173,9 +232,12 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
   Real lo = Real(0), hi = Real(0);
   Real xn[3] = {unom[0], unom[1], unom[2]};
   if (g.valid) {
-    // ---- own single-drone rows: obstacle rows (built here), box bounds; most violated one at u_nom
+    // ---- own single-drone rows: obstacle rows (built here), box bounds; most violated one at u_nom.  Written without
+    // branches: in the swarm workloads a quarter of the drones project at any step, so a branch would run its body for a
+    // few lanes of nearly every warp (ncu: 8 of 32 threads) -- selects cost less than the partial-warp passes.
     Real wv = Real(0);  // normalised slack of the most violated row so far (negative)
-    int wcon = -1;      // its obstacle index, or MDS_QP_BOX0 + component for a box bound
+    int wobs = -1;      // the most violated obstacle row, kept in registers: (a, rhs), |a|^2
+    Real w0 = Real(0), w1 = Real(0), w2 = Real(0), w3 = Real(0), wa2 = Real(1);
     const CbfAgent<Real> zero = {{Real(0), Real(0), Real(0)}, {Real(0), Real(0), Real(0)}, {Real(0), Real(0), Real(0)}};
     for (int o = 0; o < n_obs; ++o) {
       CbfAgent<Real> other = zero;
@@ -190,39 +252,37 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
       rows[n * M.RPL + M.S0 + o] = row;
       // G u = -a . u_n <= rhs
       const Real sl = rhs + (a3[0] * xn[0] + a3[1] * xn[1] + a3[2] * xn[2]);
-      if (sl < Real(0)) {
-        const Real mag = abs_(a3[0] * xn[0]) + abs_(a3[1] * xn[1]) + abs_(a3[2] * xn[2]);
-        if (sl < -qp_tol<Real>() * (abs_(rhs) + mag + Real(1e-12))) {
-          const Real a2 = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2];
-          if (!(a2 > Real(0))) escalate = 1;  // zero row with negative rhs: the cooperative path reports it as infeasible
-          const Real v = sl * rsqrt_(max_(a2, Real(1e-30)));
-          if (v < wv) { wv = v; wcon = o; }
-        }
-      }
+      const Real mag = abs_(a3[0] * xn[0]) + abs_(a3[1] * xn[1]) + abs_(a3[2] * xn[2]);
+      const bool viol = sl < -qp_tol<Real>() * (abs_(rhs) + mag + Real(1e-12));
+      const Real a2 = a3[0] * a3[0] + a3[1] * a3[1] + a3[2] * a3[2];
+      if (viol && !(a2 > Real(0))) escalate = 1;  // zero row with negative rhs: the cooperative path reports it as infeasible
+      const Real v = sl * rsqrt_(max_(a2, Real(1e-30)));
+      const bool worse = viol && v < wv;
+      wv = worse ? v : wv; wobs = worse ? o : wobs;
+      w0 = worse ? a3[0] : w0; w1 = worse ? a3[1] : w1; w2 = worse ? a3[2] : w2; w3 = worse ? rhs : w3; wa2 = worse ? a2 : wa2;
     }
-    // box bounds: |u| > umax_hi  <=>  umax - |u| < -tol (umax + |u|).  One flag per component, tested with literal indices:
-    // a component INDEX would let nvcc turn the selects into dynamically indexed accesses, i.e. move u_n and the whole
-    // parameter block C into local memory.
-    bool wb0 = false, wb1 = false, wb2 = false;
-#define MDS_BOX_WORST(K, FLAG)                                                                   \
-    {                                                                                             \
-      const Real ax = abs_(xn[K]);                                                                \
-      if (ax > C.umax_hi[K] && C.umax[K] - ax < wv) { wv = C.umax[K] - ax; wcon = MDS_QP_BOX0; wb0 = wb1 = wb2 = false; FLAG = true; } \
-    }
-    MDS_BOX_WORST(0, wb0) MDS_BOX_WORST(1, wb1) MDS_BOX_WORST(2, wb2)
-#undef MDS_BOX_WORST
-    if (wcon >= 0) {  // one projection: u_n <- u_n - t g,  t = -slack / |g|^2
-      touched = 1;
-      if (wcon == MDS_QP_BOX0) {
-        if (wb0) xn[0] = xn[0] < Real(0) ? -C.umax[0] : C.umax[0];
-        if (wb1) xn[1] = xn[1] < Real(0) ? -C.umax[1] : C.umax[1];
-        if (wb2) xn[2] = xn[2] < Real(0) ? -C.umax[2] : C.umax[2];
-      } else {
-        const R4 row = rows[n * M.RPL + M.S0 + wcon];  // g = -a
-        const Real t = -(row.w + (row.x * xn[0] + row.y * xn[1] + row.z * xn[2])) / (row.x * row.x + row.y * row.y + row.z * row.z);
-        xn[0] += t * row.x; xn[1] += t * row.y; xn[2] += t * row.z;
-      }
-      // the other single-drone rows at the projected point (the projected row itself holds with equality: skipped)
+    // box bounds: |u| > umax_hi  <=>  umax - |u| < -tol (umax + |u|); a later component wins only if strictly worse.
+    // (Literal indices: a component INDEX would let nvcc turn the selects into dynamically indexed accesses, i.e. move u_n
+    // and the whole parameter block C into local memory.)
+    const Real ax0 = abs_(xn[0]), ax1 = abs_(xn[1]), ax2 = abs_(xn[2]);
+    const Real v0 = C.umax[0] - ax0, v1 = C.umax[1] - ax1, v2 = C.umax[2] - ax2;
+    const bool b0 = ax0 > C.umax_hi[0] && v0 < wv;
+    wv = b0 ? v0 : wv;
+    const bool b1 = ax1 > C.umax_hi[1] && v1 < wv;
+    wv = b1 ? v1 : wv;
+    const bool b2 = ax2 > C.umax_hi[2] && v2 < wv;
+    const bool wb2 = b2, wb1 = b1 && !b2, wb0 = b0 && !b1 && !b2, isbox = b0 || b1 || b2;
+    // one projection: u_n <- u_n - t g (g = -a),  t = -slack / |g|^2 (t = 0 unless an obstacle row is the worst); or the box face
+    const Real t = (wobs >= 0 && !isbox) ? -(w3 + (w0 * xn[0] + w1 * xn[1] + w2 * xn[2])) / wa2 : Real(0);
+    xn[0] += t * w0; xn[1] += t * w1; xn[2] += t * w2;
+    xn[0] = wb0 ? (xn[0] < Real(0) ? -C.umax[0] : C.umax[0]) : xn[0];
+    xn[1] = wb1 ? (xn[1] < Real(0) ? -C.umax[1] : C.umax[1]) : xn[1];
+    xn[2] = wb2 ? (xn[2] < Real(0) ? -C.umax[2] : C.umax[2]) : xn[2];
+    touched = (wobs >= 0 || isbox) ? 1 : 0;
+    // the other single-drone rows at the projected point (the projected row itself holds with equality: skipped); only
+    // when there is another obstacle row than the projected one -- a rare branch
+    if (touched && n_obs > (isbox ? 0 : 1)) {
+      const int wcon = isbox ? -1 : wobs;
       for (int o = 0; o < n_obs; ++o) {
         if (o == wcon) continue;
         const R4 row = rows[n * M.RPL + M.S0 + o];
@@ -232,8 +292,9 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
           if (sl < -qp_tol<Real>() * (abs_(row.w) + mag + Real(1e-12))) escalate = 1;
         }
       }
-      if ((!wb0 && abs_(xn[0]) > C.umax_hi[0]) || (!wb1 && abs_(xn[1]) > C.umax_hi[1]) || (!wb2 && abs_(xn[2]) > C.umax_hi[2])) escalate = 1;
     }
+    // the box at the projected point (an untouched u_n is inside it)
+    if ((!wb0 && abs_(xn[0]) > C.umax_hi[0]) || (!wb1 && abs_(xn[1]) > C.umax_hi[1]) || (!wb2 && abs_(xn[2]) > C.umax_hi[2])) escalate = 1;
     if (!cbf_wz_bounds<ORD>(C, F, &lo, &hi)) fl = 1;
     // ---- publish the agent and the projected inputs
     R4 a0, a1, a2, xv;
@@ -310,7 +371,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
     }
   }
   // one group-wide OR of (escalate, infeasible 4th-input interval, projected) -- the step's only collective in the common case
-  const unsigned any = __reduce_or_sync(g.gmask, (unsigned)(escalate | (fl << 1) | (touched << 2)));
+  const unsigned any = group_or(g.gmask, NP, (unsigned)(escalate | (fl << 1) | (touched << 2)));
   int status = MDS_QP_OPTIMAL, iters = (any & 4u) ? 1 : 0;
   if (any & 2u) {
     status = MDS_QP_INFEASIBLE;
