@@ -59,6 +59,42 @@ MDS_DEV bool quat_step_coeffs(double wn2, double h, double* cs, double* k) {
   return true;
 }
 
+// Per-rotor thrust kf rpm^2 and drag torque km rpm^2, and the ground effect on the thrusts (per-prop height above the plane,
+// clipped): generic form, and fp32 with two rotors per packed instruction (mds_common.cuh F2).
+template <typename Real> MDS_DEV void rotor_forces(const DroneP<Real>& P, const Real rpm[4], Real f[4], Real zt[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[i] = P.kf * rpm[i] * rpm[i]; zt[i] = P.km * rpm[i] * rpm[i]; }
+}
+template <typename Real> MDS_DEV void ground_effect(const DroneP<Real>& P, Real pz, Real r6, Real r7, Real f[4]) {
+  const Real pr4 = Real(0.25) * P.prop_radius;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    Real h = pz + r6 * P.prop_x[i] + r7 * P.prop_y[i];
+    h = max_(h, P.gnd_eff_h_clip);
+    Real q = pr4 / h;
+    f[i] = fma_(f[i] * P.gnd_eff_coeff, q * q, f[i]);
+  }
+}
+#ifndef MDS_NO_ROTOR_PACK
+MDS_DEV void rotor_forces(const DroneP<float>& P, const float rpm[4], float f[4], float zt[4]) {
+  const F2 r01(rpm[0], rpm[1]), r23(rpm[2], rpm[3]);
+  const F2 s01 = r01 * r01, s23 = r23 * r23;
+  const F2 f01 = F2(P.kf) * s01, f23 = F2(P.kf) * s23, z01 = F2(P.km) * s01, z23 = F2(P.km) * s23;
+  f[0] = f01.v.x; f[1] = f01.v.y; f[2] = f23.v.x; f[3] = f23.v.y;
+  zt[0] = z01.v.x; zt[1] = z01.v.y; zt[2] = z23.v.x; zt[3] = z23.v.y;
+}
+MDS_DEV void ground_effect(const DroneP<float>& P, float pz, float r6, float r7, float f[4]) {
+  const float pr4 = 0.25f * P.prop_radius;
+  const F2 h01 = fma_(F2(r7), F2(P.prop_y[0], P.prop_y[1]), fma_(F2(r6), F2(P.prop_x[0], P.prop_x[1]), F2(pz)));
+  const F2 h23 = fma_(F2(r7), F2(P.prop_y[2], P.prop_y[3]), fma_(F2(r6), F2(P.prop_x[2], P.prop_x[3]), F2(pz)));
+  const F2 q01(pr4 / max_(h01.v.x, P.gnd_eff_h_clip), pr4 / max_(h01.v.y, P.gnd_eff_h_clip));
+  const F2 q23(pr4 / max_(h23.v.x, P.gnd_eff_h_clip), pr4 / max_(h23.v.y, P.gnd_eff_h_clip));
+  const F2 f01(f[0], f[1]), f23(f[2], f[3]);
+  const F2 g01 = fma_(f01 * F2(P.gnd_eff_coeff), q01 * q01, f01), g23 = fma_(f23 * F2(P.gnd_eff_coeff), q23 * q23, f23);
+  f[0] = g01.v.x; f[1] = g01.v.y; f[2] = g23.v.x; f[3] = g23.v.y;
+}
+#endif
+
 // One sub-step.  `rpm` is the clipped action; `dw` the summed downwash (0 for DYN); `fext` an optional world-frame
 // force; R = the rotation matrix of the CURRENT attitude (quat_to_mat(s.q), or the controller's copy of it).
 // Returns the world angular velocity that PyBullet would be handed: R(q_old) * w_new.
@@ -66,9 +102,8 @@ template <int SPEC, typename Real>
 MDS_DEV V3<Real> physics_substep(const DroneP<Real>& P, Drone<Real>& s, const Real rpm[4], Real dw, V3<Real> fext, const M3<Real>& R) {
   using S = PhysSpec<SPEC>;
   const Real dt = P.dt_phys;
-  Real f[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) f[i] = P.kf * rpm[i] * rpm[i];
+  Real f[4], zt[4];
+  rotor_forces(P, rpm, f, zt);
   V3<Real> extra = fext;
   if (S::physics(P) == MDS_PHYSICS_DYN_GND_DRAG_DW) {
     // ground effect: per-prop height above the plane, gated on |roll|, |pitch| < pi/2 of Bullet's getEulerFromQuaternion
@@ -78,14 +113,7 @@ MDS_DEV V3<Real> physics_substep(const DroneP<Real>& P, Drone<Real>& s, const Re
     const Real rollA = Real(2) * (s.qy * s.qz + s.qw * s.qx);
     const Real rollB = s.qw * s.qw - s.qx * s.qx - s.qy * s.qy + s.qz * s.qz;
     if (abs_(sarg) < Real(0.99999) && (rollB > Real(0) || (rollB == Real(0) && rollA == Real(0)))) {
-      const Real pr4 = Real(0.25) * P.prop_radius;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        Real h = s.p.z + R.m[6] * P.prop_x[i] + R.m[7] * P.prop_y[i];
-        h = max_(h, P.gnd_eff_h_clip);
-        Real q = pr4 / h;
-        f[i] = fma_(f[i] * P.gnd_eff_coeff, q * q, f[i]);
-      }
+      ground_effect(P, s.p.z, R.m[6], R.m[7], f);
     }
     // rotor-speed-scaled linear drag from the PREVIOUS clipped RPM
     Real wsum = Real(0.10471975511965977) * (s.rpm[0] + s.rpm[1] + s.rpm[2] + s.rpm[3]);  // 2 pi / 60
@@ -95,9 +123,8 @@ MDS_DEV V3<Real> physics_substep(const DroneP<Real>& P, Drone<Real>& s, const Re
   }
   Real thrust = (f[0] + f[1] + f[2] + f[3]) - dw;
   V3<Real> F = {fma_(R.m[2], thrust, extra.x), fma_(R.m[5], thrust, extra.y), fma_(R.m[8], thrust, extra.z) - P.m * P.g};
-  Real zt0 = P.km * rpm[0] * rpm[0], zt1 = P.km * rpm[1] * rpm[1], zt2 = P.km * rpm[2] * rpm[2], zt3 = P.km * rpm[3] * rpm[3];
   V3<Real> tau;
-  tau.z = -zt0 + zt1 - zt2 + zt3;
+  tau.z = -zt[0] + zt[1] - zt[2] + zt[3];
   if (S::drone_model(P) == MDS_DRONE_CF2X) {
     const Real l2 = P.arm_l * Real(0.70710678118654752);
     tau.x = Real(P.cf2x_torque_sign) * (f[0] + f[1] - f[2] - f[3]) * l2;
