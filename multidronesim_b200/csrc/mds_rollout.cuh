@@ -39,6 +39,8 @@ struct GroupMap {
   bool valid;        // lane maps to a real drone
   bool env_valid;    // group maps to a real env
   unsigned gmask;    // lanes of this group within the warp
+  unsigned cmask;    // mask for the synchronising calls at the stage boundaries every lane group of the warp reaches together:
+                     // gmask, or the full warp where a kernel guarantees 32 live lanes (rollout_loop_kernel FULLW)
 };
 MDS_DEV GroupMap group_map(int N, int NP, int E) {
   GroupMap g;
@@ -51,6 +53,7 @@ MDS_DEV GroupMap group_map(int N, int NP, int E) {
   g.d = g.e * N + g.n;
   const int lane0 = (tid & 31) & ~(NP - 1);
   g.gmask = NP >= 32 ? 0xffffffffu : (((1u << NP) - 1u) << lane0);
+  g.cmask = g.gmask;
   return g;
 }
 
@@ -85,7 +88,7 @@ MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* s
   typename Vec4T<Real>::type me;
   me.x = p.x; me.y = p.y; me.z = p.z; me.w = Real(0);
   sm_pos[threadIdx.x] = me;
-  __syncwarp(g.gmask);
+  __syncwarp(g.cmask);
   Real dw = Real(0);
   const int n = g.n, base = threadIdx.x - n, lane0 = (threadIdx.x & 31) - n;
   const int K1 = (N - 1) >> 1, half = (N & 1) ? 0 : (N >> 1), S0 = K1 + (half ? 1 : 0);
@@ -111,10 +114,10 @@ MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* s
       if (dz > Real(0)) dw += v;
       else give = v;
     }
-    const Real got = __shfl_sync(g.gmask, give, lane0 + src);
+    const Real got = __shfl_sync(g.cmask, give, lane0 + src);
     if (recv) dw += got;
   }
-  __syncwarp(g.gmask);
+  __syncwarp(g.cmask);
   return dw;
 }
 
@@ -124,7 +127,7 @@ MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* s
 #ifndef MDS_NO_DW_PACK
 MDS_DEV float downwash_group(const DroneP<float>& P, float4* sm_pos, V3<float> p, const GroupMap& g, int N, int NP) {
   sm_pos[threadIdx.x] = make_float4(p.x, p.y, p.z, 0.f);
-  __syncwarp(g.gmask);
+  __syncwarp(g.cmask);
   float dw = 0.f;
   const int n = g.n, base = threadIdx.x - n, lane0 = (threadIdx.x & 31) - n;
   const int K1 = (N - 1) >> 1, half = (N & 1) ? 0 : (N >> 1), S0 = K1 + (half ? 1 : 0);
@@ -151,14 +154,14 @@ MDS_DEV float downwash_group(const DroneP<float>& P, float4* sm_pos, V3<float> p
     const float v0 = (dz.v.x != 0.f && dxy2.v.x < 100.f) ? v.v.x : 0.f, v1 = (dz.v.y != 0.f && dxy2.v.y < 100.f) ? v.v.y : 0.f;
     dw += dz.v.x > 0.f ? v0 : 0.f;
     dw += dz.v.y > 0.f ? v1 : 0.f;
-    const float got0 = __shfl_sync(g.gmask, dz.v.x > 0.f ? 0.f : v0, lane0 + src[0]);
+    const float got0 = __shfl_sync(g.cmask, dz.v.x > 0.f ? 0.f : v0, lane0 + src[0]);
     if (recv[0]) dw += got0;
     if (s + 1 < S0) {
-      const float got1 = __shfl_sync(g.gmask, dz.v.y > 0.f ? 0.f : v1, lane0 + src[1]);
+      const float got1 = __shfl_sync(g.cmask, dz.v.y > 0.f ? 0.f : v1, lane0 + src[1]);
       if (recv[1]) dw += got1;
     }
   }
-  __syncwarp(g.gmask);
+  __syncwarp(g.cmask);
   return dw;
 }
 #endif
@@ -305,7 +308,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
     xv.x = xn[0]; xv.y = xn[1]; xv.z = xn[2]; xv.w = unom[3];
     x[n] = xv;
   }
-  __syncwarp(g.gmask);
+  __syncwarp(g.cmask);
   constexpr bool PACK = (NT > 1) && sizeof(Real) == 4;
   constexpr int S0C = PACK ? (NT - 1) / 2 + ((NT & 1) ? 0 : 1) : 1, NPAIR = (S0C + 1) / 2;
   F2 pa[NPAIR][3], prhs[NPAIR];  // packed path: the pair rows, slot 2q in the low halves and 2q + 1 in the high halves
@@ -371,7 +374,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
     }
   }
   // one group-wide OR of (escalate, infeasible 4th-input interval, projected) -- the step's only collective in the common case
-  const unsigned any = group_or(g.gmask, NP, (unsigned)(escalate | (fl << 1) | (touched << 2)));
+  const unsigned any = group_or(g.cmask, NP, (unsigned)(escalate | (fl << 1) | (touched << 2)));
   int status = MDS_QP_OPTIMAL, iters = (any & 4u) ? 1 : 0;
   if (any & 2u) {
     status = MDS_QP_INFEASIBLE;
@@ -420,7 +423,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
       usafe[0] = unom[0]; usafe[1] = unom[1]; usafe[2] = unom[2]; usafe[3] = unom[3];
     }
   }
-  __syncwarp(g.gmask);  // the env block may be reused by the next step
+  __syncwarp(g.cmask);  // the env block may be reused by the next step
   *iters_out = iters;
   return status;
 }
@@ -755,6 +758,22 @@ __global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_loop_ke
   StepStats acc = {0.f, 1e30f, 0, 0, 0, 0};  // qp_infeas holds infeasible | iteration-cap << 16
   float max_err = 0.f;
   int steps_done = 0;
+  // FULLW (fp32 swarms whose drones fill their lane groups, per-thread state staged in shared memory): every warp that holds
+  // a live environment runs with all 32 lanes -- the lane groups past the last environment re-run environment E - 1 without
+  // storing anything -- so the synchronising calls at the stage boundaries take the constant full-warp mask.  A group mask
+  // only known at run time costs a MATCH.ANY / REDUX / VOTE / BRA.DIV preamble per call (8 calls per step).
+#ifndef MDS_NO_FULLW
+  constexpr bool FULLW = STAGE && HAS_PID && NT > 1 && NT < 32 && (NT & (NT - 1)) == 0;
+#else
+  constexpr bool FULLW = false;
+#endif
+  const bool live = g.env_valid;
+  if (FULLW) {
+    const int first_env = g.e - (int)((threadIdx.x & 31) / NP);  // lane group 0 of this warp
+    g.env_valid = first_env < E;
+    if (g.env_valid && !live) { g.e = E - 1; g.d = g.e * N + g.n; }
+    g.cmask = 0xffffffffu;
+  }
   if (g.env_valid) {
     full_group_hint<NT>(g);
     Obs<Real> o;
@@ -800,12 +819,12 @@ __global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_loop_ke
       o = physics_core<SPEC>(P, s, rpm, fx, sm_pos, g, N, NP, HAS_PID ? &R : nullptr);
       wb = s.w;
       if (Rc.write_obs_every > 0 && --log_countdown == 0) {
-        if (g.valid) store_obs(log_slot, g.d, o, true);  // streaming stores: the log is write-once
+        if (g.valid && live) store_obs(log_slot, g.d, o, true);  // streaming stores: the log is write-once
         log_slot += obs_elems;
         log_countdown = Rc.write_obs_every;
       }
     }
-    if (g.valid) {
+    if (g.valid && live) {
       Drone<Real> s;
       s.p = o.p; s.qx = o.qx; s.qy = o.qy; s.qz = o.qz; s.qw = o.qw; s.v = o.v; s.w = wb;
 #pragma unroll
@@ -817,6 +836,7 @@ __global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_loop_ke
       steps_done = K;
     }
   }
+  if (FULLW && !live) { acc = {0.f, 1e30f, 0, 0, 0, 0}; max_err = 0.f; }  // a re-run environment counts nowhere
   acc.qp_cap = acc.qp_infeas >> 16;
   acc.qp_infeas &= 0xffff;
   if (stats) stats_block_reduce<USE_CBF>(stats, steps_done, acc, max_err);
@@ -921,6 +941,7 @@ __global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_queue_k
     full_group_hint<NT>(g);
     g.d = g.e * N + g.n;
     g.gmask = NP >= 32 ? 0xffffffffu : (((1u << NP) - 1u) << (lane & ~(NP - 1)));
+    g.cmask = g.gmask;
     Obs<Real> o;
     V3<Real> wb = {Real(0), Real(0), Real(0)};
     typename TrajSpecT<Real>::spec spec_reg;
