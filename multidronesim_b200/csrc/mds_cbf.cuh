@@ -125,8 +125,13 @@ MDS_DEV RowMap row_map(int N, int n_obs) {
   return m;
 }
 // partner drone of (lane n, slot s): >= 0 pair partner, -1 obstacle row, -2 unused slot
+// m in [-N, 2N) wrapped into [0, N): a mask when N is a power of two (N folds to a constant in the NT kernels)
+MDS_DEV int wrap_n(int m, int N) {
+  if ((N & (N - 1)) == 0) return m & (N - 1);
+  return m >= N ? m - N : (m < 0 ? m + N : m);
+}
 MDS_DEV int row_partner(const RowMap& M, int N, int n, int s) {
-  if (s < M.K1) { int m = n + s + 1; return m >= N ? m - N : m; }
+  if (s < M.K1) return wrap_n(n + s + 1, N);
   if (s < M.S0) return (n < M.half) ? n + M.half : -2;
   return -1;
 }

@@ -129,7 +129,7 @@ MDS_DEV float downwash_group(const DroneP<float>& P, float4* sm_pos, V3<float> p
   sm_pos[threadIdx.x] = make_float4(p.x, p.y, p.z, 0.f);
   __syncwarp(g.cmask);
   float dw = 0.f;
-  const int n = g.n, base = threadIdx.x - n, lane0 = (threadIdx.x & 31) - n;
+  const int n = g.n, base = threadIdx.x - n;
   const int K1 = (N - 1) >> 1, half = (N & 1) ? 0 : (N >> 1), S0 = K1 + (half ? 1 : 0);
 #pragma unroll
   for (int s = 0; s < S0; s += 2) {
@@ -140,8 +140,8 @@ MDS_DEV float downwash_group(const DroneP<float>& P, float4* sm_pos, V3<float> p
       const int sl = s + h;
       if (g.valid && sl < S0) {
         if (sl < K1) {
-          m[h] = n + sl + 1; m[h] = m[h] >= N ? m[h] - N : m[h];
-          src[h] = n - sl - 1; src[h] = src[h] < 0 ? src[h] + N : src[h];
+          m[h] = wrap_n(n + sl + 1, N);
+          src[h] = wrap_n(n - sl - 1, N);
           recv[h] = true;
         } else if (n < half) m[h] = n + half;
         else { src[h] = n - half; recv[h] = true; }
@@ -154,10 +154,10 @@ MDS_DEV float downwash_group(const DroneP<float>& P, float4* sm_pos, V3<float> p
     const float v0 = (dz.v.x != 0.f && dxy2.v.x < 100.f) ? v.v.x : 0.f, v1 = (dz.v.y != 0.f && dxy2.v.y < 100.f) ? v.v.y : 0.f;
     dw += dz.v.x > 0.f ? v0 : 0.f;
     dw += dz.v.y > 0.f ? v1 : 0.f;
-    const float got0 = __shfl_sync(g.cmask, dz.v.x > 0.f ? 0.f : v0, lane0 + src[0]);
+    const float got0 = __shfl_sync(g.cmask, dz.v.x > 0.f ? 0.f : v0, src[0], NP);  // width NP: the source is relative to the lane group
     if (recv[0]) dw += got0;
     if (s + 1 < S0) {
-      const float got1 = __shfl_sync(g.cmask, dz.v.y > 0.f ? 0.f : v1, lane0 + src[1]);
+      const float got1 = __shfl_sync(g.cmask, dz.v.y > 0.f ? 0.f : v1, src[1], NP);
       if (recv[1]) dw += got1;
     }
   }
@@ -242,7 +242,7 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
     int wobs = -1;      // the most violated obstacle row, kept in registers: (a, rhs), |a|^2
     Real w0 = Real(0), w1 = Real(0), w2 = Real(0), w3 = Real(0), wa2 = Real(1);
     const CbfAgent<Real> zero = {{Real(0), Real(0), Real(0)}, {Real(0), Real(0), Real(0)}, {Real(0), Real(0), Real(0)}};
-    for (int o = 0; o < n_obs; ++o) {
+    auto obstacle_row = [&](int o) {
       CbfAgent<Real> other = zero;
       other.p = {obstacles[4 * o], obstacles[4 * o + 1], obstacles[4 * o + 2]};
       Real a3[3], rhs, h0, Ds, c4inv;
@@ -263,7 +263,11 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
       const bool worse = viol && v < wv;
       wv = worse ? v : wv; wobs = worse ? o : wobs;
       w0 = worse ? a3[0] : w0; w1 = worse ? a3[1] : w1; w2 = worse ? a3[2] : w2; w3 = worse ? rhs : w3; wa2 = worse ? a2 : wa2;
-    }
+    };
+    // first obstacle peeled (the usual count is one): its "worst so far" state is the constants above, and the loop
+    // bookkeeping stays off the common path
+    if (n_obs > 0) obstacle_row(0);
+    for (int o = 1; o < n_obs; ++o) obstacle_row(o);
     // box bounds: |u| > umax_hi  <=>  umax - |u| < -tol (umax + |u|); a later component wins only if strictly worse.
     // (Literal indices: a component INDEX would let nvcc turn the selects into dynamically indexed accesses, i.e. move u_n
     // and the whole parameter block C into local memory.)
@@ -297,7 +301,8 @@ MDS_DEV int cbf_filter_group(const DroneP<Real>& P, const CbfP<Real>& C, const C
       }
     }
     // the box at the projected point (an untouched u_n is inside it)
-    if ((!wb0 && abs_(xn[0]) > C.umax_hi[0]) || (!wb1 && abs_(xn[1]) > C.umax_hi[1]) || (!wb2 && abs_(xn[2]) > C.umax_hi[2])) escalate = 1;
+    const bool out0 = abs_(xn[0]) > C.umax_hi[0], out1 = abs_(xn[1]) > C.umax_hi[1], out2 = abs_(xn[2]) > C.umax_hi[2];
+    escalate |= (int)((!wb0 & out0) | (!wb1 & out1) | (!wb2 & out2));  // bitwise: no short-circuit branches
     if (!cbf_wz_bounds<ORD>(C, F, &lo, &hi)) fl = 1;
     // ---- publish the agent and the projected inputs
     R4 a0, a1, a2, xv;
