@@ -522,23 +522,19 @@ template <typename Real> struct RolloutP {
   int lqr_D;
 };
 
+// min / max of doubles by ONE integer atomic each, no compare-and-swap loop (thousands of blocks hit the same two words):
+// IEEE doubles of one sign order like their bit patterns -- non-negative ones as signed integers ascending, negative ones as
+// unsigned integers descending -- and a negative double is "less than" any non-negative one in the signed view and "greater"
+// in the unsigned view.  NaNs never reach these (the statistics are sums / extrema of finite fp32 values).
 MDS_DEV void atomic_min_double(double* addr, double v) {
-  unsigned long long* a = (unsigned long long*)addr;
-  unsigned long long old = *a, assumed;
-  do {
-    assumed = old;
-    if (__longlong_as_double(assumed) <= v) break;
-    old = atomicCAS(a, assumed, __double_as_longlong(v));
-  } while (assumed != old);
+  v += 0.0;  // -0.0 -> +0.0
+  if (v >= 0.0) atomicMin(reinterpret_cast<long long*>(addr), __double_as_longlong(v));
+  else atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 MDS_DEV void atomic_max_double(double* addr, double v) {
-  unsigned long long* a = (unsigned long long*)addr;
-  unsigned long long old = *a, assumed;
-  do {
-    assumed = old;
-    if (__longlong_as_double(assumed) >= v) break;
-    old = atomicCAS(a, assumed, __double_as_longlong(v));
-  } while (assumed != old);
+  v += 0.0;
+  if (v >= 0.0) atomicMax(reinterpret_cast<long long*>(addr), __double_as_longlong(v));
+  else atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
 // L1 prefetch of the lines a thread will load much later (PID state after the QP, trajectory spec after the
