@@ -239,17 +239,18 @@ MDS_DEV void thrust_omega_pid(const DroneP<Real>& P, Pid<Real>& s, Real thrust, 
   thrust = max_(thrust, Real(0));
   Real pwm_t = clamp_((sqrt_(thrust / (P.kf * Real(4))) - Real(MDS_PWM2RPM_CONST)) / Real(MDS_PWM2RPM_SCALE),
                       Real(MDS_MIN_PWM), Real(MDS_MAX_PWM));
-  V3<Real> rate_e = (Real(-1) / dt) * (w_b - s.last_w);
   V3<Real> e = w_target - w_b;
   s.last_w = w_b;
   s.integ = s.integ - dt * e;
   s.integ.x = clamp_(clamp_(s.integ.x, Real(-1500), Real(1500)), Real(-1), Real(1));
   s.integ.y = clamp_(clamp_(s.integ.y, Real(-1500), Real(1500)), Real(-1), Real(1));
   s.integ.z = clamp_(s.integ.z, Real(-1500), Real(1500));
-  const Real kp = Real(17500), ki = Real(10), kd = Real(0);
-  V3<Real> tq = {clamp_(kp * e.x + ki * s.integ.x + kd * rate_e.x, Real(-3200), Real(3200)),
-                 clamp_(kp * e.y + ki * s.integ.y + kd * rate_e.y, Real(-3200), Real(3200)),
-                 clamp_(kp * e.z + ki * s.integ.z + kd * rate_e.z, Real(-3200), Real(3200))};
+  // the reference's derivative gain is 0 (control/low_level/thrust_omega_ctrl.py:42, 124: D_COEFF_OMEGA_TOR = 0): its term kd * (w_b - last_w) / (-dt) adds an
+  // exact +0 for every finite rate and is left out (last_w is still carried as state)
+  const Real kp = Real(17500), ki = Real(10);
+  V3<Real> tq = {clamp_(kp * e.x + ki * s.integ.x, Real(-3200), Real(3200)),
+                 clamp_(kp * e.y + ki * s.integ.y, Real(-3200), Real(3200)),
+                 clamp_(kp * e.z + ki * s.integ.z, Real(-3200), Real(3200))};
   Real pw[4];
   if (PhysSpec<SPEC>::drone_model(P) == MDS_DRONE_CF2X) {
     pw[0] = pwm_t + (Real(-0.5) * tq.x - Real(0.5) * tq.y - tq.z);

@@ -418,3 +418,26 @@ def test_swarm_streams_equal_one_swarm(lib_built):
     for k in ("drone_steps", "qp_solves", "qp_iters", "qp_infeasible", "qp_iter_cap", "max_pos_err", "min_barrier"):
         assert a[k] == b[k], k
     assert abs(a["sum_pos_err"] - b["sum_pos_err"]) < 1e-6 * a["sum_pos_err"]
+
+
+def test_extrema_statistics_across_blocks(lib_built):
+    """min_barrier / max_pos_err are folded over the blocks of a launch with integer atomics on the doubles' bit patterns
+    (mds_rollout.cuh atomic_min_double / atomic_max_double; the barrier minimum is usually NEGATIVE, the error maximum never).
+    A swarm of E environments (several blocks, last warp partly filled: the FULLW re-run groups must not count) has to report
+    the extrema of its environments rolled out one by one -- single-block launches whose results are folded here on the host --
+    and exact counters."""
+    from multidronesim_b200 import scenarios
+    E, K = 70, 96
+    big = scenarios.cbf_swarm(E, 8, order=3)
+    big["rollout"].run(K)
+    st = big["rollout"].stats_dict()
+    assert st["drone_steps"] == E * 8 * K
+    mins, maxs, solves = [], [], 0
+    for e0 in range(E):
+        one = scenarios.cbf_swarm(1, 8, order=3, env_offset=e0)
+        one["rollout"].run(K)
+        s1 = one["rollout"].stats_dict()
+        assert s1["drone_steps"] == 8 * K
+        mins.append(s1["min_barrier"]); maxs.append(s1["max_pos_err"]); solves += s1["qp_solves"]
+    assert min(mins) < 0 < max(maxs)           # the sign cases the atomics distinguish are exercised
+    assert st["min_barrier"] == min(mins) and st["max_pos_err"] == max(maxs) and st["qp_solves"] == solves
