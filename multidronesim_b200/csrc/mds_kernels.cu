@@ -764,7 +764,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   // the loop kernel packs two rare-event counters into 16 bits each: longer runs go out as several launches (whole log periods each)
   auto launch_loop = [&]() {
     RolloutLaunch<Real> RLL = RL;  // the loop kernel has its own block size (MDS_LOOP_BLOCK)
-    RLL.threads = R.use_cbf ? cbf_block_threads<Real>(NP, N, R.n_obs, MDS_LOOP_BLOCK) : MDS_LOOP_BLOCK;
+    RLL.threads = R.use_cbf ? cbf_block_threads<Real>(NP, N, R.n_obs, loop_block<Real>()) : loop_block<Real>();
     if (const char* force = getenv("MDS_LOOP_THREADS")) { const int t = atoi(force); if (t >= 32 && t <= RLL.threads && t % 32 == 0) RLL.threads = t; }  // experiment knob
     if (RLL.threads < NP) RLL.threads = NP;
     const int epb_l = RLL.threads / NP;
@@ -784,7 +784,7 @@ static int rollout_impl(const MdsDroneParams* prm, const MdsRolloutCfg* cfg, con
   cudaError_t queue_err = cudaSuccess;
   auto launch_queue = [&]() {
     RolloutLaunch<Real> RLQ = RL;
-    RLQ.threads = R.use_cbf ? cbf_block_threads<Real>(NP, N, R.n_obs, MDS_LOOP_BLOCK) : MDS_LOOP_BLOCK;
+    RLQ.threads = R.use_cbf ? cbf_block_threads<Real>(NP, N, R.n_obs, loop_block<Real>()) : loop_block<Real>();
     if (RLQ.threads < 32) RLQ.threads = 32;
     RLQ.smem = R.use_cbf ? cbf_smem_bytes<Real>(RLQ.threads, NP, N, R.n_obs) : 32;
     int per_sm = 0;

@@ -27,6 +27,11 @@ using namespace mds;
 #ifndef MDS_LOOP_BLOCK
 #define MDS_LOOP_BLOCK 256  // threads per block of the K-step loop kernel (a multiple of 32, <= MDS_BLOCK); with MDS_LOOP_MINB it sets the register cap
 #endif
+#ifndef MDS_LOOP_BLOCK_F64
+#define MDS_LOOP_BLOCK_F64 192  // fp64: 2 x 192 threads = 168 registers (2 x 256 = 128 spills 59 loads + 26 stores per warp-step: 0.184 -> 0.167 ms)
+#endif
+// threads per block of the loop kernels for a precision
+template <typename Real> constexpr int loop_block() { return sizeof(Real) == 4 ? MDS_LOOP_BLOCK : MDS_LOOP_BLOCK_F64; }
 #ifndef MDS_FUSED_MINB
 #define MDS_FUSED_MINB 4
 #endif
@@ -734,7 +739,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB 
 // SPEC: compile-time parameter switches (PhysSpec); K <= 32767 (rollout_impl splits longer runs): the rare-event counters
 // share one register.
 template <typename Real, int CTRL, bool USE_CBF, int NT, int SPEC>
-__global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_loop_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+__global__ void __launch_bounds__(loop_block<Real>(), MDS_LOOP_MINB) rollout_loop_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
                                                                   DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
                                                                   const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                   const typename TrajSpecT<Real>::seg* __restrict__ segs,
@@ -743,15 +748,15 @@ __global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_loop_ke
                                                                   int N_rt, int NP_rt) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
   using R4 = typename Vec4T<Real>::type;
-  __shared__ R4 sm_pos[MDS_LOOP_BLOCK];
+  __shared__ R4 sm_pos[loop_block<Real>()];
   // fp32 stages the per-step read-mostly data (trajectory descriptor, rate-PID state, wind) in shared memory for the launch;
   // fp64 does not: with the CBF stage's 91 KB that would leave one resident block per SM instead of two (0.41 vs 0.31 ms)
   constexpr bool STAGE = sizeof(Real) == 4;
-  __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[STAGE ? MDS_LOOP_BLOCK : 1];
+  __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[STAGE ? loop_block<Real>() : 1];
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
-  __shared__ R4 sm_pid_a[(STAGE && HAS_PID) ? MDS_LOOP_BLOCK : 1];
-  __shared__ typename Vec2T<Real>::type sm_pid_b[(STAGE && HAS_PID) ? MDS_LOOP_BLOCK : 1];
-  __shared__ R4 sm_fx[STAGE ? MDS_LOOP_BLOCK : 1];
+  __shared__ R4 sm_pid_a[(STAGE && HAS_PID) ? loop_block<Real>() : 1];
+  __shared__ typename Vec2T<Real>::type sm_pid_b[(STAGE && HAS_PID) ? loop_block<Real>() : 1];
+  __shared__ R4 sm_fx[STAGE ? loop_block<Real>() : 1];
   const PidP<Real> pid_s = STAGE ? PidP<Real>{sm_pid_a, sm_pid_b} : pid;
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
@@ -881,7 +886,7 @@ struct RolloutQueue {
 // A tile's chunk c waits (lane 0 spins on progress[tile]) until chunk c - 1 is complete; tasks are handed out in queue order
 // to warps that are running, so whoever holds the earlier chunk is making progress: no deadlock, whatever the grid size.
 template <typename Real, int CTRL, bool USE_CBF, int NT, int SPEC>
-__global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_queue_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+__global__ void __launch_bounds__(loop_block<Real>(), MDS_LOOP_MINB) rollout_queue_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
                                                                    DslP<Real> Dg, DslStateP<Real> dst, StateP<Real> st, PidP<Real> pid,
                                                                    const typename TrajSpecT<Real>::spec* __restrict__ specs,
                                                                    const typename TrajSpecT<Real>::seg* __restrict__ segs,
@@ -891,13 +896,13 @@ __global__ void __launch_bounds__(MDS_LOOP_BLOCK, MDS_LOOP_MINB) rollout_queue_k
   extern __shared__ __align__(32) unsigned char smem_raw[];
   using R4 = typename Vec4T<Real>::type;
   using R2 = typename Vec2T<Real>::type;
-  __shared__ R4 sm_pos[MDS_LOOP_BLOCK];
+  __shared__ R4 sm_pos[loop_block<Real>()];
   constexpr bool STAGE = sizeof(Real) == 4;
-  __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[STAGE ? MDS_LOOP_BLOCK : 1];
+  __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[STAGE ? loop_block<Real>() : 1];
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
-  __shared__ R4 sm_pid_a[(STAGE && HAS_PID) ? MDS_LOOP_BLOCK : 1];
-  __shared__ R2 sm_pid_b[(STAGE && HAS_PID) ? MDS_LOOP_BLOCK : 1];
-  __shared__ R4 sm_fx[STAGE ? MDS_LOOP_BLOCK : 1];
+  __shared__ R4 sm_pid_a[(STAGE && HAS_PID) ? loop_block<Real>() : 1];
+  __shared__ R2 sm_pid_b[(STAGE && HAS_PID) ? loop_block<Real>() : 1];
+  __shared__ R4 sm_fx[STAGE ? loop_block<Real>() : 1];
   // fp64 does not stage (shared-memory budget, see rollout_loop_kernel): its rate-PID state is held in two locals for the chunk
   // instead -- never read through L1 from global memory, where another SM wrote it at the end of the tile's previous chunk
   R4 pid_a_loc;
