@@ -83,19 +83,20 @@ template <int NT> MDS_DEV void full_group_hint(GroupMap& g) {
   if (NT > 0 && (NT & (NT - 1)) == 0) g.valid = true;
 }
 
-// Downwash sum for this lane's drone over its env mates; positions staged in shared memory.  Called by every lane of the
+// Downwash sum for this lane's drone over its env mates; positions staged in shared memory (env_pos: the environment's NP
+// slots -- a slice of a per-block array, or the head of the environment's CBF block, which is idle during the physics).  Called by every lane of the
 // group (two group syncs, shuffles).  Only the LOWER drone of a pair feels the other's downwash, so each unordered pair is
 // evaluated once, by the lane that owns it under the CBF stage's ownership (mds_cbf.cuh: lane n owns (n, n+s+1 mod N) for
 // s < (N-1)/2, and the "diameter" (n, n+N/2) for n < N/2 when N is even); the owner keeps the term if it is the lower one
 // and otherwise hands it to its partner with one shuffle per slot.
 template <typename Real>
-MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* sm_pos, V3<Real> p, const GroupMap& g, int N, int NP) {
+MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* env_pos, V3<Real> p, const GroupMap& g, int N, int NP) {
   typename Vec4T<Real>::type me;
   me.x = p.x; me.y = p.y; me.z = p.z; me.w = Real(0);
-  sm_pos[threadIdx.x] = me;
+  env_pos[g.n] = me;
   __syncwarp(g.cmask);
   Real dw = Real(0);
-  const int n = g.n, base = threadIdx.x - n, lane0 = (threadIdx.x & 31) - n;
+  const int n = g.n, lane0 = (threadIdx.x & 31) - n;
   const int K1 = (N - 1) >> 1, half = (N & 1) ? 0 : (N >> 1), S0 = K1 + (half ? 1 : 0);
 #pragma unroll
   for (int s = 0; s < S0; ++s) {
@@ -111,7 +112,7 @@ MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* s
     }
     Real give = Real(0);
     if (own) {
-      const auto q = sm_pos[base + m];
+      const auto q = env_pos[m];
       const Real dz = q.z - p.z, dx = q.x - p.x, dy = q.y - p.y;  // dz > 0: the partner is above, this drone is pushed down
       const Real dxy2 = dx * dx + dy * dy;
       Real v = Real(0);
@@ -130,11 +131,11 @@ MDS_DEV Real downwash_group(const DroneP<Real>& P, typename Vec4T<Real>::type* s
 // high halves; a slot this lane does not own is evaluated against the lane's own position (dz = 0: no force).  Per pair of
 // slots ~30 instructions instead of 2 x 25, and the half-populated "diameter" slot rides along for free.
 #ifndef MDS_NO_DW_PACK
-MDS_DEV float downwash_group(const DroneP<float>& P, float4* sm_pos, V3<float> p, const GroupMap& g, int N, int NP) {
-  sm_pos[threadIdx.x] = make_float4(p.x, p.y, p.z, 0.f);
+MDS_DEV float downwash_group(const DroneP<float>& P, float4* env_pos, V3<float> p, const GroupMap& g, int N, int NP) {
+  env_pos[g.n] = make_float4(p.x, p.y, p.z, 0.f);
   __syncwarp(g.cmask);
   float dw = 0.f;
-  const int n = g.n, base = threadIdx.x - n;
+  const int n = g.n;
   const int K1 = (N - 1) >> 1, half = (N & 1) ? 0 : (N >> 1), S0 = K1 + (half ? 1 : 0);
 #pragma unroll
   for (int s = 0; s < S0; s += 2) {
@@ -152,7 +153,7 @@ MDS_DEV float downwash_group(const DroneP<float>& P, float4* sm_pos, V3<float> p
         else { src[h] = n - half; recv[h] = true; }
       }
     }
-    const float4 q0 = sm_pos[base + m[0]], q1 = sm_pos[base + m[1]];
+    const float4 q0 = env_pos[m[0]], q1 = env_pos[m[1]];
     const F2 dz(q0.z - p.z, q1.z - p.z), dx(q0.x - p.x, q1.x - p.x), dy(q0.y - p.y, q1.y - p.y);  // dz > 0: the partner is above
     const F2 dxy2 = fma_(dy, dy, dx * dx);
     const F2 v = downwash_pair2(P, F2(abs_(dz.v.x), abs_(dz.v.y)), dxy2);
@@ -461,7 +462,7 @@ template <typename Real> MDS_DEV void load4(const Real* p, int d, Real v[4]) {
 // calls it): clips the action, runs the sub-steps, returns the new observation.  R0 (optional): the rotation matrix of the
 // attitude the period starts from, when the caller already has it (the inner loop of the controller stack builds it).
 template <int SPEC, typename Real>
-MDS_DEV Obs<Real> physics_core(const DroneP<Real>& P, Drone<Real>& s, const Real action[4], V3<Real> fx, typename Vec4T<Real>::type* sm_pos,
+MDS_DEV Obs<Real> physics_core(const DroneP<Real>& P, Drone<Real>& s, const Real action[4], V3<Real> fx, typename Vec4T<Real>::type* env_pos,
                                const GroupMap& g, int N, int NP, const M3<Real>* R0 = nullptr) {
   using S = PhysSpec<SPEC>;
   Real rpm[4];
@@ -472,7 +473,7 @@ MDS_DEV Obs<Real> physics_core(const DroneP<Real>& P, Drone<Real>& s, const Real
   const int substeps = S::substeps(P);
   for (int k = 0; k < substeps; ++k) {
     Real dw = Real(0);
-    if (dwash) dw = downwash_group(P, sm_pos, s.p, g, N, NP);
+    if (dwash) dw = downwash_group(P, env_pos, s.p, g, N, NP);
     if (g.valid) {
       const M3<Real> R = (R0 != nullptr && k == 0) ? *R0 : quat_to_mat(s.qx, s.qy, s.qz, s.qw);
       av = physics_substep<SPEC>(P, s, rpm, dw, fx, R);
@@ -489,7 +490,7 @@ MDS_DEV Obs<Real> physics_core(const DroneP<Real>& P, Drone<Real>& s, const Real
 // and returns the observation in registers.
 template <typename Real>
 MDS_DEV Obs<Real> physics_body(const DroneP<Real>& P, const StateP<Real>& st, const Real* __restrict__ action, const Real* __restrict__ fext,
-                               Real* __restrict__ obs, typename Vec4T<Real>::type* sm_pos, const GroupMap& g, int N, int NP) {
+                               Real* __restrict__ obs, typename Vec4T<Real>::type* env_pos, const GroupMap& g, int N, int NP) {
   Drone<Real> s;
   s.p = {Real(0), Real(0), Real(0)};
   Real act[4] = {Real(0), Real(0), Real(0), Real(0)};
@@ -499,7 +500,7 @@ MDS_DEV Obs<Real> physics_body(const DroneP<Real>& P, const StateP<Real>& st, co
     load4(action, g.d, act);
     if (fext) fx = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
   }
-  Obs<Real> o = physics_core<0>(P, s, act, fx, sm_pos, g, N, NP);
+  Obs<Real> o = physics_core<0>(P, s, act, fx, env_pos, g, N, NP);
   if (g.valid) {
     store_drone(st, g.d, s);
     if (obs) store_obs(obs, g.d, o);
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_PHYS_MINB :
   GroupMap g = group_map(N, NP, E);
   if (!g.env_valid) return;  // whole groups leave together
   full_group_hint<NT>(g);
-  physics_body(P, st, action, fext, obs, sm_pos, g, N, NP);
+  physics_body(P, st, action, fext, obs, sm_pos + (threadIdx.x - g.n), g, N, NP);
 }
 
 // ------------------------------------------------------------------ kernel: fused K-step rollout
@@ -721,7 +722,7 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_FUSED_MINB 
       prefetch_l1(reinterpret_cast<const char*>(specs + g.d) + 32);
       if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
     }
-    const Obs<Real> o = physics_body(P, st, action, fext, obs_out, sm_pos, g, N, NP);
+    const Obs<Real> o = physics_body(P, st, action, fext, obs_out, sm_pos + (threadIdx.x - g.n), g, N, NP);
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
     typename TrajSpecT<Real>::spec spec;
     spec.kind = MDS_TRAJ_WAIT;
@@ -748,19 +749,22 @@ __global__ void __launch_bounds__(loop_block<Real>(), MDS_LOOP_MINB) rollout_loo
                                                                   int N_rt, int NP_rt) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
   using R4 = typename Vec4T<Real>::type;
-  __shared__ R4 sm_pos[loop_block<Real>()];
-  // fp32 stages the per-step read-mostly data (trajectory descriptor, rate-PID state, wind) in shared memory for the launch;
+  // downwash positions: with the CBF stage they live in the head of the environment's CBF block (idle during the physics; the
+  // stage's closing group sync orders the reuse), otherwise in a per-block array.  Every KB of shared memory the kernel does
+  // not take is L1 for its spill slots (L1 = 228 KB - shared memory in use).
+  __shared__ R4 sm_pos[USE_CBF ? 1 : loop_block<Real>()];
+  // fp32 stages the per-step read-mostly data (trajectory descriptor, rate-PID state) in shared memory for the launch;
   // fp64 does not: with the CBF stage's 91 KB that would leave one resident block per SM instead of two (0.41 vs 0.31 ms)
   constexpr bool STAGE = sizeof(Real) == 4;
   __shared__ __align__(16) typename TrajSpecT<Real>::spec sm_spec[STAGE ? loop_block<Real>() : 1];
   constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
   __shared__ R4 sm_pid_a[(STAGE && HAS_PID) ? loop_block<Real>() : 1];
   __shared__ typename Vec2T<Real>::type sm_pid_b[(STAGE && HAS_PID) ? loop_block<Real>() : 1];
-  __shared__ R4 sm_fx[STAGE ? loop_block<Real>() : 1];
   const PidP<Real> pid_s = STAGE ? PidP<Real>{sm_pid_a, sm_pid_b} : pid;
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
   GroupMap g = group_map(N, NP, E);
+  R4* const env_pos = USE_CBF ? reinterpret_cast<R4*>(S.env0 + (size_t)g.el * S.stride) : sm_pos + (threadIdx.x - g.n);
   StepStats acc = {0.f, 1e30f, 0, 0, 0, 0};  // qp_infeas holds infeasible | iteration-cap << 16
   float max_err = 0.f;
   int steps_done = 0;
@@ -796,10 +800,7 @@ __global__ void __launch_bounds__(loop_block<Real>(), MDS_LOOP_MINB) rollout_loo
       o = load_obs(obs, g.d);
       spec = specs[g.d];
       wb = {st.pos_wx[g.d].w, st.vel_wy[g.d].w, st.wz[g.d]};
-      if (has_fx) {
-        fx_reg = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
-        if (STAGE) { R4 f4; f4.x = fx_reg.x; f4.y = fx_reg.y; f4.z = fx_reg.z; f4.w = Real(0); sm_fx[threadIdx.x] = f4; }
-      }
+      if (has_fx && !STAGE) fx_reg = {fext[3 * g.d], fext[3 * g.d + 1], fext[3 * g.d + 2]};
       if (STAGE && HAS_PID) { sm_pid_a[threadIdx.x] = pid.a[g.d]; sm_pid_b[threadIdx.x] = pid.b[g.d]; }
     }
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
@@ -818,11 +819,11 @@ __global__ void __launch_bounds__(loop_block<Real>(), MDS_LOOP_MINB) rollout_loo
 #pragma unroll
       for (int i = 0; i < 4; ++i) s.rpm[i] = o.rpm[i];
       V3<Real> fx = fx_reg;
-      if (STAGE) {
+      if (STAGE) {  // fp32 is short of registers: the wind (rarely set) is re-read every step, 12 B per drone from L1
         fx = {Real(0), Real(0), Real(0)};
-        if (has_fx && g.valid) { const R4 f4 = sm_fx[threadIdx.x]; fx = {f4.x, f4.y, f4.z}; }
+        if (has_fx && g.valid) fx = {__ldg(fext + 3 * g.d), __ldg(fext + 3 * g.d + 1), __ldg(fext + 3 * g.d + 2)};
       }
-      o = physics_core<SPEC>(P, s, rpm, fx, sm_pos, g, N, NP, HAS_PID ? &R : nullptr);
+      o = physics_core<SPEC>(P, s, rpm, fx, env_pos, g, N, NP, HAS_PID ? &R : nullptr);
       wb = s.w;
       if (Rc.write_obs_every > 0 && --log_countdown == 0) {
         if (g.valid && live) store_obs(log_slot, g.d, o, true);  // streaming stores: the log is write-once
@@ -991,7 +992,7 @@ __global__ void __launch_bounds__(loop_block<Real>(), MDS_LOOP_MINB) rollout_que
         fx = {Real(0), Real(0), Real(0)};
         if (has_fx && g.valid) { const R4 f4 = sm_fx[threadIdx.x]; fx = {f4.x, f4.y, f4.z}; }
       }
-      o = physics_core<SPEC>(P, s, rpm, fx, sm_pos, g, N, NP, HAS_PID ? &R : nullptr);
+      o = physics_core<SPEC>(P, s, rpm, fx, sm_pos + (threadIdx.x - g.n), g, N, NP, HAS_PID ? &R : nullptr);
       wb = s.w;
       if (every > 0 && --log_countdown == 0) {
         if (g.valid && !dup) store_obs(log_slot, g.d, o, true);
