@@ -47,12 +47,13 @@ struct GroupMap {
   unsigned cmask;    // mask for the synchronising calls at the stage boundaries every lane group of the warp reaches together:
                      // gmask, or the full warp where a kernel guarantees 32 live lanes (rollout_loop_kernel FULLW)
 };
-MDS_DEV GroupMap group_map(int N, int NP, int E) {
+// tile: which block-sized slice of the environments this block works on (blockIdx.x, or the iteration of a persistent kernel)
+MDS_DEV GroupMap group_map(int N, int NP, int E, int tile) {
   GroupMap g;
   const int tid = threadIdx.x, lg = __ffs(NP) - 1;  // NP is a power of two
   g.el = tid >> lg;
   g.n = tid & (NP - 1);
-  g.e = blockIdx.x * (blockDim.x >> lg) + g.el;  // blockDim.x <= MDS_BLOCK (launch_geometry)
+  g.e = tile * (blockDim.x >> lg) + g.el;  // blockDim.x <= MDS_BLOCK (launch_geometry)
   g.env_valid = g.e < E;
   g.valid = g.env_valid && g.n < N;
   g.d = g.e * N + g.n;
@@ -61,6 +62,8 @@ MDS_DEV GroupMap group_map(int N, int NP, int E) {
   g.cmask = g.gmask;
   return g;
 }
+
+MDS_DEV GroupMap group_map(int N, int NP, int E) { return group_map(N, NP, E, (int)blockIdx.x); }
 
 // OR over the lane group.  __reduce_or_sync with a partial run-time mask makes the lane groups of a warp take turns
 // (WARPSYNC.EXCLUSIVE: 6 instructions per group, 24 per warp); log2(NP) butterfly shuffles serve all groups at once.
@@ -669,19 +672,35 @@ template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ sta
   }
 }
 
-// controller stack alone: obs (HBM) -> action (HBM)
+// controller stack alone: obs (HBM) -> action (HBM).
+// PERSISTENT: the grid is the resident set (MDS_CTRL_MINB blocks per SM; fewer for small swarms) and every block walks the
+// block-sized tiles of the environments with stride gridDim.x.  One block per tile at 64 registers (4 resident blocks, 182 KB of
+// shared memory, 41 KB of L1 left for 960-byte frames) ran at IPC 1.6, latency-bound on its first loads and its spills, with a
+// statistics reduction + block barrier per tile (9 % of the instructions, 20 % of the stall samples).  The same stack inside
+// the K-step loop kernel reaches IPC 2.8 with 16 warps at 128 registers -- so this kernel now runs in that configuration,
+// prefetches the NEXT tile's observation / trajectory descriptor / PID state into L1 while it works on the current one,
+// accumulates its statistics in registers and reduces them once.
+#ifndef MDS_CTRL_PERSISTENT
+#define MDS_CTRL_PERSISTENT 1
+#endif
 template <typename Real, int CTRL, bool USE_CBF, int NT>
-__global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_CTRL_MINB : 2) ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
-                                                               DslP<Real> Dg, DslStateP<Real> dst, PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
-                                                               const typename TrajSpecT<Real>::seg* __restrict__ segs,
-                                                               const Real* __restrict__ obs, Real* __restrict__ action,
-                                                               double* __restrict__ stats, double t, int E, int N_rt, int NP_rt) {
+__global__ void __launch_bounds__(MDS_BLOCK, MDS_CTRL_PERSISTENT ? 2 : (sizeof(Real) == 4 ? MDS_CTRL_MINB : 2))
+    ctrl_step_kernel(DroneP<Real> P, RolloutP<Real> Rc, GeoP<Real> G, LqrP<Real> L, CbfP<Real> C,
+                     DslP<Real> Dg, DslStateP<Real> dst, PidP<Real> pid, const typename TrajSpecT<Real>::spec* __restrict__ specs,
+                     const typename TrajSpecT<Real>::seg* __restrict__ segs,
+                     const Real* __restrict__ obs, Real* __restrict__ action,
+                     double* __restrict__ stats, double t, int E, int N_rt, int NP_rt) {
   extern __shared__ __align__(32) unsigned char smem_raw[];
   const int N = ct_n<NT>(N_rt), NP = ct_np<NT>(NP_rt);
   CbfSmem<Real> S = cbf_smem_carve<Real>(smem_raw, NP, N, Rc.n_obs);
-  GroupMap g = group_map(N, NP, E);
-  StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
-  if (g.env_valid) {
+  constexpr bool HAS_PID = (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK);
+  const int epb = blockDim.x / NP, n_tiles = (E + epb - 1) / epb;
+  StepStats acc = {0.f, 1e30f, 0, 0, 0, 0};
+  float max_err = 0.f;
+  int n_done = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    GroupMap g = group_map(N, NP, E, tile);
+    if (!g.env_valid) continue;  // whole lane groups skip together (only in the last tile)
     full_group_hint<NT>(g);
     Real rpm[4] = {Real(0), Real(0), Real(0), Real(0)};
     Obs<Real> o;
@@ -690,12 +709,26 @@ __global__ void __launch_bounds__(MDS_BLOCK, sizeof(Real) == 4 ? MDS_CTRL_MINB :
     if (g.valid) {  // every global load of this thread is issued here, before the first dependent instruction
       o = load_obs(obs, g.d);
       spec = specs[g.d];
-      if (CTRL == MDS_CTRL_LQR_OMEGA || CTRL == MDS_CTRL_LQR_YANK) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
+      if (HAS_PID) { prefetch_l1(pid.a + g.d); prefetch_l1(pid.b + g.d); }
+      const int e_next = g.e + (int)gridDim.x * epb;  // this lane's environment in the block's next tile
+      if (e_next < E) {
+        const size_t d_next = (size_t)e_next * N + g.n;
+        const char* on = reinterpret_cast<const char*>(obs + d_next * MDS_OBS_DIM);
+        prefetch_l1(on); prefetch_l1(on + 16 * sizeof(Real));
+        prefetch_l1(specs + d_next); prefetch_l1(reinterpret_cast<const char*>(specs + d_next) + 32);
+        if (HAS_PID) { prefetch_l1(pid.a + d_next); prefetch_l1(pid.b + d_next); }
+      }
     }
+    StepStats ss = {0.f, 1e30f, 0, 0, 0, 0};
     ctrl_body<Real, CTRL, USE_CBF, (NT < 0), 0, NT>(P, Rc, G, L, C, Dg, dst, S, pid, spec, segs, o, g, N, NP, t, rpm, ss, g.d);
-    if (g.valid) store4(action, g.d, rpm);
+    if (g.valid) {
+      store4(action, g.d, rpm);
+      ++n_done;
+      acc.err += ss.err; max_err = fmaxf(max_err, ss.err); acc.min_h = fminf(acc.min_h, ss.min_h);
+      acc.qp_solves += ss.qp_solves; acc.qp_iters += ss.qp_iters; acc.qp_infeas += ss.qp_infeas; acc.qp_cap += ss.qp_cap;
+    }
   }
-  if (stats) stats_block_reduce<USE_CBF>(stats, g.valid ? 1 : 0, ss, ss.err);
+  if (stats) stats_block_reduce<USE_CBF>(stats, n_done, acc, max_err);
 }
 
 // One launch per control step inside a rollout: the env advances under the PREVIOUS step's action, and the

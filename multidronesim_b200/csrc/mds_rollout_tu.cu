@@ -61,7 +61,19 @@ struct CtrlLauncher {
     auto kern = pdk ? ctrl_step_kernel<Real, CT, CB, (PDKC ? -1 : 0)>
                     : ((a.N == 8) ? ctrl_step_kernel<Real, CT, CB, 8> : ctrl_step_kernel<Real, CT, CB, 0>);
     if (set_attr) err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
-    kern<<<a.blocks, a.threads, a.smem, a.cs>>>(a.Pd, a.R, a.G, a.L, a.C, a.Dg, a.Ds, a.Pi, a.specs, a.segs, obs_in, a.action, a.stats, t, a.E, a.N, a.NP);
+    // persistent grid: the resident set (the kernel walks the tiles); small swarms keep one block per tile
+    int grid = a.blocks;
+#if MDS_CTRL_PERSISTENT
+    static int resident_blocks = 0;  // per process: every device of a box is the same part
+    if (resident_blocks == 0) {
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      resident_blocks = 2 * (sms > 0 ? sms : 148);
+    }
+    if (grid > resident_blocks) grid = resident_blocks;
+#endif
+    kern<<<grid, a.threads, a.smem, a.cs>>>(a.Pd, a.R, a.G, a.L, a.C, a.Dg, a.Ds, a.Pi, a.specs, a.segs, obs_in, a.action, a.stats, t, a.E, a.N, a.NP);
   }
 };
 template <> cudaError_t launch_ctrl_kernel<Real>(const RolloutLaunch<Real>& a, double t, const Real* obs_in, bool set_attr) {
