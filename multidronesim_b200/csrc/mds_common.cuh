@@ -154,7 +154,7 @@ template <typename Real> struct DroneP {
   Real gnd_eff_coeff, prop_radius, gnd_eff_h_clip, drag_xy, drag_z, dw1, dw2, dw3, dw_dz_clip;
   Real prop_x[4], prop_y[4];
   Real z_floor, dt_phys, dt_ctrl;
-  Real inv_m, inv_ixx, inv_iyy, inv_izz;  // derived on the host (to_dev): no divisions by constants in the kernels
+  Real inv_m, inv_ixx, inv_iyy, inv_izz, inv_4kf;  // derived on the host (to_dev): no divisions by constants in the kernels
   int substeps, drone_model, physics, cf2x_torque_sign, renormalize_quat, ground_clamp, x_frame_mixer;
 };
 template <typename Real> inline DroneP<Real> to_dev(const MdsDroneParams& p) {
@@ -168,6 +168,7 @@ template <typename Real> inline DroneP<Real> to_dev(const MdsDroneParams& p) {
   for (int i = 0; i < 4; ++i) { d.prop_x[i] = Real(p.prop_x[i]); d.prop_y[i] = Real(p.prop_y[i]); }
   d.z_floor = Real(p.z_floor); d.dt_phys = Real(p.dt_phys); d.dt_ctrl = Real(p.dt_ctrl);
   d.inv_m = Real(1.0 / p.m); d.inv_ixx = Real(1.0 / p.ixx); d.inv_iyy = Real(1.0 / p.iyy); d.inv_izz = Real(1.0 / p.izz);
+  d.inv_4kf = Real(1.0 / (4.0 * p.kf));
   d.substeps = p.substeps; d.drone_model = p.drone_model; d.physics = p.physics;
   d.cf2x_torque_sign = p.cf2x_torque_sign; d.renormalize_quat = p.renormalize_quat; d.ground_clamp = p.ground_clamp; d.x_frame_mixer = p.x_frame_mixer;
   return d;

@@ -237,13 +237,14 @@ template <int SPEC = 0, typename Real>
 MDS_DEV void thrust_omega_pid(const DroneP<Real>& P, Pid<Real>& s, Real thrust, V3<Real> w_target, V3<Real> w_b, Real rpm[4]) {
   const Real dt = P.dt_ctrl;
   thrust = max_(thrust, Real(0));
-  Real pwm_t = clamp_((sqrt_(thrust / (P.kf * Real(4))) - Real(MDS_PWM2RPM_CONST)) / Real(MDS_PWM2RPM_SCALE),
+  // divisions by constants as multiplications by their host-side reciprocals (an fp64 division is a ~28-instruction sequence)
+  Real pwm_t = clamp_((sqrt_(thrust * P.inv_4kf) - Real(MDS_PWM2RPM_CONST)) * Real(1.0 / MDS_PWM2RPM_SCALE),
                       Real(MDS_MIN_PWM), Real(MDS_MAX_PWM));
   V3<Real> e = w_target - w_b;
   s.last_w = w_b;
   s.integ = s.integ - dt * e;
-  s.integ.x = clamp_(clamp_(s.integ.x, Real(-1500), Real(1500)), Real(-1), Real(1));
-  s.integ.y = clamp_(clamp_(s.integ.y, Real(-1500), Real(1500)), Real(-1), Real(1));
+  s.integ.x = clamp_(s.integ.x, Real(-1), Real(1));  // the reference clips to +-1500 and then x, y to +-1: the second clip subsumes the first
+  s.integ.y = clamp_(s.integ.y, Real(-1), Real(1));
   s.integ.z = clamp_(s.integ.z, Real(-1500), Real(1500));
   // the reference's derivative gain is 0 (control/low_level/thrust_omega_ctrl.py:42, 124: D_COEFF_OMEGA_TOR = 0): its term kd * (w_b - last_w) / (-dt) adds an
   // exact +0 for every finite rate and is left out (last_w is still carried as state)
