@@ -101,13 +101,105 @@ MDS_DEV float atan2_(float y, float x) {
   if (x < 0.f) r = 3.14159265358979324f - r;
   return copysignf(r, y);
 }
-MDS_DEV double atan2_(double y, double x) { return atan2(y, x); }
 MDS_DEV float asin_(float x) { return asinf(x); }
-MDS_DEV double asin_(double x) { return asin(x); }
 MDS_DEV float acos_(float x) { return acosf(x); }
 MDS_DEV double acos_(double x) { return acos(x); }
 MDS_DEV float exp_(float x) { return expf(x); }
-MDS_DEV double exp_(double x) { return exp(x); }
+// fp64 exp for finite arguments in [-700, 700] (clamped: the one caller is the downwash Gaussian, argument <= 0, and
+// exp(-700) = 1e-304 is zero to it): 2^k e^r with k = rint(x log2 e) by the 1.5 * 2^52 trick, r = x - k ln 2 in two parts,
+// |r| <= 0.347, e^r as its degree-13 Taylor polynomial (truncation 4e-18), the exponent added as an integer.  24 instructions
+// against libdevice's 65 (special cases, sub-normal results); measured 1 ulp against glibc on 2e7 arguments
+// (tests/test_device_math.py re-evaluates these tables in numpy).
+MDS_DEV double exp_(double x) {
+  x = fmin(fmax(x, -700.0), 700.0);
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int k = __double2loint(t);
+  const double kd = t - 6755399441055744.0;
+  double r = fma(kd, -6.93147180369123816490e-01, x);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;
+  p = fma(p, r, 2.08767569878681e-09);
+  p = fma(p, r, 2.505210838544172e-08);
+  p = fma(p, r, 2.755731922398589e-07);
+  p = fma(p, r, 2.7557319223985893e-06);
+  p = fma(p, r, 2.48015873015873e-05);
+  p = fma(p, r, 1.984126984126984e-04);
+  p = fma(p, r, 1.388888888888889e-03);
+  p = fma(p, r, 8.333333333333333e-03);
+  p = fma(p, r, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return __longlong_as_double(__double_as_longlong(p) + ((long long)k << 52));
+}
+// a / b and 1 / b.  fp32: the plain operators (approximate under -use_fast_math, IEEE otherwise).  fp64, for normal finite
+// b != 0 and results in the normal range: MUFU.RCP64H + two Newton steps + one residual correction, 8 instructions against the
+// 15 + out-of-line slow path nvcc emits for `/`; bit-equal to IEEE division on 2e7 random pairs in the CPU emulation.
+MDS_DEV float rcp_(float b) { return 1.f / b; }
+MDS_DEV float div_(float a, float b) { return a / b; }
+MDS_DEV double rcp_(double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  return fma(r, e, r);
+}
+MDS_DEV double div_(double a, double b) {
+  const double r = rcp_(b), q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+// fp64 atan2 / asin of the observation's Euler angles: the fp32 scheme above (one division, reduction to |t| <= tan(pi/8),
+// octant fix-ups) with an 11-term minimax polynomial in t^2, and asin as x + x z R(z) on |x| <= 1/2, pi/2 - 2 asin(sqrt((1 - |x|) / 2))
+// beyond (13 terms; coefficients by Chebyshev fit at 60 digits).  ~40 and ~30 instructions against libdevice's 88 and 129;
+// 1.3 / 2 ulp against glibc on 2e7 arguments.  Finite arguments only (the callers' are: quaternion products).
+MDS_DEV double atan2_(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  const bool mid = mn > 0.41421356237309503 * mx;
+  const double num = mid ? mn - mx : mn, den = mid ? mn + mx : mx;
+  const double t = den > 0.0 ? div_(num, den) : 0.0;  // atan2(0, 0) = 0
+  const double z = t * t;
+  double p = -0.019176887119062259;
+  p = fma(p, z, 0.0392316582955871913);
+  p = fma(p, z, -0.0508544973794025986);
+  p = fma(p, z, 0.0585814891280220988);
+  p = fma(p, z, -0.06664511447381948);
+  p = fma(p, z, 0.0769218319082608656);
+  p = fma(p, z, -0.0909090457812390189);
+  p = fma(p, z, 0.111111110152563617);
+  p = fma(p, z, -0.142857142846665429);
+  p = fma(p, z, 0.199999999999955207);
+  p = fma(p, z, -0.333333333333333302);
+  double r = fma(t * z, p, t);
+  if (mid) r += 0.78539816339744831;
+  if (ay > ax) r = 1.5707963267948966 - r;
+  if (x < 0.0) r = 3.1415926535897932 - r;
+  return copysign(r, y);
+}
+MDS_DEV double asin_(double x) {
+  const double a = fabs(x);
+  const bool big = a > 0.5;
+  const double z = big ? 0.5 * (1.0 - a) : a * a;
+  const double s = big ? sqrt(z) : a;
+  double p = 0.0287578513674215647;
+  p = fma(p, z, -0.0148518870712472032);
+  p = fma(p, z, 0.0174008794426940224);
+  p = fma(p, z, 0.0054575067186403583);
+  p = fma(p, z, 0.0103228143501857793);
+  p = fma(p, z, 0.0114791774151849059);
+  p = fma(p, z, 0.0139712129735529333);
+  p = fma(p, z, 0.0173523927208699729);
+  p = fma(p, z, 0.0223721729421498879);
+  p = fma(p, z, 0.0303819441385312473);
+  p = fma(p, z, 0.0446428571463554298);
+  p = fma(p, z, 0.0749999999999843293);
+  p = fma(p, z, 0.166666666666666678);
+  double r = fma(s * z, p, s);
+  if (big) r = 1.5707963267948966 - 2.0 * r;
+  return copysign(r, x);
+}
 MDS_DEV float tan_(float x) { return tanf(x); }
 MDS_DEV double tan_(double x) { return tan(x); }
 MDS_DEV float fma_(float a, float b, float c) { return fmaf(a, b, c); }
@@ -269,7 +361,7 @@ template <typename Real> MDS_DEV void store_drone(const StateP<Real>& s, int d, 
 // Bullet getMatrixFromQuaternion (xyzw; self-normalising s = 2/|q|^2) -- SURVEY A.2
 template <typename Real> MDS_DEV M3<Real> quat_to_mat(Real x, Real y, Real z, Real w) {
   Real d = x * x + y * y + z * z + w * w;
-  Real s = Real(2) / d;
+  Real s = Real(2) * rcp_(d);
   Real xs = x * s, ys = y * s, zs = z * s;
   Real wx = w * xs, wy = w * ys, wz = w * zs, xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
   M3<Real> R;

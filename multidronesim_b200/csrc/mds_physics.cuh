@@ -10,10 +10,10 @@ namespace mds {
 // Downwash on the LOWER drone of a pair: dz > 0 its distance below the other, dxy2 the squared distance in
 // the plane; only pairs within 10 m in the plane interact:  alpha * exp(-(dxy / beta)^2 / 2).
 template <typename Real> MDS_DEV Real downwash_pair(const DroneP<Real>& P, Real dz, Real dxy2) {
-  Real q = P.prop_radius / (Real(4) * max_(dz, P.dw_dz_clip));  // clip: App. A.4 regularisation (0 = upstream)
+  Real q = div_(P.prop_radius, Real(4) * max_(dz, P.dw_dz_clip));  // clip: App. A.4 regularisation (0 = upstream); callers pass dz > 0
   Real alpha = P.dw1 * q * q;
   Real beta = P.dw2 * dz + P.dw3;
-  return alpha * exp_(Real(-0.5) * dxy2 / (beta * beta));
+  return alpha * exp_(div_(Real(-0.5) * dxy2, beta * beta));
 }
 // two pairs at once (fp32, packed arithmetic; the reciprocals and the exponentials are per half: MUFU has no packed form)
 MDS_DEV F2 downwash_pair2(const DroneP<float>& P, F2 dz, F2 dxy2) {

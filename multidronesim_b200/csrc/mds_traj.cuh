@@ -50,9 +50,9 @@ template <typename Real> MDS_DEV Ref<Real> eval_lemniscate(const Real* p, double
   Real s2 = s * s, c2 = c * c;
   Real cos2 = c2 - s2, sin2 = Real(2) * s * c;          // cos 2th, sin 2th
   Real cos4 = Real(2) * cos2 * cos2 - Real(1);         // cos 4th
-  Real den = Real(1) + s2, inv = Real(1) / den, inv2 = inv * inv;
+  Real den = Real(1) + s2, inv = rcp_(den), inv2 = inv * inv;
   Real k3 = cos2 - Real(3);
-  Real ik3 = Real(1) / (k3 * k3 * k3);
+  Real ik3 = rcp_(k3 * k3 * k3);
   Ref<Real> o;
   o.p = {p[2] + a * s * c * inv, p[3] + a * c * inv, p[4]};
   o.v = {-a * om * (s2 * s2 + s2 + (s2 - Real(1)) * c2) * inv2, -a * om * s * (s2 + Real(2) * c2 + Real(1)) * inv2, Real(0)};
