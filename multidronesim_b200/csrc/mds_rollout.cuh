@@ -19,7 +19,7 @@ using namespace mds;
 #define MDS_BLOCK 256
 #endif
 #ifndef MDS_CTRL_MINB
-#define MDS_CTRL_MINB 4  // resident blocks per SM the controller kernel is compiled for (64 registers)
+#define MDS_CTRL_MINB 4  // resident blocks per SM of the NON-persistent controller kernel (64 registers; MDS_CTRL_PERSISTENT=0 builds it)
 #endif
 #ifndef MDS_LOOP_MINB
 #define MDS_LOOP_MINB 2  // the K-step loop kernel serves small swarms: registers before occupancy
@@ -673,7 +673,7 @@ template <bool USE_CBF> MDS_DEV void stats_block_reduce(double* __restrict__ sta
 }
 
 // controller stack alone: obs (HBM) -> action (HBM).
-// PERSISTENT: the grid is the resident set (MDS_CTRL_MINB blocks per SM; fewer for small swarms) and every block walks the
+// PERSISTENT: the grid is the resident set (2 blocks per SM; fewer for small swarms) and every block walks the
 // block-sized tiles of the environments with stride gridDim.x.  One block per tile at 64 registers (4 resident blocks, 182 KB of
 // shared memory, 41 KB of L1 left for 960-byte frames) ran at IPC 1.6, latency-bound on its first loads and its spills, with a
 // statistics reduction + block barrier per tile (9 % of the instructions, 20 % of the stall samples).  The same stack inside
