@@ -441,3 +441,32 @@ def test_extrema_statistics_across_blocks(lib_built):
         mins.append(s1["min_barrier"]); maxs.append(s1["max_pos_err"]); solves += s1["qp_solves"]
     assert min(mins) < 0 < max(maxs)           # the sign cases the atomics distinguish are exercised
     assert st["min_barrier"] == min(mins) and st["max_pos_err"] == max(maxs) and st["qp_solves"] == solves
+
+
+def test_persistent_ctrl_kernel_walks_its_tiles(lib_built):
+    """ctrl_step_kernel is persistent (mds_rollout.cuh): its grid is capped at the resident set (2 blocks per SM) and every block
+    walks block-sized tiles of the environments with stride gridDim.x.  Small swarms never make a block take a second tile,
+    so this runs the two-launch plan on 21 003 environments (657 tiles on at most 296 blocks, last tile partly filled) and
+    checks (a) environments first, interior, at tile / grid-stride boundaries and last against the same environments
+    rolled out alone -- environments never interact, and a one-environment launch is a single tile -- bit for bit, and
+    (b) that the statistics count every drone-step exactly once."""
+    from multidronesim_b200 import scenarios
+    E, K = 21003, 6
+    big = scenarios.cbf_swarm(E, 8, order=3)
+    big["rollout"].run(K, stages=4)
+    st = big["rollout"].stats_dict()
+    assert st["drone_steps"] == E * 8 * K
+    # the K-step loop kernel (plan 6) is the same arithmetic compiled as one loop body: its QP counters agree up to the few
+    # borderline decisions fp32 rounding can flip among 126 018 environment-steps (the swarm starts from rest: some early QPs
+    # are infeasible and fall back, as in the reference)
+    ref = scenarios.cbf_swarm(E, 8, order=3)
+    ref["rollout"].run(K, stages=6)
+    sr = ref["rollout"].stats_dict()
+    for k in ("qp_solves", "qp_iters", "qp_infeasible", "qp_iter_cap"):
+        assert abs(st[k] - sr[k]) <= 0.02 * max(sr[k], 50.0), (k, st[k], sr[k])
+    obs_big = big["env"].obs
+    assert bool(torch.isfinite(obs_big).all())
+    for e0 in (0, 31, 32, 296 * 32 - 1, 296 * 32, 296 * 32 + 33, 2 * 296 * 32 + 5, E - 4, E - 1):
+        small = scenarios.cbf_swarm(1, 8, order=3, env_offset=e0)
+        small["rollout"].run(K, stages=4)
+        assert torch.equal(small["env"].obs[0], obs_big[e0]), e0
