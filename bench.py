@@ -462,6 +462,7 @@ def run_gpu_arm(args):
                 "launches_per_step": P_STREAMS, "envs_per_launch": E // P_STREAMS, "achieved": tf, "peak": fpk,
                 "unit": "TFLOP/s", "frac": tf / fpk, "peak_source": fpk_src, "peak_nominal": fpk_nominal, "peak_fma_chain": fpk_chain,
                 "frac_counters": cap.get("fp_frac_counters") if cap else None,
+                "frac_counters_scalar_only": cap.get("fp_frac_counters_scalar_only") if cap else None,
                 "frac_counters_source": (f"profiles/{cap['report']}: executed (fadd + fmul + 2 ffma + 2 fadd2 + 2 fmul2 + 4 ffma2) per cycle / (2 x ffma peak_sustained); scalar opcodes from the hardware counters, "
                                          "packed fp32 opcodes from the SASS page of the same ncu --set full capture (the counters leave them out)"
                                          if cap and cap.get("fp_frac_counters") is not None else None),
